@@ -1308,16 +1308,19 @@ int orc_get_local_map(void* h, int cls, const double centre_t[3], float* out, in
   return n;
 }
 
-// Whole-window map, cube index order, for bit-exact map comparisons.
+// Whole-window map in the order of the gather loops (i, j, k nested,
+// laserMapping.cpp:513-517), each cube in its stored order; for bit-exact map comparisons.
 int orc_get_map(void* h, int cls, float* out, int cap) {
   auto* m = (orc::Mapper*)h;
   auto& arr = cls == 0 ? m->corner_ : m->surf_;
   int n = 0;
-  for (auto& c : arr)
-    for (auto& p : c) {
-      if (out && n < cap) std::memcpy(out + 4 * (size_t)n, &p, 16);
-      ++n;
-    }
+  for (int i = 0; i < 21; ++i)
+    for (int j = 0; j < 21; ++j)
+      for (int k = 0; k < 11; ++k)
+        for (auto& p : arr[m->ind(i, j, k)]) {
+          if (out && n < cap) std::memcpy(out + 4 * (size_t)n, &p, 16);
+          ++n;
+        }
   return n;
 }
 void orc_get_window(void* h, int cen[3]) {

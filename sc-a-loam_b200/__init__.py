@@ -1,0 +1,288 @@
+"""sc-a-loam_b200 -- B200-native scan-to-map registration (host-side Python view).
+
+Thin ctypes binding of the C ABI in include/s2m.h (csrc/libs2m.so).  The product
+is the CUDA library; this module only marshals numpy / torch buffers into it, the
+way a ROS shim would marshal PointCloud2 payloads.
+
+There is NO CPU fallback: importing works without a GPU (so the build and the
+symbol table can be checked), but creating a context raises if the library or a
+CUDA device is missing.  Nothing here imports or calls oracle/.
+
+Directory name has a hyphen, so load it with importlib (see __graft_entry__.py):
+    pkg = load_package()           # -> module 'sc_a_loam_b200'
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libs2m.so")
+
+S2M_OK = 0
+S2M_MAP_TOO_SMALL = 1
+
+# every symbol include/s2m.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "s2m_default_params", "s2m_create", "s2m_destroy", "s2m_strerror", "s2m_last_error", "s2m_set_stream",
+    "s2m_register", "s2m_register_batch", "s2m_register_batch_dev", "s2m_get_correction",
+    "s2m_transform_cloud", "s2m_map_upload", "s2m_map_download", "s2m_get_local_map", "s2m_get_surround",
+    "s2m_get_window", "s2m_debug_knn", "s2m_trace_cloud", "s2m_trace_knn", "s2m_trace_lm",
+    "s2m_launch_count", "s2m_set_profiling", "s2m_k4_profile", "s2m_shard_unique_id", "s2m_shard_init",
+    "s2m_shard_profile",
+]
+
+
+class Params(ctypes.Structure):
+    _fields_ = [("line_res", ctypes.c_float), ("plane_res", ctypes.c_float), ("device", ctypes.c_int),
+                ("batch", ctypes.c_int), ("cap_corner_in", ctypes.c_int), ("cap_surf_in", ctypes.c_int),
+                ("cap_map_corner", ctypes.c_int), ("cap_map_surf", ctypes.c_int),
+                ("skip_optimization", ctypes.c_int), ("trace", ctypes.c_int),
+                ("shard_rank", ctypes.c_int), ("shard_world", ctypes.c_int)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("n_corner_in", ctypes.c_int), ("n_surf_in", ctypes.c_int),
+                ("n_corner_ds", ctypes.c_int), ("n_surf_ds", ctypes.c_int),
+                ("n_map_corner", ctypes.c_int), ("n_map_surf", ctypes.c_int),
+                ("n_edge", ctypes.c_int * 2), ("n_plane", ctypes.c_int * 2),
+                ("optimized", ctypes.c_int), ("lm_iters", ctypes.c_int * 2), ("lm_term", ctypes.c_int * 2),
+                ("cost_initial", ctypes.c_double * 2), ("cost_final", ctypes.c_double * 2)]
+
+
+class S2MError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """dlopen csrc/libs2m.so and declare the prototypes. Fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise S2MError("%s not built: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                       "There is no CPU fallback." % path)
+    L = ctypes.CDLL(path)
+    vp, ci, cll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+    L.s2m_default_params.argtypes = [ctypes.POINTER(Params)]
+    L.s2m_default_params.restype = None
+    L.s2m_create.argtypes = [ctypes.POINTER(Params), ctypes.POINTER(vp)]
+    L.s2m_destroy.argtypes = [vp]
+    L.s2m_destroy.restype = None
+    L.s2m_strerror.argtypes = [ci]
+    L.s2m_strerror.restype = ctypes.c_char_p
+    L.s2m_last_error.argtypes = [vp]
+    L.s2m_last_error.restype = ctypes.c_char_p
+    L.s2m_set_stream.argtypes = [vp, vp]
+    L.s2m_register.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp, vp, vp]
+    L.s2m_register_batch.argtypes = [vp] + [vp] * 11
+    L.s2m_register_batch_dev.argtypes = [vp] + [vp] * 11
+    L.s2m_get_correction.argtypes = [vp, ci, vp, vp]
+    L.s2m_transform_cloud.argtypes = [vp, ci, vp, ci, vp]
+    L.s2m_map_upload.argtypes = [vp, ci, vp, ci, vp, ci]
+    L.s2m_map_download.argtypes = [vp, ci, ci, vp, ci]
+    L.s2m_get_local_map.argtypes = [vp, ci, ci, vp, vp, ci]
+    L.s2m_get_surround.argtypes = [vp, ci, vp, ci]
+    L.s2m_get_window.argtypes = [vp, ci, vp]
+    L.s2m_debug_knn.argtypes = [vp, ci, ci, vp, vp, ci, vp, vp]
+    L.s2m_trace_cloud.argtypes = [vp, ci, ci, vp, ci]
+    L.s2m_trace_knn.argtypes = [vp, ci, ci, ci, vp, vp, vp, ci]
+    L.s2m_trace_lm.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
+    L.s2m_launch_count.argtypes = [vp]
+    L.s2m_launch_count.restype = cll
+    L.s2m_set_profiling.argtypes = [vp, ci]
+    L.s2m_k4_profile.argtypes = [vp, ci, vp, vp, vp]
+    L.s2m_shard_unique_id.argtypes = [vp]
+    L.s2m_shard_init.argtypes = [vp, vp]
+    L.s2m_shard_profile.argtypes = [vp, ci, vp, vp]
+    _lib = L
+    return L
+
+
+def default_params():
+    p = Params()
+    load_library().s2m_default_params(ctypes.byref(p))
+    return p
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+class Registrar:
+    """One context = `batch` independent laserMapping instances on one GPU.
+
+    Mirrors the reference node's state and per-frame step (laserMapping.cpp:232-906):
+    register() is one pass of process() for one sequence, register_batch() one pass
+    for every slot.
+    """
+
+    def __init__(self, line_res=0.4, plane_res=0.8, device=0, batch=1, cap_corner_in=16384,
+                 cap_surf_in=131072, cap_map_corner=1 << 19, cap_map_surf=1 << 20,
+                 skip_optimization=False, trace=False):
+        self.L = load_library()
+        p = default_params()
+        p.line_res, p.plane_res, p.device, p.batch = line_res, plane_res, device, batch
+        p.cap_corner_in, p.cap_surf_in = cap_corner_in, cap_surf_in
+        p.cap_map_corner, p.cap_map_surf = cap_map_corner, cap_map_surf
+        p.skip_optimization, p.trace = int(skip_optimization), int(trace)
+        self.params = p
+        self.batch = batch
+        h = ctypes.c_void_p()
+        rc = self.L.s2m_create(ctypes.byref(p), ctypes.byref(h))
+        if rc != 0 or not h:
+            raise S2MError("s2m_create failed: %s (no CUDA device? there is no CPU fallback)"
+                           % self.L.s2m_strerror(rc).decode())
+        self.h = h
+        self.stats = Stats()
+        self._bstats = (Stats * batch)()
+        self._status = np.zeros(batch, np.int32)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.s2m_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise S2MError("%s: %s" % (self.L.s2m_strerror(rc).decode(), self.L.s2m_last_error(self.h).decode()))
+        return rc
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(self.L.s2m_set_stream(self.h, ctypes.c_void_p(cuda_stream_handle)))
+
+    # ---- one sequence -------------------------------------------------------
+    def register(self, corner, surf, q_wodom, t_wodom):
+        """-> (status, q_w[4], t_w[3]); status 0 ok, 1 map too small (pose = guess)."""
+        corner, surf = _f32(corner).reshape(-1, 4), _f32(surf).reshape(-1, 4)
+        q, t = _f64(q_wodom), _f64(t_wodom)
+        qo, to = np.zeros(4), np.zeros(3)
+        rc = self.L.s2m_register(self.h, corner.ctypes.data, len(corner), surf.ctypes.data, len(surf),
+                                 q.ctypes.data, t.ctypes.data, qo.ctypes.data, to.ctypes.data,
+                                 ctypes.byref(self.stats))
+        return self._check(rc), qo, to
+
+    # ---- every slot -----------------------------------------------------------
+    def register_batch(self, corner, corner_off, surf, surf_off, q_wodom, t_wodom, active=None, device_ptrs=False):
+        """corner/surf: packed (n,4) float32 host arrays, or raw device pointers (ints) if device_ptrs.
+        -> (status[B], q_w[B,4], t_w[B,3]); per-slot stats in self.batch_stats."""
+        B = self.batch
+        co, so = np.ascontiguousarray(corner_off, np.int32), np.ascontiguousarray(surf_off, np.int32)
+        assert len(co) == B + 1 and len(so) == B + 1
+        q, t = _f64(q_wodom).reshape(B, 4), _f64(t_wodom).reshape(B, 3)
+        qo, to = np.zeros((B, 4)), np.zeros((B, 3))
+        act = None if active is None else np.ascontiguousarray(active, np.int32)
+        if device_ptrs:
+            cp, sp = ctypes.c_void_p(int(corner)), ctypes.c_void_p(int(surf))
+            fn = self.L.s2m_register_batch_dev
+        else:
+            corner, surf = _f32(corner).reshape(-1, 4), _f32(surf).reshape(-1, 4)
+            cp, sp = corner.ctypes.data, surf.ctypes.data
+            fn = self.L.s2m_register_batch
+        rc = fn(self.h, cp, co.ctypes.data, sp, so.ctypes.data, q.ctypes.data, t.ctypes.data,
+                None if act is None else act.ctypes.data, qo.ctypes.data, to.ctypes.data,
+                ctypes.cast(self._bstats, ctypes.c_void_p), self._status.ctypes.data)
+        self._check(rc)
+        return self._status.copy(), qo, to
+
+    @property
+    def batch_stats(self):
+        return self._bstats
+
+    # ---- state ----------------------------------------------------------------
+    def correction(self, slot=0):
+        q, t = np.zeros(4), np.zeros(3)
+        self._check(self.L.s2m_get_correction(self.h, slot, q.ctypes.data, t.ctypes.data))
+        return q, t
+
+    def window(self, slot=0):
+        c = np.zeros(3, np.int32)
+        self._check(self.L.s2m_get_window(self.h, slot, c.ctypes.data))
+        return c
+
+    def transform_cloud(self, pts, slot=0):
+        pts = _f32(pts).reshape(-1, 4)
+        out = np.zeros_like(pts)
+        self._check(self.L.s2m_transform_cloud(self.h, slot, pts.ctypes.data, len(pts), out.ctypes.data))
+        return out
+
+    def map_upload(self, corner, surf, slot=0):
+        corner, surf = _f32(corner).reshape(-1, 4), _f32(surf).reshape(-1, 4)
+        return self._check(self.L.s2m_map_upload(self.h, slot, corner.ctypes.data, len(corner),
+                                                 surf.ctypes.data, len(surf)))
+
+    def map_download(self, cls, slot=0):
+        n = self._check(self.L.s2m_map_download(self.h, slot, cls, None, 0))
+        out = np.zeros((max(n, 1), 4), np.float32)
+        self._check(self.L.s2m_map_download(self.h, slot, cls, out.ctypes.data, n))
+        return out[:n]
+
+    def local_map(self, cls, centre_t, slot=0):
+        c = _f64(centre_t)
+        cap = int(self.params.cap_map_corner if cls == 0 else self.params.cap_map_surf)
+        out = np.zeros((cap, 4), np.float32)
+        n = self._check(self.L.s2m_get_local_map(self.h, slot, cls, c.ctypes.data, out.ctypes.data, cap))
+        return out[:n].copy()
+
+    def surround(self, slot=0):
+        n = self._check(self.L.s2m_get_surround(self.h, slot, None, 0))
+        out = np.zeros((max(n, 1), 4), np.float32)
+        self._check(self.L.s2m_get_surround(self.h, slot, out.ctypes.data, n))
+        return out[:n]
+
+    def debug_knn(self, cls, centre_t, q_xyz, slot=0):
+        q = _f32(q_xyz).reshape(-1, 3)
+        c = _f64(centre_t)
+        idx = np.zeros((len(q), 5), np.int32)
+        d2 = np.zeros((len(q), 5), np.float32)
+        self._check(self.L.s2m_debug_knn(self.h, slot, cls, c.ctypes.data, q.ctypes.data, len(q),
+                                         idx.ctypes.data, d2.ctypes.data))
+        return idx, d2
+
+    # ---- trace of the last call (trace=True) --------------------------------------
+    def trace_cloud(self, cls, slot=0):
+        cap = int(self.params.cap_corner_in if cls == 0 else self.params.cap_surf_in)
+        out = np.zeros((cap, 4), np.float32)
+        n = self._check(self.L.s2m_trace_cloud(self.h, slot, cls, out.ctypes.data, cap))
+        return out[:n].copy()
+
+    def trace_knn(self, outer, cls, slot=0):
+        cap = int(self.params.cap_corner_in if cls == 0 else self.params.cap_surf_in)
+        idx = np.zeros((cap, 5), np.int32)
+        d2 = np.zeros((cap, 5), np.float32)
+        used = np.zeros(cap, np.uint8)
+        n = self._check(self.L.s2m_trace_knn(self.h, slot, outer, cls, idx.ctypes.data, d2.ctypes.data,
+                                             used.ctypes.data, cap))
+        return idx[:n].copy(), d2[:n].copy(), used[:n].copy()
+
+    def trace_lm(self, outer, slot=0):
+        pose, sums, iters = np.zeros(7), np.zeros(28), np.zeros((4, 6))
+        n, term = ctypes.c_int(), ctypes.c_int()
+        self._check(self.L.s2m_trace_lm(self.h, slot, outer, pose.ctypes.data, sums.ctypes.data,
+                                        iters.ctypes.data, ctypes.byref(n), ctypes.byref(term)))
+        return pose, sums, iters, n.value, term.value
+
+    # ---- measurement ----------------------------------------------------------------
+    def launch_count(self):
+        return int(self.L.s2m_launch_count(self.h))
+
+    def set_profiling(self, on=True):
+        self._check(self.L.s2m_set_profiling(self.h, int(on)))
+
+    def k4_profile(self, reset=True):
+        ms, n, b = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+        self._check(self.L.s2m_k4_profile(self.h, int(reset), ctypes.byref(ms), ctypes.byref(n), ctypes.byref(b)))
+        return ms.value, n.value, b.value

@@ -1,0 +1,766 @@
+// s2m_api.cu -- context, per-frame orchestration and the C ABI of include/s2m.h.
+//
+// Host-side rows of the reference kept here (all tiny, FP64, no contraction):
+//   A  transformAssociateToMap   laserMapping.cpp:143-147
+//   B  centre cube + window shift :313-508 (a window in WORLD cube coordinates;
+//      shifting the reference's pointer arrays == moving that window, clearing a
+//      recycled slab == dropping store entries whose cube left the window)
+//   C  valid block                :510-530
+//   U  transformUpdate            :149-153
+// Everything else runs on the device (s2m_kernels.cu) on one stream, with a
+// single device->host read-back (poses + counters) per call.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/s2m.h"
+#include "s2m_internal.h"
+
+using namespace s2m;
+
+namespace {
+
+struct SlotHost {
+  int cen[3] = {10, 10, 5};                 // laserCloudCenWidth/Height/Depth (:74-76)
+  double q_wmap_wodom[4] = {0, 0, 0, 1};    // :116-117
+  double t_wmap_wodom[3] = {0, 0, 0};
+  double pose[7] = {0, 0, 0, 1, 0, 0, 0};   // parameters[7] (:110)
+  int n_store[2] = {0, 0};                  // entries per class (after the last call)
+  int val_lo[3] = {0, 0, 0}, val_hi[3] = {-1, -1, -1};
+  bool force_pending_check = false;         // after an upload every entry is raw
+  unsigned long long seq[2] = {0, 0};
+  long long frames = 0;
+};
+
+struct HostTables {  // one pinned block, copied to the device in one go
+  FrameDesc desc[kMaxBatch];
+  int in_off[2 * kMaxBatch + 1];
+  int lp_off[2 * kMaxBatch + 1];
+  int hash_off[2 * kMaxBatch + 1];
+};
+
+}  // namespace
+
+struct s2m_ctx {
+  s2m_params P;
+  Dev d;
+  int cur = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::vector<SlotHost> slots;
+  HostTables* ht = nullptr;      // pinned
+  HostTables* d_ht = nullptr;    // device copy (desc/in_off/lp_off/hash_off point into it)
+  SlotOut* h_out = nullptr;      // pinned
+  int* h_err = nullptr;          // pinned
+  LmState* lm_trace = nullptr;   // [2][B] device
+  LmState* h_lm = nullptr;       // pinned [2][B]
+  std::vector<void*> allocs;
+  std::string err;
+  long long launches = 0;
+  int hash_cap_total = 0;
+  // profiling of the fused association kernel
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> k4_events;
+  size_t k4_used = 0;
+  double k4_ms = 0, k4_bytes = 0;
+  long long k4_launches = 0;
+  std::vector<std::pair<int, int>> k4_pending_outer;  // (event index, outer) awaiting byte accounting
+  int last_total_in = 0;
+};
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                     \
+      return S2M_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+template <typename T>
+static int dev_alloc(s2m_ctx* ctx, T** p, size_t n) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+  ctx->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+extern "C" void s2m_default_params(s2m_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->line_res = 0.4f;   // laserMapping.cpp:915
+  p->plane_res = 0.8f;  // :916
+  p->device = 0;
+  p->batch = 1;
+  p->cap_corner_in = 16384;
+  p->cap_surf_in = 131072;
+  p->cap_map_corner = 1 << 20;
+  p->cap_map_surf = 1 << 21;
+  p->shard_world = 1;
+}
+
+extern "C" const char* s2m_strerror(int code) {
+  switch (code) {
+    case S2M_OK: return "ok";
+    case S2M_MAP_TOO_SMALL: return "map corner and surf num are not enough (pose = odometry guess)";
+    case S2M_ERR_CUDA: return "CUDA error";
+    case S2M_ERR_ARG: return "bad argument";
+    case S2M_ERR_CAPACITY: return "capacity exceeded";
+    case S2M_ERR_RANGE: return "coordinates outside the supported lattice range";
+    case S2M_ERR_NCCL: return "NCCL error";
+    default: return "unknown";
+  }
+}
+extern "C" const char* s2m_last_error(s2m_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" void s2m_destroy(s2m_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->P.device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->ht) cudaFreeHost(ctx->ht);
+  if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  if (ctx->h_err) cudaFreeHost(ctx->h_err);
+  if (ctx->h_lm) cudaFreeHost(ctx->h_lm);
+  for (auto& e : ctx->k4_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+static int create_impl(s2m_ctx* ctx) {
+  const s2m_params& P = ctx->P;
+  CK(cudaSetDevice(P.device));
+  CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  Dev& d = ctx->d;
+  std::memset(&d, 0, sizeof(d));
+  const int B = P.batch, G = 2 * B;
+  d.B = B; d.G = G;
+  d.inv_leaf[0] = 1.0f / P.line_res;   // pcl::VoxelGrid::setLeafSize: inverse_leaf_size = 1 / leaf (float)
+  d.inv_leaf[1] = 1.0f / P.plane_res;
+  const long long cap_in = (long long)B * ((long long)P.cap_corner_in + P.cap_surf_in);
+  const long long cap_lp = (long long)B * ((long long)P.cap_map_corner + P.cap_map_surf);
+  if (cap_in + cap_lp >= (1ll << 30)) { ctx->err = "capacities too large (packed index space is 30 bits)"; return S2M_ERR_ARG; }
+  d.cap_in = (int)cap_in; d.cap_lp = (int)cap_lp; d.cap_sort = (int)(cap_in + cap_lp);
+  d.max_tiles = (P.cap_corner_in + P.cap_surf_in + kTile - 1) / kTile;
+
+  CK(cudaMallocHost((void**)&ctx->ht, sizeof(HostTables)));
+  CK(cudaMallocHost((void**)&ctx->h_out, sizeof(SlotOut) * B));
+  CK(cudaMallocHost((void**)&ctx->h_err, sizeof(int)));
+  CK(cudaMallocHost((void**)&ctx->h_lm, sizeof(LmState) * 2 * B));
+  std::memset(ctx->ht, 0, sizeof(HostTables));
+  if (dev_alloc(ctx, &ctx->d_ht, 1)) return S2M_ERR_CUDA;
+  d.desc = ctx->d_ht->desc; d.in_off = ctx->d_ht->in_off; d.lp_off = ctx->d_ht->lp_off; d.hash_off = ctx->d_ht->hash_off;
+
+  int rc = 0;
+  rc |= dev_alloc(ctx, &d.st_base, G); rc |= dev_alloc(ctx, &d.st_cap, G);
+  rc |= dev_alloc(ctx, &d.in_pts, d.cap_in);
+  rc |= dev_alloc(ctx, &d.vkey, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.vkey2, d.cap_sort + 1);
+  rc |= dev_alloc(ctx, &d.vval, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.vval2, d.cap_sort + 1);
+  rc |= dev_alloc(ctx, &d.flag, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.scan, d.cap_sort + 1);
+  rc |= dev_alloc(ctx, &d.bbox, 6 * G);
+  rc |= dev_alloc(ctx, &d.ds_pts, d.cap_in); rc |= dev_alloc(ctx, &d.ds_off, G + 1);
+  for (int b = 0; b < 2; ++b) { rc |= dev_alloc(ctx, &d.st_key[b], d.cap_lp); rc |= dev_alloc(ctx, &d.st_pt[b], d.cap_lp); }
+  rc |= dev_alloc(ctx, &d.st_n, G); rc |= dev_alloc(ctx, &d.st_n_new, G);
+  rc |= dev_alloc(ctx, &d.rng_start, G * kCols); rc |= dev_alloc(ctx, &d.loc_off, G * (kCols + 1));
+  rc |= dev_alloc(ctx, &d.ckey, d.cap_lp); rc |= dev_alloc(ctx, &d.ckey2, d.cap_lp);
+  rc |= dev_alloc(ctx, &d.cval, d.cap_lp); rc |= dev_alloc(ctx, &d.cval2, d.cap_lp);
+  rc |= dev_alloc(ctx, &d.cand, d.cap_lp);
+  // cell tables: per segment a power of two >= 2 x entries, >= 1024
+  long long hcap = 0;
+  for (int g = 0; g < G; ++g) hcap += next_pow2(std::max(1024, 2 * (g < B ? P.cap_map_corner : P.cap_map_surf)));
+  if (hcap >= (1ll << 31)) { ctx->err = "cell tables too large"; return S2M_ERR_ARG; }
+  ctx->hash_cap_total = (int)hcap;
+  rc |= dev_alloc(ctx, &d.hash_tab, (size_t)hcap); rc |= dev_alloc(ctx, &d.hash_full, (size_t)hcap);
+  rc |= dev_alloc(ctx, &d.cs_off, G + 1);
+  rc |= dev_alloc(ctx, &d.rec, (size_t)d.cap_in * 6); rc |= dev_alloc(ctx, &d.rec_valid, d.cap_in);
+  rc |= dev_alloc(ctx, &d.partials, (size_t)B * d.max_tiles * kPartial);
+  rc |= dev_alloc(ctx, &d.lm, B); rc |= dev_alloc(ctx, &d.out, B); rc |= dev_alloc(ctx, &d.err_flag, 1);
+  rc |= dev_alloc(ctx, &ctx->lm_trace, 2 * B);
+  if (P.trace) {
+    rc |= dev_alloc(ctx, &d.tr_idx, (size_t)2 * d.cap_in * 5); rc |= dev_alloc(ctx, &d.tr_d2, (size_t)2 * d.cap_in * 5);
+    rc |= dev_alloc(ctx, &d.tr_used, (size_t)2 * d.cap_in);
+  }
+  rc |= dev_alloc(ctx, &d.dl_pt, d.cap_in);
+  rc |= dev_alloc(ctx, &d.ins_key, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.ins_ckey, d.cap_sort + 1);
+  rc |= dev_alloc(ctx, &d.ins_pt, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.ins_cpt, d.cap_sort + 1);
+  rc |= dev_alloc(ctx, &d.run_off, G + 1);
+  rc |= dev_alloc(ctx, &d.aflag, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.ascan, d.cap_sort + 1);
+  d.cub_tmp_bytes = cub_temp_bytes(d.cap_sort + 1, d.cap_lp + 1);
+  rc |= dev_alloc(ctx, (char**)&d.cub_tmp, d.cub_tmp_bytes);
+  if (rc) return S2M_ERR_CUDA;
+
+  std::vector<int> base(G), cap(G);
+  int acc = 0;
+  for (int g = 0; g < G; ++g) {
+    base[g] = acc;
+    cap[g] = g < B ? P.cap_map_corner : P.cap_map_surf;
+    acc += cap[g];
+  }
+  CK(cudaMemcpy(d.st_base, base.data(), sizeof(int) * G, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d.st_cap, cap.data(), sizeof(int) * G, cudaMemcpyHostToDevice));
+  CK(cudaMemset(d.st_n, 0, sizeof(int) * G));
+  CK(cudaMemset(d.st_n_new, 0, sizeof(int) * G));
+  CK(cudaMemset(d.err_flag, 0, sizeof(int)));
+  CK(cudaMemset(d.out, 0, sizeof(SlotOut) * B));
+  CK(cudaMemset(d.lm, 0, sizeof(LmState) * B));
+  CK(cudaMemset(d.ds_off, 0, sizeof(int) * (G + 1)));
+  ctx->slots.assign(B, SlotHost());
+  return S2M_OK;
+}
+
+extern "C" int s2m_create(const s2m_params* p, s2m_ctx** out) {
+  if (!p || !out) return S2M_ERR_ARG;
+  *out = nullptr;
+  if (p->batch < 1 || p->batch > kMaxBatch || !(p->line_res > 0.03f) || !(p->plane_res > 0.03f) ||
+      p->cap_corner_in < 1 || p->cap_surf_in < 1 || p->cap_map_corner < 1 || p->cap_map_surf < 1)
+    return S2M_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || p->device < 0 || p->device >= ndev) return S2M_ERR_CUDA;
+  s2m_ctx* ctx = new s2m_ctx();
+  ctx->P = *p;
+  if (ctx->P.shard_world < 1) ctx->P.shard_world = 1;
+  int rc = create_impl(ctx);
+  if (rc != S2M_OK) {
+    fprintf(stderr, "s2m_create: %s\n", ctx->err.c_str());
+    s2m_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return S2M_OK;
+}
+
+extern "C" int s2m_set_stream(s2m_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return S2M_OK;
+}
+
+extern "C" long long s2m_launch_count(s2m_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- host rows A, B, C ------------------------------------------------------
+static void row_A(SlotHost& s, const double q_wodom[4], const double t_wodom[3]) {
+  quat_mul_exact(s.q_wmap_wodom, q_wodom, s.pose);
+  double r[3];
+  quat_rotate_exact(s.q_wmap_wodom, t_wodom[0], t_wodom[1], t_wodom[2], r);
+  for (int i = 0; i < 3; ++i) s.pose[4 + i] = xdadd(r[i], s.t_wmap_wodom[i]);
+}
+static void row_U(SlotHost& s, const double q_wodom[4], const double t_wodom[3]) {
+  double qi[4], r[3];
+  quat_inverse_exact(q_wodom, qi);
+  quat_mul_exact(s.pose, qi, s.q_wmap_wodom);
+  quat_rotate_exact(s.q_wmap_wodom, t_wodom[0], t_wodom[1], t_wodom[2], r);
+  for (int i = 0; i < 3; ++i) s.t_wmap_wodom[i] = xdsub(s.pose[4 + i], r[i]);
+}
+// rows B + C for a sensor at t: moves the window, fills the descriptor boxes
+static void rows_BC(SlotHost& s, const double t[3], FrameDesc& fd) {
+  const int W[3] = {kWinI, kWinJ, kWinK};
+  int wc[3];
+  for (int a = 0; a < 3; ++a) {
+    wc[a] = cube_of(t[a]);
+    int c = wc[a] + s.cen[a];
+    while (c < 3) { c++; s.cen[a]++; }
+    while (c >= W[a] - 3) { c--; s.cen[a]--; }
+  }
+  const int half[3] = {2, 2, 1};
+  for (int a = 0; a < 3; ++a) {
+    fd.win_lo[a] = -s.cen[a];
+    fd.win_hi[a] = W[a] - 1 - s.cen[a];
+    fd.val_lo[a] = std::max(wc[a] - half[a], fd.win_lo[a]);
+    fd.val_hi[a] = std::min(wc[a] + half[a], fd.win_hi[a]);
+    fd.origin[a] = 50 * fd.val_lo[a] - 25;
+  }
+}
+
+// offsets that depend on the (host-known) store sizes
+static void fill_store_tables(s2m_ctx* ctx, int* total_lp, int* hash_total) {
+  const int B = ctx->d.B, G = ctx->d.G;
+  HostTables& T = *ctx->ht;
+  int acc = 0, hacc = 0;
+  for (int g = 0; g < G; ++g) {
+    const int n = ctx->slots[g < B ? g : g - B].n_store[g >= B];
+    T.lp_off[g] = acc; acc += n;
+    T.hash_off[g] = hacc; hacc += next_pow2(std::max(1024, 2 * n));
+  }
+  T.lp_off[G] = acc; T.hash_off[G] = hacc;
+  *total_lp = acc; *hash_total = hacc;
+}
+
+static int finish_call(s2m_ctx* ctx) {
+  CK(cudaMemcpyAsync(ctx->h_out, ctx->d.out, sizeof(SlotOut) * ctx->d.B, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_err, ctx->d.err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  if (*ctx->h_err != 0) {
+    int e = *ctx->h_err;
+    cudaMemsetAsync(ctx->d.err_flag, 0, sizeof(int), ctx->stream);
+    ctx->err = std::string("device reported: ") + s2m_strerror(e);
+    return e;
+  }
+  return S2M_OK;
+}
+
+// one frame for all active slots; inputs already packed in d.in_pts
+static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, const double* q_wodom,
+                     const double* t_wodom, const int* active, double* q_out, double* t_out, s2m_stats* stats,
+                     int* status) {
+  Dev& d = ctx->d;
+  const int B = d.B, G = d.G;
+  HostTables& T = *ctx->ht;
+  cudaStream_t s = ctx->stream;
+  const int total_in = T.in_off[G];
+  bool check_pending = false;
+  int tiles = 0;
+  for (int b = 0; b < B; ++b) {
+    SlotHost& sh = ctx->slots[b];
+    FrameDesc& fd = T.desc[b];
+    fd.active = active ? (active[b] != 0) : 1;
+    fd.allow_opt = !ctx->P.skip_optimization;
+    if (!fd.active) continue;
+    row_A(sh, q_wodom + 4 * b, t_wodom + 3 * b);
+    std::memcpy(fd.pose, sh.pose, sizeof(fd.pose));
+    rows_BC(sh, sh.pose + 4, fd);
+    fd.seq_base[0] = sh.seq[0]; fd.seq_base[1] = sh.seq[1];
+    bool moved = sh.force_pending_check;
+    for (int a = 0; a < 3; ++a) moved = moved || fd.val_lo[a] != sh.val_lo[a] || fd.val_hi[a] != sh.val_hi[a];
+    check_pending = check_pending || moved;
+    for (int a = 0; a < 3; ++a) { sh.val_lo[a] = fd.val_lo[a]; sh.val_hi[a] = fd.val_hi[a]; }
+    sh.force_pending_check = false;
+    const int nq = (corner_off[b + 1] - corner_off[b]) + (surf_off[b + 1] - surf_off[b]);
+    tiles = std::max(tiles, (nq + kTile - 1) / kTile);
+  }
+  int total_lp, hash_total;
+  fill_store_tables(ctx, &total_lp, &hash_total);
+  CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, s));
+
+  long long k = 0;
+  k += launch_voxel_filter(d, total_in, s);
+  k += launch_local_index(d, ctx->cur, total_lp, hash_total, s);
+  k += launch_guard(d, s);
+  for (int outer = 0; outer < 2; ++outer) {  // laserMapping.cpp:563
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->profiling) {
+      if (ctx->k4_used == ctx->k4_events.size()) {
+        cudaEvent_t a, b2;
+        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b2));
+        ctx->k4_events.push_back({a, b2});
+      }
+      e0 = ctx->k4_events[ctx->k4_used].first; e1 = ctx->k4_events[ctx->k4_used].second;
+      ctx->k4_used++;
+      CK(cudaEventRecord(e0, s));
+    }
+    k += launch_associate(d, outer, tiles, ctx->P.trace != 0, s);
+    if (ctx->profiling) CK(cudaEventRecord(e1, s));
+    k += launch_lm_begin(d, outer, s);
+    for (int it = 0; it < 4; ++it) {  // options.max_num_iterations = 4 (:716)
+      k += launch_evaluate(d, tiles, s);
+      k += launch_lm_after(d, outer, s);
+    }
+    if (ctx->P.trace)
+      CK(cudaMemcpyAsync(ctx->lm_trace + (size_t)outer * B, d.lm, sizeof(LmState) * B, cudaMemcpyDeviceToDevice, s));
+  }
+  k += launch_finish_pose(d, s);
+  k += launch_map_update(d, ctx->cur, total_in, total_lp, check_pending, false, s);
+  ctx->launches += k;
+  int rc = finish_call(ctx);
+  if (rc != S2M_OK) return rc;
+  // swap store buffers
+  ctx->cur ^= 1;
+  std::swap(d.st_n, d.st_n_new);
+
+  for (int b = 0; b < B; ++b) {
+    if (!T.desc[b].active) { if (status) status[b] = S2M_OK; continue; }
+    SlotHost& sh = ctx->slots[b];
+    const SlotOut& o = ctx->h_out[b];
+    std::memcpy(sh.pose, o.pose, sizeof(sh.pose));
+    row_U(sh, q_wodom + 4 * b, t_wodom + 3 * b);  // :735
+    sh.n_store[0] = o.n_store[0]; sh.n_store[1] = o.n_store[1];
+    sh.seq[0] += (unsigned long long)o.n_ds[0]; sh.seq[1] += (unsigned long long)o.n_ds[1];
+    sh.frames++;
+    for (int i = 0; i < 4; ++i) q_out[4 * b + i] = sh.pose[i];
+    for (int i = 0; i < 3; ++i) t_out[3 * b + i] = sh.pose[4 + i];
+    if (status) status[b] = o.optimized ? S2M_OK : S2M_MAP_TOO_SMALL;
+    if (stats) {
+      s2m_stats& st = stats[b];
+      st.n_corner_in = corner_off[b + 1] - corner_off[b]; st.n_surf_in = surf_off[b + 1] - surf_off[b];
+      st.n_corner_ds = o.n_ds[0]; st.n_surf_ds = o.n_ds[1];
+      st.n_map_corner = o.n_local[0]; st.n_map_surf = o.n_local[1];
+      for (int i = 0; i < 2; ++i) {
+        st.n_edge[i] = o.n_edge[i]; st.n_plane[i] = o.n_plane[i];
+        st.lm_iters[i] = o.lm_iters[i]; st.lm_term[i] = o.lm_term[i];
+        st.cost_initial[i] = o.cost_initial[i]; st.cost_final[i] = o.cost_final[i];
+      }
+      st.optimized = o.optimized;
+    }
+  }
+  // algorithmic bytes of the two association launches of this frame:
+  // (Nc+Ns)(16 + 27*8) + 16 * candidates visited + 48 * accepted correspondences
+  if (ctx->profiling) {
+    for (int outer = 0; outer < 2; ++outer) {
+      double bytes = 0;
+      for (int b = 0; b < B; ++b) {
+        const SlotOut& o = ctx->h_out[b];
+        if (!T.desc[b].active || !o.optimized) continue;
+        bytes += (double)(o.n_ds[0] + o.n_ds[1]) * (16.0 + 27.0 * 8.0) + 16.0 * (o.cand[0] + o.cand[1]) +
+                 48.0 * (o.n_edge[outer] + o.n_plane[outer]);
+      }
+      ctx->k4_bytes += bytes;
+    }
+  }
+  return S2M_OK;
+}
+
+static int check_offsets(s2m_ctx* ctx, const int* corner_off, const int* surf_off) {
+  const int B = ctx->d.B;
+  HostTables& T = *ctx->ht;
+  if (corner_off[0] != 0 || surf_off[0] != 0) { ctx->err = "offset arrays must start at 0"; return S2M_ERR_ARG; }
+  for (int b = 0; b < B; ++b) {
+    const int nc = corner_off[b + 1] - corner_off[b], ns = surf_off[b + 1] - surf_off[b];
+    if (nc < 0 || ns < 0) { ctx->err = "offsets must be non-decreasing"; return S2M_ERR_ARG; }
+    if (nc > ctx->P.cap_corner_in || ns > ctx->P.cap_surf_in) { ctx->err = "incoming cloud larger than cap_*_in"; return S2M_ERR_CAPACITY; }
+  }
+  // class-major segments: [corner of slot 0..B-1][surf of slot 0..B-1]
+  const int NC = corner_off[B];
+  for (int b = 0; b <= B; ++b) T.in_off[b] = corner_off[b];
+  for (int b = 0; b <= B; ++b) T.in_off[B + b] = NC + surf_off[b];
+  return S2M_OK;
+}
+
+static int register_batch_impl(s2m_ctx* ctx, const float* corner, const int* corner_off, const float* surf,
+                               const int* surf_off, const double* q_wodom, const double* t_wodom, const int* active,
+                               double* q_out, double* t_out, s2m_stats* stats, int* status, cudaMemcpyKind kind) {
+  if (!ctx || !corner_off || !surf_off || !q_wodom || !t_wodom || !q_out || !t_out) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  int rc = check_offsets(ctx, corner_off, surf_off);
+  if (rc != S2M_OK) return rc;
+  const int B = ctx->d.B;
+  const int NC = corner_off[B], NS = surf_off[B];
+  if (NC > 0) CK(cudaMemcpyAsync(ctx->d.in_pts, corner, sizeof(float4) * (size_t)NC, kind, ctx->stream));
+  if (NS > 0) CK(cudaMemcpyAsync(ctx->d.in_pts + NC, surf, sizeof(float4) * (size_t)NS, kind, ctx->stream));
+  return run_frame(ctx, corner_off, surf_off, q_wodom, t_wodom, active, q_out, t_out, stats, status);
+}
+
+extern "C" int s2m_register_batch(s2m_ctx* ctx, const float* corner, const int* corner_off, const float* surf,
+                                  const int* surf_off, const double* q_wodom, const double* t_wodom,
+                                  const int* active, double* q_out, double* t_out, s2m_stats* stats, int* status) {
+  return register_batch_impl(ctx, corner, corner_off, surf, surf_off, q_wodom, t_wodom, active, q_out, t_out, stats,
+                             status, cudaMemcpyHostToDevice);
+}
+extern "C" int s2m_register_batch_dev(s2m_ctx* ctx, const float* corner, const int* corner_off, const float* surf,
+                                      const int* surf_off, const double* q_wodom, const double* t_wodom,
+                                      const int* active, double* q_out, double* t_out, s2m_stats* stats,
+                                      int* status) {
+  return register_batch_impl(ctx, corner, corner_off, surf, surf_off, q_wodom, t_wodom, active, q_out, t_out, stats,
+                             status, cudaMemcpyDeviceToDevice);
+}
+
+extern "C" int s2m_register(s2m_ctx* ctx, const float* corner, int nc, const float* surf, int ns,
+                            const double q_wodom[4], const double t_wodom[3], double q_out[4], double t_out[3],
+                            s2m_stats* stats) {
+  if (!ctx || nc < 0 || ns < 0) return S2M_ERR_ARG;
+  const int B = ctx->d.B;
+  std::vector<int> co(B + 1, nc), so(B + 1, ns), act(B, 0);
+  co[0] = so[0] = 0;
+  act[0] = 1;
+  std::vector<double> q(4 * B, 0.0), t(3 * B, 0.0), qo(4 * B), to(3 * B);
+  std::vector<s2m_stats> st(B);
+  std::vector<int> status(B, 0);
+  std::memcpy(q.data(), q_wodom, 32); std::memcpy(t.data(), t_wodom, 24);
+  int rc = s2m_register_batch(ctx, corner, co.data(), surf, so.data(), q.data(), t.data(), act.data(), qo.data(),
+                              to.data(), st.data(), status.data());
+  if (rc != S2M_OK) return rc;
+  std::memcpy(q_out, qo.data(), 32); std::memcpy(t_out, to.data(), 24);
+  if (stats) *stats = st[0];
+  return status[0];
+}
+
+extern "C" int s2m_get_correction(s2m_ctx* ctx, int slot, double q[4], double t[3]) {
+  if (!ctx || slot < 0 || slot >= ctx->d.B) return S2M_ERR_ARG;
+  std::memcpy(q, ctx->slots[slot].q_wmap_wodom, 32);
+  std::memcpy(t, ctx->slots[slot].t_wmap_wodom, 24);
+  return S2M_OK;
+}
+extern "C" int s2m_get_window(s2m_ctx* ctx, int slot, int cen[3]) {
+  if (!ctx || slot < 0 || slot >= ctx->d.B) return S2M_ERR_ARG;
+  std::memcpy(cen, ctx->slots[slot].cen, 12);
+  return S2M_OK;
+}
+
+extern "C" int s2m_transform_cloud(s2m_ctx* ctx, int slot, const float* in, int n, float* out) {
+  if (!ctx || slot < 0 || slot >= ctx->d.B || n < 0) return S2M_ERR_ARG;
+  if (n > ctx->d.cap_sort) return S2M_ERR_CAPACITY;
+  if (n == 0) return S2M_OK;
+  CK(cudaSetDevice(ctx->P.device));
+  // scratch: ins_pt / ins_cpt (float4, cap_sort+1) and the first 7 doubles of rec
+  CK(cudaMemcpyAsync(ctx->d.ins_pt, in, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d.partials, ctx->slots[slot].pose, 56, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_transform_cloud(ctx->d.partials, ctx->d.ins_pt, ctx->d.ins_cpt, n, ctx->stream);
+  CK(cudaMemcpyAsync(out, ctx->d.ins_cpt, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return S2M_OK;
+}
+
+// ---- map access ---------------------------------------------------------------
+extern "C" int s2m_map_upload(s2m_ctx* ctx, int slot, const float* corner, int nc, const float* surf, int ns) {
+  if (!ctx || slot < 0 || slot >= ctx->d.B || nc < 0 || ns < 0) return S2M_ERR_ARG;
+  if (nc > ctx->P.cap_map_corner || ns > ctx->P.cap_map_surf || nc + ns > ctx->d.cap_in) return S2M_ERR_CAPACITY;
+  CK(cudaSetDevice(ctx->P.device));
+  Dev& d = ctx->d;
+  const int B = d.B, G = d.G;
+  HostTables& T = *ctx->ht;
+  cudaStream_t s = ctx->stream;
+  SlotHost& sh = ctx->slots[slot];
+  // forget the slot's current entries
+  int zero = 0;
+  CK(cudaMemcpyAsync(d.st_n + slot, &zero, 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d.st_n + B + slot, &zero, 4, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  sh.n_store[0] = sh.n_store[1] = 0;
+  std::vector<int> dsoff(G + 1, 0);
+  for (int g = 0; g <= G; ++g) dsoff[g] = (g > slot ? nc : 0) + (g > B + slot ? ns : 0);
+  for (int b = 0; b < B; ++b) {
+    FrameDesc& fd = T.desc[b];
+    fd.active = (b == slot);
+    fd.allow_opt = 0;
+    if (b != slot) continue;
+    const int W[3] = {kWinI, kWinJ, kWinK};
+    for (int a = 0; a < 3; ++a) {
+      fd.win_lo[a] = -sh.cen[a]; fd.win_hi[a] = W[a] - 1 - sh.cen[a];
+      fd.val_lo[a] = 1; fd.val_hi[a] = 0;  // nothing is valid: every point stays raw
+      fd.origin[a] = 0;
+    }
+    fd.seq_base[0] = fd.seq_base[1] = 0;
+  }
+  int total_lp, hash_total;
+  fill_store_tables(ctx, &total_lp, &hash_total);
+  CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d.ds_off, dsoff.data(), sizeof(int) * (G + 1), cudaMemcpyHostToDevice, s));
+  if (nc) CK(cudaMemcpyAsync(d.ds_pts, corner, sizeof(float4) * (size_t)nc, cudaMemcpyHostToDevice, s));
+  if (ns) CK(cudaMemcpyAsync(d.ds_pts + nc, surf, sizeof(float4) * (size_t)ns, cudaMemcpyHostToDevice, s));
+  ctx->launches += launch_map_update(d, ctx->cur, nc + ns, total_lp, false, true, s);
+  int rc = finish_call(ctx);
+  if (rc != S2M_OK) return rc;
+  ctx->cur ^= 1;
+  std::swap(d.st_n, d.st_n_new);
+  const SlotOut& o = ctx->h_out[slot];
+  sh.n_store[0] = o.n_store[0]; sh.n_store[1] = o.n_store[1];
+  sh.seq[0] = (unsigned long long)nc; sh.seq[1] = (unsigned long long)ns;
+  sh.force_pending_check = true;
+  sh.val_lo[0] = 1; sh.val_hi[0] = 0;
+  return (nc + ns) - (o.n_store[0] + o.n_store[1]);
+}
+
+static bool host_entry_dead(const SlotHost& sh, uint64_t key) {
+  int ci, cj, ck;
+  unpack_cube(key_cube(key), ci, cj, ck);
+  const int W[3] = {kWinI, kWinJ, kWinK};
+  const int c[3] = {ci, cj, ck};
+  for (int a = 0; a < 3; ++a)
+    if (c[a] < -sh.cen[a] || c[a] > W[a] - 1 - sh.cen[a]) return true;
+  return false;
+}
+
+static int download_store(s2m_ctx* ctx, int slot, int cls, std::vector<uint64_t>& keys, std::vector<float>& pts) {
+  Dev& d = ctx->d;
+  const int g = cls * d.B + slot;
+  const int n = ctx->slots[slot].n_store[cls];
+  keys.resize(n); pts.resize((size_t)4 * n);
+  if (n == 0) return S2M_OK;
+  int base = 0;
+  for (int h = 0; h < g; ++h) base += (h < d.B ? ctx->P.cap_map_corner : ctx->P.cap_map_surf);
+  CK(cudaMemcpyAsync(keys.data(), d.st_key[ctx->cur] + base, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(pts.data(), d.st_pt[ctx->cur] + base, sizeof(float4) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return S2M_OK;
+}
+
+extern "C" int s2m_map_download(s2m_ctx* ctx, int slot, int cls, float* out, int cap) {
+  if (!ctx || slot < 0 || slot >= ctx->d.B || cls < 0 || cls > 1) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  std::vector<uint64_t> keys;
+  std::vector<float> pts;
+  int rc = download_store(ctx, slot, cls, keys, pts);
+  if (rc != S2M_OK) return rc;
+  int n = 0;
+  for (size_t i = 0; i < keys.size(); ++i) {
+    if (host_entry_dead(ctx->slots[slot], keys[i])) continue;  // evicted lazily at the next update
+    if (out && n < cap) std::memcpy(out + 4 * (size_t)n, &pts[4 * i], 16);
+    ++n;
+  }
+  return n;
+}
+
+// prepares the descriptor of `slot` for a sensor at centre_t (rows B, C) and uploads the tables
+static int prepare_local(s2m_ctx* ctx, int slot, const double centre_t[3], int* total_lp, int* hash_total) {
+  HostTables& T = *ctx->ht;
+  for (int b = 0; b < ctx->d.B; ++b) T.desc[b].active = (b == slot);
+  FrameDesc& fd = T.desc[slot];
+  rows_BC(ctx->slots[slot], centre_t, fd);
+  fill_store_tables(ctx, total_lp, hash_total);
+  CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, ctx->stream));
+  return S2M_OK;
+}
+
+extern "C" int s2m_get_local_map(s2m_ctx* ctx, int slot, int cls, const double centre_t[3], float* out, int cap) {
+  if (!ctx || slot < 0 || slot >= ctx->d.B || cls < 0 || cls > 1 || !centre_t) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  int total_lp, hash_total;
+  int rc = prepare_local(ctx, slot, centre_t, &total_lp, &hash_total);
+  if (rc != S2M_OK) return rc;
+  ctx->launches += launch_local_index(ctx->d, ctx->cur, total_lp, hash_total, ctx->stream);
+  const int g = cls * ctx->d.B + slot;
+  ctx->launches += launch_gather_local(ctx->d, ctx->cur, g, ctx->d.ins_pt, ctx->stream);
+  rc = finish_call(ctx);
+  if (rc != S2M_OK) return rc;
+  const int n = ctx->h_out[slot].n_local[cls];
+  if (out && n > 0) {
+    CK(cudaMemcpyAsync(out, ctx->d.ins_pt, sizeof(float4) * (size_t)std::min(n, cap), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return n;
+}
+
+extern "C" int s2m_debug_knn(s2m_ctx* ctx, int slot, int cls, const double centre_t[3], const float* q_xyz, int n,
+                             int32_t* idx5, float* d2_5) {
+  if (!ctx || slot < 0 || slot >= ctx->d.B || cls < 0 || cls > 1 || !centre_t || n < 0) return S2M_ERR_ARG;
+  if ((size_t)n * 5 > (size_t)ctx->d.cap_sort) return S2M_ERR_CAPACITY;
+  CK(cudaSetDevice(ctx->P.device));
+  int total_lp, hash_total;
+  int rc = prepare_local(ctx, slot, centre_t, &total_lp, &hash_total);
+  if (rc != S2M_OK) return rc;
+  Dev& d = ctx->d;
+  cudaStream_t s = ctx->stream;
+  ctx->launches += launch_local_index(d, ctx->cur, total_lp, hash_total, s);
+  // scratch: queries in dl_pt/ins_pt area, results in vval (int32) and flag (float bits)
+  float* dq = (float*)d.ins_pt;
+  int32_t* didx = (int32_t*)d.vval;
+  float* dd2 = (float*)d.flag;
+  if (n) CK(cudaMemcpyAsync(dq, q_xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s));
+  ctx->launches += launch_knn_debug(d, slot, cls, dq, n, didx, dd2, s);
+  rc = finish_call(ctx);
+  if (rc != S2M_OK) return rc;
+  if (n) {
+    CK(cudaMemcpyAsync(idx5, didx, sizeof(int32_t) * 5 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(d2_5, dd2, sizeof(float) * 5 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return ctx->h_out[slot].n_local[cls];
+}
+
+extern "C" int s2m_get_surround(s2m_ctx* ctx, int slot, float* out, int cap) {
+  if (!ctx || slot < 0 || slot >= ctx->d.B) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  // corner then surf of each valid cube, cubes in gather order (laserMapping.cpp:810-815)
+  std::vector<uint64_t> keys[2];
+  std::vector<float> pts[2];
+  for (int c = 0; c < 2; ++c) {
+    int rc = download_store(ctx, slot, c, keys[c], pts[c]);
+    if (rc != S2M_OK) return rc;
+  }
+  const SlotHost& sh = ctx->slots[slot];
+  int n = 0;
+  for (int ci = sh.val_lo[0]; ci <= sh.val_hi[0]; ++ci)
+    for (int cj = sh.val_lo[1]; cj <= sh.val_hi[1]; ++cj)
+      for (int ck = sh.val_lo[2]; ck <= sh.val_hi[2]; ++ck)
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t cube = pack_cube(ci, cj, ck);
+          auto lo = std::lower_bound(keys[c].begin(), keys[c].end(), store_key(cube, 0, 0));
+          auto hi = std::lower_bound(keys[c].begin(), keys[c].end(), store_key(cube + 1, 0, 0));
+          for (auto it = lo; it != hi; ++it) {
+            if (out && n < cap) std::memcpy(out + 4 * (size_t)n, &pts[c][4 * (it - keys[c].begin())], 16);
+            ++n;
+          }
+        }
+  return n;
+}
+
+// ---- trace ----------------------------------------------------------------------
+static int seg_ds_range(s2m_ctx* ctx, int slot, int cls, int* off, int* n) {
+  std::vector<int> dsoff(ctx->d.G + 1);
+  CK(cudaMemcpyAsync(dsoff.data(), ctx->d.ds_off, sizeof(int) * (ctx->d.G + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int g = cls * ctx->d.B + slot;
+  *off = dsoff[g]; *n = dsoff[g + 1] - dsoff[g];
+  return S2M_OK;
+}
+extern "C" int s2m_trace_cloud(s2m_ctx* ctx, int slot, int cls, float* out, int cap) {
+  if (!ctx || slot < 0 || slot >= ctx->d.B || cls < 0 || cls > 1) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  int off, n;
+  int rc = seg_ds_range(ctx, slot, cls, &off, &n);
+  if (rc != S2M_OK) return rc;
+  if (out && n > 0) {
+    CK(cudaMemcpyAsync(out, ctx->d.ds_pts + off, sizeof(float4) * (size_t)std::min(n, cap), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return n;
+}
+extern "C" int s2m_trace_knn(s2m_ctx* ctx, int slot, int outer, int cls, int32_t* idx5, float* d2_5, uint8_t* used,
+                             int cap) {
+  if (!ctx || !ctx->P.trace || slot < 0 || slot >= ctx->d.B || cls < 0 || cls > 1 || outer < 0 || outer > 1) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  int off, n;
+  int rc = seg_ds_range(ctx, slot, cls, &off, &n);
+  if (rc != S2M_OK) return rc;
+  const int m = std::min(n, cap);
+  if (m > 0) {
+    const size_t o = (size_t)outer * ctx->d.cap_in + off;
+    CK(cudaMemcpyAsync(idx5, ctx->d.tr_idx + 5 * o, sizeof(int32_t) * 5 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(d2_5, ctx->d.tr_d2 + 5 * o, sizeof(float) * 5 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(used, ctx->d.tr_used + o, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return n;
+}
+extern "C" int s2m_trace_lm(s2m_ctx* ctx, int slot, int outer, double pose7[7], double sums28[28], double iters24[24],
+                            int* n_iter, int* termination) {
+  if (!ctx || !ctx->P.trace || slot < 0 || slot >= ctx->d.B || outer < 0 || outer > 1) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  LmState* h = ctx->h_lm;
+  CK(cudaMemcpyAsync(h, ctx->lm_trace + (size_t)outer * ctx->d.B + slot, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(pose7, h->x, 56);
+  std::memcpy(sums28, h->init_sums, 28 * 8);
+  std::memcpy(iters24, h->it_log, 24 * 8);
+  *n_iter = h->iteration;
+  *termination = h->termination;
+  return S2M_OK;
+}
+
+// ---- profiling ------------------------------------------------------------------
+extern "C" int s2m_set_profiling(s2m_ctx* ctx, int on) {
+  if (!ctx) return S2M_ERR_ARG;
+  ctx->profiling = on != 0;
+  return S2M_OK;
+}
+extern "C" int s2m_k4_profile(s2m_ctx* ctx, int reset, double* ms_total, long long* launches, double* alg_bytes) {
+  if (!ctx) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < ctx->k4_used; ++i) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->k4_events[i].first, ctx->k4_events[i].second));
+    ctx->k4_ms += ms;
+    ctx->k4_launches++;
+  }
+  ctx->k4_used = 0;
+  if (ms_total) *ms_total = ctx->k4_ms;
+  if (launches) *launches = ctx->k4_launches;
+  if (alg_bytes) *alg_bytes = ctx->k4_bytes;
+  if (reset) { ctx->k4_ms = 0; ctx->k4_launches = 0; ctx->k4_bytes = 0; }
+  return S2M_OK;
+}
+
+// ---- sharded-map mode: not wired in this build ------------------------------------
+extern "C" int s2m_shard_unique_id(void*) { return S2M_ERR_NCCL; }
+extern "C" int s2m_shard_init(s2m_ctx*, const void*) { return S2M_ERR_NCCL; }
+extern "C" int s2m_shard_profile(s2m_ctx*, int, double*, long long*) { return S2M_ERR_NCCL; }

@@ -1,0 +1,158 @@
+// s2m_internal.h -- device data layout shared by the kernels and the C-ABI layer.
+//
+// Vocabulary (follows the reference, laserMapping.cpp):
+//   slot     one independent sequence: own map, window, odometry correction
+//   class    0 = corner, 1 = surf
+//   segment  g = 2*slot + class; every per-point array is packed by segment
+//   cube     50 m map cube; (ci,cj,ck) are WORLD cube coordinates, i.e. the
+//            reference's array index minus laserCloudCenWidth/Height/Depth
+//   window   the 21x21x11 cubes the reference keeps (:77-79)
+//   valid    the 5x5x3 block around the sensor, clipped to the window (:513-530)
+//   store    the device map of one segment: entries sorted by a 64-bit key
+//            [cube:30][pending:1][payload:33]; filtered entries (payload = voxel
+//            coordinate inside the cube, one per cube x voxel) precede pending
+//            entries (payload = arrival number; raw points pushed into cubes
+//            outside the valid block, :753-759 vs :789-791).  Key order ==
+//            the reference's gather order (i, j, k loops, each cube's cloud in
+//            VoxelGrid output order followed by pushed-back raw points).
+//   local    concatenation of the valid cubes of a store, in key order; the
+//            position in it is the kNN index the reference would report
+//   cell     1 m lattice cell floor(p); candidates of a query are the points of
+//            its 27 neighbouring cells (exact for the reference's d2[4] < 1 gate)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "s2m_math.cuh"
+
+namespace s2m {
+
+constexpr int kTile = 128;       // queries per block of the association / evaluation kernels
+constexpr int kPartial = 32;     // doubles per block partial: 28 sums, n_edge, n_plane, cand_corner, cand_surf
+constexpr int kCols = 25;        // (i,j) columns of the valid block
+constexpr int kValidCubes = 75;
+constexpr int kMaxBatch = 64;    // 7 segment bits in the 32-bit cell sort key
+constexpr int kWinI = 21, kWinJ = 21, kWinK = 11;
+constexpr uint64_t kSentinel64 = ~0ull;
+constexpr uint32_t kSentinel32 = ~0u;
+
+// store key helpers -----------------------------------------------------------
+constexpr int kCubeBiasIJ = 2048, kCubeBiasK = 32;
+S2M_HD uint32_t pack_cube(int ci, int cj, int ck) {
+  return ((uint32_t)(ci + kCubeBiasIJ) << 18) | ((uint32_t)(cj + kCubeBiasIJ) << 6) | (uint32_t)(ck + kCubeBiasK);
+}
+S2M_HD bool cube_in_range(int ci, int cj, int ck) {
+  return ci > -kCubeBiasIJ && ci < kCubeBiasIJ - 1 && cj > -kCubeBiasIJ && cj < kCubeBiasIJ - 1 &&
+         ck > -kCubeBiasK && ck < kCubeBiasK - 1;
+}
+S2M_HD void unpack_cube(uint32_t c, int& ci, int& cj, int& ck) {
+  ci = (int)(c >> 18) - kCubeBiasIJ; cj = (int)((c >> 6) & 0xFFF) - kCubeBiasIJ; ck = (int)(c & 0x3F) - kCubeBiasK;
+}
+S2M_HD uint64_t store_key(uint32_t cube, uint32_t pending, uint64_t payload) {
+  return ((uint64_t)cube << 34) | ((uint64_t)pending << 33) | (payload & 0x1FFFFFFFFull);
+}
+S2M_HD uint32_t key_cube(uint64_t k) { return (uint32_t)(k >> 34); }
+S2M_HD uint32_t key_pending(uint64_t k) { return (uint32_t)((k >> 33) & 1); }
+S2M_HD uint64_t key_payload(uint64_t k) { return k & 0x1FFFFFFFFull; }
+
+// voxel coordinate of p relative to the first voxel touching the cube, per axis
+S2M_HD int voxel_rel(float p, int cube, float inv_leaf) {
+  float lo = (float)(50.0 * (double)cube - 25.0);
+  return voxel_coord(p, inv_leaf) - voxel_coord(lo, inv_leaf);
+}
+
+struct FrameDesc {          // per slot, written by the host every call
+  double pose[7];           // initial guess q_w_curr, t_w_curr (row A)
+  int win_lo[3], win_hi[3]; // window, world cube coords, inclusive
+  int val_lo[3], val_hi[3]; // valid block clipped to the window, inclusive (lo > hi: none)
+  int origin[3];            // first 1 m cell of the valid block: 50*val_lo - 25
+  int active;               // slot takes part in this call
+  int allow_opt;            // 0: skip rows K..S
+  int pad;
+  unsigned long long seq_base[2];
+};
+
+struct SlotOut {            // per slot, read back by the host after every call
+  double pose[7];
+  int n_ds[2], n_local[2], n_store[2];
+  int n_edge[2], n_plane[2];
+  int optimized, lm_iters[2], lm_term[2];
+  int pad;
+  double cost_initial[2], cost_final[2];
+  double cand[2];           // candidate points visited by corner / surf queries (outer 0)
+};
+
+// All device pointers of one context (sizes are host-known capacities).
+struct Dev {
+  int B, G;                     // slots, segments
+  float inv_leaf[2];
+  // ---- per call small tables (device copies of host arrays)
+  FrameDesc* desc;              // [B]
+  int* in_off;                  // [G+1] packed offsets of the incoming clouds
+  int* lp_off;                  // [G+1] packed offsets of the local/store index space (host upper bounds)
+  int* st_base;                 // [G]   base of each segment in the store arrays
+  int* st_cap;                  // [G]
+  int* hash_off;                // [G+1] base of each segment's cell table
+  // ---- incoming + down-sampled scan
+  float4* in_pts;               // [cap_in] packed by segment
+  uint64_t *vkey, *vkey2;       // [cap_sort]
+  uint32_t *vval, *vval2;       // [cap_sort]
+  uint32_t *flag, *scan;        // [cap_sort]
+  float* bbox;                  // [G][6]
+  float4* ds_pts;               // [cap_in] packed, voxel-filtered scan (sensor frame)
+  int* ds_off;                  // [G+1] device-computed
+  // ---- store (double buffered)
+  uint64_t* st_key[2];
+  float4* st_pt[2];
+  int* st_n;                    // [G] entries in the current buffer
+  int* st_n_new;                // [G]
+  // ---- local map + cell index
+  int* rng_start;               // [G][25]
+  int* loc_off;                 // [G][26]
+  uint32_t *ckey, *ckey2, *cval, *cval2;  // [cap_lp]
+  float4* cand;                 // [cap_lp] cell-sorted local points, w = local index bits
+  unsigned long long* hash_tab; // cell tables
+  uint32_t* hash_full;          // exact counts for saturated entries
+  int* cs_off;                  // [G+1] first sorted position of each segment
+  // ---- association / solve
+  double* rec;                  // [cap_in][6] cached correspondences
+  uint8_t* rec_valid;           // [cap_in]
+  double* partials;             // [B][max_tiles][kPartial]
+  int max_tiles;
+  LmState* lm;                  // [B]
+  SlotOut* out;                 // [B]
+  int* err_flag;                // device error code (0 ok)
+  // ---- trace (optional)
+  int32_t* tr_idx;              // [2][cap_in][5]
+  float* tr_d2;                 // [2][cap_in][5]
+  uint8_t* tr_used;             // [2][cap_in]
+  // ---- map update
+  float4* dl_pt;                // [cap_in] transformed scan points (world, float)
+  uint64_t *ins_key, *ins_ckey; // [cap_sort]
+  float4 *ins_pt, *ins_cpt;     // [cap_sort]
+  int* run_off;                 // [G+1]
+  uint32_t *aflag, *ascan;      // [cap_lp + 1]
+  // ---- cub temp
+  void* cub_tmp;
+  size_t cub_tmp_bytes;
+  int cap_in, cap_sort, cap_lp;
+};
+
+// launchers (s2m_kernels.cu); every one returns the number of kernels it launched
+size_t cub_temp_bytes(int cap_sort, int cap_lp);
+int launch_voxel_filter(const Dev& d, int total_in, cudaStream_t s);
+int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, cudaStream_t s);
+int launch_guard(const Dev& d, cudaStream_t s);
+int launch_associate(const Dev& d, int outer, int tiles, bool trace, cudaStream_t s);
+int launch_lm_begin(const Dev& d, int outer, cudaStream_t s);
+int launch_evaluate(const Dev& d, int tiles, cudaStream_t s);
+int launch_lm_after(const Dev& d, int outer, cudaStream_t s);
+int launch_finish_pose(const Dev& d, cudaStream_t s);
+int launch_map_update(const Dev& d, int cur, int total_in, int total_lp, bool check_pending, bool identity_pose,
+                      cudaStream_t s);
+int launch_knn_debug(const Dev& d, int slot, int cls, const float* d_q, int n, int32_t* d_idx, float* d_d2,
+                     cudaStream_t s);
+int launch_transform_cloud(const double* d_pose7, const float4* in, float4* out, int n, cudaStream_t s);
+int launch_gather_local(const Dev& d, int cur, int g, float4* out, cudaStream_t s);
+
+}  // namespace s2m

@@ -1,0 +1,884 @@
+// s2m_kernels.cu -- sm_100a kernels of the scan-to-map registration engine.
+//
+// Kernel map (SURVEY.md section 2.3 numbering; reference rows of section 8a):
+//   K1  vox_*            scan voxel-grid filter                 row V  laserMapping.cpp:543-551
+//   K3  range/local_key/cand_build  local map + 1 m cell index  rows C,T :510-540, :559-560
+//   K4  associate_kernel transform + exact kNN5 + edge PCA / plane QR + residual,
+//                        Jacobian, Huber + block reduction      rows P,K,E,F,R,L,Q :578-706
+//   K5  evaluate_kernel  re-evaluation at LM trial poses from cached correspondences
+//   K6  lm_*_kernel      6x6 trust-region LM step               row S  :713-721
+//   K2  delta_*/merge_*  map insert, per-voxel re-centroid, window evict   rows I,W,B :737-802
+//   K7  transform_cloud_kernel  full-resolution cloud transform  row X  :845-849
+// Sorting / prefix sums use CUB device primitives (plumbing); everything on the
+// registration hot path (K4, K5, K6) is hand-written.
+#include <cub/cub.cuh>
+
+#include "s2m_internal.h"
+
+namespace s2m {
+
+// ----------------------------------------------------------------------------
+// small device helpers
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ int find_seg(const int* __restrict__ off, int nseg, int i) {
+  int lo = 0, hi = nseg;  // largest g in [0,nseg) with off[g] <= i
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int lower_bound_u64(const uint64_t* __restrict__ a, int n, uint64_t key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int lower_bound_u32(const uint32_t* __restrict__ a, int n, uint32_t key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int seg_cls(const Dev& d, int g) { return g >= d.B; }
+__device__ __forceinline__ int seg_slot(const Dev& d, int g) { return g >= d.B ? g - d.B : g; }
+__device__ __forceinline__ void set_err(const Dev& d, int code) { atomicCAS(d.err_flag, 0, code); }
+__device__ __forceinline__ uint32_t cell_hash(uint32_t k) {
+  k *= 0x9E3779B1u;
+  return k ^ (k >> 15);
+}
+
+// ----------------------------------------------------------------------------
+// K1: scan voxel-grid filter (pcl::VoxelGrid semantics)
+// ----------------------------------------------------------------------------
+__global__ void vox_bbox_kernel(Dev d) {
+  const int g = blockIdx.x;
+  const int a = d.in_off[g], b = d.in_off[g + 1];
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
+    float4 p = d.in_pts[i];
+    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+    mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+  }
+  __shared__ float sm[6][32];
+  for (int k = 0; k < 3; ++k)
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+      mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+    }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) for (int k = 0; k < 3; ++k) { sm[k][w] = mn[k]; sm[3 + k][w] = mx[k]; }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const int nw = blockDim.x >> 5;
+    float v = sm[threadIdx.x][0];
+    for (int i = 1; i < nw; ++i) v = threadIdx.x < 3 ? fminf(v, sm[threadIdx.x][i]) : fmaxf(v, sm[threadIdx.x][i]);
+    d.bbox[6 * g + threadIdx.x] = v;
+  }
+}
+
+__global__ void vox_key_kernel(Dev d, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = find_seg(d.in_off, d.G, i);
+  const float inv = d.inv_leaf[seg_cls(d, g)];
+  const float* bb = d.bbox + 6 * g;
+  // "Leaf size is too small for the input dataset": PCL warns and passes the input through
+  const long long dx = (long long)xfmul(xfsub(bb[3], bb[0]), inv) + 1;
+  const long long dy = (long long)xfmul(xfsub(bb[4], bb[1]), inv) + 1;
+  const long long dz = (long long)xfmul(xfsub(bb[5], bb[2]), inv) + 1;
+  uint64_t key;
+  if (dx * dy * dz > 2147483647LL) {
+    key = (uint64_t)(i - d.in_off[g]);
+  } else {
+    const float4 p = d.in_pts[i];
+    const int m0 = (int)floorf(xfmul(bb[0], inv)), m1 = (int)floorf(xfmul(bb[1], inv)), m2 = (int)floorf(xfmul(bb[2], inv));
+    const int i0 = (int)(floorf(xfmul(p.x, inv)) - (float)m0);
+    const int i1 = (int)(floorf(xfmul(p.y, inv)) - (float)m1);
+    const int i2 = (int)(floorf(xfmul(p.z, inv)) - (float)m2);
+    if ((unsigned)i0 >= (1u << 18) || (unsigned)i1 >= (1u << 18) || (unsigned)i2 >= (1u << 18)) set_err(d, -4);
+    key = ((uint64_t)(i2 & 0x3FFFF) << 36) | ((uint64_t)(i1 & 0x3FFFF) << 18) | (uint64_t)(i0 & 0x3FFFF);
+  }
+  d.vkey[i] = ((uint64_t)g << 54) | key;
+  d.vval[i] = (uint32_t)i;
+}
+
+// flag[p] = 1 where a run of equal keys starts; flag[n] = 0 so scan[n] = number of runs
+__global__ void head_flag_kernel(const uint64_t* __restrict__ keys, uint32_t* __restrict__ flag, int n) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > n) return;
+  flag[p] = (p < n) && (p == 0 || keys[p] != keys[p - 1]);
+}
+
+__global__ void vox_centroid_kernel(Dev d, int n) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n || !d.flag[p]) return;
+  const uint64_t key = d.vkey2[p];
+  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+  int e = p;
+  for (; e < n && d.vkey2[e] == key; ++e) {  // sequential float sums in (stable) sorted order
+    const float4 q = d.in_pts[d.vval2[e]];
+    sx = xfadd(sx, q.x); sy = xfadd(sy, q.y); sz = xfadd(sz, q.z); si = xfadd(si, q.w);
+  }
+  const float c = (float)(e - p);
+  d.ds_pts[d.scan[p]] = make_float4(xfdiv(sx, c), xfdiv(sy, c), xfdiv(sz, c), xfdiv(si, c));
+}
+
+__global__ void ds_off_kernel(Dev d, int n) {
+  const int g = threadIdx.x + blockIdx.x * blockDim.x;
+  if (g > d.G) return;
+  const int a = d.in_off[g];
+  d.ds_off[g] = d.scan[a < n ? a : n];
+  if (g < d.G) d.out[seg_slot(d, g)].n_ds[seg_cls(d, g)] = (int)d.scan[min(d.in_off[g + 1], n)] - (int)d.scan[min(a, n)];
+}
+
+// ----------------------------------------------------------------------------
+// K3: local map (valid cubes of the store, gather order) and its 1 m cell index
+// ----------------------------------------------------------------------------
+__global__ void range_kernel(Dev d, int cur) {
+  const int g = blockIdx.x, c = threadIdx.x;
+  const FrameDesc& fd = d.desc[seg_slot(d, g)];
+  const uint64_t* keys = d.st_key[cur] + d.st_base[g];
+  const int n = d.st_n[g];
+  int lo = 0, len = 0;
+  if (c < kCols && fd.active) {
+    const int wi = fd.val_lo[0] + c / 5, wj = fd.val_lo[1] + c % 5;
+    if (wi <= fd.val_hi[0] && wj <= fd.val_hi[1] && fd.val_lo[2] <= fd.val_hi[2]) {
+      lo = lower_bound_u64(keys, n, store_key(pack_cube(wi, wj, fd.val_lo[2]), 0, 0));
+      const int hi = lower_bound_u64(keys, n, store_key(pack_cube(wi, wj, fd.val_hi[2]) + 1, 0, 0));
+      len = hi - lo;
+    }
+  }
+  int incl = len;
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (c >= o) incl += v;
+  }
+  if (c < kCols) {
+    d.rng_start[g * kCols + c] = lo;
+    d.loc_off[g * (kCols + 1) + c] = incl - len;
+  }
+  if (c == kCols - 1) {
+    d.loc_off[g * (kCols + 1) + kCols] = incl;
+    d.out[seg_slot(d, g)].n_local[seg_cls(d, g)] = incl;
+  }
+}
+
+// store index of local index l of segment g
+__device__ __forceinline__ int local_to_store(const Dev& d, int g, int l) {
+  const int* lo = d.loc_off + g * (kCols + 1);
+  int a = 0, b = kCols;  // largest col with lo[col] <= l
+  while (b - a > 1) {
+    int m = (a + b) >> 1;
+    if (lo[m] <= l) a = m; else b = m;
+  }
+  return d.rng_start[g * kCols + a] + (l - lo[a]);
+}
+
+__global__ void local_key_kernel(Dev d, int cur, int total_lp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_lp) return;
+  const int g = find_seg(d.lp_off, d.G, i);
+  const int l = i - d.lp_off[g];
+  uint32_t key = kSentinel32;
+  if (l < d.loc_off[g * (kCols + 1) + kCols]) {
+    const float4 p = d.st_pt[cur][d.st_base[g] + local_to_store(d, g, l)];
+    const FrameDesc& fd = d.desc[seg_slot(d, g)];
+    const int rx = (int)floorf(p.x) - fd.origin[0], ry = (int)floorf(p.y) - fd.origin[1],
+              rz = (int)floorf(p.z) - fd.origin[2];
+    if ((unsigned)rx > 255u || (unsigned)ry > 255u || (unsigned)rz > 255u) set_err(d, -4);
+    key = ((uint32_t)g << 24) | ((uint32_t)(rz & 255) << 16) | ((uint32_t)(ry & 255) << 8) | (uint32_t)(rx & 255);
+  }
+  d.ckey[i] = key;
+  d.cval[i] = (uint32_t)l;
+}
+
+__global__ void cs_off_kernel(Dev d, int total_lp) {
+  const int g = threadIdx.x + blockIdx.x * blockDim.x;
+  if (g > d.G) return;
+  d.cs_off[g] = lower_bound_u32(d.ckey2, total_lp, (uint32_t)g << 24);
+}
+
+// cell table entry: [cell key:24][count:10][start:30]; count 1023 = see hash_full
+__global__ void cand_build_kernel(Dev d, int cur, int total_lp) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total_lp) return;
+  const uint32_t key = d.ckey2[p];
+  if (key == kSentinel32) return;
+  const int g = key >> 24;
+  const int l = (int)d.cval2[p];
+  const float4 q = d.st_pt[cur][d.st_base[g] + local_to_store(d, g, l)];
+  d.cand[p] = make_float4(q.x, q.y, q.z, __int_as_float(l));
+  if (p == 0 || d.ckey2[p - 1] != key) {
+    int e = p + 1;
+    while (e < total_lp && d.ckey2[e] == key) ++e;
+    const uint32_t count = (uint32_t)(e - p);
+    const uint32_t k24 = key & 0xFFFFFFu;
+    const unsigned long long entry = ((unsigned long long)k24 << 40) |
+                                     ((unsigned long long)(count < 1023u ? count : 1023u) << 30) |
+                                     (unsigned long long)p;
+    const int base = d.hash_off[g];
+    const uint32_t mask = (uint32_t)(d.hash_off[g + 1] - base) - 1u;
+    uint32_t s = cell_hash(k24) & mask;
+    for (;;) {
+      unsigned long long old = atomicCAS(d.hash_tab + base + s, kSentinel64, entry);
+      if (old == kSentinel64) break;
+      s = (s + 1) & mask;
+    }
+    if (count >= 1023u) d.hash_full[base + s] = count;
+  }
+}
+
+// Exact bounded kNN(5) of one query over the 27 cells around it.  Distances are
+// the reference's float ((dx*dx)+(dy*dy))+(dz*dz); order is (d2, local index).
+// bp = position in d.cand of each neighbour (-1 if none).
+struct Knn5 {
+  float bd[5];
+  int bl[5], bp[5];
+};
+__device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[3], float qx, float qy, float qz,
+                                          Knn5& r) {
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { r.bd[k] = INFINITY; r.bl[k] = 0x7fffffff; r.bp[k] = -1; }
+  const int cx = (int)floorf(qx) - origin[0], cy = (int)floorf(qy) - origin[1], cz = (int)floorf(qz) - origin[2];
+  const int base = d.hash_off[g];
+  const uint32_t mask = (uint32_t)(d.hash_off[g + 1] - base) - 1u;
+  const unsigned long long* __restrict__ tab = d.hash_tab + base;
+  int visited = 0;
+  for (int dz = -1; dz <= 1; ++dz) {
+    const int z = cz + dz;
+    if ((unsigned)z > 255u) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = cy + dy;
+      if ((unsigned)y > 255u) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = cx + dx;
+        if ((unsigned)x > 255u) continue;
+        const uint32_t k24 = ((uint32_t)z << 16) | ((uint32_t)y << 8) | (uint32_t)x;
+        uint32_t s = cell_hash(k24) & mask;
+        unsigned long long e;
+        for (;;) {
+          e = tab[s];
+          if (e == kSentinel64 || (uint32_t)(e >> 40) == k24) break;
+          s = (s + 1) & mask;
+        }
+        if (e == kSentinel64) continue;
+        uint32_t count = (uint32_t)(e >> 30) & 1023u;
+        const int start = (int)(e & 0x3FFFFFFFull);
+        if (count == 1023u) count = d.hash_full[base + s];
+        visited += (int)count;
+        for (uint32_t j = 0; j < count; ++j) {
+          const float4 c = __ldg(d.cand + start + j);
+          const float dd = dist2(qx, qy, qz, c.x, c.y, c.z);
+          const int l = __float_as_int(c.w);
+          if (dd < r.bd[4] || (dd == r.bd[4] && l < r.bl[4])) {
+            r.bd[4] = dd; r.bl[4] = l; r.bp[4] = start + (int)j;
+#pragma unroll
+            for (int k = 4; k > 0; --k) {
+              const bool sw = r.bd[k - 1] > r.bd[k] || (r.bd[k - 1] == r.bd[k] && r.bl[k - 1] > r.bl[k]);
+              if (sw) {
+                float tf = r.bd[k]; r.bd[k] = r.bd[k - 1]; r.bd[k - 1] = tf;
+                int ti = r.bl[k]; r.bl[k] = r.bl[k - 1]; r.bl[k - 1] = ti;
+                ti = r.bp[k]; r.bp[k] = r.bp[k - 1]; r.bp[k - 1] = ti;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  return visited;
+}
+
+__global__ void knn_debug_kernel(Dev d, int g, const float* __restrict__ q, int n, int32_t* __restrict__ idx,
+                                 float* __restrict__ d2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Knn5 r;
+  knn5_cells(d, g, d.desc[seg_slot(d, g)].origin, q[3 * i], q[3 * i + 1], q[3 * i + 2], r);
+  const bool ok = r.bd[4] < 1.0f;  // the reference's gate; beyond it the bounded search is not exact
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    idx[5 * i + k] = ok ? r.bl[k] : -1;
+    d2[5 * i + k] = ok ? r.bd[k] : INFINITY;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// block reduction of kPartial doubles (fixed tree => deterministic)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void block_reduce_store(double* acc /*kPartial*/, double* __restrict__ dst) {
+  __shared__ double sm[kTile / 32][kPartial];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < kPartial; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (l == 0) sm[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kPartial) {
+    double v = sm[0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < kTile / 32; ++i) v += sm[i][threadIdx.x];
+    dst[threadIdx.x] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// K4: fused association.  One thread per down-sampled scan point of one slot.
+// ----------------------------------------------------------------------------
+template <bool kTrace>
+__global__ void __launch_bounds__(kTile) associate_kernel(Dev d, int outer) {
+  const int slot = blockIdx.y;
+  if (!d.out[slot].optimized) return;
+  const int gc = slot, gs = d.B + slot;
+  const int dc0 = d.ds_off[gc], nc = d.ds_off[gc + 1] - dc0;
+  const int ds0 = d.ds_off[gs], nq = nc + d.ds_off[gs + 1] - ds0;
+  const int q = blockIdx.x * kTile + threadIdx.x;
+  if (blockIdx.x * kTile >= nq) return;
+  __shared__ double pose[7];
+  __shared__ int origin[3];
+  if (threadIdx.x < 7) pose[threadIdx.x] = d.lm[slot].x[threadIdx.x];
+  if (threadIdx.x < 3) origin[threadIdx.x] = d.desc[slot].origin[threadIdx.x];
+  __syncthreads();
+
+  double acc[kPartial];
+#pragma unroll
+  for (int k = 0; k < kPartial; ++k) acc[k] = 0.0;
+
+  if (q < nq) {
+    const int cls = q >= nc;
+    const int di = cls ? ds0 + (q - nc) : dc0 + q;
+    const float4 p = d.ds_pts[di];
+    float w[3];
+    xf_point(pose, p.x, p.y, p.z, w);
+    Knn5 r;
+    const int visited = knn5_cells(d, cls ? gs : gc, origin, w[0], w[1], w[2], r);
+    acc[30 + cls] = (double)visited;
+    bool used = false;
+    double rec[6] = {0, 0, 0, 0, 0, 0};
+    if (r.bd[4] < 1.0f) {  // laserMapping.cpp:585 / :653
+      float nb[5][3];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float4 c = __ldg(d.cand + r.bp[k]);
+        nb[k][0] = c.x; nb[k][1] = c.y; nb[k][2] = c.z;
+      }
+      const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
+      Sums28& S = *reinterpret_cast<Sums28*>(acc);
+      if (cls == 0) {
+        used = edge_fit(nb, rec, rec + 3);
+        if (used) { accum_edge(S, pose, cp, rec, rec + 3); acc[28] = 1.0; }
+      } else {
+        used = plane_fit(nb, rec, rec[3]);
+        if (used) { accum_plane(S, pose, cp, rec, rec[3]); acc[29] = 1.0; }
+      }
+    }
+    double2* ro = reinterpret_cast<double2*>(d.rec + 6 * (size_t)di);
+    ro[0] = make_double2(rec[0], rec[1]);
+    ro[1] = make_double2(rec[2], rec[3]);
+    ro[2] = make_double2(rec[4], rec[5]);
+    d.rec_valid[di] = used;
+    if (kTrace) {
+      const size_t o = ((size_t)outer * d.cap_in + di);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const bool have = r.bp[k] >= 0;
+        d.tr_idx[5 * o + k] = have ? r.bl[k] : -1;
+        d.tr_d2[5 * o + k] = have ? r.bd[k] : INFINITY;
+      }
+      d.tr_used[o] = used;
+    }
+  }
+  block_reduce_store(acc, d.partials + ((size_t)slot * d.max_tiles + blockIdx.x) * kPartial);
+}
+
+// ----------------------------------------------------------------------------
+// K5: evaluation at the LM candidate pose from the cached correspondences
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile) evaluate_kernel(Dev d) {
+  const int slot = blockIdx.y;
+  if (!d.out[slot].optimized) return;
+  const LmState& L = d.lm[slot];
+  if (L.done || !L.have_candidate) return;
+  const int gc = slot, gs = d.B + slot;
+  const int dc0 = d.ds_off[gc], nc = d.ds_off[gc + 1] - dc0;
+  const int ds0 = d.ds_off[gs], nq = nc + d.ds_off[gs + 1] - ds0;
+  if (blockIdx.x * kTile >= nq) return;
+  __shared__ double pose[7];
+  if (threadIdx.x < 7) pose[threadIdx.x] = L.xc[threadIdx.x];
+  __syncthreads();
+  double acc[kPartial];
+#pragma unroll
+  for (int k = 0; k < kPartial; ++k) acc[k] = 0.0;
+  const int q = blockIdx.x * kTile + threadIdx.x;
+  const int di = q < nc ? dc0 + q : ds0 + (q - nc);
+  if (q < nq && d.rec_valid[di]) {
+    const float4 p = d.ds_pts[di];
+    const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
+    const double2* ri = reinterpret_cast<const double2*>(d.rec + 6 * (size_t)di);
+    const double2 a = ri[0], b = ri[1], c = ri[2];
+    const double rec[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+    Sums28& S = *reinterpret_cast<Sums28*>(acc);
+    if (q < nc) { accum_edge(S, pose, cp, rec, rec + 3); acc[28] = 1.0; }
+    else { accum_plane(S, pose, cp, rec, rec[3]); acc[29] = 1.0; }
+  }
+  block_reduce_store(acc, d.partials + ((size_t)slot * d.max_tiles + blockIdx.x) * kPartial);
+}
+
+// ----------------------------------------------------------------------------
+// K6: trust-region LM on the reduced system; one warp per slot
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void sum_partials(const Dev& d, int slot, double* sm /*kPartial, shared*/) {
+  const int nq = (d.ds_off[slot + 1] - d.ds_off[slot]) + (d.ds_off[d.B + slot + 1] - d.ds_off[d.B + slot]);
+  const int tiles = (nq + kTile - 1) / kTile;
+  const double* p = d.partials + (size_t)slot * d.max_tiles * kPartial;
+  double v = 0.0;
+  for (int t = 0; t < tiles; ++t) v += p[(size_t)t * kPartial + threadIdx.x];  // fixed order
+  sm[threadIdx.x] = v;
+  __syncwarp();
+}
+
+__global__ void guard_kernel(Dev d) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= d.B) return;
+  const FrameDesc& fd = d.desc[s];
+  SlotOut& o = d.out[s];
+  // laserMapping.cpp:555
+  const int opt = fd.active && fd.allow_opt && o.n_local[0] > 10 && o.n_local[1] > 50;
+  o.optimized = opt;
+  for (int k = 0; k < 2; ++k) {
+    o.n_edge[k] = o.n_plane[k] = 0; o.lm_iters[k] = 0; o.lm_term[k] = 0;
+    o.cost_initial[k] = o.cost_final[k] = 0.0; o.cand[k] = 0.0;
+  }
+  LmState& L = d.lm[s];
+  for (int i = 0; i < 7; ++i) L.x[i] = L.xc[i] = fd.pose[i];
+  L.done = !opt; L.have_candidate = 0; L.iteration = 0;
+}
+
+__global__ void lm_begin_kernel(Dev d, int outer) {
+  const int slot = blockIdx.x;
+  if (!d.out[slot].optimized) return;
+  __shared__ double sm[kPartial];
+  sum_partials(d, slot, sm);
+  if (threadIdx.x == 0) {
+    Sums28 S;
+    for (int i = 0; i < 28; ++i) S.v[i] = sm[i];
+    SlotOut& o = d.out[slot];
+    o.n_edge[outer] = (int)sm[28]; o.n_plane[outer] = (int)sm[29];
+    if (outer == 0) { o.cand[0] = sm[30]; o.cand[1] = sm[31]; }
+    LmState& L = d.lm[slot];
+    double x0[7];
+    for (int i = 0; i < 7; ++i) x0[i] = L.x[i];
+    lm_begin(L, x0, S, (int)sm[28] + (int)sm[29], 4);
+    o.lm_iters[outer] = L.iteration; o.lm_term[outer] = L.termination;
+    o.cost_initial[outer] = L.initial_cost; o.cost_final[outer] = L.final_cost;
+  }
+}
+
+__global__ void lm_after_kernel(Dev d, int outer) {
+  const int slot = blockIdx.x;
+  if (!d.out[slot].optimized) return;
+  LmState& L = d.lm[slot];
+  if (L.done || !L.have_candidate) return;
+  __shared__ double sm[kPartial];
+  sum_partials(d, slot, sm);
+  if (threadIdx.x == 0) {
+    Sums28 S;
+    for (int i = 0; i < 28; ++i) S.v[i] = sm[i];
+    lm_after_eval(L, S, 4);
+    SlotOut& o = d.out[slot];
+    o.lm_iters[outer] = L.iteration; o.lm_term[outer] = L.termination;
+    o.cost_final[outer] = L.final_cost;
+  }
+}
+
+__global__ void finish_pose_kernel(Dev d) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= d.B) return;
+  SlotOut& o = d.out[s];
+  for (int i = 0; i < 7; ++i) o.pose[i] = o.optimized ? d.lm[s].x[i] : d.desc[s].pose[i];
+}
+
+// ----------------------------------------------------------------------------
+// K2: map update -- insert (row I), per-voxel re-centroid of the valid cubes
+// (row W), eviction of cubes that left the window (row B), as one sorted merge.
+// delta sort key: [segment:7][window-relative cube:13][pending:1][payload:33]
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ bool in_box(int ci, int cj, int ck, const int lo[3], const int hi[3]) {
+  return ci >= lo[0] && ci <= hi[0] && cj >= lo[1] && cj <= hi[1] && ck >= lo[2] && ck <= hi[2];
+}
+__device__ __forceinline__ uint64_t delta_key(int g, const FrameDesc& fd, int ci, int cj, int ck, uint32_t pend,
+                                              uint64_t payload) {
+  const uint32_t rel = (uint32_t)(((ci - fd.win_lo[0]) * kWinJ + (cj - fd.win_lo[1])) * kWinK + (ck - fd.win_lo[2]));
+  return ((uint64_t)g << 47) | ((uint64_t)rel << 34) | ((uint64_t)pend << 33) | (payload & 0x1FFFFFFFFull);
+}
+__device__ __forceinline__ uint64_t voxel_payload(const Dev& d, int cls, float x, float y, float z, int ci, int cj,
+                                                  int ck) {
+  const float inv = d.inv_leaf[cls];
+  const int vx = voxel_rel(x, ci, inv), vy = voxel_rel(y, cj, inv), vz = voxel_rel(z, ck, inv);
+  if ((unsigned)vx > 2047u || (unsigned)vy > 2047u || (unsigned)vz > 2047u) set_err(d, -4);
+  return ((uint64_t)(vz & 2047) << 22) | ((uint64_t)(vy & 2047) << 11) | (uint64_t)(vx & 2047);
+}
+
+__global__ void delta_key_kernel(Dev d, int front, int n_delta, bool identity_pose) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_delta) return;
+  uint64_t key = kSentinel64;
+  uint32_t val = 0;
+  if (i >= front) {
+    const int di = i - front;
+    if (di < d.ds_off[d.G]) {
+      const int g = find_seg(d.ds_off, d.G, di);
+      const FrameDesc& fd = d.desc[seg_slot(d, g)];
+      const float4 p = d.ds_pts[di];
+      float w[3];
+      if (identity_pose) { w[0] = p.x; w[1] = p.y; w[2] = p.z; }
+      else xf_point(d.out[seg_slot(d, g)].pose, p.x, p.y, p.z, w);
+      d.dl_pt[di] = make_float4(w[0], w[1], w[2], p.w);
+      const int ci = cube_of((double)w[0]), cj = cube_of((double)w[1]), ck = cube_of((double)w[2]);
+      if (fd.active && in_box(ci, cj, ck, fd.win_lo, fd.win_hi)) {  // laserMapping.cpp:753-755
+        if (!cube_in_range(ci, cj, ck)) set_err(d, -4);
+        if (in_box(ci, cj, ck, fd.val_lo, fd.val_hi))
+          key = delta_key(g, fd, ci, cj, ck, 0, voxel_payload(d, seg_cls(d, g), w[0], w[1], w[2], ci, cj, ck));
+        else
+          key = delta_key(g, fd, ci, cj, ck, 1, fd.seq_base[seg_cls(d, g)] + (unsigned long long)(di - d.ds_off[g]));
+        val = (uint32_t)di;
+      }
+    }
+    d.vkey[i] = key;
+    d.vval[i] = val;
+  }
+  // the front region is pre-filled with the sentinel by a memset and then
+  // populated by pending_gather_kernel
+}
+
+// raw points already sitting in cubes that are valid now: they join this frame's re-filter
+__global__ void pending_gather_kernel(Dev d, int cur) {
+  const int g = blockIdx.x;
+  const FrameDesc& fd = d.desc[seg_slot(d, g)];
+  if (!fd.active) return;
+  __shared__ int lo_s[kValidCubes], off_s[kValidCubes + 1];
+  const uint64_t* keys = d.st_key[cur] + d.st_base[g];
+  const int n = d.st_n[g];
+  const int t = threadIdx.x;
+  if (t < kValidCubes) {
+    const int ci = fd.val_lo[0] + t / 15, cj = fd.val_lo[1] + (t / 3) % 5, ck = fd.val_lo[2] + t % 3;
+    int lo = 0, len = 0;
+    if (ci <= fd.val_hi[0] && cj <= fd.val_hi[1] && ck <= fd.val_hi[2]) {
+      const uint32_t cube = pack_cube(ci, cj, ck);
+      lo = lower_bound_u64(keys, n, store_key(cube, 1, 0));
+      len = lower_bound_u64(keys, n, store_key(cube + 1, 0, 0)) - lo;
+    }
+    lo_s[t] = lo;
+    off_s[t + 1] = len;
+  }
+  __syncthreads();
+  if (t == 0) {
+    off_s[0] = 0;
+    for (int k = 0; k < kValidCubes; ++k) off_s[k + 1] += off_s[k];
+  }
+  __syncthreads();
+  for (int c = 0; c < kValidCubes; ++c) {
+    const int len = off_s[c + 1] - off_s[c];
+    const int ci = fd.val_lo[0] + c / 15, cj = fd.val_lo[1] + (c / 3) % 5, ck = fd.val_lo[2] + c % 3;
+    for (int j = t; j < len; j += blockDim.x) {
+      const int src = d.st_base[g] + lo_s[c] + j;
+      const float4 p = d.st_pt[cur][src];
+      const int pos = d.lp_off[g] + off_s[c] + j;
+      d.vkey[pos] = delta_key(g, fd, ci, cj, ck, 0, voxel_payload(d, seg_cls(d, g), p.x, p.y, p.z, ci, cj, ck));
+      d.vval[pos] = 0x80000000u | (uint32_t)src;
+    }
+  }
+}
+
+__device__ __forceinline__ float4 delta_point(const Dev& d, int cur, uint32_t v) {
+  return (v & 0x80000000u) ? d.st_pt[cur][v & 0x7FFFFFFFu] : d.dl_pt[v];
+}
+
+// one thread per run of equal delta keys: re-centroid (old centroid first, then
+// raw points in arrival order -- the order a stable sort gives pcl::VoxelGrid)
+__global__ void delta_reduce_kernel(Dev d, int cur, int n_delta) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_delta || !d.flag[p]) return;
+  const uint64_t key = d.vkey2[p];
+  if (key == kSentinel64) return;
+  const int r = (int)d.scan[p];
+  const int g = (int)(key >> 47);
+  const FrameDesc& fd = d.desc[seg_slot(d, g)];
+  const int rel = (int)((key >> 34) & 0x1FFF);
+  const int ci = fd.win_lo[0] + rel / (kWinJ * kWinK), cj = fd.win_lo[1] + (rel / kWinK) % kWinJ,
+            ck = fd.win_lo[2] + rel % kWinK;
+  const uint64_t wkey = store_key(pack_cube(ci, cj, ck), (uint32_t)((key >> 33) & 1), key & 0x1FFFFFFFFull);
+  if ((key >> 33) & 1) {  // raw point for a cube outside the valid block: stays raw
+    d.ins_key[r] = wkey;
+    d.ins_pt[r] = delta_point(d, cur, d.vval2[p]);
+    return;
+  }
+  const uint64_t* keys = d.st_key[cur] + d.st_base[g];
+  const int n = d.st_n[g];
+  const int pos = lower_bound_u64(keys, n, wkey);
+  const bool exists = pos < n && keys[pos] == wkey;
+  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+  int cnt = 0;
+  if (exists) {
+    const float4 o = d.st_pt[cur][d.st_base[g] + pos];
+    sx = xfadd(sx, o.x); sy = xfadd(sy, o.y); sz = xfadd(sz, o.z); si = xfadd(si, o.w);
+    cnt = 1;
+  }
+  for (int e = p; e < n_delta && d.vkey2[e] == key; ++e) {
+    const float4 q = delta_point(d, cur, d.vval2[e]);
+    sx = xfadd(sx, q.x); sy = xfadd(sy, q.y); sz = xfadd(sz, q.z); si = xfadd(si, q.w);
+    ++cnt;
+  }
+  const float c = (float)cnt;
+  const float4 cen = make_float4(xfdiv(sx, c), xfdiv(sy, c), xfdiv(sz, c), xfdiv(si, c));
+  if (exists) {
+    d.st_pt[cur][d.st_base[g] + pos] = cen;  // key unchanged, updated in place before the merge copy
+  } else {
+    d.ins_key[r] = wkey;
+    d.ins_pt[r] = cen;
+  }
+}
+
+__global__ void ins_flag_kernel(const uint64_t* __restrict__ ins_key, uint32_t* __restrict__ flag, int n) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n) return;
+  flag[r] = (r < n) && ins_key[r] != kSentinel64;
+}
+__global__ void ins_compact_kernel(Dev d, int n) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n || d.ins_key[r] == kSentinel64) return;
+  const int o = (int)d.ascan[r];
+  d.ins_ckey[o] = d.ins_key[r];
+  d.ins_cpt[o] = d.ins_pt[r];
+}
+// run_off[g] = compacted-insert offset of segment g (reuses d.run_off)
+__global__ void ins_off_kernel(Dev d, int n_delta) {
+  const int g = threadIdx.x + blockIdx.x * blockDim.x;
+  if (g > d.G) return;
+  const int pos = lower_bound_u64(d.vkey2, n_delta, (uint64_t)g << 47);
+  const int run = (int)d.scan[pos];  // scan has n_delta+1 entries
+  d.run_off[g] = (int)d.ascan[run];  // ascan here = exclusive scan of insert flags over runs
+}
+
+__device__ __forceinline__ bool entry_dead(const FrameDesc& fd, uint64_t key) {
+  int ci, cj, ck;
+  unpack_cube(key_cube(key), ci, cj, ck);
+  if (!in_box(ci, cj, ck, fd.win_lo, fd.win_hi)) return true;           // cube left the window (:346-347 ...)
+  return key_pending(key) && in_box(ci, cj, ck, fd.val_lo, fd.val_hi);  // raw point merged by this re-filter
+}
+__global__ void alive_flag_kernel(Dev d, int cur, int total_lp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > total_lp) return;
+  uint32_t f = 0;
+  if (i < total_lp) {
+    const int g = find_seg(d.lp_off, d.G, i);
+    const int l = i - d.lp_off[g];
+    if (l < d.st_n[g]) {
+      const FrameDesc& fd = d.desc[seg_slot(d, g)];
+      f = fd.active ? !entry_dead(fd, d.st_key[cur][d.st_base[g] + l]) : 1u;
+    }
+  }
+  d.aflag[i] = f;
+}
+__global__ void merge_old_kernel(Dev d, int cur, int total_lp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_lp || !d.aflag[i]) return;
+  const int g = find_seg(d.lp_off, d.G, i);
+  const int l = i - d.lp_off[g];
+  const int src = d.st_base[g] + l;
+  const uint64_t key = d.st_key[cur][src];
+  const int io = d.run_off[g], nins = d.run_off[g + 1] - io;
+  const int pos = (int)(d.ascan[i] - d.ascan[d.lp_off[g]]) + lower_bound_u64(d.ins_ckey + io, nins, key);
+  if (pos >= d.st_cap[g]) { set_err(d, -3); return; }
+  d.st_key[cur ^ 1][d.st_base[g] + pos] = key;
+  d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.st_pt[cur][src];
+}
+__global__ void merge_new_kernel(Dev d, int cur, int n_max) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_max || j >= d.run_off[d.G]) return;
+  const int g = find_seg(d.run_off, d.G, j);
+  const uint64_t key = d.ins_ckey[j];
+  const int lb = lower_bound_u64(d.st_key[cur] + d.st_base[g], d.st_n[g], key);
+  const int pos = (j - d.run_off[g]) + (int)(d.ascan[d.lp_off[g] + lb] - d.ascan[d.lp_off[g]]);
+  if (pos >= d.st_cap[g]) { set_err(d, -3); return; }
+  d.st_key[cur ^ 1][d.st_base[g] + pos] = key;
+  d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.ins_cpt[j];
+}
+__global__ void store_count_kernel(Dev d) {
+  const int g = threadIdx.x + blockIdx.x * blockDim.x;
+  if (g >= d.G) return;
+  const int n = (int)(d.ascan[d.lp_off[g + 1]] - d.ascan[d.lp_off[g]]) + (d.run_off[g + 1] - d.run_off[g]);
+  if (n > d.st_cap[g]) set_err(d, -3);
+  d.st_n_new[g] = min(n, d.st_cap[g]);
+  d.out[seg_slot(d, g)].n_store[seg_cls(d, g)] = n;
+}
+
+// ----------------------------------------------------------------------------
+// K7 and utilities
+// ----------------------------------------------------------------------------
+__global__ void transform_cloud_kernel(const double* __restrict__ pose7, const float4* __restrict__ in,
+                                       float4* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  __shared__ double pose[7];
+  if (threadIdx.x < 7) pose[threadIdx.x] = pose7[threadIdx.x];
+  __syncthreads();
+  const float4 p = in[i];
+  float w[3];
+  xf_point(pose, p.x, p.y, p.z, w);
+  out[i] = make_float4(w[0], w[1], w[2], p.w);
+}
+__global__ void gather_local_kernel(Dev d, int cur, int g, float4* __restrict__ out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= d.loc_off[g * (kCols + 1) + kCols]) return;
+  out[l] = d.st_pt[cur][d.st_base[g] + local_to_store(d, g, l)];
+}
+
+// ----------------------------------------------------------------------------
+// launchers
+// ----------------------------------------------------------------------------
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+size_t cub_temp_bytes(int cap_sort, int cap_lp) {
+  size_t a = 0, b = 0, c = 0, e = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, cap_sort);
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, cap_lp);
+  cub::DeviceScan::ExclusiveSum(nullptr, c, (uint32_t*)nullptr, (uint32_t*)nullptr, cap_sort + 1);
+  cub::DeviceScan::ExclusiveSum(nullptr, e, (uint32_t*)nullptr, (uint32_t*)nullptr, cap_lp + 1);
+  return std::max(std::max(a, b), std::max(c, e)) + 256;
+}
+
+int launch_voxel_filter(const Dev& d, int n, cudaStream_t s) {
+  int k = 0;
+  if (n > 0) {
+    vox_bbox_kernel<<<d.G, 256, 0, s>>>(d); ++k;
+    vox_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n); ++k;
+    size_t tb = d.cub_tmp_bytes;
+    int gbits = 1;
+    while ((1 << gbits) < d.G) ++gbits;
+    cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n, 0, 54 + gbits, s);
+    ++k;
+  }
+  head_flag_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(d.vkey2, d.flag, n); ++k;
+  size_t tb = d.cub_tmp_bytes;
+  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.flag, d.scan, n + 1, s); ++k;
+  if (n > 0) { vox_centroid_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n); ++k; }
+  ds_off_kernel<<<cdiv(d.G + 1, 128), 128, 0, s>>>(d, n); ++k;
+  return k;
+}
+
+int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, cudaStream_t s) {
+  int k = 0;
+  range_kernel<<<d.G, 32, 0, s>>>(d, cur); ++k;
+  cudaMemsetAsync(d.hash_tab, 0xFF, sizeof(unsigned long long) * (size_t)hash_total, s);
+  if (total_lp > 0) {
+    local_key_kernel<<<cdiv(total_lp, 256), 256, 0, s>>>(d, cur, total_lp); ++k;
+    size_t tb = d.cub_tmp_bytes;
+    cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.ckey, d.ckey2, d.cval, d.cval2, total_lp, 0, 32, s);
+    ++k;
+  }
+  cs_off_kernel<<<cdiv(d.G + 1, 128), 128, 0, s>>>(d, total_lp); ++k;
+  if (total_lp > 0) { cand_build_kernel<<<cdiv(total_lp, 256), 256, 0, s>>>(d, cur, total_lp); ++k; }
+  return k;
+}
+
+int launch_guard(const Dev& d, cudaStream_t s) {
+  guard_kernel<<<cdiv(d.B, 64), 64, 0, s>>>(d);
+  return 1;
+}
+int launch_associate(const Dev& d, int outer, int tiles, bool trace, cudaStream_t s) {
+  if (tiles <= 0) return 0;
+  dim3 grid(tiles, d.B);
+  if (trace) associate_kernel<true><<<grid, kTile, 0, s>>>(d, outer);
+  else associate_kernel<false><<<grid, kTile, 0, s>>>(d, outer);
+  return 1;
+}
+int launch_lm_begin(const Dev& d, int outer, cudaStream_t s) {
+  lm_begin_kernel<<<d.B, kPartial, 0, s>>>(d, outer);
+  return 1;
+}
+int launch_evaluate(const Dev& d, int tiles, cudaStream_t s) {
+  if (tiles <= 0) return 0;
+  dim3 grid(tiles, d.B);
+  evaluate_kernel<<<grid, kTile, 0, s>>>(d);
+  return 1;
+}
+int launch_lm_after(const Dev& d, int outer, cudaStream_t s) {
+  lm_after_kernel<<<d.B, kPartial, 0, s>>>(d, outer);
+  return 1;
+}
+int launch_finish_pose(const Dev& d, cudaStream_t s) {
+  finish_pose_kernel<<<cdiv(d.B, 64), 64, 0, s>>>(d);
+  return 1;
+}
+
+int launch_map_update(const Dev& d, int cur, int total_in, int total_lp, bool check_pending, bool identity_pose,
+                      cudaStream_t s) {
+  int k = 0;
+  const int front = check_pending ? total_lp : 0;
+  const int n_delta = front + total_in;
+  if (front > 0) {
+    cudaMemsetAsync(d.vkey, 0xFF, sizeof(uint64_t) * (size_t)front, s);
+    cudaMemsetAsync(d.vval, 0, sizeof(uint32_t) * (size_t)front, s);
+    pending_gather_kernel<<<d.G, 128, 0, s>>>(d, cur); ++k;
+  }
+  if (n_delta > 0) {
+    delta_key_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, front, n_delta, identity_pose); ++k;
+    size_t tb = d.cub_tmp_bytes;
+    int gbits = 1;
+    while ((1 << gbits) < d.G) ++gbits;
+    // the sentinel is all ones inside the sorted bit range too, so it stays at the end
+    cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n_delta, 0, 47 + gbits, s);
+    ++k;
+  }
+  head_flag_kernel<<<cdiv(n_delta + 1, 256), 256, 0, s>>>(d.vkey2, d.flag, n_delta); ++k;
+  size_t tb = d.cub_tmp_bytes;
+  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.flag, d.scan, n_delta + 1, s); ++k;
+  cudaMemsetAsync(d.ins_key, 0xFF, sizeof(uint64_t) * (size_t)(n_delta + 1), s);
+  if (n_delta > 0) { delta_reduce_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, cur, n_delta); ++k; }
+  // compact the inserts (runs that created a new store entry)
+  ins_flag_kernel<<<cdiv(n_delta + 1, 256), 256, 0, s>>>(d.ins_key, d.aflag, n_delta); ++k;
+  tb = d.cub_tmp_bytes;
+  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.aflag, d.ascan, n_delta + 1, s); ++k;
+  if (n_delta > 0) { ins_compact_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, n_delta); ++k; }
+  ins_off_kernel<<<cdiv(d.G + 1, 128), 128, 0, s>>>(d, n_delta); ++k;
+  // survivors of the old store
+  alive_flag_kernel<<<cdiv(total_lp + 1, 256), 256, 0, s>>>(d, cur, total_lp); ++k;
+  tb = d.cub_tmp_bytes;
+  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.aflag, d.ascan, total_lp + 1, s); ++k;
+  if (total_lp > 0) { merge_old_kernel<<<cdiv(total_lp, 256), 256, 0, s>>>(d, cur, total_lp); ++k; }
+  if (n_delta > 0) { merge_new_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, cur, n_delta); ++k; }
+  store_count_kernel<<<cdiv(d.G, 128), 128, 0, s>>>(d); ++k;
+  return k;
+}
+
+int launch_knn_debug(const Dev& d, int slot, int cls, const float* d_q, int n, int32_t* d_idx, float* d_d2,
+                     cudaStream_t s) {
+  if (n <= 0) return 0;
+  knn_debug_kernel<<<cdiv(n, 128), 128, 0, s>>>(d, cls * d.B + slot, d_q, n, d_idx, d_d2);
+  return 1;
+}
+int launch_transform_cloud(const double* d_pose7, const float4* in, float4* out, int n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  transform_cloud_kernel<<<cdiv(n, 256), 256, 0, s>>>(d_pose7, in, out, n);
+  return 1;
+}
+int launch_gather_local(const Dev& d, int cur, int g, float4* out, cudaStream_t s) {
+  // upper bound on the local size is the store size; the kernel bounds itself
+  const int n = d.cap_lp;
+  gather_local_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, cur, g, out);
+  return 1;
+}
+
+}  // namespace s2m

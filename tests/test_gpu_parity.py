@@ -1,0 +1,244 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): kNN indices and float distances bit-exact; poses within
+1e-4 m / 1e-5 rad of the reference-path restatement (observed agreement is ~1e-9)."""
+import numpy as np
+import pytest
+
+import harness
+import oracle
+from conftest import rot_angle
+
+pytestmark = pytest.mark.gpu
+
+TOL_T, TOL_R = 1e-4, 1e-5  # metres, radians (north_star)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def seq_hdl(built):
+    return harness.sequence(20261018, "HDL64", 12)
+
+
+@pytest.fixture(scope="module")
+def seq_vlp(built):
+    return harness.sequence(7, "VLP16", 10, step_m=0.5)
+
+
+def run_oracle(seq, n, line, plane, **kw):
+    truth, odom, frames = seq
+    O = oracle.Oracle(line, plane, **kw)
+    poses = []
+    for f in range(n):
+        rc, q, t = O.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+        poses.append(np.r_[q, t])
+    return O, np.array(poses)
+
+
+def test_scan_voxel_filter_bit_exact(s2m, seq_hdl):
+    """Row V on the incoming clouds: same points, same order, same bits."""
+    truth, odom, frames = seq_hdl
+    R = s2m.Registrar(0.4, 0.8, trace=True)
+    O = oracle.Oracle(0.4, 0.8, trace=True)
+    c, s = frames[0]
+    R.register(c, s, odom[0, :4], odom[0, 4:])
+    O.register(c, s, odom[0, :4], odom[0, 4:])
+    for cls in (0, 1):
+        got, want = R.trace_cloud(cls), O.trace_cloud(cls)
+        assert got.shape == want.shape and len(got) > 100
+        assert np.array_equal(bits(got), bits(want))
+    assert R.stats.n_corner_ds == O.stats.n_corner_ds and R.stats.n_surf_ds == O.stats.n_surf_ds
+
+
+def test_first_frame_takes_guard_path(s2m, seq_hdl):
+    truth, odom, frames = seq_hdl
+    R = s2m.Registrar(0.4, 0.8)
+    rc, q, t = R.register(frames[0][0], frames[0][1], odom[0, :4], odom[0, 4:])
+    assert rc == s2m.S2M_MAP_TOO_SMALL and R.stats.optimized == 0
+    assert np.array_equal(np.r_[q, t], odom[0])  # identity correction: pose == odometry guess, bit for bit
+    rc, q, t = R.register(frames[1][0], frames[1][1], odom[1, :4], odom[1, 4:])
+    assert rc == 0 and R.stats.optimized == 1
+
+
+@pytest.mark.parametrize("sensor", ["hdl", "vlp"])
+def test_map_evolution_bit_exact_without_optimisation(s2m, seq_hdl, seq_vlp, sensor):
+    """Rows B, C, V, I, W with pose = guess on both sides: maps stay bit-identical frame after frame."""
+    seq, line, plane = (seq_hdl, 0.4, 0.8) if sensor == "hdl" else (seq_vlp, 0.2, 0.4)
+    truth, odom, frames = seq
+    R = s2m.Registrar(line, plane, skip_optimization=True)
+    O = oracle.Oracle(line, plane, skip_optimization=True)
+    for f in range(8):
+        c, s = frames[f]
+        _, qg, tg = R.register(c, s, odom[f, :4], odom[f, 4:])
+        _, qo, to = O.register(c, s, odom[f, :4], odom[f, 4:])
+        assert np.array_equal(np.r_[qg, tg], np.r_[qo, to])
+        if f in (0, 3, 7):
+            for cls in (0, 1):
+                got, want = R.map_download(cls), O.get_map(cls)
+                assert got.shape == want.shape, (f, cls, got.shape, want.shape)
+                assert np.array_equal(bits(got), bits(want)), (f, cls)
+    lm_g, lm_o = R.local_map(1, odom[7, 4:]), O.local_map(1, odom[7, 4:])
+    assert np.array_equal(bits(lm_g), bits(lm_o))
+
+
+def test_knn_bit_exact_on_uploaded_map(s2m, seq_hdl):
+    """Row K through s2m_debug_knn: indices and float distances identical to the canonical
+    brute force and to the KD-tree, on the gather order both sides define."""
+    O1, _ = run_oracle(seq_hdl, 8, 0.4, 0.8)
+    truth, odom, frames = seq_hdl
+    cm, sm = O1.get_map(0), O1.get_map(1)
+    R = s2m.Registrar(0.4, 0.8)
+    O = oracle.Oracle(0.4, 0.8)
+    assert R.map_upload(cm, sm) == 0 and O.map_upload(cm, sm) == 0
+    centre = odom[8, 4:]
+    rng = np.random.default_rng(5)
+    ties = 0
+    for cls, mp in ((0, cm), (1, sm)):
+        lg, lo = R.local_map(cls, centre), O.local_map(cls, centre)
+        assert np.array_equal(bits(lg), bits(lo)) and len(lg) > 1000
+        # queries: map points jittered (dense hits) plus far points (gate misses)
+        q = mp[rng.integers(0, len(mp), 4000), :3] + rng.normal(size=(4000, 3)).astype(np.float32) * 0.3
+        q = np.r_[q, rng.uniform(-200, 200, (200, 3))].astype(np.float32)
+        ig, dg = R.debug_knn(cls, centre, q)
+        ib, db = O.debug_knn(cls, centre, q, method=0)
+        ik, dk = O.debug_knn(cls, centre, q, method=1)
+        gate = db[:, 4] < 1.0
+        assert gate.sum() > 1000
+        assert np.array_equal(gate, dg[:, 4] < 1.0)          # same queries pass the reference's gate
+        assert np.array_equal(ig[gate], ib[gate])            # indices bit-exact
+        assert np.array_equal(bits(dg[gate]), bits(db[gate]))  # float distances bit-exact
+        assert (ig[~gate] == -1).all()
+        same = (ik[gate] == ib[gate]).all(1)
+        ties += int((~same).sum())                           # KD-tree differs only on exact ties
+        assert np.array_equal(bits(dk[gate]), bits(db[gate]))
+    assert ties <= 2
+
+
+def test_registration_matches_oracle_on_uploaded_map(s2m, seq_hdl):
+    """One full registration (rows A..W) from identical maps: kNN of the first outer iteration
+    bit-exact inside the real flow, reduced normal equations and poses within tolerance."""
+    O1, _ = run_oracle(seq_hdl, 8, 0.4, 0.8)
+    truth, odom, frames = seq_hdl
+    cm, sm = O1.get_map(0), O1.get_map(1)
+    R = s2m.Registrar(0.4, 0.8, trace=True)
+    O = oracle.Oracle(0.4, 0.8, trace=True, use_kdtree=False)
+    R.map_upload(cm, sm)
+    O.map_upload(cm, sm)
+    c, s = frames[8]
+    rg, qg, tg = R.register(c, s, odom[8, :4], odom[8, 4:])
+    ro, qo, to = O.register(c, s, odom[8, :4], odom[8, 4:])
+    assert rg == ro == 0
+    assert (R.stats.n_map_corner, R.stats.n_map_surf) == (O.stats.n_map_corner, O.stats.n_map_surf)
+    for cls in (0, 1):
+        ig, dg, ug = R.trace_knn(0, cls)
+        io, do, uo = O.trace_knn(0, cls)
+        gate = do[:, 4] < 1.0
+        assert len(ig) == len(io) and gate.sum() > 200
+        assert np.array_equal(ig[gate], io[gate]) and np.array_equal(bits(dg[gate]), bits(do[gate]))
+        assert np.array_equal(ug, uo)  # same correspondences accepted (no threshold flips)
+    assert list(R.stats.n_edge) == list(O.stats.n_edge) and list(R.stats.n_plane) == list(O.stats.n_plane)
+    for outer in (0, 1):
+        pg, sg, itg, ng, termg = R.trace_lm(outer)
+        po, so, ito, no, termo = O.trace_lm(outer)
+        assert np.allclose(sg, so, rtol=1e-9, atol=1e-9 * np.abs(so).max())
+        assert (ng, termg) == (no, termo)
+        assert np.abs(pg - po).max() < 1e-9
+    assert np.linalg.norm(tg - to) < TOL_T and rot_angle(qg, qo) < TOL_R
+    assert np.linalg.norm(tg - to) < 1e-8  # what we actually observe
+
+
+@pytest.mark.parametrize("sensor", ["hdl", "vlp"])
+def test_stream_poses_within_tolerance(s2m, seq_hdl, seq_vlp, sensor):
+    """N-frame replay, each side on its own map: per-scan poses agree within the north_star tolerance."""
+    seq, line, plane = (seq_hdl, 0.4, 0.8) if sensor == "hdl" else (seq_vlp, 0.2, 0.4)
+    truth, odom, frames = seq
+    n = len(frames)
+    O, poses_o = run_oracle(seq, n, line, plane)
+    R = s2m.Registrar(line, plane)
+    worst_t = worst_r = 0.0
+    for f in range(n):
+        rc, q, t = R.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+        worst_t = max(worst_t, float(np.linalg.norm(t - poses_o[f, 4:])))
+        worst_r = max(worst_r, rot_angle(q, poses_o[f, :4]))
+    assert worst_t < TOL_T and worst_r < TOL_R, (worst_t, worst_r)
+    # and mapping did its job: closer to the truth than the drifting odometry
+    assert np.linalg.norm(t - truth[n - 1, 4:]) < np.linalg.norm(odom[n - 1, 4:] - truth[n - 1, 4:])
+    qc, tc = R.correction()
+    assert abs(np.linalg.norm(qc) - 1) < 1e-9
+
+
+def test_batch_slots_are_independent_and_identical_to_single(s2m, seq_hdl, seq_vlp):
+    """register_batch over 3 slots == 3 single-slot contexts, bit for bit (no cross-talk)."""
+    truth, odom, frames = seq_hdl
+    n = 6
+    B = 3
+    RB = s2m.Registrar(0.4, 0.8, batch=B, cap_map_corner=1 << 17, cap_map_surf=1 << 18)
+    singles = [s2m.Registrar(0.4, 0.8, cap_map_corner=1 << 17, cap_map_surf=1 << 18) for _ in range(B)]
+    for f in range(n):
+        # slot b replays the sequence with a lag of b frames (different inputs per slot, ragged sizes)
+        fr = [max(f - b, 0) for b in range(B)]
+        corner = np.concatenate([frames[i][0] for i in fr])
+        surf = np.concatenate([frames[i][1] for i in fr])
+        co = np.cumsum([0] + [len(frames[i][0]) for i in fr]).astype(np.int32)
+        so = np.cumsum([0] + [len(frames[i][1]) for i in fr]).astype(np.int32)
+        q = np.array([odom[i, :4] for i in fr])
+        t = np.array([odom[i, 4:] for i in fr])
+        active = np.array([1 if f - b >= 0 else 0 for b in range(B)], np.int32)
+        st, qo, to = RB.register_batch(corner, co, surf, so, q, t, active)
+        for b in range(B):
+            if not active[b]:
+                continue
+            rc, q1, t1 = singles[b].register(frames[fr[b]][0], frames[fr[b]][1], odom[fr[b], :4], odom[fr[b], 4:])
+            assert st[b] == rc
+            assert np.array_equal(qo[b], q1) and np.array_equal(to[b], t1), (f, b)
+
+
+def test_window_shift_and_eviction(s2m, built):
+    """Drive the sensor 400 m along +x in 60 m hops with a tiny synthetic cloud: the window must
+    follow (cen decreases), cubes that leave it are dropped, exactly like the oracle."""
+    rng = np.random.default_rng(9)
+    R = s2m.Registrar(0.4, 0.8, skip_optimization=True)
+    O = oracle.Oracle(0.4, 0.8, skip_optimization=True)
+    for step in range(9):
+        x = 60.0 * step - 30.0
+        corner = np.c_[rng.uniform(-20, 20, (300, 3)), np.zeros(300)].astype(np.float32)
+        surf = np.c_[rng.uniform(-140, 140, (3000, 2)), rng.uniform(-3, 3, 3000), np.zeros(3000)].astype(np.float32)
+        q, t = np.array([0, 0, 0.0, 1.0]), np.array([x, -70.0 * step, 0.3 * step])
+        R.register(corner, surf, q, t)
+        O.register(corner, surf, q, t)
+        assert np.array_equal(R.window(), O.window()), step
+    assert not np.array_equal(O.window(), [10, 10, 5])
+    for cls in (0, 1):
+        got, want = R.map_download(cls), O.get_map(cls)
+        assert got.shape == want.shape and np.array_equal(bits(got), bits(want))
+
+
+def test_empty_and_tiny_inputs(s2m, built):
+    R = s2m.Registrar(0.4, 0.8)
+    e = np.zeros((0, 4), np.float32)
+    rc, q, t = R.register(e, e, [0, 0, 0, 1.0], [1.0, 2.0, 3.0])
+    assert rc == s2m.S2M_MAP_TOO_SMALL and np.array_equal(t, [1.0, 2.0, 3.0])
+    one = np.array([[1, 2, 3, 0.5]], np.float32)
+    rc, q, t = R.register(one, one, [0, 0, 0, 1.0], [0.0, 0.0, 0.0])
+    assert rc == s2m.S2M_MAP_TOO_SMALL
+    assert len(R.map_download(0)) == 1 and len(R.map_download(1)) == 1
+    with pytest.raises(s2m.S2MError):
+        R.register(np.zeros((20000, 4), np.float32), e, [0, 0, 0, 1.0], [0, 0, 0.0])  # > cap_corner_in
+
+
+def test_transform_cloud_bit_exact(s2m, seq_hdl):
+    truth, odom, frames = seq_hdl
+    R = s2m.Registrar(0.4, 0.8)
+    R.register(frames[0][0], frames[0][1], odom[0, :4], odom[0, 4:])
+    pts = frames[0][1]
+    got = R.transform_cloud(pts)
+    q, t = odom[0, :4], odom[0, 4:]
+    v = pts[:, :3].astype(np.float64)
+    u = np.broadcast_to(q[:3], v.shape)
+    uv = np.cross(u, v)
+    uv = uv + uv
+    want = ((v + q[3] * uv) + np.cross(u, uv) + t).astype(np.float32)
+    assert np.array_equal(bits(got[:, :3]), bits(want)) and np.array_equal(got[:, 3], pts[:, 3])
