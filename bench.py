@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- scan-to-map registrations/s on synthetic HDL-64 sequences (BASELINE.json metric).
+
+Workload "hdl64_batch_replay" (BASELINE config 4, SURVEY 8e "batch replay"): every GPU holds
+S independent HDL-64 sequences (own map, own pose chain); one STEP advances every sequence by
+one frame = S scan-to-map registrations (laserMapping.cpp:310-802 each), all inside the same
+kernel launches.  No data-path collective; weak scaling (S per GPU fixed).
+
+  value : registrations/s, inputs already resident in HBM (s2m_register_batch_dev)
+  e2e   : the same through s2m_register_batch with pinned HOST buffers (H2D of the clouds and
+          D2H of poses/counters inside the timed region)
+  roofline : the fused association kernel (K4) -- algorithmic bytes of SURVEY 8d / CUDA-event time
+  cpu_baseline : the oracle (restated reference path, 1 core) on a bounded sample of the workload
+
+--impl reference times the reference path's CPU restatement (oracle/, one sequence per host
+thread) on the same workload/metric; the real PCL+Ceres binary cannot be built here.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scan_to_map_registrations_per_s"
+UNIT = "registrations/s"
+N_WORLDS = 8          # distinct synthetic worlds/trajectories (BASELINE config 4: 8 sequences)
+PREFILL = 20          # untimed frames that build each sequence's map before warm-up
+SENSOR = "HDL64"
+LINE_RES, PLANE_RES = 0.4, 0.8  # aloam_velodyne_HDL_64.launch:11-12
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def make_worlds(n_frames, rank, threads):
+    """N_WORLDS replayable HDL-64 sequences: truth poses + per-frame (corner, surf) clouds."""
+    import harness
+    worlds = []
+    for w in range(N_WORLDS):
+        seed = 20261018 + w
+        truth = harness.trajectory(seed, n_frames, 1.0)
+        frames = []
+        for f in range(n_frames):
+            xyz = harness.scan(seed, SENSOR, truth[f], f, 0.02)
+            frames.append(harness.features(SENSOR, xyz))
+        worlds.append((seed, truth, frames))
+    return worlds
+
+
+def slot_odometry(worlds, n_slots, rank):
+    """Slot s replays world s % N_WORLDS with its own odometry drift (so every slot is a
+    different registration problem: different guesses, poses and maps)."""
+    import harness
+    odo = []
+    for s in range(n_slots):
+        seed, truth, _ = worlds[s % N_WORLDS]
+        odo.append(harness.odometry(seed * 7919 + 104729 * (s // N_WORLDS) + 15485863 * rank, truth, 0.02, 0.1))
+    return odo
+
+
+def pack_step(worlds, n_slots, f):
+    cs = [worlds[s % N_WORLDS][2][f][0] for s in range(n_slots)]
+    ss = [worlds[s % N_WORLDS][2][f][1] for s in range(n_slots)]
+    co = np.cumsum([0] + [len(c) for c in cs]).astype(np.int32)
+    so = np.cumsum([0] + [len(c) for c in ss]).astype(np.int32)
+    return np.concatenate(cs), co, np.concatenate(ss), so
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons of one GPU, sampled during the timed region (NVML)."""
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.reasons, self.stop_flag = device, [], set(), False
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def result(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}
+        return {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def k4_traffic():
+    """dram bytes per K4 launch from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "k4_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return None
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_baseline(worlds, odo, n_frames, max_seconds=25.0):
+    """Oracle (restated reference path) on ONE core over a bounded sample: each world's frames
+    after the prefill, sequence after sequence."""
+    import oracle
+    regs, t_total = 0, 0.0
+    per_phase = np.zeros(7)
+    for w in range(N_WORLDS):
+        O = oracle.Oracle(LINE_RES, PLANE_RES)
+        _, truth, frames = worlds[w]
+        od = odo[w]
+        for f in range(n_frames):
+            c, s = frames[f]
+            t0 = time.perf_counter()
+            O.register(c, s, od[f, :4], od[f, 4:])
+            dt = time.perf_counter() - t0
+            if f >= PREFILL:
+                t_total += dt
+                regs += 1
+                per_phase += np.array(O.stats.t_ms[:7])
+        if t_total > max_seconds:
+            break
+    return {"value": regs / t_total, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d registrations: frames %d..%d of %d HDL-64 worlds, sequentially on one core "
+                      "(oracle/ = CPU restatement of laserMapping.cpp:310-802; PCL/Ceres not installable here)"
+                      % (regs, PREFILL, n_frames - 1, w + 1),
+            "ms_per_registration": 1e3 * t_total / regs,
+            "phase_ms": {k: round(float(v) / regs, 3) for k, v in
+                         zip(["shift", "tree", "data", "solver", "add", "filter", "whole"], per_phase)}}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    import oracle
+    cores = os.cpu_count() or 1
+    n_seq = min(cores, 64)
+    n_frames = PREFILL + args.warmup + args.steps
+    worlds = make_worlds(n_frames, 0, cores)
+    odo = slot_odometry(worlds, n_seq, 0)
+    oracles = [oracle.Oracle(LINE_RES, PLANE_RES) for _ in range(n_seq)]
+
+    def run_frames(s, f0, f1):
+        frames = worlds[s % N_WORLDS][2]
+        for f in range(f0, f1):
+            c, su = frames[f]
+            oracles[s].register(c, su, odo[s][f, :4], odo[s][f, 4:])
+
+    def parallel(f0, f1):
+        th = [threading.Thread(target=run_frames, args=(s, f0, f1)) for s in range(n_seq)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+
+    parallel(0, PREFILL + args.warmup)  # ctypes releases the GIL: one sequence per host thread
+    t0 = time.perf_counter()
+    parallel(PREFILL + args.warmup, n_frames)
+    dt = time.perf_counter() - t0
+    value = n_seq * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "hdl64_batch_replay", "sensor": "HDL-64 synthetic 64x1900",
+                       "line_res": LINE_RES, "plane_res": PLANE_RES, "sequences": n_seq,
+                       "distinct_worlds": N_WORLDS, "prefill_frames": PREFILL},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_seq, "kind": "port",
+                             "sample": "%d sequences x %d frames, one sequence per host thread (%d cores); oracle/ "
+                                       "restatement of the reference path" % (n_seq, args.steps, cores)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    S = args.seqs
+    n_frames = PREFILL + args.warmup + args.steps
+    cores = os.cpu_count() or 1
+    t_gen = time.perf_counter()
+    worlds = make_worlds(n_frames, rank, max(1, cores // world))
+    odo = slot_odometry(worlds, S, rank)
+    t_gen = time.perf_counter() - t_gen
+    steps = [pack_step(worlds, S, f) for f in range(n_frames)]
+    q_all = np.array([[odo[s][f, :4] for s in range(S)] for f in range(n_frames)])
+    t_all = np.array([[odo[s][f, 4:] for s in range(S)] for f in range(n_frames)])
+    max_c = max(int(np.diff(st[1]).max()) for st in steps)
+    max_s = max(int(np.diff(st[3]).max()) for st in steps)
+    stream = torch.cuda.Stream()  # a real (non-default) stream: the library launches on it, the events time it
+    torch.cuda.set_stream(stream)
+
+    def make_ctx():
+        R = pkg.Registrar(LINE_RES, PLANE_RES, device=local_rank, batch=S, cap_corner_in=max_c + 64,
+                          cap_surf_in=max_s + 64, cap_map_corner=args.cap_map_corner, cap_map_surf=args.cap_map_surf)
+        R.set_stream(stream.cuda_stream)
+        return R
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed_loop(R, call, sampler=None):
+        for f in range(PREFILL + args.warmup):
+            call(R, f)
+        barrier()
+        if sampler:
+            sampler.start()
+        evs = []
+        l0 = R.launch_count()
+        wall0 = time.perf_counter()
+        for f in range(PREFILL + args.warmup, n_frames):
+            flush.fill_(f & 0xFF)  # evict L2 between steps (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            call(R, f)
+            e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        wall = time.perf_counter() - wall0
+        if sampler:
+            sampler.stop_flag = True
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, R.launch_count() - l0, wall
+
+    # ---- arm 1: inputs resident in HBM -------------------------------------------------------
+    dev_steps = [(torch.from_numpy(c).cuda(), co, torch.from_numpy(s).cuda(), so) for c, co, s, so in steps]
+
+    def call_dev(R, f):
+        c, co, s, so = dev_steps[f]
+        return R.register_batch(c.data_ptr(), co, s.data_ptr(), so, q_all[f], t_all[f], device_ptrs=True)
+
+    R = make_ctx()
+    sampler = ClockSampler(local_rank)
+    R.set_profiling(False)
+    # profile K4 only inside the timed steps: enable after warm-up via a wrapper
+    state = {"armed": False}
+
+    def call_dev_prof(R, f):
+        if f == PREFILL + args.warmup and not state["armed"]:
+            R.set_profiling(True)
+            R.k4_profile(reset=True)
+            state["armed"] = True
+        return call_dev(R, f)
+
+    ms_dev, launches, wall_dev = timed_loop(R, call_dev_prof, sampler)
+    k4_ms, k4_n, k4_bytes = R.k4_profile(reset=True)
+    stats = [R.batch_stats[s] for s in range(S)]
+    shape = {"Nc_in": float(np.mean([st.n_corner_in for st in stats])), "Ns_in": float(np.mean([st.n_surf_in for st in stats])),
+             "Nc": float(np.mean([st.n_corner_ds for st in stats])), "Ns": float(np.mean([st.n_surf_ds for st in stats])),
+             "Mc": float(np.mean([st.n_map_corner for st in stats])), "Ms": float(np.mean([st.n_map_surf for st in stats])),
+             "n_edge": float(np.mean([st.n_edge[1] for st in stats])), "n_plane": float(np.mean([st.n_plane[1] for st in stats]))}
+    R.close()
+    del dev_steps
+    torch.cuda.empty_cache()
+
+    # ---- arm 2: end to end from pinned host buffers ----------------------------------------------
+    pin_steps = []
+    for c, co, s, so in steps:
+        pc, ps = torch.from_numpy(c).pin_memory(), torch.from_numpy(s).pin_memory()
+        pin_steps.append((pc, co, ps, so))
+
+    def call_host(R, f):
+        pc, co, ps, so = pin_steps[f]
+        fn = R.L.s2m_register_batch
+        B = R.batch
+        qo, to = np.zeros((B, 4)), np.zeros((B, 3))
+        q, t = np.ascontiguousarray(q_all[f]), np.ascontiguousarray(t_all[f])
+        rc = fn(R.h, pc.data_ptr(), co.ctypes.data, ps.data_ptr(), so.ctypes.data, q.ctypes.data, t.ctypes.data,
+                None, qo.ctypes.data, to.ctypes.data, ctypes.cast(R._bstats, ctypes.c_void_p), R._status.ctypes.data)
+        R._check(rc)
+        return qo, to
+
+    R2 = make_ctx()
+    ms_e2e, _, wall_e2e = timed_loop(R2, call_host)
+    R2.close()
+    h2d = float(np.mean([steps[f][0].nbytes + steps[f][2].nbytes for f in range(PREFILL + args.warmup, n_frames)]))
+    h2d += 64 * 128  # per-step descriptor block (poses, windows, offsets) -- order of magnitude
+    d2h = float(S * 168 + 4)  # poses + per-slot counters + error flag read back every step
+
+    if rank != 0:
+        return 0
+    regs = world * S * args.steps
+    value = regs / (ms_dev * 1e-3)
+    e2e_value = regs / (ms_e2e * 1e-3)
+    peak, peak_src = measured_peak()
+    ach = (k4_bytes / max(k4_n, 1)) / (1e-3 * k4_ms / max(k4_n, 1)) / 1e9 if k4_ms > 0 else 0.0
+    traffic = k4_traffic()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "hdl64_batch_replay", "sensor": "HDL-64 synthetic 64x1900 (121600 rays/sweep)",
+                   "line_res": LINE_RES, "plane_res": PLANE_RES, "sequences_per_gpu": S, "distinct_worlds": N_WORLDS,
+                   "prefill_frames": PREFILL, "registrations_per_step": world * S, "parallelism": "replicas-of-sequences x%d" % world,
+                   "l2": "flushed between steps (256 MiB write outside the per-step event pairs)",
+                   "timing": "CUDA events per step on the launching stream, summed; max over ranks",
+                   "per_registration_mean": shape, "datagen_s": round(t_gen, 1),
+                   "host_wall_ms_per_step": round(1e3 * wall_dev / args.steps, 3)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "associate_kernel (K4: transform+kNN5+PCA/QR+residual/J+Huber+reduce)",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                     "bytes_per_launch_algorithmic": k4_bytes / max(k4_n, 1), "launches": int(k4_n),
+                     "avg_launch_us": 1e3 * k4_ms / max(k4_n, 1),
+                     "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                     "traffic_source": traffic.get("source") if traffic else None},
+        "clocks": sampler.result(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(worlds, odo, n_frames)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seqs", type=int, default=64, help="independent sequences per GPU (<=64)")
+    ap.add_argument("--cap-map-corner", type=int, default=1 << 17)
+    ap.add_argument("--cap-map-surf", type=int, default=1 << 17)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # the harness ray-caster uses OpenMP: share the host cores between the ranks of this node
+    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // max(world, 1))))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    return run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

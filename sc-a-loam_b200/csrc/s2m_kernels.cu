@@ -768,11 +768,10 @@ int launch_voxel_filter(const Dev& d, int n, cudaStream_t s) {
     int gbits = 1;
     while ((1 << gbits) < d.G) ++gbits;
     cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n, 0, 54 + gbits, s);
-    ++k;
   }
   head_flag_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(d.vkey2, d.flag, n); ++k;
   size_t tb = d.cub_tmp_bytes;
-  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.flag, d.scan, n + 1, s); ++k;
+  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.flag, d.scan, n + 1, s);
   if (n > 0) { vox_centroid_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n); ++k; }
   ds_off_kernel<<<cdiv(d.G + 1, 128), 128, 0, s>>>(d, n); ++k;
   return k;
@@ -786,7 +785,6 @@ int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, cuda
     local_key_kernel<<<cdiv(total_lp, 256), 256, 0, s>>>(d, cur, total_lp); ++k;
     size_t tb = d.cub_tmp_bytes;
     cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.ckey, d.ckey2, d.cval, d.cval2, total_lp, 0, 32, s);
-    ++k;
   }
   cs_off_kernel<<<cdiv(d.G + 1, 128), 128, 0, s>>>(d, total_lp); ++k;
   if (total_lp > 0) { cand_build_kernel<<<cdiv(total_lp, 256), 256, 0, s>>>(d, cur, total_lp); ++k; }
@@ -840,23 +838,22 @@ int launch_map_update(const Dev& d, int cur, int total_in, int total_lp, bool ch
     while ((1 << gbits) < d.G) ++gbits;
     // the sentinel is all ones inside the sorted bit range too, so it stays at the end
     cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n_delta, 0, 47 + gbits, s);
-    ++k;
   }
   head_flag_kernel<<<cdiv(n_delta + 1, 256), 256, 0, s>>>(d.vkey2, d.flag, n_delta); ++k;
   size_t tb = d.cub_tmp_bytes;
-  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.flag, d.scan, n_delta + 1, s); ++k;
+  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.flag, d.scan, n_delta + 1, s);
   cudaMemsetAsync(d.ins_key, 0xFF, sizeof(uint64_t) * (size_t)(n_delta + 1), s);
   if (n_delta > 0) { delta_reduce_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, cur, n_delta); ++k; }
   // compact the inserts (runs that created a new store entry)
   ins_flag_kernel<<<cdiv(n_delta + 1, 256), 256, 0, s>>>(d.ins_key, d.aflag, n_delta); ++k;
   tb = d.cub_tmp_bytes;
-  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.aflag, d.ascan, n_delta + 1, s); ++k;
+  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.aflag, d.ascan, n_delta + 1, s);
   if (n_delta > 0) { ins_compact_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, n_delta); ++k; }
   ins_off_kernel<<<cdiv(d.G + 1, 128), 128, 0, s>>>(d, n_delta); ++k;
   // survivors of the old store
   alive_flag_kernel<<<cdiv(total_lp + 1, 256), 256, 0, s>>>(d, cur, total_lp); ++k;
   tb = d.cub_tmp_bytes;
-  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.aflag, d.ascan, total_lp + 1, s); ++k;
+  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.aflag, d.ascan, total_lp + 1, s);
   if (total_lp > 0) { merge_old_kernel<<<cdiv(total_lp, 256), 256, 0, s>>>(d, cur, total_lp); ++k; }
   if (n_delta > 0) { merge_new_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, cur, n_delta); ++k; }
   store_count_kernel<<<cdiv(d.G, 128), 128, 0, s>>>(d); ++k;
