@@ -110,7 +110,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.05)
 
     def result(self):
         if not self.samples:
@@ -299,7 +299,8 @@ def run_ours(args, rank, world, local_rank):
         return call_dev(R, f)
 
     ms_dev, launches, wall_dev = timed_loop(R, call_dev_prof, sampler)
-    k4_ms, k4_n, k4_bytes = R.k4_profile(reset=True)
+    k4_ms, k4_n, k4_bytes = R.k4_profile(reset=False)
+    phases = R.phase_profile(reset=True)
     stats = [R.batch_stats[s] for s in range(S)]
     shape = {"Nc_in": float(np.mean([st.n_corner_in for st in stats])), "Ns_in": float(np.mean([st.n_surf_in for st in stats])),
              "Nc": float(np.mean([st.n_corner_ds for st in stats])), "Ns": float(np.mean([st.n_surf_ds for st in stats])),
@@ -351,6 +352,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "flushed between steps (256 MiB write outside the per-step event pairs)",
                    "timing": "CUDA events per step on the launching stream, summed; max over ranks",
                    "per_registration_mean": shape, "datagen_s": round(t_gen, 1),
+                   "phase_ms_per_step": {k: round(v / args.steps, 4) for k, v in phases.items()},
                    "host_wall_ms_per_step": round(1e3 * wall_dev / args.steps, 3)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},

@@ -163,6 +163,18 @@ long long s2m_launch_count(s2m_ctx* ctx);
 int s2m_set_profiling(s2m_ctx* ctx, int on);
 int s2m_k4_profile(s2m_ctx* ctx, int reset, double* ms_total, long long* launches,
                    double* alg_bytes);
+/* CUDA-event time (ms) per phase of the frames run with profiling on -- the
+ * reference's stopwatch phases (laserMapping.cpp:308-859 t_shift, t_tree, t_data,
+ * t_solver, t_add, t_filter) regrouped by kernel family. */
+#define S2M_PHASE_INPUT 0     /* copy of the incoming clouds into the packed device buffer */
+#define S2M_PHASE_VOXEL 1     /* scan voxel-grid filter (row V) */
+#define S2M_PHASE_INDEX 2     /* local map + 1 m cell index (rows C, T) */
+#define S2M_PHASE_ASSOCIATE 3 /* fused association kernel, both outer iterations (rows P..Q) */
+#define S2M_PHASE_SOLVE 4     /* LM evaluations + steps (row S) */
+#define S2M_PHASE_UPDATE 5    /* map insert / re-filter / evict (rows I, W, B) */
+#define S2M_PHASE_READBACK 6  /* pose + counter read-back and host synchronisation */
+#define S2M_N_PHASES 7
+int s2m_phase_profile(s2m_ctx* ctx, int reset, double ms[S2M_N_PHASES]);
 
 /* Sharded-map mode (BASELINE config 5): x-slabs of cubes per GPU, one allreduce
  * of the 28-double normal-equation block per evaluation.  nccl_unique_id is the

@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libs2m.so")
+LIB_PATH = os.environ.get("S2M_LIB") or os.path.join(_HERE, "csrc", "libs2m.so")  # S2M_LIB: tuning variants only
 
 S2M_OK = 0
 S2M_MAP_TOO_SMALL = 1
@@ -28,7 +28,7 @@ EXPORTS = [
     "s2m_register", "s2m_register_batch", "s2m_register_batch_dev", "s2m_get_correction",
     "s2m_transform_cloud", "s2m_map_upload", "s2m_map_download", "s2m_get_local_map", "s2m_get_surround",
     "s2m_get_window", "s2m_debug_knn", "s2m_trace_cloud", "s2m_trace_knn", "s2m_trace_lm",
-    "s2m_launch_count", "s2m_set_profiling", "s2m_k4_profile", "s2m_shard_unique_id", "s2m_shard_init",
+    "s2m_launch_count", "s2m_set_profiling", "s2m_k4_profile", "s2m_phase_profile", "s2m_shard_unique_id", "s2m_shard_init",
     "s2m_shard_profile",
 ]
 
@@ -95,6 +95,7 @@ def load_library(path=LIB_PATH):
     L.s2m_launch_count.restype = cll
     L.s2m_set_profiling.argtypes = [vp, ci]
     L.s2m_k4_profile.argtypes = [vp, ci, vp, vp, vp]
+    L.s2m_phase_profile.argtypes = [vp, ci, vp]
     L.s2m_shard_unique_id.argtypes = [vp]
     L.s2m_shard_init.argtypes = [vp, vp]
     L.s2m_shard_profile.argtypes = [vp, ci, vp, vp]
@@ -281,6 +282,13 @@ class Registrar:
 
     def set_profiling(self, on=True):
         self._check(self.L.s2m_set_profiling(self.h, int(on)))
+
+    PHASES = ["input", "voxel", "index", "associate", "solve", "update", "readback"]
+
+    def phase_profile(self, reset=True):
+        ms = np.zeros(len(self.PHASES))
+        self._check(self.L.s2m_phase_profile(self.h, int(reset), ms.ctypes.data))
+        return dict(zip(self.PHASES, ms.tolist()))
 
     def k4_profile(self, reset=True):
         ms, n, b = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()

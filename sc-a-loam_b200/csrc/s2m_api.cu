@@ -53,21 +53,48 @@ struct s2m_ctx {
   HostTables* d_ht = nullptr;    // device copy (desc/in_off/lp_off/hash_off point into it)
   SlotOut* h_out = nullptr;      // pinned
   int* h_err = nullptr;          // pinned
+  int* h_dsoff = nullptr;        // pinned [G+1]: down-sampled counts read back mid-frame
+  cudaEvent_t ev_ds = nullptr;
   LmState* lm_trace = nullptr;   // [2][B] device
   LmState* h_lm = nullptr;       // pinned [2][B]
   std::vector<void*> allocs;
   std::string err;
   long long launches = 0;
   int hash_cap_total = 0;
-  // profiling of the fused association kernel
+  // profiling: CUDA events at phase boundaries of every frame (on the launching stream)
   bool profiling = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> k4_events;
-  size_t k4_used = 0;
-  double k4_ms = 0, k4_bytes = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_phase;      // phase id that ENDS at this event (-1: frame start)
+  size_t ev_used = 0;
+  double phase_ms[S2M_N_PHASES] = {0};
+  double k4_bytes = 0, k4_scanned = 0, k4_cand27 = 0;
   long long k4_launches = 0;
-  std::vector<std::pair<int, int>> k4_pending_outer;  // (event index, outer) awaiting byte accounting
-  int last_total_in = 0;
+  int sm_count = 148;
 };
+
+static int prof_mark(s2m_ctx* ctx, int phase) {
+  if (!ctx->profiling) return 0;
+  if (ctx->ev_used == ctx->ev_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return -1;
+    ctx->ev_pool.push_back(e);
+    ctx->ev_phase.push_back(0);
+  }
+  ctx->ev_phase[ctx->ev_used] = phase;
+  cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream);
+  ctx->ev_used++;
+  return 0;
+}
+static void prof_resolve(s2m_ctx* ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  for (size_t i = 1; i < ctx->ev_used; ++i) {
+    if (ctx->ev_phase[i] < 0) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev_pool[i - 1], ctx->ev_pool[i]) == cudaSuccess) ctx->phase_ms[ctx->ev_phase[i]] += ms;
+    if (ctx->ev_phase[i] == S2M_PHASE_ASSOCIATE) ctx->k4_launches++;
+  }
+  ctx->ev_used = 0;
+}
 
 #define CK(call)                                                                         \
   do {                                                                                   \
@@ -128,8 +155,10 @@ extern "C" void s2m_destroy(s2m_ctx* ctx) {
   if (ctx->ht) cudaFreeHost(ctx->ht);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   if (ctx->h_err) cudaFreeHost(ctx->h_err);
+  if (ctx->h_dsoff) cudaFreeHost(ctx->h_dsoff);
+  if (ctx->ev_ds) cudaEventDestroy(ctx->ev_ds);
   if (ctx->h_lm) cudaFreeHost(ctx->h_lm);
-  for (auto& e : ctx->k4_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -138,6 +167,7 @@ static int create_impl(s2m_ctx* ctx) {
   const s2m_params& P = ctx->P;
   CK(cudaSetDevice(P.device));
   CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, P.device));
   ctx->stream = ctx->own_stream;
   Dev& d = ctx->d;
   std::memset(&d, 0, sizeof(d));
@@ -154,6 +184,8 @@ static int create_impl(s2m_ctx* ctx) {
   CK(cudaMallocHost((void**)&ctx->ht, sizeof(HostTables)));
   CK(cudaMallocHost((void**)&ctx->h_out, sizeof(SlotOut) * B));
   CK(cudaMallocHost((void**)&ctx->h_err, sizeof(int)));
+  CK(cudaMallocHost((void**)&ctx->h_dsoff, sizeof(int) * (2 * kMaxBatch + 1)));
+  CK(cudaEventCreateWithFlags(&ctx->ev_ds, cudaEventDisableTiming));
   CK(cudaMallocHost((void**)&ctx->h_lm, sizeof(LmState) * 2 * B));
   std::memset(ctx->ht, 0, sizeof(HostTables));
   if (dev_alloc(ctx, &ctx->d_ht, 1)) return S2M_ERR_CUDA;
@@ -170,19 +202,21 @@ static int create_impl(s2m_ctx* ctx) {
   for (int b = 0; b < 2; ++b) { rc |= dev_alloc(ctx, &d.st_key[b], d.cap_lp); rc |= dev_alloc(ctx, &d.st_pt[b], d.cap_lp); }
   rc |= dev_alloc(ctx, &d.st_n, G); rc |= dev_alloc(ctx, &d.st_n_new, G);
   rc |= dev_alloc(ctx, &d.rng_start, G * kCols); rc |= dev_alloc(ctx, &d.loc_off, G * (kCols + 1));
-  rc |= dev_alloc(ctx, &d.ckey, d.cap_lp); rc |= dev_alloc(ctx, &d.ckey2, d.cap_lp);
-  rc |= dev_alloc(ctx, &d.cval, d.cap_lp); rc |= dev_alloc(ctx, &d.cval2, d.cap_lp);
-  rc |= dev_alloc(ctx, &d.cand, d.cap_lp);
+  const size_t ccap = (size_t)std::max(d.cap_lp, d.cap_in);
+  rc |= dev_alloc(ctx, &d.ckey, ccap); rc |= dev_alloc(ctx, &d.ckey2, ccap);
+  rc |= dev_alloc(ctx, &d.cval, ccap); rc |= dev_alloc(ctx, &d.cval2, ccap);
+  rc |= dev_alloc(ctx, &d.cand, d.cap_lp); rc |= dev_alloc(ctx, &d.qperm, d.cap_in);
   // cell tables: per segment a power of two >= 2 x entries, >= 1024
   long long hcap = 0;
   for (int g = 0; g < G; ++g) hcap += next_pow2(std::max(1024, 2 * (g < B ? P.cap_map_corner : P.cap_map_surf)));
   if (hcap >= (1ll << 31)) { ctx->err = "cell tables too large"; return S2M_ERR_ARG; }
   ctx->hash_cap_total = (int)hcap;
-  rc |= dev_alloc(ctx, &d.hash_tab, (size_t)hcap); rc |= dev_alloc(ctx, &d.hash_full, (size_t)hcap);
+  rc |= dev_alloc(ctx, &d.hash_tab, (size_t)hcap); rc |= dev_alloc(ctx, &d.hash_aux, (size_t)hcap);
   rc |= dev_alloc(ctx, &d.cs_off, G + 1);
   rc |= dev_alloc(ctx, &d.rec, (size_t)d.cap_in * 6); rc |= dev_alloc(ctx, &d.rec_valid, d.cap_in);
   rc |= dev_alloc(ctx, &d.partials, (size_t)B * d.max_tiles * kPartial);
   rc |= dev_alloc(ctx, &d.lm, B); rc |= dev_alloc(ctx, &d.out, B); rc |= dev_alloc(ctx, &d.err_flag, 1);
+  rc |= dev_alloc(ctx, &d.ticket, B); rc |= dev_alloc(ctx, &d.cand27, 2 * B);
   rc |= dev_alloc(ctx, &ctx->lm_trace, 2 * B);
   if (P.trace) {
     rc |= dev_alloc(ctx, &d.tr_idx, (size_t)2 * d.cap_in * 5); rc |= dev_alloc(ctx, &d.tr_d2, (size_t)2 * d.cap_in * 5);
@@ -209,6 +243,7 @@ static int create_impl(s2m_ctx* ctx) {
   CK(cudaMemset(d.st_n, 0, sizeof(int) * G));
   CK(cudaMemset(d.st_n_new, 0, sizeof(int) * G));
   CK(cudaMemset(d.err_flag, 0, sizeof(int)));
+  CK(cudaMemset(d.ticket, 0, sizeof(int) * B));
   CK(cudaMemset(d.out, 0, sizeof(SlotOut) * B));
   CK(cudaMemset(d.lm, 0, sizeof(LmState) * B));
   CK(cudaMemset(d.ds_off, 0, sizeof(int) * (G + 1)));
@@ -342,36 +377,48 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   fill_store_tables(ctx, &total_lp, &hash_total);
   CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, s));
 
+  // blocks per slot of the association / evaluation kernels: enough to fill the GPU
+  // (about 4 blocks of 128 threads per SM over all slots), never more than the tiles
   long long k = 0;
+  prof_mark(ctx, S2M_PHASE_INPUT);
   k += launch_voxel_filter(d, total_in, s);
+  // the down-sampled counts come back while the local index is being built, so the
+  // later launches (query order, association grid, map update) use exact sizes
+  CK(cudaMemcpyAsync(ctx->h_dsoff, d.ds_off, sizeof(int) * (G + 1), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(ctx->ev_ds, s));
+  prof_mark(ctx, S2M_PHASE_VOXEL);
   k += launch_local_index(d, ctx->cur, total_lp, hash_total, s);
   k += launch_guard(d, s);
+  CK(cudaEventSynchronize(ctx->ev_ds));
+  const int n_ds = ctx->h_dsoff[G];
+  tiles = 0;
+  for (int b = 0; b < B; ++b) {
+    const int nq = (ctx->h_dsoff[b + 1] - ctx->h_dsoff[b]) + (ctx->h_dsoff[B + b + 1] - ctx->h_dsoff[B + b]);
+    tiles = std::max(tiles, (nq + kTile - 1) / kTile);
+  }
+  k += launch_query_order(d, n_ds, s);
+  prof_mark(ctx, S2M_PHASE_INDEX);
+  // one resident wave: S2M_K4_MINB blocks per SM shared by the B slots
+  int blocks = std::max(1, std::min(tiles, (S2M_K4_MINB * ctx->sm_count) / B));
   for (int outer = 0; outer < 2; ++outer) {  // laserMapping.cpp:563
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ctx->profiling) {
-      if (ctx->k4_used == ctx->k4_events.size()) {
-        cudaEvent_t a, b2;
-        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b2));
-        ctx->k4_events.push_back({a, b2});
-      }
-      e0 = ctx->k4_events[ctx->k4_used].first; e1 = ctx->k4_events[ctx->k4_used].second;
-      ctx->k4_used++;
-      CK(cudaEventRecord(e0, s));
+    if (ctx->profiling && outer == 0) {  // C-bar of the byte formula, outside the K4 event bracket
+      launch_count_candidates(d, blocks, s);
+      prof_mark(ctx, S2M_PHASE_INDEX);
     }
-    k += launch_associate(d, outer, tiles, ctx->P.trace != 0, s);
-    if (ctx->profiling) CK(cudaEventRecord(e1, s));
-    k += launch_lm_begin(d, outer, s);
-    for (int it = 0; it < 4; ++it) {  // options.max_num_iterations = 4 (:716)
-      k += launch_evaluate(d, tiles, s);
-      k += launch_lm_after(d, outer, s);
-    }
+    k += launch_associate(d, outer, blocks, ctx->P.trace != 0, s);
+    prof_mark(ctx, S2M_PHASE_ASSOCIATE);
+    for (int it = 0; it < 4; ++it)  // options.max_num_iterations = 4 (:716)
+      k += launch_evaluate(d, outer, blocks, s);
+    prof_mark(ctx, S2M_PHASE_SOLVE);
     if (ctx->P.trace)
       CK(cudaMemcpyAsync(ctx->lm_trace + (size_t)outer * B, d.lm, sizeof(LmState) * B, cudaMemcpyDeviceToDevice, s));
   }
   k += launch_finish_pose(d, s);
-  k += launch_map_update(d, ctx->cur, total_in, total_lp, check_pending, false, s);
+  k += launch_map_update(d, ctx->cur, n_ds, total_lp, check_pending, false, s);
+  prof_mark(ctx, S2M_PHASE_UPDATE);
   ctx->launches += k;
   int rc = finish_call(ctx);
+  prof_mark(ctx, S2M_PHASE_READBACK);
   if (rc != S2M_OK) return rc;
   // swap store buffers
   ctx->cur ^= 1;
@@ -405,16 +452,24 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   // algorithmic bytes of the two association launches of this frame:
   // (Nc+Ns)(16 + 27*8) + 16 * candidates visited + 48 * accepted correspondences
   if (ctx->profiling) {
+    std::vector<unsigned long long> c27(2 * B);
+    CK(cudaMemcpy(c27.data(), d.cand27, sizeof(unsigned long long) * 2 * B, cudaMemcpyDeviceToHost));
     for (int outer = 0; outer < 2; ++outer) {
       double bytes = 0;
       for (int b = 0; b < B; ++b) {
         const SlotOut& o = ctx->h_out[b];
         if (!T.desc[b].active || !o.optimized) continue;
-        bytes += (double)(o.n_ds[0] + o.n_ds[1]) * (16.0 + 27.0 * 8.0) + 16.0 * (o.cand[0] + o.cand[1]) +
+        bytes += (double)(o.n_ds[0] + o.n_ds[1]) * (16.0 + 27.0 * 8.0) + 16.0 * (double)(c27[2 * b] + c27[2 * b + 1]) +
                  48.0 * (o.n_edge[outer] + o.n_plane[outer]);
       }
       ctx->k4_bytes += bytes;
+      ctx->k4_scanned += 0;
     }
+    for (int b = 0; b < B; ++b)
+      if (T.desc[b].active && ctx->h_out[b].optimized) {
+        ctx->k4_scanned += ctx->h_out[b].cand[0] + ctx->h_out[b].cand[1];
+        ctx->k4_cand27 += (double)(c27[2 * b] + c27[2 * b + 1]);
+      }
   }
   return S2M_OK;
 }
@@ -444,6 +499,7 @@ static int register_batch_impl(s2m_ctx* ctx, const float* corner, const int* cor
   if (rc != S2M_OK) return rc;
   const int B = ctx->d.B;
   const int NC = corner_off[B], NS = surf_off[B];
+  prof_mark(ctx, -1);
   if (NC > 0) CK(cudaMemcpyAsync(ctx->d.in_pts, corner, sizeof(float4) * (size_t)NC, kind, ctx->stream));
   if (NS > 0) CK(cudaMemcpyAsync(ctx->d.in_pts + NC, surf, sizeof(float4) * (size_t)NS, kind, ctx->stream));
   return run_frame(ctx, corner_off, surf_off, q_wodom, t_wodom, active, q_out, t_out, stats, status);
@@ -745,18 +801,25 @@ extern "C" int s2m_set_profiling(s2m_ctx* ctx, int on) {
 extern "C" int s2m_k4_profile(s2m_ctx* ctx, int reset, double* ms_total, long long* launches, double* alg_bytes) {
   if (!ctx) return S2M_ERR_ARG;
   CK(cudaSetDevice(ctx->P.device));
-  CK(cudaStreamSynchronize(ctx->stream));
-  for (size_t i = 0; i < ctx->k4_used; ++i) {
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, ctx->k4_events[i].first, ctx->k4_events[i].second));
-    ctx->k4_ms += ms;
-    ctx->k4_launches++;
-  }
-  ctx->k4_used = 0;
-  if (ms_total) *ms_total = ctx->k4_ms;
+  prof_resolve(ctx);
+  if (ms_total) *ms_total = ctx->phase_ms[S2M_PHASE_ASSOCIATE];
   if (launches) *launches = ctx->k4_launches;
   if (alg_bytes) *alg_bytes = ctx->k4_bytes;
-  if (reset) { ctx->k4_ms = 0; ctx->k4_launches = 0; ctx->k4_bytes = 0; }
+  if (reset) {
+    for (double& v : ctx->phase_ms) v = 0;
+    ctx->k4_launches = 0; ctx->k4_bytes = 0;
+  }
+  return S2M_OK;
+}
+extern "C" int s2m_phase_profile(s2m_ctx* ctx, int reset, double ms[S2M_N_PHASES]) {
+  if (!ctx || !ms) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  prof_resolve(ctx);
+  for (int i = 0; i < S2M_N_PHASES; ++i) ms[i] = ctx->phase_ms[i];
+  if (reset) {
+    for (double& v : ctx->phase_ms) v = 0;
+    ctx->k4_launches = 0; ctx->k4_bytes = 0;
+  }
   return S2M_OK;
 }
 

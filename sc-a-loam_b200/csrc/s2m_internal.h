@@ -27,6 +27,9 @@
 
 namespace s2m {
 
+#ifndef S2M_K4_MINB
+#define S2M_K4_MINB 3  // resident blocks per SM the association kernel is compiled for
+#endif
 constexpr int kTile = 128;       // queries per block of the association / evaluation kernels
 constexpr int kPartial = 32;     // doubles per block partial: 28 sums, n_edge, n_plane, cand_corner, cand_surf
 constexpr int kCols = 25;        // (i,j) columns of the valid block
@@ -111,14 +114,17 @@ struct Dev {
   int* loc_off;                 // [G][26]
   uint32_t *ckey, *ckey2, *cval, *cval2;  // [cap_lp]
   float4* cand;                 // [cap_lp] cell-sorted local points, w = local index bits
+  uint32_t* qperm;              // [cap_in] query order of the association kernel (packed ds indices)
   unsigned long long* hash_tab; // cell tables
-  uint32_t* hash_full;          // exact counts for saturated entries
+  uint2* hash_aux;              // per table slot: (points of the cell itself, exact 3-cell count)
   int* cs_off;                  // [G+1] first sorted position of each segment
   // ---- association / solve
   double* rec;                  // [cap_in][6] cached correspondences
   uint8_t* rec_valid;           // [cap_in]
-  double* partials;             // [B][max_tiles][kPartial]
+  double* partials;             // [B][max_tiles][kPartial], one row per working block
   int max_tiles;
+  int* ticket;                  // [B] last-block election counters
+  unsigned long long* cand27;   // [B][2] profiling: map points in the 27 cells of all queries
   LmState* lm;                  // [B]
   SlotOut* out;                 // [B]
   int* err_flag;                // device error code (0 ok)
@@ -143,12 +149,12 @@ size_t cub_temp_bytes(int cap_sort, int cap_lp);
 int launch_voxel_filter(const Dev& d, int total_in, cudaStream_t s);
 int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, cudaStream_t s);
 int launch_guard(const Dev& d, cudaStream_t s);
-int launch_associate(const Dev& d, int outer, int tiles, bool trace, cudaStream_t s);
-int launch_lm_begin(const Dev& d, int outer, cudaStream_t s);
-int launch_evaluate(const Dev& d, int tiles, cudaStream_t s);
-int launch_lm_after(const Dev& d, int outer, cudaStream_t s);
+int launch_query_order(const Dev& d, int n_ds, cudaStream_t s);
+int launch_associate(const Dev& d, int outer, int blocks_per_slot, bool trace, cudaStream_t s);
+int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s);
+int launch_count_candidates(const Dev& d, int blocks_per_slot, cudaStream_t s);
 int launch_finish_pose(const Dev& d, cudaStream_t s);
-int launch_map_update(const Dev& d, int cur, int total_in, int total_lp, bool check_pending, bool identity_pose,
+int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, bool check_pending, bool identity_pose,
                       cudaStream_t s);
 int launch_knn_debug(const Dev& d, int slot, int cls, const float* d_q, int n, int32_t* d_idx, float* d_d2,
                      cudaStream_t s);

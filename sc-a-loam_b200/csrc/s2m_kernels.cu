@@ -204,7 +204,12 @@ __global__ void cs_off_kernel(Dev d, int total_lp) {
   d.cs_off[g] = lower_bound_u32(d.ckey2, total_lp, (uint32_t)g << 24);
 }
 
-// cell table entry: [cell key:24][count:10][start:30]; count 1023 = see hash_full
+// Cell table entry: [cell key:24][count3:10][start3:30].  (start3, count3) is the
+// contiguous run of d.cand holding the cell AND its two x-neighbours of the same
+// (y,z) row -- cell keys sort x-fastest, so one probe at the centre cell of a row
+// yields all three cells.  hash_aux[slot] = (points of the cell itself, exact
+// count3); read when count3 saturates (1023) or when the centre cell of a row is
+// empty and the two side cells are probed on their own.
 __global__ void cand_build_kernel(Dev d, int cur, int total_lp) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total_lp) return;
@@ -217,11 +222,22 @@ __global__ void cand_build_kernel(Dev d, int cur, int total_lp) {
   if (p == 0 || d.ckey2[p - 1] != key) {
     int e = p + 1;
     while (e < total_lp && d.ckey2[e] == key) ++e;
-    const uint32_t count = (uint32_t)(e - p);
+    const uint32_t own = (uint32_t)(e - p);
+    const uint32_t rx = key & 255u;
+    int s3 = p, e3 = e;
+    if (rx > 0u && p > 0 && d.ckey2[p - 1] == key - 1u) {
+      s3 = p - 1;
+      while (s3 > 0 && d.ckey2[s3 - 1] == key - 1u) --s3;
+    }
+    if (rx < 255u && e < total_lp && d.ckey2[e] == key + 1u) {
+      e3 = e + 1;
+      while (e3 < total_lp && d.ckey2[e3] == key + 1u) ++e3;
+    }
+    const uint32_t count3 = (uint32_t)(e3 - s3);
     const uint32_t k24 = key & 0xFFFFFFu;
     const unsigned long long entry = ((unsigned long long)k24 << 40) |
-                                     ((unsigned long long)(count < 1023u ? count : 1023u) << 30) |
-                                     (unsigned long long)p;
+                                     ((unsigned long long)(count3 < 1023u ? count3 : 1023u) << 30) |
+                                     (unsigned long long)s3;
     const int base = d.hash_off[g];
     const uint32_t mask = (uint32_t)(d.hash_off[g + 1] - base) - 1u;
     uint32_t s = cell_hash(k24) & mask;
@@ -230,69 +246,206 @@ __global__ void cand_build_kernel(Dev d, int cur, int total_lp) {
       if (old == kSentinel64) break;
       s = (s + 1) & mask;
     }
-    if (count >= 1023u) d.hash_full[base + s] = count;
+    d.hash_aux[base + s] = make_uint2(own, count3);
   }
 }
 
 // Exact bounded kNN(5) of one query over the 27 cells around it.  Distances are
-// the reference's float ((dx*dx)+(dy*dy))+(dz*dz); order is (d2, local index).
-// bp = position in d.cand of each neighbour (-1 if none).
+// the reference's float ((dx*dx)+(dy*dy))+(dz*dz); order is (d2, local index):
+// both live in one 64-bit key (float bits of a non-negative d2 are monotonic).
 struct Knn5 {
-  float bd[5];
-  int bl[5], bp[5];
+  unsigned long long key[5];  // d2 bits << 32 | local index
+  int pos[5];                 // position in d.cand (-1: none)
 };
-__device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[3], float qx, float qy, float qz,
-                                          Knn5& r) {
+__device__ __forceinline__ float knn_d2(const Knn5& r, int k) { return __uint_as_float((uint32_t)(r.key[k] >> 32)); }
+__device__ __forceinline__ int knn_idx(const Knn5& r, int k) { return (int)(uint32_t)r.key[k]; }
+
+__device__ __forceinline__ void knn_offer(Knn5& r, float qx, float qy, float qz, const float4 c, int pos) {
+  const float dd = dist2(qx, qy, qz, c.x, c.y, c.z);
+  unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | (uint32_t)__float_as_int(c.w);
+  if (key < r.key[4]) {  // branch-free sorted insertion
 #pragma unroll
-  for (int k = 0; k < 5; ++k) { r.bd[k] = INFINITY; r.bl[k] = 0x7fffffff; r.bp[k] = -1; }
-  const int cx = (int)floorf(qx) - origin[0], cy = (int)floorf(qy) - origin[1], cz = (int)floorf(qz) - origin[2];
+    for (int i = 0; i < 5; ++i) {
+      const bool lt = key < r.key[i];
+      const unsigned long long tk = r.key[i];
+      const int tp = r.pos[i];
+      r.key[i] = lt ? key : tk;
+      r.pos[i] = lt ? pos : tp;
+      key = lt ? tk : key;
+      pos = lt ? tp : pos;
+    }
+  }
+}
+__device__ __forceinline__ void knn_scan_range(const float4* __restrict__ cand, int start, int count, float qx,
+                                               float qy, float qz, Knn5& r) {
+  float4 c = __ldg(cand + start);
+#pragma unroll 1
+  for (int j = 0; j < count; ++j) {  // the next point is in flight while this one is offered
+    const float4 nx = __ldg(cand + start + min(j + 1, count - 1));
+    knn_offer(r, qx, qy, qz, c, start + j);
+    c = nx;
+  }
+}
+__device__ __forceinline__ unsigned long long cell_probe(const unsigned long long* __restrict__ tab, uint32_t mask,
+                                                         uint32_t k24, uint32_t& s) {
+  s = cell_hash(k24) & mask;
+  unsigned long long e = tab[s];
+  while (e != kSentinel64 && (uint32_t)(e >> 40) != k24) {
+    s = (s + 1) & mask;
+    e = tab[s];
+  }
+  return e;
+}
+
+// Query order.  The association kernel walks the down-sampled scan points of a
+// segment in the order of their 1 m map cell at the frame's initial pose, so the
+// lanes of a warp probe the same rows and scan overlapping runs (L1 hits, equal
+// trip counts).  Pure scheduling: results do not depend on it.
+__global__ void query_key_kernel(Dev d, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = find_seg(d.ds_off, d.G, i);
+  const int slot = seg_slot(d, g);
+  const FrameDesc& fd = d.desc[slot];
+  const float4 p = d.ds_pts[i];
+  float w[3];
+  xf_point(fd.pose, p.x, p.y, p.z, w);
+  const int cx = min(max((int)floorf(w[0]) - fd.origin[0], 0), 255);
+  const int cy = min(max((int)floorf(w[1]) - fd.origin[1], 0), 255);
+  const int cz = min(max((int)floorf(w[2]) - fd.origin[2], 0), 255);
+  d.ckey[i] = ((uint32_t)g << 24) | ((uint32_t)cz << 16) | ((uint32_t)cy << 8) | (uint32_t)cx;
+  d.cval[i] = (uint32_t)i;
+}
+
+// per-thread staging of the nine row probes (one column per thread)
+struct KnnStage {
+  unsigned long long e[9][kTile];
+  uint32_t sl[9][kTile];
+};
+
+// Exact bounded kNN(5).  Rows (dy,dz) of three x-adjacent cells are visited near
+// to far; a row is skipped when a lower bound of the FLOAT distance to any point
+// in it already exceeds the current 5th distance.  The bound is built with the
+// same rounding steps as dist2() ((0 + by*by) + bz*bz with by, bz the exact
+// distances to the row's boundary planes), and rounding is monotonic, so no point
+// that could enter the result is ever skipped.
+// Returns the number of candidate points scanned.
+__device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[3], float qx, float qy, float qz,
+                                          Knn5& r, KnnStage& st) {
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { r.key[k] = ((unsigned long long)0x7F800000u << 32) | 0x7FFFFFFFu; r.pos[k] = -1; }
+  const float fly = floorf(qy), flz = floorf(qz);
+  const int cx = (int)floorf(qx) - origin[0], cy = (int)fly - origin[1], cz = (int)flz - origin[2];
   const int base = d.hash_off[g];
   const uint32_t mask = (uint32_t)(d.hash_off[g + 1] - base) - 1u;
   const unsigned long long* __restrict__ tab = d.hash_tab + base;
-  int visited = 0;
-  for (int dz = -1; dz <= 1; ++dz) {
-    const int z = cz + dz;
-    if ((unsigned)z > 255u) continue;
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int y = cy + dy;
-      if ((unsigned)y > 255u) continue;
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int x = cx + dx;
-        if ((unsigned)x > 255u) continue;
-        const uint32_t k24 = ((uint32_t)z << 16) | ((uint32_t)y << 8) | (uint32_t)x;
-        uint32_t s = cell_hash(k24) & mask;
-        unsigned long long e;
-        for (;;) {
-          e = tab[s];
-          if (e == kSentinel64 || (uint32_t)(e >> 40) == k24) break;
-          s = (s + 1) & mask;
-        }
-        if (e == kSentinel64) continue;
-        uint32_t count = (uint32_t)(e >> 30) & 1023u;
-        const int start = (int)(e & 0x3FFFFFFFull);
-        if (count == 1023u) count = d.hash_full[base + s];
-        visited += (int)count;
-        for (uint32_t j = 0; j < count; ++j) {
-          const float4 c = __ldg(d.cand + start + j);
-          const float dd = dist2(qx, qy, qz, c.x, c.y, c.z);
-          const int l = __float_as_int(c.w);
-          if (dd < r.bd[4] || (dd == r.bd[4] && l < r.bl[4])) {
-            r.bd[4] = dd; r.bl[4] = l; r.bp[4] = start + (int)j;
+  const bool cx_ok = (unsigned)cx <= 255u;
+  const int t = threadIdx.x;
+  {  // phase 1: the nine centre-cell probes, issued back to back (independent loads)
+    uint32_t k24[9], sl[9];
+    unsigned long long e[9];
 #pragma unroll
-            for (int k = 4; k > 0; --k) {
-              const bool sw = r.bd[k - 1] > r.bd[k] || (r.bd[k - 1] == r.bd[k] && r.bl[k - 1] > r.bl[k]);
-              if (sw) {
-                float tf = r.bd[k]; r.bd[k] = r.bd[k - 1]; r.bd[k - 1] = tf;
-                int ti = r.bl[k]; r.bl[k] = r.bl[k - 1]; r.bl[k - 1] = ti;
-                ti = r.bp[k]; r.bp[k] = r.bp[k - 1]; r.bp[k - 1] = ti;
-              }
-            }
-          }
-        }
+    for (int rr = 0; rr < 9; ++rr) {
+      const int z = cz + rr / 3 - 1, y = cy + rr % 3 - 1;
+      const bool ok = (unsigned)z <= 255u && (unsigned)y <= 255u && cx_ok;
+      k24[rr] = ((uint32_t)(z & 255) << 16) | ((uint32_t)(y & 255) << 8) | (uint32_t)(cx & 255);
+      sl[rr] = cell_hash(k24[rr]) & mask;
+      e[rr] = ok ? tab[sl[rr]] : kSentinel64;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 9; ++rr) {
+      while (e[rr] != kSentinel64 && (uint32_t)(e[rr] >> 40) != k24[rr]) {
+        sl[rr] = (sl[rr] + 1) & mask;
+        e[rr] = tab[sl[rr]];
       }
+      st.e[rr][t] = e[rr];
+      st.sl[rr][t] = sl[rr];
     }
   }
+  // exact distances from the query to the cell's boundary planes (fractional parts are exact)
+  const float fy = xfsub(qy, fly), fz = xfsub(qz, flz);
+  const float gy = xfsub(1.0f, fy), gz = xfsub(1.0f, fz);
+  const int sy = fy < 0.5f ? -1 : 1, sz = fz < 0.5f ? -1 : 1;  // side of the nearer boundary
+  // phase 2: rows near to far (one copy of the scan code; the staging lives in shared memory)
+  int visited = 0;
+#pragma unroll 1
+  for (int o = 0; o < 9; ++o) {
+    // order: centre, (sy,0), (0,sz), (sy,sz), (-sy,0), (0,-sz), (-sy,sz), (sy,-sz), (-sy,-sz)
+    const int dy = (o == 1 || o == 3 || o == 7) ? sy : ((o == 4 || o == 6 || o == 8) ? -sy : 0);
+    const int dz = (o == 2 || o == 3 || o == 6) ? sz : ((o == 5 || o == 7 || o == 8) ? -sz : 0);
+    const int z = cz + dz, y = cy + dy;
+    if ((unsigned)z > 255u || (unsigned)y > 255u || cx < -1 || cx > 256) continue;
+    const float by = dy == 0 ? 0.0f : (dy < 0 ? fy : gy), bz = dz == 0 ? 0.0f : (dz < 0 ? fz : gz);
+    const float bound = xfadd(xfmul(by, by), xfmul(bz, bz));
+    if (bound > knn_d2(r, 4)) continue;  // strict: a tie at the 5th distance may still win on the index
+    const int rr = (dz + 1) * 3 + (dy + 1);
+    const unsigned long long e = st.e[rr][t];
+    int start[2], count[2] = {0, 0};
+    if (e != kSentinel64) {
+      uint32_t c3 = (uint32_t)(e >> 30) & 1023u;
+      if (c3 == 1023u) c3 = d.hash_aux[base + st.sl[rr][t]].y;
+      start[0] = (int)(e & 0x3FFFFFFFull);
+      count[0] = (int)c3;
+    } else {
+      // centre cell empty: its x-neighbours on their own (the tail / head of their 3-cell runs)
+      const uint32_t row24 = ((uint32_t)z << 16) | ((uint32_t)y << 8);
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const int x = cx + (side ? 1 : -1);
+        if ((unsigned)x > 255u) continue;
+        uint32_t s;
+        const unsigned long long en = cell_probe(tab, mask, row24 | (uint32_t)x, s);
+        if (en == kSentinel64) continue;
+        const uint2 ax = d.hash_aux[base + s];
+        start[side] = (int)(en & 0x3FFFFFFFull) + (side ? 0 : (int)(ax.y - ax.x));
+        count[side] = (int)ax.x;
+      }
+    }
+    visited += count[0] + count[1];
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h)
+      if (count[h] > 0) knn_scan_range(d.cand, start[h], count[h], qx, qy, qz, r);
+  }
   return visited;
+}
+
+// number of map points in the 27 cells around a query (the C-bar of SURVEY 8d's
+// algorithmic-byte formula), independent of what the pruned search above reads
+__device__ __forceinline__ int cells27_count(const Dev& d, int g, const int origin[3], float qx, float qy, float qz) {
+  const int cx = (int)floorf(qx) - origin[0], cy = (int)floorf(qy) - origin[1], cz = (int)floorf(qz) - origin[2];
+  const int base = d.hash_off[g];
+  const uint32_t mask = (uint32_t)(d.hash_off[g + 1] - base) - 1u;
+  int n = 0;
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = cx + dx, y = cy + dy, z = cz + dz;
+        if ((unsigned)x > 255u || (unsigned)y > 255u || (unsigned)z > 255u) continue;
+        uint32_t s;
+        const unsigned long long e = cell_probe(d.hash_tab + base, mask, ((uint32_t)z << 16) | ((uint32_t)y << 8) | (uint32_t)x, s);
+        if (e != kSentinel64) n += (int)d.hash_aux[base + s].x;
+      }
+  return n;
+}
+// profiling only: per slot, candidates in the 27 cells of every query at the slot's current pose
+__global__ void __launch_bounds__(kTile) count_candidates_kernel(Dev d) {
+  const int slot = blockIdx.y;
+  if (!d.out[slot].optimized) return;
+  int dc0, nc, ds0, nq;
+  dc0 = d.ds_off[slot]; nc = d.ds_off[slot + 1] - dc0;
+  ds0 = d.ds_off[d.B + slot]; nq = nc + d.ds_off[d.B + slot + 1] - ds0;
+  unsigned long long cnt[2] = {0, 0};
+  for (int q = blockIdx.x * kTile + threadIdx.x; q < nq; q += gridDim.x * kTile) {
+    const int cls = q >= nc;
+    const float4 p = d.ds_pts[cls ? ds0 + (q - nc) : dc0 + q];
+    float w[3];
+    xf_point(d.lm[slot].x, p.x, p.y, p.z, w);
+    cnt[cls] += (unsigned long long)cells27_count(d, cls ? d.B + slot : slot, d.desc[slot].origin, w[0], w[1], w[2]);
+  }
+  for (int c = 0; c < 2; ++c) {
+    for (int o = 16; o > 0; o >>= 1) cnt[c] += __shfl_down_sync(0xffffffffu, cnt[c], o);
+    if ((threadIdx.x & 31) == 0 && cnt[c]) atomicAdd(d.cand27 + 2 * slot + c, cnt[c]);
+  }
 }
 
 __global__ void knn_debug_kernel(Dev d, int g, const float* __restrict__ q, int n, int32_t* __restrict__ idx,
@@ -300,87 +453,131 @@ __global__ void knn_debug_kernel(Dev d, int g, const float* __restrict__ q, int 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Knn5 r;
-  knn5_cells(d, g, d.desc[seg_slot(d, g)].origin, q[3 * i], q[3 * i + 1], q[3 * i + 2], r);
-  const bool ok = r.bd[4] < 1.0f;  // the reference's gate; beyond it the bounded search is not exact
+  __shared__ KnnStage st;
+  knn5_cells(d, g, d.desc[seg_slot(d, g)].origin, q[3 * i], q[3 * i + 1], q[3 * i + 2], r, st);
+  const bool ok = knn_d2(r, 4) < 1.0f;  // the reference's gate; beyond it the bounded search is not exact
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    idx[5 * i + k] = ok ? r.bl[k] : -1;
-    d2[5 * i + k] = ok ? r.bd[k] : INFINITY;
+    idx[5 * i + k] = ok ? knn_idx(r, k) : -1;
+    d2[5 * i + k] = ok ? knn_d2(r, k) : INFINITY;
   }
 }
 
 // ----------------------------------------------------------------------------
-// block reduction of kPartial doubles (fixed tree => deterministic)
+// Block-level accumulation.  Each thread adds the 28 sums of its own queries into
+// its column of a shared array; the block reduces the columns once, in a fixed
+// tree (deterministic), and writes one partial per block.  The block that
+// finishes last for a slot (ticket counter) sums the partials in block order and
+// runs the LM step -- no separate reduction / solver launch.
 // ----------------------------------------------------------------------------
-__device__ __forceinline__ void block_reduce_store(double* acc /*kPartial*/, double* __restrict__ dst) {
-  __shared__ double sm[kTile / 32][kPartial];
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+struct BlockAcc {
+  double v[kPartial][kTile];
+};
+__device__ __forceinline__ void acc_zero(BlockAcc& A) {
 #pragma unroll
-  for (int k = 0; k < kPartial; ++k) {
-    double v = acc[k];
+  for (int k = 0; k < kPartial; ++k) A.v[k][threadIdx.x] = 0.0;
+}
+__device__ __forceinline__ void acc_add(BlockAcc& A, const Sums28& S, double n_edge, double n_plane, double cand_c,
+                                        double cand_s) {
+#pragma unroll
+  for (int k = 0; k < 28; ++k) A.v[k][threadIdx.x] += S.v[k];
+  A.v[28][threadIdx.x] += n_edge; A.v[29][threadIdx.x] += n_plane;
+  A.v[30][threadIdx.x] += cand_c; A.v[31][threadIdx.x] += cand_s;
+}
+__device__ __forceinline__ void acc_store(BlockAcc& A, double* __restrict__ dst) {
+  __syncthreads();
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (int k = w; k < kPartial; k += kTile / 32) {
+    double v = 0.0;
+#pragma unroll
+    for (int c = 0; c < kTile / 32; ++c) v += A.v[k][l + 32 * c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (l == 0) sm[w][k] = v;
+    if (l == 0) dst[k] = v;
+  }
+}
+// true in exactly one block per (launch, slot): the last of `nwork` blocks to get here
+__device__ __forceinline__ bool block_is_last(int* ticket, int nwork) {
+  __shared__ int last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(ticket, 1);
+    last = (t == nwork - 1);
+    if (last) *ticket = 0;  // self-cleaning for the next launch
   }
   __syncthreads();
+  return last != 0;
+}
+__device__ __forceinline__ void sum_partials(const Dev& d, int slot, int nwork, double* sm /*kPartial, shared*/) {
   if (threadIdx.x < kPartial) {
-    double v = sm[0][threadIdx.x];
-#pragma unroll
-    for (int i = 1; i < kTile / 32; ++i) v += sm[i][threadIdx.x];
-    dst[threadIdx.x] = v;
+    const double* p = d.partials + (size_t)slot * d.max_tiles * kPartial;
+    double v = 0.0;
+    for (int b = 0; b < nwork; ++b) v += __ldcg(p + (size_t)b * kPartial + threadIdx.x);  // fixed order
+    sm[threadIdx.x] = v;
   }
+  __syncthreads();
+}
+__device__ __forceinline__ void slot_counts(const Dev& d, int slot, int& dc0, int& nc, int& ds0, int& nq) {
+  dc0 = d.ds_off[slot]; nc = d.ds_off[slot + 1] - dc0;
+  ds0 = d.ds_off[d.B + slot]; nq = nc + d.ds_off[d.B + slot + 1] - ds0;
 }
 
 // ----------------------------------------------------------------------------
-// K4: fused association.  One thread per down-sampled scan point of one slot.
+// K4: fused association.  One thread per down-sampled scan point; a block walks
+// tiles of kTile points of one slot (grid.x blocks per slot, grid.y = slots).
 // ----------------------------------------------------------------------------
 template <bool kTrace>
-__global__ void __launch_bounds__(kTile) associate_kernel(Dev d, int outer) {
+__global__ void __launch_bounds__(kTile, S2M_K4_MINB) associate_kernel(Dev d, int outer) {
   const int slot = blockIdx.y;
   if (!d.out[slot].optimized) return;
-  const int gc = slot, gs = d.B + slot;
-  const int dc0 = d.ds_off[gc], nc = d.ds_off[gc + 1] - dc0;
-  const int ds0 = d.ds_off[gs], nq = nc + d.ds_off[gs + 1] - ds0;
-  const int q = blockIdx.x * kTile + threadIdx.x;
-  if (blockIdx.x * kTile >= nq) return;
+  int dc0, nc, ds0, nq;
+  slot_counts(d, slot, dc0, nc, ds0, nq);
+  const int ntiles = (nq + kTile - 1) / kTile;
+  const int nwork = max(1, min((int)gridDim.x, ntiles));
+  if ((int)blockIdx.x >= nwork) return;
   __shared__ double pose[7];
   __shared__ int origin[3];
+  __shared__ BlockAcc A;
+  __shared__ KnnStage stage;
+  __shared__ double red[kPartial];
   if (threadIdx.x < 7) pose[threadIdx.x] = d.lm[slot].x[threadIdx.x];
   if (threadIdx.x < 3) origin[threadIdx.x] = d.desc[slot].origin[threadIdx.x];
+  acc_zero(A);
   __syncthreads();
 
-  double acc[kPartial];
-#pragma unroll
-  for (int k = 0; k < kPartial; ++k) acc[k] = 0.0;
-
-  if (q < nq) {
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int q = tile * kTile + threadIdx.x;
+    if (q >= nq) continue;
     const int cls = q >= nc;
-    const int di = cls ? ds0 + (q - nc) : dc0 + q;
+    const int di = (int)d.qperm[cls ? ds0 + (q - nc) : dc0 + q];
     const float4 p = d.ds_pts[di];
     float w[3];
     xf_point(pose, p.x, p.y, p.z, w);
     Knn5 r;
-    const int visited = knn5_cells(d, cls ? gs : gc, origin, w[0], w[1], w[2], r);
-    acc[30 + cls] = (double)visited;
+    const int visited = knn5_cells(d, cls ? d.B + slot : slot, origin, w[0], w[1], w[2], r, stage);
     bool used = false;
     double rec[6] = {0, 0, 0, 0, 0, 0};
-    if (r.bd[4] < 1.0f) {  // laserMapping.cpp:585 / :653
+    Sums28 S;
+    S.zero();
+    if (knn_d2(r, 4) < 1.0f) {  // laserMapping.cpp:585 / :653
       float nb[5][3];
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const float4 c = __ldg(d.cand + r.bp[k]);
+        const float4 c = __ldg(d.cand + r.pos[k]);
         nb[k][0] = c.x; nb[k][1] = c.y; nb[k][2] = c.z;
       }
       const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
-      Sums28& S = *reinterpret_cast<Sums28*>(acc);
       if (cls == 0) {
         used = edge_fit(nb, rec, rec + 3);
-        if (used) { accum_edge(S, pose, cp, rec, rec + 3); acc[28] = 1.0; }
+        if (used) accum_edge(S, pose, cp, rec, rec + 3);
       } else {
         used = plane_fit(nb, rec, rec[3]);
-        if (used) { accum_plane(S, pose, cp, rec, rec[3]); acc[29] = 1.0; }
+        if (used) accum_plane(S, pose, cp, rec, rec[3]);
       }
     }
+    acc_add(A, S, (used && cls == 0) ? 1.0 : 0.0, (used && cls == 1) ? 1.0 : 0.0, cls == 0 ? (double)visited : 0.0,
+            cls == 1 ? (double)visited : 0.0);
     double2* ro = reinterpret_cast<double2*>(d.rec + 6 * (size_t)di);
     ro[0] = make_double2(rec[0], rec[1]);
     ro[1] = make_double2(rec[2], rec[3]);
@@ -390,60 +587,79 @@ __global__ void __launch_bounds__(kTile) associate_kernel(Dev d, int outer) {
       const size_t o = ((size_t)outer * d.cap_in + di);
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const bool have = r.bp[k] >= 0;
-        d.tr_idx[5 * o + k] = have ? r.bl[k] : -1;
-        d.tr_d2[5 * o + k] = have ? r.bd[k] : INFINITY;
+        const bool have = r.pos[k] >= 0;
+        d.tr_idx[5 * o + k] = have ? knn_idx(r, k) : -1;
+        d.tr_d2[5 * o + k] = have ? knn_d2(r, k) : INFINITY;
       }
       d.tr_used[o] = used;
     }
   }
-  block_reduce_store(acc, d.partials + ((size_t)slot * d.max_tiles + blockIdx.x) * kPartial);
+  acc_store(A, d.partials + ((size_t)slot * d.max_tiles + blockIdx.x) * kPartial);
+  if (!block_is_last(d.ticket + slot, nwork)) return;
+  // ---- last block of this slot: reduce and start the LM solve (row S) ----
+  sum_partials(d, slot, nwork, red);
+  if (threadIdx.x == 0) {
+    Sums28 S;
+    for (int i = 0; i < 28; ++i) S.v[i] = red[i];
+    SlotOut& o = d.out[slot];
+    o.n_edge[outer] = (int)red[28]; o.n_plane[outer] = (int)red[29];
+    if (outer == 0) { o.cand[0] = red[30]; o.cand[1] = red[31]; }
+    LmState& L = d.lm[slot];
+    double x0[7];
+    for (int i = 0; i < 7; ++i) x0[i] = L.x[i];
+    lm_begin(L, x0, S, (int)red[28] + (int)red[29], 4);
+    o.lm_iters[outer] = L.iteration; o.lm_term[outer] = L.termination;
+    o.cost_initial[outer] = L.initial_cost; o.cost_final[outer] = L.final_cost;
+  }
 }
 
 // ----------------------------------------------------------------------------
-// K5: evaluation at the LM candidate pose from the cached correspondences
+// K5 + K6: evaluation at the LM candidate pose from the cached correspondences,
+// then (last block) the accept / reject decision and the next trust-region step.
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTile) evaluate_kernel(Dev d) {
+__global__ void __launch_bounds__(kTile) evaluate_kernel(Dev d, int outer) {
   const int slot = blockIdx.y;
   if (!d.out[slot].optimized) return;
-  const LmState& L = d.lm[slot];
+  LmState& L = d.lm[slot];
   if (L.done || !L.have_candidate) return;
-  const int gc = slot, gs = d.B + slot;
-  const int dc0 = d.ds_off[gc], nc = d.ds_off[gc + 1] - dc0;
-  const int ds0 = d.ds_off[gs], nq = nc + d.ds_off[gs + 1] - ds0;
-  if (blockIdx.x * kTile >= nq) return;
+  int dc0, nc, ds0, nq;
+  slot_counts(d, slot, dc0, nc, ds0, nq);
+  const int ntiles = (nq + kTile - 1) / kTile;
+  const int nwork = max(1, min((int)gridDim.x, ntiles));
+  if ((int)blockIdx.x >= nwork) return;
   __shared__ double pose[7];
+  __shared__ BlockAcc A;
+  __shared__ double red[kPartial];
   if (threadIdx.x < 7) pose[threadIdx.x] = L.xc[threadIdx.x];
+  acc_zero(A);
   __syncthreads();
-  double acc[kPartial];
-#pragma unroll
-  for (int k = 0; k < kPartial; ++k) acc[k] = 0.0;
-  const int q = blockIdx.x * kTile + threadIdx.x;
-  const int di = q < nc ? dc0 + q : ds0 + (q - nc);
-  if (q < nq && d.rec_valid[di]) {
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int q = tile * kTile + threadIdx.x;
+    if (q >= nq) continue;
+    const int di = q < nc ? dc0 + q : ds0 + (q - nc);
+    if (!d.rec_valid[di]) continue;
     const float4 p = d.ds_pts[di];
     const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
     const double2* ri = reinterpret_cast<const double2*>(d.rec + 6 * (size_t)di);
     const double2 a = ri[0], b = ri[1], c = ri[2];
     const double rec[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-    Sums28& S = *reinterpret_cast<Sums28*>(acc);
-    if (q < nc) { accum_edge(S, pose, cp, rec, rec + 3); acc[28] = 1.0; }
-    else { accum_plane(S, pose, cp, rec, rec[3]); acc[29] = 1.0; }
+    Sums28 S;
+    S.zero();
+    if (q < nc) accum_edge(S, pose, cp, rec, rec + 3);
+    else accum_plane(S, pose, cp, rec, rec[3]);
+    acc_add(A, S, q < nc ? 1.0 : 0.0, q < nc ? 0.0 : 1.0, 0.0, 0.0);
   }
-  block_reduce_store(acc, d.partials + ((size_t)slot * d.max_tiles + blockIdx.x) * kPartial);
-}
-
-// ----------------------------------------------------------------------------
-// K6: trust-region LM on the reduced system; one warp per slot
-// ----------------------------------------------------------------------------
-__device__ __forceinline__ void sum_partials(const Dev& d, int slot, double* sm /*kPartial, shared*/) {
-  const int nq = (d.ds_off[slot + 1] - d.ds_off[slot]) + (d.ds_off[d.B + slot + 1] - d.ds_off[d.B + slot]);
-  const int tiles = (nq + kTile - 1) / kTile;
-  const double* p = d.partials + (size_t)slot * d.max_tiles * kPartial;
-  double v = 0.0;
-  for (int t = 0; t < tiles; ++t) v += p[(size_t)t * kPartial + threadIdx.x];  // fixed order
-  sm[threadIdx.x] = v;
-  __syncwarp();
+  acc_store(A, d.partials + ((size_t)slot * d.max_tiles + blockIdx.x) * kPartial);
+  if (!block_is_last(d.ticket + slot, nwork)) return;
+  sum_partials(d, slot, nwork, red);
+  if (threadIdx.x == 0) {
+    Sums28 S;
+    for (int i = 0; i < 28; ++i) S.v[i] = red[i];
+    lm_after_eval(L, S, 4);
+    SlotOut& o = d.out[slot];
+    o.lm_iters[outer] = L.iteration; o.lm_term[outer] = L.termination;
+    o.cost_final[outer] = L.final_cost;
+  }
 }
 
 __global__ void guard_kernel(Dev d) {
@@ -461,43 +677,7 @@ __global__ void guard_kernel(Dev d) {
   LmState& L = d.lm[s];
   for (int i = 0; i < 7; ++i) L.x[i] = L.xc[i] = fd.pose[i];
   L.done = !opt; L.have_candidate = 0; L.iteration = 0;
-}
-
-__global__ void lm_begin_kernel(Dev d, int outer) {
-  const int slot = blockIdx.x;
-  if (!d.out[slot].optimized) return;
-  __shared__ double sm[kPartial];
-  sum_partials(d, slot, sm);
-  if (threadIdx.x == 0) {
-    Sums28 S;
-    for (int i = 0; i < 28; ++i) S.v[i] = sm[i];
-    SlotOut& o = d.out[slot];
-    o.n_edge[outer] = (int)sm[28]; o.n_plane[outer] = (int)sm[29];
-    if (outer == 0) { o.cand[0] = sm[30]; o.cand[1] = sm[31]; }
-    LmState& L = d.lm[slot];
-    double x0[7];
-    for (int i = 0; i < 7; ++i) x0[i] = L.x[i];
-    lm_begin(L, x0, S, (int)sm[28] + (int)sm[29], 4);
-    o.lm_iters[outer] = L.iteration; o.lm_term[outer] = L.termination;
-    o.cost_initial[outer] = L.initial_cost; o.cost_final[outer] = L.final_cost;
-  }
-}
-
-__global__ void lm_after_kernel(Dev d, int outer) {
-  const int slot = blockIdx.x;
-  if (!d.out[slot].optimized) return;
-  LmState& L = d.lm[slot];
-  if (L.done || !L.have_candidate) return;
-  __shared__ double sm[kPartial];
-  sum_partials(d, slot, sm);
-  if (threadIdx.x == 0) {
-    Sums28 S;
-    for (int i = 0; i < 28; ++i) S.v[i] = sm[i];
-    lm_after_eval(L, S, 4);
-    SlotOut& o = d.out[slot];
-    o.lm_iters[outer] = L.iteration; o.lm_term[outer] = L.termination;
-    o.cost_final[outer] = L.final_cost;
-  }
+  d.ticket[s] = 0;
 }
 
 __global__ void finish_pose_kernel(Dev d) {
@@ -791,29 +971,37 @@ int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, cuda
   return k;
 }
 
+int launch_query_order(const Dev& d, int n_ds, cudaStream_t s) {
+  if (n_ds <= 0) return 0;
+  query_key_kernel<<<cdiv(n_ds, 256), 256, 0, s>>>(d, n_ds);
+  size_t tb = d.cub_tmp_bytes;
+  int gbits = 1;
+  while ((1 << gbits) < d.G) ++gbits;
+  cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.ckey, d.ckey2, d.cval, d.qperm, n_ds, 0, 24 + gbits, s);
+  return 1;
+}
 int launch_guard(const Dev& d, cudaStream_t s) {
   guard_kernel<<<cdiv(d.B, 64), 64, 0, s>>>(d);
   return 1;
 }
-int launch_associate(const Dev& d, int outer, int tiles, bool trace, cudaStream_t s) {
-  if (tiles <= 0) return 0;
-  dim3 grid(tiles, d.B);
+int launch_associate(const Dev& d, int outer, int blocks_per_slot, bool trace, cudaStream_t s) {
+  if (blocks_per_slot <= 0) return 0;
+  dim3 grid(blocks_per_slot, d.B);
   if (trace) associate_kernel<true><<<grid, kTile, 0, s>>>(d, outer);
   else associate_kernel<false><<<grid, kTile, 0, s>>>(d, outer);
   return 1;
 }
-int launch_lm_begin(const Dev& d, int outer, cudaStream_t s) {
-  lm_begin_kernel<<<d.B, kPartial, 0, s>>>(d, outer);
+int launch_count_candidates(const Dev& d, int blocks_per_slot, cudaStream_t s) {
+  if (blocks_per_slot <= 0) return 0;
+  cudaMemsetAsync(d.cand27, 0, sizeof(unsigned long long) * 2 * d.B, s);
+  dim3 grid(blocks_per_slot, d.B);
+  count_candidates_kernel<<<grid, kTile, 0, s>>>(d);
   return 1;
 }
-int launch_evaluate(const Dev& d, int tiles, cudaStream_t s) {
-  if (tiles <= 0) return 0;
-  dim3 grid(tiles, d.B);
-  evaluate_kernel<<<grid, kTile, 0, s>>>(d);
-  return 1;
-}
-int launch_lm_after(const Dev& d, int outer, cudaStream_t s) {
-  lm_after_kernel<<<d.B, kPartial, 0, s>>>(d, outer);
+int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s) {
+  if (blocks_per_slot <= 0) return 0;
+  dim3 grid(blocks_per_slot, d.B);
+  evaluate_kernel<<<grid, kTile, 0, s>>>(d, outer);
   return 1;
 }
 int launch_finish_pose(const Dev& d, cudaStream_t s) {
@@ -821,8 +1009,9 @@ int launch_finish_pose(const Dev& d, cudaStream_t s) {
   return 1;
 }
 
-int launch_map_update(const Dev& d, int cur, int total_in, int total_lp, bool check_pending, bool identity_pose,
+int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, bool check_pending, bool identity_pose,
                       cudaStream_t s) {
+  const int total_in = n_ds;  // exact number of down-sampled points (host read it back)
   int k = 0;
   const int front = check_pending ? total_lp : 0;
   const int n_delta = front + total_in;
