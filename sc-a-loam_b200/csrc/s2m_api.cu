@@ -400,6 +400,8 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   prof_mark(ctx, S2M_PHASE_INDEX);
   // one resident wave: S2M_K4_MINB blocks per SM shared by the B slots
   int blocks = std::max(1, std::min(tiles, (S2M_K4_MINB * ctx->sm_count) / B));
+  // the evaluation kernel is a light streaming pass: about four records per thread
+  const int eval_blocks = std::max(1, std::min((tiles + 3) / 4, d.max_tiles));
   for (int outer = 0; outer < 2; ++outer) {  // laserMapping.cpp:563
     if (ctx->profiling && outer == 0) {  // C-bar of the byte formula, outside the K4 event bracket
       launch_count_candidates(d, blocks, s);
@@ -408,7 +410,7 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
     k += launch_associate(d, outer, blocks, ctx->P.trace != 0, s);
     prof_mark(ctx, S2M_PHASE_ASSOCIATE);
     for (int it = 0; it < 4; ++it)  // options.max_num_iterations = 4 (:716)
-      k += launch_evaluate(d, outer, blocks, s);
+      k += launch_evaluate(d, outer, eval_blocks, s);
     prof_mark(ctx, S2M_PHASE_SOLVE);
     if (ctx->P.trace)
       CK(cudaMemcpyAsync(ctx->lm_trace + (size_t)outer * B, d.lm, sizeof(LmState) * B, cudaMemcpyDeviceToDevice, s));

@@ -28,7 +28,7 @@
 namespace s2m {
 
 #ifndef S2M_K4_MINB
-#define S2M_K4_MINB 3  // resident blocks per SM the association kernel is compiled for
+#define S2M_K4_MINB 6  // resident blocks per SM the association kernel is compiled for
 #endif
 constexpr int kTile = 128;       // queries per block of the association / evaluation kernels
 constexpr int kPartial = 32;     // doubles per block partial: 28 sums, n_edge, n_plane, cand_corner, cand_surf
@@ -101,7 +101,7 @@ struct Dev {
   uint64_t *vkey, *vkey2;       // [cap_sort]
   uint32_t *vval, *vval2;       // [cap_sort]
   uint32_t *flag, *scan;        // [cap_sort]
-  float* bbox;                  // [G][6]
+  uint32_t* bbox;               // [G][6] min xyz / max xyz, order-preserving uint encoding
   float4* ds_pts;               // [cap_in] packed, voxel-filtered scan (sensor frame)
   int* ds_off;                  // [G+1] device-computed
   // ---- store (double buffered)

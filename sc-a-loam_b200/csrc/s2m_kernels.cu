@@ -55,31 +55,45 @@ __device__ __forceinline__ uint32_t cell_hash(uint32_t k) {
 // ----------------------------------------------------------------------------
 // K1: scan voxel-grid filter (pcl::VoxelGrid semantics)
 // ----------------------------------------------------------------------------
-__global__ void vox_bbox_kernel(Dev d) {
-  const int g = blockIdx.x;
-  const int a = d.in_off[g], b = d.in_off[g + 1];
-  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
-    float4 p = d.in_pts[i];
-    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
-    mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
-    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+// order-preserving float <-> uint so atomicMin/atomicMax work on floats
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+// bbox[g][0..2] = min (init 0xFFFFFFFF), bbox[g][3..5] = max (init 0), ordered-uint encoded
+__global__ void vox_bbox_kernel(Dev d, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int g = -1;
+  uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+  if (i < n) {
+    g = find_seg(d.in_off, d.G, i);
+    const float4 p = d.in_pts[i];
+    mn[0] = mx[0] = f2ord(p.x); mn[1] = mx[1] = f2ord(p.y); mn[2] = mx[2] = f2ord(p.z);
   }
-  __shared__ float sm[6][32];
-  for (int k = 0; k < 3; ++k)
-    for (int o = 16; o > 0; o >>= 1) {
-      mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-      mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-    }
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) for (int k = 0; k < 3; ++k) { sm[k][w] = mn[k]; sm[3 + k][w] = mx[k]; }
-  __syncthreads();
-  if (threadIdx.x < 6) {
-    const int nw = blockDim.x >> 5;
-    float v = sm[threadIdx.x][0];
-    for (int i = 1; i < nw; ++i) v = threadIdx.x < 3 ? fminf(v, sm[threadIdx.x][i]) : fmaxf(v, sm[threadIdx.x][i]);
-    d.bbox[6 * g + threadIdx.x] = v;
+  // warp-aggregate when the whole warp lies in one segment (the common case)
+  const int g0 = __shfl_sync(0xffffffffu, g, 0);
+  if (__all_sync(0xffffffffu, g == g0)) {
+    if (g0 < 0) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      for (int o = 16; o > 0; o >>= 1) {
+        mn[k] = min(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+        mx[k] = max(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+      }
+    if (lane < 3) atomicMin(d.bbox + 6 * g0 + lane, mn[lane]);
+    else if (lane < 6) atomicMax(d.bbox + 6 * g0 + lane, mx[lane - 3]);
+  } else if (g >= 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { atomicMin(d.bbox + 6 * g + k, mn[k]); atomicMax(d.bbox + 6 * g + 3 + k, mx[k]); }
   }
+}
+__global__ void vox_bbox_init_kernel(Dev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 6 * d.G) d.bbox[i] = (i % 6) < 3 ? 0xFFFFFFFFu : 0u;
 }
 
 __global__ void vox_key_kernel(Dev d, int n) {
@@ -87,7 +101,9 @@ __global__ void vox_key_kernel(Dev d, int n) {
   if (i >= n) return;
   const int g = find_seg(d.in_off, d.G, i);
   const float inv = d.inv_leaf[seg_cls(d, g)];
-  const float* bb = d.bbox + 6 * g;
+  float bb[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) bb[k] = ord2f(d.bbox[6 * g + k]);
   // "Leaf size is too small for the input dataset": PCL warns and passes the input through
   const long long dx = (long long)xfmul(xfsub(bb[3], bb[0]), inv) + 1;
   const long long dy = (long long)xfmul(xfsub(bb[4], bb[1]), inv) + 1;
@@ -96,15 +112,16 @@ __global__ void vox_key_kernel(Dev d, int n) {
   if (dx * dy * dz > 2147483647LL) {
     key = (uint64_t)(i - d.in_off[g]);
   } else {
+    // pcl::VoxelGrid: idx = ijk0 + ijk1*div_x + ijk2*div_x*div_y, an int (< 2^31 by the test above)
     const float4 p = d.in_pts[i];
     const int m0 = (int)floorf(xfmul(bb[0], inv)), m1 = (int)floorf(xfmul(bb[1], inv)), m2 = (int)floorf(xfmul(bb[2], inv));
+    const int d0 = (int)floorf(xfmul(bb[3], inv)) - m0 + 1, d1 = (int)floorf(xfmul(bb[4], inv)) - m1 + 1;
     const int i0 = (int)(floorf(xfmul(p.x, inv)) - (float)m0);
     const int i1 = (int)(floorf(xfmul(p.y, inv)) - (float)m1);
     const int i2 = (int)(floorf(xfmul(p.z, inv)) - (float)m2);
-    if ((unsigned)i0 >= (1u << 18) || (unsigned)i1 >= (1u << 18) || (unsigned)i2 >= (1u << 18)) set_err(d, -4);
-    key = ((uint64_t)(i2 & 0x3FFFF) << 36) | ((uint64_t)(i1 & 0x3FFFF) << 18) | (uint64_t)(i0 & 0x3FFFF);
+    key = (uint64_t)((long long)i0 + (long long)i1 * d0 + (long long)i2 * d0 * d1) & 0x7FFFFFFFull;
   }
-  d.vkey[i] = ((uint64_t)g << 54) | key;
+  d.vkey[i] = ((uint64_t)g << 31) | key;
   d.vval[i] = (uint32_t)i;
 }
 
@@ -470,27 +487,34 @@ __global__ void knn_debug_kernel(Dev d, int g, const float* __restrict__ q, int 
 // finishes last for a slot (ticket counter) sums the partials in block order and
 // runs the LM step -- no separate reduction / solver launch.
 // ----------------------------------------------------------------------------
+constexpr int kAccCols = kTile / 4;  // four neighbouring lanes share one accumulator column
 struct BlockAcc {
-  double v[kPartial][kTile];
+  double v[kPartial][kAccCols];
 };
 __device__ __forceinline__ void acc_zero(BlockAcc& A) {
+  if (threadIdx.x < kAccCols) {
 #pragma unroll
-  for (int k = 0; k < kPartial; ++k) A.v[k][threadIdx.x] = 0.0;
+    for (int k = 0; k < kPartial; ++k) A.v[k][threadIdx.x] = 0.0;
+  }
 }
+// every lane of the warp must call this (zeros where it has nothing to add)
 __device__ __forceinline__ void acc_add(BlockAcc& A, const Sums28& S, double n_edge, double n_plane, double cand_c,
                                         double cand_s) {
+  const int col = threadIdx.x >> 2;
+  const bool lead = (threadIdx.x & 3) == 0;
 #pragma unroll
-  for (int k = 0; k < 28; ++k) A.v[k][threadIdx.x] += S.v[k];
-  A.v[28][threadIdx.x] += n_edge; A.v[29][threadIdx.x] += n_plane;
-  A.v[30][threadIdx.x] += cand_c; A.v[31][threadIdx.x] += cand_s;
+  for (int k = 0; k < kPartial; ++k) {
+    double v = k < 28 ? S.v[k < 28 ? k : 0] : (k == 28 ? n_edge : (k == 29 ? n_plane : (k == 30 ? cand_c : cand_s)));
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (lead) A.v[k][col] += v;
+  }
 }
 __device__ __forceinline__ void acc_store(BlockAcc& A, double* __restrict__ dst) {
   __syncthreads();
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   for (int k = w; k < kPartial; k += kTile / 32) {
-    double v = 0.0;
-#pragma unroll
-    for (int c = 0; c < kTile / 32; ++c) v += A.v[k][l + 32 * c];
+    double v = A.v[k][l];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if (l == 0) dst[k] = v;
@@ -518,6 +542,21 @@ __device__ __forceinline__ void sum_partials(const Dev& d, int slot, int nwork, 
   }
   __syncthreads();
 }
+// The LM state lives in global memory; the serial solver step runs on a shared-memory
+// copy (one coalesced load/store by the whole block instead of ~100 dependent L2 round trips).
+static_assert(sizeof(LmState) % 8 == 0, "LmState is copied as 8-byte words");
+__device__ __forceinline__ void lm_load(LmState* sh, const LmState* gl) {
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gl);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(sh);
+  for (int i = threadIdx.x; i < (int)(sizeof(LmState) / 8); i += blockDim.x) dst[i] = __ldcg(src + i);
+  __syncthreads();
+}
+__device__ __forceinline__ void lm_store(LmState* gl, const LmState* sh) {
+  __syncthreads();
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(sh);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(gl);
+  for (int i = threadIdx.x; i < (int)(sizeof(LmState) / 8); i += blockDim.x) dst[i] = src[i];
+}
 __device__ __forceinline__ void slot_counts(const Dev& d, int slot, int& dc0, int& nc, int& ds0, int& nq) {
   dc0 = d.ds_off[slot]; nc = d.ds_off[slot + 1] - dc0;
   ds0 = d.ds_off[d.B + slot]; nq = nc + d.ds_off[d.B + slot + 1] - ds0;
@@ -527,6 +566,14 @@ __device__ __forceinline__ void slot_counts(const Dev& d, int slot, int& dc0, in
 // K4: fused association.  One thread per down-sampled scan point; a block walks
 // tiles of kTile points of one slot (grid.x blocks per slot, grid.y = slots).
 // ----------------------------------------------------------------------------
+// hand-off between the two phases of a tile (one column per thread)
+struct TileXfer {
+  int di[kTile];       // packed down-sampled index of the query
+  int pos[5][kTile];   // positions of its 5 neighbours in d.cand
+  int list[kTile];     // compacted list of the threads whose query passed the 1 m gate
+  int wcount[kTile / 32];
+};
+
 template <bool kTrace>
 __global__ void __launch_bounds__(kTile, S2M_K4_MINB) associate_kernel(Dev d, int outer) {
   const int slot = blockIdx.y;
@@ -540,84 +587,126 @@ __global__ void __launch_bounds__(kTile, S2M_K4_MINB) associate_kernel(Dev d, in
   __shared__ int origin[3];
   __shared__ BlockAcc A;
   __shared__ KnnStage stage;
+  __shared__ TileXfer xf;
   __shared__ double red[kPartial];
   if (threadIdx.x < 7) pose[threadIdx.x] = d.lm[slot].x[threadIdx.x];
   if (threadIdx.x < 3) origin[threadIdx.x] = d.desc[slot].origin[threadIdx.x];
   acc_zero(A);
   __syncthreads();
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  double cand_c = 0.0, cand_s = 0.0;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int q = tile * kTile + threadIdx.x;
-    if (q >= nq) continue;
-    const int cls = q >= nc;
-    const int di = (int)d.qperm[cls ? ds0 + (q - nc) : dc0 + q];
-    const float4 p = d.ds_pts[di];
-    float w[3];
-    xf_point(pose, p.x, p.y, p.z, w);
-    Knn5 r;
-    const int visited = knn5_cells(d, cls ? d.B + slot : slot, origin, w[0], w[1], w[2], r, stage);
-    bool used = false;
-    double rec[6] = {0, 0, 0, 0, 0, 0};
+    // ---- phase A: transform + exact kNN(5), one thread per query ----
+    const int q = tile * kTile + t;
+    bool gate = false;
+    if (q < nq) {
+      const int cls = q >= nc;
+      const int di = (int)d.qperm[cls ? ds0 + (q - nc) : dc0 + q];
+      const float4 p = d.ds_pts[di];
+      float w[3];
+      xf_point(pose, p.x, p.y, p.z, w);
+      Knn5 r;
+      const int visited = knn5_cells(d, cls ? d.B + slot : slot, origin, w[0], w[1], w[2], r, stage);
+      if (cls) cand_s += (double)visited; else cand_c += (double)visited;
+      gate = knn_d2(r, 4) < 1.0f;  // laserMapping.cpp:585 / :653
+      xf.di[t] = cls ? -(di + 1) : di;  // sign carries the class
+#pragma unroll
+      for (int k = 0; k < 5; ++k) xf.pos[k][t] = r.pos[k];
+      d.rec_valid[di] = 0;
+      if (kTrace) {
+        const size_t o = ((size_t)outer * d.cap_in + di);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const bool have = r.pos[k] >= 0;
+          d.tr_idx[5 * o + k] = have ? knn_idx(r, k) : -1;
+          d.tr_d2[5 * o + k] = have ? knn_d2(r, k) : INFINITY;
+        }
+        d.tr_used[o] = 0;
+      }
+    }
+    // ---- compaction of the gated queries (thread order => deterministic) ----
+    const unsigned bal = __ballot_sync(0xffffffffu, gate);
+    if (lane == 0) xf.wcount[wid] = __popc(bal);
+    __syncthreads();
+    int before = 0, n_items = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < kTile / 32; ++w2) {
+      const int c = xf.wcount[w2];
+      if (w2 < wid) before += c;
+      n_items += c;
+    }
+    if (gate) xf.list[before + __popc(bal & ((1u << lane) - 1u))] = t;
+    __syncthreads();
+    // ---- phase B: edge PCA / plane QR + residual, Jacobian, Huber; dense lanes ----
     Sums28 S;
     S.zero();
-    if (knn_d2(r, 4) < 1.0f) {  // laserMapping.cpp:585 / :653
+    double ne = 0.0, np = 0.0;
+    if (t < n_items) {
+      const int src = xf.list[t];
+      const int dv = xf.di[src];
+      const int cls = dv < 0;
+      const int di = cls ? -dv - 1 : dv;
+      const float4 p = d.ds_pts[di];
       float nb[5][3];
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const float4 c = __ldg(d.cand + r.pos[k]);
+        const float4 c = __ldg(d.cand + xf.pos[k][src]);
         nb[k][0] = c.x; nb[k][1] = c.y; nb[k][2] = c.z;
       }
       const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
+      double rec[6] = {0, 0, 0, 0, 0, 0};
+      bool used;
       if (cls == 0) {
         used = edge_fit(nb, rec, rec + 3);
-        if (used) accum_edge(S, pose, cp, rec, rec + 3);
+        if (used) { accum_edge(S, pose, cp, rec, rec + 3); ne = 1.0; }
       } else {
         used = plane_fit(nb, rec, rec[3]);
-        if (used) accum_plane(S, pose, cp, rec, rec[3]);
+        if (used) { accum_plane(S, pose, cp, rec, rec[3]); np = 1.0; }
+      }
+      if (used) {
+        double2* ro = reinterpret_cast<double2*>(d.rec + 6 * (size_t)di);
+        ro[0] = make_double2(rec[0], rec[1]);
+        ro[1] = make_double2(rec[2], rec[3]);
+        ro[2] = make_double2(rec[4], rec[5]);
+        d.rec_valid[di] = 1;
+        if (kTrace) d.tr_used[(size_t)outer * d.cap_in + di] = 1;
       }
     }
-    acc_add(A, S, (used && cls == 0) ? 1.0 : 0.0, (used && cls == 1) ? 1.0 : 0.0, cls == 0 ? (double)visited : 0.0,
-            cls == 1 ? (double)visited : 0.0);
-    double2* ro = reinterpret_cast<double2*>(d.rec + 6 * (size_t)di);
-    ro[0] = make_double2(rec[0], rec[1]);
-    ro[1] = make_double2(rec[2], rec[3]);
-    ro[2] = make_double2(rec[4], rec[5]);
-    d.rec_valid[di] = used;
-    if (kTrace) {
-      const size_t o = ((size_t)outer * d.cap_in + di);
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const bool have = r.pos[k] >= 0;
-        d.tr_idx[5 * o + k] = have ? knn_idx(r, k) : -1;
-        d.tr_d2[5 * o + k] = have ? knn_d2(r, k) : INFINITY;
-      }
-      d.tr_used[o] = used;
-    }
+    if (wid * 32 < n_items) acc_add(A, S, ne, np, 0.0, 0.0);  // warp-uniform: whole warps without items skip
+    __syncthreads();  // xf is rewritten by the next tile
+  }
+  {
+    Sums28 Z;
+    Z.zero();
+    acc_add(A, Z, 0.0, 0.0, cand_c, cand_s);
   }
   acc_store(A, d.partials + ((size_t)slot * d.max_tiles + blockIdx.x) * kPartial);
   if (!block_is_last(d.ticket + slot, nwork)) return;
   // ---- last block of this slot: reduce and start the LM solve (row S) ----
   sum_partials(d, slot, nwork, red);
+  __shared__ LmState Ls;
+  lm_load(&Ls, d.lm + slot);
   if (threadIdx.x == 0) {
     Sums28 S;
     for (int i = 0; i < 28; ++i) S.v[i] = red[i];
     SlotOut& o = d.out[slot];
     o.n_edge[outer] = (int)red[28]; o.n_plane[outer] = (int)red[29];
     if (outer == 0) { o.cand[0] = red[30]; o.cand[1] = red[31]; }
-    LmState& L = d.lm[slot];
     double x0[7];
-    for (int i = 0; i < 7; ++i) x0[i] = L.x[i];
-    lm_begin(L, x0, S, (int)red[28] + (int)red[29], 4);
-    o.lm_iters[outer] = L.iteration; o.lm_term[outer] = L.termination;
-    o.cost_initial[outer] = L.initial_cost; o.cost_final[outer] = L.final_cost;
+    for (int i = 0; i < 7; ++i) x0[i] = Ls.x[i];
+    lm_begin(Ls, x0, S, (int)red[28] + (int)red[29], 4);
+    o.lm_iters[outer] = Ls.iteration; o.lm_term[outer] = Ls.termination;
+    o.cost_initial[outer] = Ls.initial_cost; o.cost_final[outer] = Ls.final_cost;
   }
+  lm_store(d.lm + slot, &Ls);
 }
 
 // ----------------------------------------------------------------------------
 // K5 + K6: evaluation at the LM candidate pose from the cached correspondences,
 // then (last block) the accept / reject decision and the next trust-region step.
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTile) evaluate_kernel(Dev d, int outer) {
+__global__ void __launch_bounds__(kTile, 4) evaluate_kernel(Dev d, int outer) {
   const int slot = blockIdx.y;
   if (!d.out[slot].optimized) return;
   LmState& L = d.lm[slot];
@@ -633,33 +722,38 @@ __global__ void __launch_bounds__(kTile) evaluate_kernel(Dev d, int outer) {
   if (threadIdx.x < 7) pose[threadIdx.x] = L.xc[threadIdx.x];
   acc_zero(A);
   __syncthreads();
+  // each thread keeps the sums of all its records in registers; one reduction per block
+  Sums28 S;
+  S.zero();
+  double ne = 0.0, np = 0.0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int q = tile * kTile + threadIdx.x;
-    if (q >= nq) continue;
     const int di = q < nc ? dc0 + q : ds0 + (q - nc);
-    if (!d.rec_valid[di]) continue;
-    const float4 p = d.ds_pts[di];
-    const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
-    const double2* ri = reinterpret_cast<const double2*>(d.rec + 6 * (size_t)di);
-    const double2 a = ri[0], b = ri[1], c = ri[2];
-    const double rec[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-    Sums28 S;
-    S.zero();
-    if (q < nc) accum_edge(S, pose, cp, rec, rec + 3);
-    else accum_plane(S, pose, cp, rec, rec[3]);
-    acc_add(A, S, q < nc ? 1.0 : 0.0, q < nc ? 0.0 : 1.0, 0.0, 0.0);
+    if (q < nq && d.rec_valid[di]) {
+      const float4 p = d.ds_pts[di];
+      const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
+      const double2* ri = reinterpret_cast<const double2*>(d.rec + 6 * (size_t)di);
+      const double2 a = ri[0], b = ri[1], c = ri[2];
+      const double rec[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+      if (q < nc) { accum_edge(S, pose, cp, rec, rec + 3); ne += 1.0; }
+      else { accum_plane(S, pose, cp, rec, rec[3]); np += 1.0; }
+    }
   }
+  acc_add(A, S, ne, np, 0.0, 0.0);
   acc_store(A, d.partials + ((size_t)slot * d.max_tiles + blockIdx.x) * kPartial);
   if (!block_is_last(d.ticket + slot, nwork)) return;
   sum_partials(d, slot, nwork, red);
+  __shared__ LmState Ls;
+  lm_load(&Ls, d.lm + slot);
   if (threadIdx.x == 0) {
     Sums28 S;
     for (int i = 0; i < 28; ++i) S.v[i] = red[i];
-    lm_after_eval(L, S, 4);
+    lm_after_eval(Ls, S, 4);
     SlotOut& o = d.out[slot];
-    o.lm_iters[outer] = L.iteration; o.lm_term[outer] = L.termination;
-    o.cost_final[outer] = L.final_cost;
+    o.lm_iters[outer] = Ls.iteration; o.lm_term[outer] = Ls.termination;
+    o.cost_final[outer] = Ls.final_cost;
   }
+  lm_store(d.lm + slot, &Ls);
 }
 
 __global__ void guard_kernel(Dev d) {
@@ -942,12 +1036,13 @@ size_t cub_temp_bytes(int cap_sort, int cap_lp) {
 int launch_voxel_filter(const Dev& d, int n, cudaStream_t s) {
   int k = 0;
   if (n > 0) {
-    vox_bbox_kernel<<<d.G, 256, 0, s>>>(d); ++k;
+    vox_bbox_init_kernel<<<cdiv(6 * d.G, 256), 256, 0, s>>>(d); ++k;
+    vox_bbox_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n); ++k;
     vox_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n); ++k;
     size_t tb = d.cub_tmp_bytes;
     int gbits = 1;
     while ((1 << gbits) < d.G) ++gbits;
-    cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n, 0, 54 + gbits, s);
+    cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n, 0, 31 + gbits, s);
   }
   head_flag_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(d.vkey2, d.flag, n); ++k;
   size_t tb = d.cub_tmp_bytes;

@@ -107,16 +107,18 @@ S2M_HD void quat_rotate(const double q[4], const double v[3], double out[3]) {
   out[2] = v[2] + q[3] * uz + (q[0] * uy - q[1] * ux);
 }
 
-// Largest-eigenvalue direction and the two largest eigenvalues of a symmetric
-// 3x3 (cyclic Jacobi, FP64).  a = {xx, xy, xz, yy, yz, zz}.
-S2M_HD void eig3_top(const double a_in[6], double& lam_mid, double& lam_max, double dir[3]) {
+// The two largest eigenvalues of a symmetric 3x3 (cyclic Jacobi on the six
+// unique entries, FP64) and, only if asked, the unit eigenvector of the largest.
+// a = {xx, xy, xz, yy, yz, zz}.  The vector is the best-conditioned cross product
+// of two rows of (A - lambda_max I): exact to rounding when lambda_max is isolated,
+// which the caller guarantees (it is used only when lambda_max > 3 lambda_mid).
+S2M_HD void eig3_top(const double a_in[6], double& lam_mid, double& lam_max) {
   double a00 = a_in[0], a01 = a_in[1], a02 = a_in[2], a11 = a_in[3], a12 = a_in[4], a22 = a_in[5];
-  double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   const double total = a00 * a00 + a11 * a11 + a22 * a22 + 2 * (a01 * a01 + a02 * a02 + a12 * a12);
   for (int sweep = 0; sweep < 12; ++sweep) {
     double off = a01 * a01 + a02 * a02 + a12 * a12;
     if (off <= 1e-32 * total || off == 0.0) break;
-#define S2M_JROT(app, aqq, apq, arp, arq, p, q)                         \
+#define S2M_JROT(app, aqq, apq, arp, arq)                               \
   if (apq != 0.0) {                                                     \
     double theta = (aqq - app) / (2.0 * apq);                           \
     double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0)); \
@@ -124,42 +126,47 @@ S2M_HD void eig3_top(const double a_in[6], double& lam_mid, double& lam_max, dou
     app -= t * apq; aqq += t * apq; apq = 0.0;                          \
     double rp = arp, rq = arq;                                          \
     arp = c * rp - s * rq; arq = s * rp + c * rq;                       \
-    for (int k = 0; k < 3; ++k) {                                       \
-      double vp = v[k][p], vq = v[k][q];                                \
-      v[k][p] = c * vp - s * vq; v[k][q] = s * vp + c * vq;             \
-    }                                                                   \
   }
-    S2M_JROT(a00, a11, a01, a02, a12, 0, 1)
-    S2M_JROT(a00, a22, a02, a01, a12, 0, 2)
-    S2M_JROT(a11, a22, a12, a01, a02, 1, 2)
+    S2M_JROT(a00, a11, a01, a02, a12)
+    S2M_JROT(a00, a22, a02, a01, a12)
+    S2M_JROT(a11, a22, a12, a01, a02)
 #undef S2M_JROT
   }
-  double l[3] = {a00, a11, a22};
-  int imax = 0;
-  if (l[1] > l[imax]) imax = 1;
-  if (l[2] > l[imax]) imax = 2;
-  int i1 = (imax + 1) % 3, i2 = (imax + 2) % 3;
-  lam_max = l[imax];
-  lam_mid = l[i1] > l[i2] ? l[i1] : l[i2];
-  dir[0] = v[0][imax]; dir[1] = v[1][imax]; dir[2] = v[2][imax];
+  const double hi = fmax(a00, fmax(a11, a22)), lo = fmin(a00, fmin(a11, a22));
+  lam_max = hi;
+  lam_mid = (a00 + a11 + a22) - hi - lo;
+}
+S2M_HD void eig3_vector(const double a[6], double lam, double dir[3]) {
+  const double r0[3] = {a[0] - lam, a[1], a[2]}, r1[3] = {a[1], a[3] - lam, a[4]}, r2[3] = {a[2], a[4], a[5] - lam};
+  double c0[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+  double c1[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+  double c2[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+  double n0 = c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2];
+  double n1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2];
+  double n2 = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
+  if (n1 > n0) { c0[0] = c1[0]; c0[1] = c1[1]; c0[2] = c1[2]; n0 = n1; }
+  if (n2 > n0) { c0[0] = c2[0]; c0[1] = c2[1]; c0[2] = c2[2]; n0 = n2; }
+  const double inv = 1.0 / sqrt(n0);
+  dir[0] = c0[0] * inv; dir[1] = c0[1] * inv; dir[2] = c0[2] * inv;
 }
 
 // Edge fit (laserMapping.cpp:585-622): 5 neighbours -> centre and unit direction;
 // accepted iff lambda_max > 3 * lambda_mid.
 S2M_HD bool edge_fit(const float nb[5][3], double c[3], double u[3]) {
-  double p[5][3];
   c[0] = c[1] = c[2] = 0;
   for (int j = 0; j < 5; ++j)
-    for (int k = 0; k < 3; ++k) { p[j][k] = (double)nb[j][k]; c[k] = c[k] + p[j][k]; }
+    for (int k = 0; k < 3; ++k) c[k] = c[k] + (double)nb[j][k];
   for (int k = 0; k < 3; ++k) c[k] = c[k] / 5.0;
   double a[6] = {0, 0, 0, 0, 0, 0};
   for (int j = 0; j < 5; ++j) {
-    double x = p[j][0] - c[0], y = p[j][1] - c[1], z = p[j][2] - c[2];
+    double x = (double)nb[j][0] - c[0], y = (double)nb[j][1] - c[1], z = (double)nb[j][2] - c[2];
     a[0] += x * x; a[1] += x * y; a[2] += x * z; a[3] += y * y; a[4] += y * z; a[5] += z * z;
   }
   double lmid, lmax;
-  eig3_top(a, lmid, lmax, u);
-  return lmax > 3 * lmid;
+  eig3_top(a, lmid, lmax);
+  if (!(lmax > 3 * lmid)) { u[0] = u[1] = u[2] = 0; return false; }
+  eig3_vector(a, lmax, u);
+  return true;
 }
 
 // Plane fit (laserMapping.cpp:651-687): least squares A n = -1 by column-pivoted
@@ -333,45 +340,72 @@ S2M_HD double grad_max_norm(const double x[7], const double g[6]) {
 }
 
 // Solve (S H S + diag/radius) y = S g by Cholesky; step = -y; fills model_change.
+// Every loop is fully unrolled so the 6x6 work stays in registers (this runs on a
+// single thread at the tail of the evaluation kernel: its latency is on the
+// critical path of every LM iteration).
 S2M_HD bool lm_compute_step(LmState& L) {
-  double A[6][6], gs[6];
+  double A[21], gs[6];  // upper triangle of S H S, row-major packed like L.H
+#pragma unroll
   for (int a = 0; a < 6; ++a) {
     gs[a] = L.g[a] * L.scale[a];
-    for (int b = 0; b < 6; ++b) A[a][b] = L.H[tri(a, b)] * L.scale[a] * L.scale[b];
+#pragma unroll
+    for (int b = a; b < 6; ++b) A[tri(a, b)] = L.H[tri(a, b)] * L.scale[a] * L.scale[b];
   }
-  if (!L.reuse_diag)
-    for (int a = 0; a < 6; ++a) L.diag[a] = fmin(fmax(A[a][a], 1e-6), 1e32);
+  if (!L.reuse_diag) {
+#pragma unroll
+    for (int a = 0; a < 6; ++a) L.diag[a] = fmin(fmax(A[tri(a, a)], 1e-6), 1e32);
+  }
   L.reuse_diag = 1;
-  double C[6][6];
-  for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) C[a][b] = A[a][b];
-  for (int a = 0; a < 6; ++a) C[a][a] += L.diag[a] / L.radius;
+  double C[21];  // Cholesky factor, C[tri(j,i)] = L_ij for i >= j (stored by column index first)
+#pragma unroll
+  for (int k = 0; k < 21; ++k) C[k] = A[k];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) C[tri(a, a)] += L.diag[a] / L.radius;
   bool ok = true;
-  for (int j = 0; j < 6; ++j) {  // in-place lower Cholesky
-    double s = C[j][j];
-    for (int k = 0; k < j; ++k) s -= C[j][k] * C[j][k];
-    if (!(s > 0)) { ok = false; break; }
-    double dj = sqrt(s);
-    C[j][j] = dj;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = C[tri(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= C[tri(k, j)] * C[tri(k, j)];
+    if (!(s > 0)) ok = false;
+    const double dj = sqrt(ok ? s : 1.0);
+    C[tri(j, j)] = dj;
+    const double inv = 1.0 / dj;
+#pragma unroll
     for (int i = j + 1; i < 6; ++i) {
-      double t = C[i][j];
-      for (int k = 0; k < j; ++k) t -= C[i][k] * C[j][k];
-      C[i][j] = t / dj;
+      double t = C[tri(j, i)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= C[tri(k, i)] * C[tri(k, j)];
+      C[tri(j, i)] = t * inv;
     }
   }
   double y[6];
-  if (ok) {
-    for (int i = 0; i < 6; ++i) { double s = gs[i]; for (int k = 0; k < i; ++k) s -= C[i][k] * y[k]; y[i] = s / C[i][i]; }
-    for (int i = 5; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 6; ++k) s -= C[k][i] * y[k]; y[i] = s / C[i][i]; }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = gs[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= C[tri(k, i)] * y[k];
+    y[i] = s / C[tri(i, i)];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double s = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) s -= C[tri(i, k)] * y[k];
+    y[i] = s / C[tri(i, i)];
   }
   double mcc = 0;
+#pragma unroll
   for (int a = 0; a < 6; ++a) {
     L.step[a] = ok ? -y[a] : 0.0;
     if (!(L.step[a] == L.step[a]) || fabs(L.step[a]) > 1e300) ok = false;
   }
   if (ok) {
+#pragma unroll
     for (int a = 0; a < 6; ++a) {
       double hs = 0;
-      for (int b = 0; b < 6; ++b) hs += A[a][b] * L.step[b];
+#pragma unroll
+      for (int b = 0; b < 6; ++b) hs += A[tri(a, b)] * L.step[b];
       mcc += L.step[a] * (gs[a] + 0.5 * hs);
     }
     mcc = -mcc;
@@ -455,7 +489,8 @@ S2M_HD void lm_after_eval(LmState& L, const Sums28& S, int max_iterations) {
     L.final_cost = cand_cost;
     for (int i = 0; i < 21; ++i) L.H[i] = S.v[i];
     for (int i = 0; i < 6; ++i) L.g[i] = S.v[21 + i];
-    double dnm = 1.0 - pow(2.0 * rel - 1.0, 3);
+    const double tq = 2.0 * rel - 1.0;
+    double dnm = 1.0 - tq * tq * tq;  // Ceres: 1 - pow(2 rho - 1, 3)
     L.radius = L.radius / fmax(1.0 / 3.0, dnm);
     L.radius = fmin(1e16, L.radius);
     L.decrease_factor = 2.0;
