@@ -205,7 +205,8 @@ static int create_impl(s2m_ctx* ctx) {
   const size_t ccap = (size_t)std::max(d.cap_lp, d.cap_in);
   rc |= dev_alloc(ctx, &d.ckey, ccap); rc |= dev_alloc(ctx, &d.ckey2, ccap);
   rc |= dev_alloc(ctx, &d.cval, ccap); rc |= dev_alloc(ctx, &d.cval2, ccap);
-  rc |= dev_alloc(ctx, &d.cand, d.cap_lp); rc |= dev_alloc(ctx, &d.qperm, d.cap_in);
+  rc |= dev_alloc(ctx, &d.cand, d.cap_lp); rc |= dev_alloc(ctx, &d.qperm, d.cap_in); rc |= dev_alloc(ctx, &d.inv, d.cap_lp);
+  rc |= dev_alloc(ctx, &d.nbr, (size_t)d.cap_in * 6); rc |= dev_alloc(ctx, &d.scanned, 2 * B);
   // cell tables: per segment a power of two >= 2 x entries, >= 1024
   long long hcap = 0;
   for (int g = 0; g < G; ++g) hcap += next_pow2(std::max(1024, 2 * (g < B ? P.cap_map_corner : P.cap_map_surf)));
@@ -398,8 +399,10 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   }
   k += launch_query_order(d, n_ds, s);
   prof_mark(ctx, S2M_PHASE_INDEX);
-  // one resident wave: S2M_K4_MINB blocks per SM shared by the B slots
-  int blocks = std::max(1, std::min(tiles, (S2M_K4_MINB * ctx->sm_count) / B));
+  // one resident wave each: S2M_K4x_MINB blocks per SM shared by the B slots
+  const int knn_blocks = std::max(1, std::min(tiles, (S2M_K4A_MINB * ctx->sm_count) / B));
+  const int fit_blocks = std::max(1, std::min(tiles, (S2M_K4B_MINB * ctx->sm_count) / B));
+  const int blocks = knn_blocks;
   // the evaluation kernel is a light streaming pass: about four records per thread
   const int eval_blocks = std::max(1, std::min((tiles + 3) / 4, d.max_tiles));
   for (int outer = 0; outer < 2; ++outer) {  // laserMapping.cpp:563
@@ -407,7 +410,7 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
       launch_count_candidates(d, blocks, s);
       prof_mark(ctx, S2M_PHASE_INDEX);
     }
-    k += launch_associate(d, outer, blocks, ctx->P.trace != 0, s);
+    k += launch_associate(d, outer, knn_blocks, fit_blocks, ctx->P.trace != 0, s);
     prof_mark(ctx, S2M_PHASE_ASSOCIATE);
     for (int it = 0; it < 4; ++it)  // options.max_num_iterations = 4 (:716)
       k += launch_evaluate(d, outer, eval_blocks, s);

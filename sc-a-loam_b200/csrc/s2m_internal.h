@@ -27,8 +27,11 @@
 
 namespace s2m {
 
-#ifndef S2M_K4_MINB
-#define S2M_K4_MINB 6  // resident blocks per SM the association kernel is compiled for
+#ifndef S2M_K4A_MINB
+#define S2M_K4A_MINB 8  // resident blocks per SM the kNN kernel is compiled for
+#endif
+#ifndef S2M_K4B_MINB
+#define S2M_K4B_MINB 4  // ... and the fit / residual kernel
 #endif
 constexpr int kTile = 128;       // queries per block of the association / evaluation kernels
 constexpr int kPartial = 32;     // doubles per block partial: 28 sums, n_edge, n_plane, cand_corner, cand_surf
@@ -114,7 +117,10 @@ struct Dev {
   int* loc_off;                 // [G][26]
   uint32_t *ckey, *ckey2, *cval, *cval2;  // [cap_lp]
   float4* cand;                 // [cap_lp] cell-sorted local points, w = local index bits
+  int* inv;                     // [cap_lp] local index -> position in cand (packed by lp_off)
   uint32_t* qperm;              // [cap_in] query order of the association kernel (packed ds indices)
+  int* nbr;                     // [cap_in][6] K4a -> K4b: ds index (or -1 when gated out) + 5 neighbour positions
+  unsigned long long* scanned;  // [B][2] candidate points actually scanned (statistics)
   unsigned long long* hash_tab; // cell tables
   uint2* hash_aux;              // per table slot: (points of the cell itself, exact 3-cell count)
   int* cs_off;                  // [G+1] first sorted position of each segment
@@ -150,7 +156,7 @@ int launch_voxel_filter(const Dev& d, int total_in, cudaStream_t s);
 int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, cudaStream_t s);
 int launch_guard(const Dev& d, cudaStream_t s);
 int launch_query_order(const Dev& d, int n_ds, cudaStream_t s);
-int launch_associate(const Dev& d, int outer, int blocks_per_slot, bool trace, cudaStream_t s);
+int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s);
 int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s);
 int launch_count_candidates(const Dev& d, int blocks_per_slot, cudaStream_t s);
 int launch_finish_pose(const Dev& d, cudaStream_t s);

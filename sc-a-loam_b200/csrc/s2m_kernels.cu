@@ -236,6 +236,7 @@ __global__ void cand_build_kernel(Dev d, int cur, int total_lp) {
   const int l = (int)d.cval2[p];
   const float4 q = d.st_pt[cur][d.st_base[g] + local_to_store(d, g, l)];
   d.cand[p] = make_float4(q.x, q.y, q.z, __int_as_float(l));
+  d.inv[d.lp_off[g] + l] = p;  // local index -> position in d.cand
   if (p == 0 || d.ckey2[p - 1] != key) {
     int e = p + 1;
     while (e < total_lp && d.ckey2[e] == key) ++e;
@@ -271,36 +272,26 @@ __global__ void cand_build_kernel(Dev d, int cur, int total_lp) {
 // the reference's float ((dx*dx)+(dy*dy))+(dz*dz); order is (d2, local index):
 // both live in one 64-bit key (float bits of a non-negative d2 are monotonic).
 struct Knn5 {
-  unsigned long long key[5];  // d2 bits << 32 | local index
-  int pos[5];                 // position in d.cand (-1: none)
+  unsigned long long key[5];  // d2 bits << 32 | local index, ascending
 };
 __device__ __forceinline__ float knn_d2(const Knn5& r, int k) { return __uint_as_float((uint32_t)(r.key[k] >> 32)); }
 __device__ __forceinline__ int knn_idx(const Knn5& r, int k) { return (int)(uint32_t)r.key[k]; }
+// "none" marker: the search starts from the reference's gate (d2 = 1.0f, index 0), see knn5_cells
+constexpr unsigned long long kKnnInit = (unsigned long long)0x3F800000u << 32;
 
-__device__ __forceinline__ void knn_offer(Knn5& r, float qx, float qy, float qz, const float4 c, int pos) {
+__device__ __forceinline__ void knn_offer(Knn5& r, float qx, float qy, float qz, const float4 c) {
   const float dd = dist2(qx, qy, qz, c.x, c.y, c.z);
-  unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | (uint32_t)__float_as_int(c.w);
-  if (key < r.key[4]) {  // branch-free sorted insertion
+  if (dd > knn_d2(r, 4)) return;  // cheap float test first; ties go through the exact 64-bit compare
+  const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | (uint32_t)__float_as_int(c.w);
+  if (key < r.key[4]) {  // replace the 5th, then bubble it up (compare-exchange chain)
+    r.key[4] = key;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const bool lt = key < r.key[i];
-      const unsigned long long tk = r.key[i];
-      const int tp = r.pos[i];
-      r.key[i] = lt ? key : tk;
-      r.pos[i] = lt ? pos : tp;
-      key = lt ? tk : key;
-      pos = lt ? tp : pos;
+    for (int i = 4; i > 0; --i) {
+      const unsigned long long lo = r.key[i - 1], hi = r.key[i];
+      const bool sw = hi < lo;
+      r.key[i - 1] = sw ? hi : lo;
+      r.key[i] = sw ? lo : hi;
     }
-  }
-}
-__device__ __forceinline__ void knn_scan_range(const float4* __restrict__ cand, int start, int count, float qx,
-                                               float qy, float qz, Knn5& r) {
-  float4 c = __ldg(cand + start);
-#pragma unroll 1
-  for (int j = 0; j < count; ++j) {  // the next point is in flight while this one is offered
-    const float4 nx = __ldg(cand + start + min(j + 1, count - 1));
-    knn_offer(r, qx, qy, qz, c, start + j);
-    c = nx;
   }
 }
 __device__ __forceinline__ unsigned long long cell_probe(const unsigned long long* __restrict__ tab, uint32_t mask,
@@ -314,24 +305,15 @@ __device__ __forceinline__ unsigned long long cell_probe(const unsigned long lon
   return e;
 }
 
-// Query order.  The association kernel walks the down-sampled scan points of a
-// segment in the order of their 1 m map cell at the frame's initial pose, so the
-// lanes of a warp probe the same rows and scan overlapping runs (L1 hits, equal
-// trip counts).  Pure scheduling: results do not depend on it.
-__global__ void query_key_kernel(Dev d, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int g = find_seg(d.ds_off, d.G, i);
-  const int slot = seg_slot(d, g);
-  const FrameDesc& fd = d.desc[slot];
-  const float4 p = d.ds_pts[i];
-  float w[3];
-  xf_point(fd.pose, p.x, p.y, p.z, w);
-  const int cx = min(max((int)floorf(w[0]) - fd.origin[0], 0), 255);
-  const int cy = min(max((int)floorf(w[1]) - fd.origin[1], 0), 255);
-  const int cz = min(max((int)floorf(w[2]) - fd.origin[2], 0), 255);
-  d.ckey[i] = ((uint32_t)g << 24) | ((uint32_t)cz << 16) | ((uint32_t)cy << 8) | (uint32_t)cx;
-  d.cval[i] = (uint32_t)i;
+__device__ __forceinline__ void knn_scan_range(const float4* __restrict__ cand, int start, int count, float qx,
+                                               float qy, float qz, Knn5& r) {
+  float4 c = __ldg(cand + start);
+#pragma unroll 1
+  for (int j = 0; j < count; ++j) {  // the next point is in flight while this one is offered
+    const float4 nx = __ldg(cand + start + min(j + 1, count - 1));
+    knn_offer(r, qx, qy, qz, c);
+    c = nx;
+  }
 }
 
 // per-thread staging of the nine row probes (one column per thread)
@@ -340,17 +322,19 @@ struct KnnStage {
   uint32_t sl[9][kTile];
 };
 
-// Exact bounded kNN(5).  Rows (dy,dz) of three x-adjacent cells are visited near
-// to far; a row is skipped when a lower bound of the FLOAT distance to any point
-// in it already exceeds the current 5th distance.  The bound is built with the
-// same rounding steps as dist2() ((0 + by*by) + bz*bz with by, bz the exact
-// distances to the row's boundary planes), and rounding is monotonic, so no point
-// that could enter the result is ever skipped.
+// Rows (dy,dz) of three x-adjacent cells are visited near to far; a row is skipped when
+// a lower bound of the FLOAT distance to any point in it exceeds the current 5th
+// distance.  The bound is built with the same rounding steps as dist2() ((0 + by*by) +
+// bz*bz with by, bz the exact distances to the row's boundary planes) and rounding is
+// monotonic, so no point that could enter the result is ever skipped.
 // Returns the number of candidate points scanned.
 __device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[3], float qx, float qy, float qz,
                                           Knn5& r, KnnStage& st) {
+  // The result is only used when the 5th distance is < 1.0 (laserMapping.cpp:585, :653), so the
+  // search starts from that bound: key (1.0f, index 0) is larger than every (d2 < 1, any index)
+  // and not larger than any (d2 >= 1, .) -- candidates at 1 m or more never enter.
 #pragma unroll
-  for (int k = 0; k < 5; ++k) { r.key[k] = ((unsigned long long)0x7F800000u << 32) | 0x7FFFFFFFu; r.pos[k] = -1; }
+  for (int k = 0; k < 5; ++k) r.key[k] = kKnnInit;
   const float fly = floorf(qy), flz = floorf(qz);
   const int cx = (int)floorf(qx) - origin[0], cy = (int)fly - origin[1], cz = (int)flz - origin[2];
   const int base = d.hash_off[g];
@@ -424,6 +408,26 @@ __device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[
       if (count[h] > 0) knn_scan_range(d.cand, start[h], count[h], qx, qy, qz, r);
   }
   return visited;
+}
+
+// Query order.  The association kernels walk the down-sampled scan points of a
+// segment in the order of their 1 m map cell at the frame's initial pose, so the
+// lanes of a warp probe the same rows and scan overlapping runs (L1 hits, similar
+// trip counts).  Pure scheduling: results do not depend on it.
+__global__ void query_key_kernel(Dev d, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = find_seg(d.ds_off, d.G, i);
+  const int slot = seg_slot(d, g);
+  const FrameDesc& fd = d.desc[slot];
+  const float4 p = d.ds_pts[i];
+  float w[3];
+  xf_point(fd.pose, p.x, p.y, p.z, w);
+  const int cx = min(max((int)floorf(w[0]) - fd.origin[0], 0), 255);
+  const int cy = min(max((int)floorf(w[1]) - fd.origin[1], 0), 255);
+  const int cz = min(max((int)floorf(w[2]) - fd.origin[2], 0), 255);
+  d.ckey[i] = ((uint32_t)g << 24) | ((uint32_t)cz << 16) | ((uint32_t)cy << 8) | (uint32_t)cx;
+  d.cval[i] = (uint32_t)i;
 }
 
 // number of map points in the 27 cells around a query (the C-bar of SURVEY 8d's
@@ -566,16 +570,78 @@ __device__ __forceinline__ void slot_counts(const Dev& d, int slot, int& dc0, in
 // K4: fused association.  One thread per down-sampled scan point; a block walks
 // tiles of kTile points of one slot (grid.x blocks per slot, grid.y = slots).
 // ----------------------------------------------------------------------------
-// hand-off between the two phases of a tile (one column per thread)
+// ----------------------------------------------------------------------------
+// K4 = two back-to-back kernels over the same tiles of 128 queries (walked in map-cell
+// order, d.qperm):
+//   K4a knn_kernel      : transform + exact bounded kNN(5) + the 1 m gate. Integer/float
+//                         only, few registers -> high occupancy hides the probe latency.
+//   K4b fit_kernel      : gated queries compacted per tile (dense lanes) -> edge PCA / plane
+//                         QR + residual, Jacobian, Huber (FP64) -> block reduction -> the
+//                         last block of a slot starts the LM solve.
+// The hand-off is 24 bytes per query (5 neighbour positions + class/gate word).
+// ----------------------------------------------------------------------------
+template <bool kTrace>
+__global__ void __launch_bounds__(kTile, S2M_K4A_MINB) knn_kernel(Dev d, int outer) {
+  const int slot = blockIdx.y;
+  if (!d.out[slot].optimized) return;
+  int dc0, nc, ds0, nq;
+  slot_counts(d, slot, dc0, nc, ds0, nq);
+  const int ntiles = (nq + kTile - 1) / kTile;
+  __shared__ double pose[7];
+  __shared__ int origin[3];
+  __shared__ KnnStage stage;
+  __shared__ unsigned long long cand_s[2];
+  if (threadIdx.x < 7) pose[threadIdx.x] = d.lm[slot].x[threadIdx.x];
+  if (threadIdx.x < 3) origin[threadIdx.x] = d.desc[slot].origin[threadIdx.x];
+  if (threadIdx.x < 2) cand_s[threadIdx.x] = 0ull;
+  __syncthreads();
+  unsigned long long visited_c = 0, visited_s = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int q = tile * kTile + threadIdx.x;
+    if (q >= nq) continue;
+    const int cls = q >= nc;
+    const int pos_q = cls ? ds0 + (q - nc) : dc0 + q;  // position in the packed, cell-ordered query list
+    const int di = (int)d.qperm[pos_q];
+    const float4 p = d.ds_pts[di];
+    float w[3];
+    xf_point(pose, p.x, p.y, p.z, w);
+    Knn5 r;
+    const int visited = knn5_cells(d, cls ? d.B + slot : slot, origin, w[0], w[1], w[2], r, stage);
+    if (cls) visited_s += (unsigned long long)visited; else visited_c += (unsigned long long)visited;
+    const bool gate = knn_d2(r, 4) < 1.0f;  // laserMapping.cpp:585 / :653
+    int* nb = d.nbr + 6 * (size_t)pos_q;
+    nb[0] = gate ? di : -1;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) nb[1 + k] = knn_idx(r, k);  // local indices; K4b maps them to d.cand
+    d.rec_valid[di] = 0;
+    if (kTrace) {
+      const size_t o = ((size_t)outer * d.cap_in + di);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const bool have = r.key[k] != kKnnInit;
+        d.tr_idx[5 * o + k] = have ? knn_idx(r, k) : -1;
+        d.tr_d2[5 * o + k] = have ? knn_d2(r, k) : INFINITY;
+      }
+      d.tr_used[o] = 0;
+    }
+  }
+  // scanned-candidate counters (statistics only)
+  for (int o = 16; o > 0; o >>= 1) {
+    visited_c += __shfl_down_sync(0xffffffffu, visited_c, o);
+    visited_s += __shfl_down_sync(0xffffffffu, visited_s, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&cand_s[0], visited_c); atomicAdd(&cand_s[1], visited_s); }
+  __syncthreads();
+  if (threadIdx.x < 2 && cand_s[threadIdx.x]) atomicAdd(d.scanned + 2 * slot + threadIdx.x, cand_s[threadIdx.x]);
+}
+
 struct TileXfer {
-  int di[kTile];       // packed down-sampled index of the query
-  int pos[5][kTile];   // positions of its 5 neighbours in d.cand
-  int list[kTile];     // compacted list of the threads whose query passed the 1 m gate
+  int list[kTile];  // compacted list of the tile's gated queries (tile-local index)
   int wcount[kTile / 32];
 };
 
 template <bool kTrace>
-__global__ void __launch_bounds__(kTile, S2M_K4_MINB) associate_kernel(Dev d, int outer) {
+__global__ void __launch_bounds__(kTile, S2M_K4B_MINB) fit_kernel(Dev d, int outer) {
   const int slot = blockIdx.y;
   if (!d.out[slot].optimized) return;
   int dc0, nc, ds0, nq;
@@ -584,48 +650,18 @@ __global__ void __launch_bounds__(kTile, S2M_K4_MINB) associate_kernel(Dev d, in
   const int nwork = max(1, min((int)gridDim.x, ntiles));
   if ((int)blockIdx.x >= nwork) return;
   __shared__ double pose[7];
-  __shared__ int origin[3];
   __shared__ BlockAcc A;
-  __shared__ KnnStage stage;
   __shared__ TileXfer xf;
   __shared__ double red[kPartial];
   if (threadIdx.x < 7) pose[threadIdx.x] = d.lm[slot].x[threadIdx.x];
-  if (threadIdx.x < 3) origin[threadIdx.x] = d.desc[slot].origin[threadIdx.x];
   acc_zero(A);
   __syncthreads();
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  double cand_c = 0.0, cand_s = 0.0;
-
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    // ---- phase A: transform + exact kNN(5), one thread per query ----
+    // ---- compaction of the gated queries of this tile (thread order => deterministic) ----
     const int q = tile * kTile + t;
-    bool gate = false;
-    if (q < nq) {
-      const int cls = q >= nc;
-      const int di = (int)d.qperm[cls ? ds0 + (q - nc) : dc0 + q];
-      const float4 p = d.ds_pts[di];
-      float w[3];
-      xf_point(pose, p.x, p.y, p.z, w);
-      Knn5 r;
-      const int visited = knn5_cells(d, cls ? d.B + slot : slot, origin, w[0], w[1], w[2], r, stage);
-      if (cls) cand_s += (double)visited; else cand_c += (double)visited;
-      gate = knn_d2(r, 4) < 1.0f;  // laserMapping.cpp:585 / :653
-      xf.di[t] = cls ? -(di + 1) : di;  // sign carries the class
-#pragma unroll
-      for (int k = 0; k < 5; ++k) xf.pos[k][t] = r.pos[k];
-      d.rec_valid[di] = 0;
-      if (kTrace) {
-        const size_t o = ((size_t)outer * d.cap_in + di);
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const bool have = r.pos[k] >= 0;
-          d.tr_idx[5 * o + k] = have ? knn_idx(r, k) : -1;
-          d.tr_d2[5 * o + k] = have ? knn_d2(r, k) : INFINITY;
-        }
-        d.tr_used[o] = 0;
-      }
-    }
-    // ---- compaction of the gated queries (thread order => deterministic) ----
+    const int pos_q = q < nc ? dc0 + q : ds0 + (q - nc);
+    const bool gate = q < nq && d.nbr[6 * (size_t)pos_q] >= 0;
     const unsigned bal = __ballot_sync(0xffffffffu, gate);
     if (lane == 0) xf.wcount[wid] = __popc(bal);
     __syncthreads();
@@ -638,20 +674,21 @@ __global__ void __launch_bounds__(kTile, S2M_K4_MINB) associate_kernel(Dev d, in
     }
     if (gate) xf.list[before + __popc(bal & ((1u << lane) - 1u))] = t;
     __syncthreads();
-    // ---- phase B: edge PCA / plane QR + residual, Jacobian, Huber; dense lanes ----
+    // ---- edge PCA / plane QR + residual, Jacobian, Huber on dense lanes ----
     Sums28 S;
     S.zero();
     double ne = 0.0, np = 0.0;
     if (t < n_items) {
-      const int src = xf.list[t];
-      const int dv = xf.di[src];
-      const int cls = dv < 0;
-      const int di = cls ? -dv - 1 : dv;
+      const int qs = tile * kTile + xf.list[t];
+      const int cls = qs >= nc;
+      const int* nb_i = d.nbr + 6 * (size_t)(cls ? ds0 + (qs - nc) : dc0 + qs);
+      const int di = nb_i[0];
       const float4 p = d.ds_pts[di];
       float nb[5][3];
+      const int* __restrict__ inv = d.inv + d.lp_off[cls ? d.B + slot : slot];
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const float4 c = __ldg(d.cand + xf.pos[k][src]);
+        const float4 c = __ldg(d.cand + inv[nb_i[1 + k]]);
         nb[k][0] = c.x; nb[k][1] = c.y; nb[k][2] = c.z;
       }
       const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
@@ -673,13 +710,8 @@ __global__ void __launch_bounds__(kTile, S2M_K4_MINB) associate_kernel(Dev d, in
         if (kTrace) d.tr_used[(size_t)outer * d.cap_in + di] = 1;
       }
     }
-    if (wid * 32 < n_items) acc_add(A, S, ne, np, 0.0, 0.0);  // warp-uniform: whole warps without items skip
+    if (wid * 32 < n_items) acc_add(A, S, ne, np, 0.0, 0.0);  // warp-uniform: warps without items skip
     __syncthreads();  // xf is rewritten by the next tile
-  }
-  {
-    Sums28 Z;
-    Z.zero();
-    acc_add(A, Z, 0.0, 0.0, cand_c, cand_s);
   }
   acc_store(A, d.partials + ((size_t)slot * d.max_tiles + blockIdx.x) * kPartial);
   if (!block_is_last(d.ticket + slot, nwork)) return;
@@ -692,7 +724,7 @@ __global__ void __launch_bounds__(kTile, S2M_K4_MINB) associate_kernel(Dev d, in
     for (int i = 0; i < 28; ++i) S.v[i] = red[i];
     SlotOut& o = d.out[slot];
     o.n_edge[outer] = (int)red[28]; o.n_plane[outer] = (int)red[29];
-    if (outer == 0) { o.cand[0] = red[30]; o.cand[1] = red[31]; }
+    if (outer == 0) { o.cand[0] = (double)d.scanned[2 * slot]; o.cand[1] = (double)d.scanned[2 * slot + 1]; }
     double x0[7];
     for (int i = 0; i < 7; ++i) x0[i] = Ls.x[i];
     lm_begin(Ls, x0, S, (int)red[28] + (int)red[29], 4);
@@ -1079,12 +1111,18 @@ int launch_guard(const Dev& d, cudaStream_t s) {
   guard_kernel<<<cdiv(d.B, 64), 64, 0, s>>>(d);
   return 1;
 }
-int launch_associate(const Dev& d, int outer, int blocks_per_slot, bool trace, cudaStream_t s) {
-  if (blocks_per_slot <= 0) return 0;
-  dim3 grid(blocks_per_slot, d.B);
-  if (trace) associate_kernel<true><<<grid, kTile, 0, s>>>(d, outer);
-  else associate_kernel<false><<<grid, kTile, 0, s>>>(d, outer);
-  return 1;
+int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s) {
+  if (knn_blocks <= 0 || fit_blocks <= 0) return 0;
+  if (outer == 0) cudaMemsetAsync(d.scanned, 0, sizeof(unsigned long long) * 2 * d.B, s);
+  dim3 ga(knn_blocks, d.B), gb(fit_blocks, d.B);
+  if (trace) {
+    knn_kernel<true><<<ga, kTile, 0, s>>>(d, outer);
+    fit_kernel<true><<<gb, kTile, 0, s>>>(d, outer);
+  } else {
+    knn_kernel<false><<<ga, kTile, 0, s>>>(d, outer);
+    fit_kernel<false><<<gb, kTile, 0, s>>>(d, outer);
+  }
+  return 2;
 }
 int launch_count_candidates(const Dev& d, int blocks_per_slot, cudaStream_t s) {
   if (blocks_per_slot <= 0) return 0;
