@@ -127,13 +127,14 @@ class Registrar:
 
     def __init__(self, line_res=0.4, plane_res=0.8, device=0, batch=1, cap_corner_in=16384,
                  cap_surf_in=131072, cap_map_corner=1 << 19, cap_map_surf=1 << 20,
-                 skip_optimization=False, trace=False):
+                 skip_optimization=False, trace=False, shard_rank=0, shard_world=1):
         self.L = load_library()
         p = default_params()
         p.line_res, p.plane_res, p.device, p.batch = line_res, plane_res, device, batch
         p.cap_corner_in, p.cap_surf_in = cap_corner_in, cap_surf_in
         p.cap_map_corner, p.cap_map_surf = cap_map_corner, cap_map_surf
         p.skip_optimization, p.trace = int(skip_optimization), int(trace)
+        p.shard_rank, p.shard_world = shard_rank, shard_world
         self.params = p
         self.batch = batch
         h = ctypes.c_void_p()
@@ -275,6 +276,23 @@ class Registrar:
         self._check(self.L.s2m_trace_lm(self.h, slot, outer, pose.ctypes.data, sums.ctypes.data,
                                         iters.ctypes.data, ctypes.byref(n), ctypes.byref(term)))
         return pose, sums, iters, n.value, term.value
+
+    # ---- sharded map (BASELINE config 5) ----------------------------------------------------
+    @staticmethod
+    def shard_unique_id():
+        buf = ctypes.create_string_buffer(128)
+        rc = load_library().s2m_shard_unique_id(buf)
+        if rc != 0:
+            raise S2MError("s2m_shard_unique_id failed (NCCL not loadable)")
+        return buf.raw
+
+    def shard_init(self, id128):
+        self._check(self.L.s2m_shard_init(self.h, ctypes.create_string_buffer(id128, 128)))
+
+    def shard_profile(self, reset=True):
+        ms, n = ctypes.c_double(), ctypes.c_longlong()
+        self._check(self.L.s2m_shard_profile(self.h, int(reset), ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     # ---- measurement ----------------------------------------------------------------
     def launch_count(self):

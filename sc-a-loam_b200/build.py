@@ -48,7 +48,7 @@ def build_cuda(force=False, verbose=False):
         if p.wait() != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if force or procs or _newer(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         subprocess.check_call(cmd)
     return LIB
 

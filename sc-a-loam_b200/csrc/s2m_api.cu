@@ -9,7 +9,10 @@
 //   U  transformUpdate            :149-153
 // Everything else runs on the device (s2m_kernels.cu) on one stream, with a
 // single device->host read-back (poses + counters) per call.
+#include <dlfcn.h>
+
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -43,6 +46,32 @@ struct HostTables {  // one pinned block, copied to the device in one go
 
 }  // namespace
 
+// ---- NCCL, resolved at run time --------------------------------------------------------------
+// Only the sharded-map mode needs it. dlopen("libnccl.so.2") returns the copy the process
+// already loaded (torch's), so no second NCCL is ever linked in.
+namespace nccl {
+typedef struct { char internal[128]; } UniqueId;
+typedef void* Comm;
+enum { kSum = 0, kInt32 = 2, kFloat64 = 8 };  // ncclRedOp_t / ncclDataType_t values (stable ABI)
+static int (*GetUniqueId)(UniqueId*) = nullptr;
+static int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+static int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+static int (*CommDestroy)(Comm) = nullptr;
+static const char* (*GetErrorString)(int) = nullptr;
+static bool load() {
+  if (AllReduce) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return false;
+  GetUniqueId = (int (*)(UniqueId*))dlsym(h, "ncclGetUniqueId");
+  CommInitRank = (int (*)(Comm*, int, UniqueId, int))dlsym(h, "ncclCommInitRank");
+  AllReduce = (int (*)(const void*, void*, size_t, int, int, Comm, cudaStream_t))dlsym(h, "ncclAllReduce");
+  CommDestroy = (int (*)(Comm))dlsym(h, "ncclCommDestroy");
+  GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+}
+}  // namespace nccl
+
 struct s2m_ctx {
   s2m_params P;
   Dev d;
@@ -70,6 +99,12 @@ struct s2m_ctx {
   double k4_bytes = 0, k4_scanned = 0, k4_cand27 = 0;
   long long k4_launches = 0;
   int sm_count = 148;
+  // sharded-map mode
+  nccl::Comm comm = nullptr;
+  std::vector<cudaEvent_t> ar_pool;
+  size_t ar_used = 0;
+  double ar_ms = 0;
+  long long ar_count = 0;
 };
 
 static int prof_mark(s2m_ctx* ctx, int phase) {
@@ -159,6 +194,8 @@ extern "C" void s2m_destroy(s2m_ctx* ctx) {
   if (ctx->ev_ds) cudaEventDestroy(ctx->ev_ds);
   if (ctx->h_lm) cudaFreeHost(ctx->h_lm);
   for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
+  for (auto& e : ctx->ar_pool) cudaEventDestroy(e);
+  if (ctx->comm && nccl::CommDestroy) nccl::CommDestroy(ctx->comm);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -173,6 +210,15 @@ static int create_impl(s2m_ctx* ctx) {
   std::memset(&d, 0, sizeof(d));
   const int B = P.batch, G = 2 * B;
   d.B = B; d.G = G;
+  d.shard_world = P.shard_world;
+  d.shard_lo = -INFINITY; d.shard_hi = INFINITY;
+  if (P.shard_world > 1) {
+    // contiguous slabs of cube columns of the initial window (world cube columns -10..10) per rank
+    const int lo_col = -10 + (kWinI * P.shard_rank) / P.shard_world;
+    const int hi_col = -10 + (kWinI * (P.shard_rank + 1)) / P.shard_world;
+    if (P.shard_rank > 0) d.shard_lo = (float)(50.0 * lo_col - 25.0);
+    if (P.shard_rank < P.shard_world - 1) d.shard_hi = (float)(50.0 * hi_col - 25.0);
+  }
   d.inv_leaf[0] = 1.0f / P.line_res;   // pcl::VoxelGrid::setLeafSize: inverse_leaf_size = 1 / leaf (float)
   d.inv_leaf[1] = 1.0f / P.plane_res;
   const long long cap_in = (long long)B * ((long long)P.cap_corner_in + P.cap_surf_in);
@@ -218,6 +264,7 @@ static int create_impl(s2m_ctx* ctx) {
   rc |= dev_alloc(ctx, &d.partials, (size_t)B * d.max_tiles * kPartial);
   rc |= dev_alloc(ctx, &d.lm, B); rc |= dev_alloc(ctx, &d.out, B); rc |= dev_alloc(ctx, &d.err_flag, 1);
   rc |= dev_alloc(ctx, &d.ticket, B); rc |= dev_alloc(ctx, &d.cand27, 2 * B);
+  rc |= dev_alloc(ctx, &d.shard_sums, (size_t)B * kPartial); rc |= dev_alloc(ctx, &d.shard_counts, G);
   rc |= dev_alloc(ctx, &ctx->lm_trace, 2 * B);
   if (P.trace) {
     rc |= dev_alloc(ctx, &d.tr_idx, (size_t)2 * d.cap_in * 5); rc |= dev_alloc(ctx, &d.tr_d2, (size_t)2 * d.cap_in * 5);
@@ -263,6 +310,7 @@ extern "C" int s2m_create(const s2m_params* p, s2m_ctx** out) {
   s2m_ctx* ctx = new s2m_ctx();
   ctx->P = *p;
   if (ctx->P.shard_world < 1) ctx->P.shard_world = 1;
+  if (ctx->P.shard_rank < 0 || ctx->P.shard_rank >= ctx->P.shard_world) { delete ctx; return S2M_ERR_ARG; }
   int rc = create_impl(ctx);
   if (rc != S2M_OK) {
     fprintf(stderr, "s2m_create: %s\n", ctx->err.c_str());
@@ -282,6 +330,25 @@ extern "C" int s2m_set_stream(s2m_ctx* ctx, void* cuda_stream) {
 }
 
 extern "C" long long s2m_launch_count(s2m_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- sharded map: allreduce of the per-rank sums (latency-bound: 32 doubles per slot) ----------
+static int shard_allreduce(s2m_ctx* ctx, void* buf, size_t count, int dtype) {
+  if (ctx->P.shard_world <= 1 || !ctx->comm) return S2M_OK;  // comm-less = single-rank debugging of the filters
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->profiling) {
+    while (ctx->ar_pool.size() < ctx->ar_used + 2) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      ctx->ar_pool.push_back(e);
+    }
+    e0 = ctx->ar_pool[ctx->ar_used++]; e1 = ctx->ar_pool[ctx->ar_used++];
+    CK(cudaEventRecord(e0, ctx->stream));
+  }
+  const int rc = nccl::AllReduce(buf, buf, count, dtype, nccl::kSum, ctx->comm, ctx->stream);
+  if (rc != 0) { ctx->err = std::string("ncclAllReduce: ") + (nccl::GetErrorString ? nccl::GetErrorString(rc) : "?"); return S2M_ERR_NCCL; }
+  if (ctx->profiling) CK(cudaEventRecord(e1, ctx->stream));
+  return S2M_OK;
+}
 
 // ---- host rows A, B, C ------------------------------------------------------
 static void row_A(SlotHost& s, const double q_wodom[4], const double t_wodom[3]) {
@@ -389,6 +456,8 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   CK(cudaEventRecord(ctx->ev_ds, s));
   prof_mark(ctx, S2M_PHASE_VOXEL);
   k += launch_local_index(d, ctx->cur, total_lp, hash_total, s);
+  const bool sharded = ctx->P.shard_world > 1;
+  if (sharded) { int rs = shard_allreduce(ctx, d.shard_counts, (size_t)G, nccl::kInt32); if (rs != S2M_OK) return rs; }
   k += launch_guard(d, s);
   CK(cudaEventSynchronize(ctx->ev_ds));
   const int n_ds = ctx->h_dsoff[G];
@@ -411,9 +480,20 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
       prof_mark(ctx, S2M_PHASE_INDEX);
     }
     k += launch_associate(d, outer, knn_blocks, fit_blocks, ctx->P.trace != 0, s);
+    if (sharded) {  // one 32-double block per slot across the ranks, then the LM step on every rank
+      int rs = shard_allreduce(ctx, d.shard_sums, (size_t)B * kPartial, nccl::kFloat64);
+      if (rs != S2M_OK) return rs;
+      k += launch_lm_shard(d, outer, 0, s);
+    }
     prof_mark(ctx, S2M_PHASE_ASSOCIATE);
-    for (int it = 0; it < 4; ++it)  // options.max_num_iterations = 4 (:716)
+    for (int it = 0; it < 4; ++it) {  // options.max_num_iterations = 4 (:716)
       k += launch_evaluate(d, outer, eval_blocks, s);
+      if (sharded) {
+        int rs = shard_allreduce(ctx, d.shard_sums, (size_t)B * kPartial, nccl::kFloat64);
+        if (rs != S2M_OK) return rs;
+        k += launch_lm_shard(d, outer, 1, s);
+      }
+    }
     prof_mark(ctx, S2M_PHASE_SOLVE);
     if (ctx->P.trace)
       CK(cudaMemcpyAsync(ctx->lm_trace + (size_t)outer * B, d.lm, sizeof(LmState) * B, cudaMemcpyDeviceToDevice, s));
@@ -829,6 +909,35 @@ extern "C" int s2m_phase_profile(s2m_ctx* ctx, int reset, double ms[S2M_N_PHASES
 }
 
 // ---- sharded-map mode: not wired in this build ------------------------------------
-extern "C" int s2m_shard_unique_id(void*) { return S2M_ERR_NCCL; }
-extern "C" int s2m_shard_init(s2m_ctx*, const void*) { return S2M_ERR_NCCL; }
-extern "C" int s2m_shard_profile(s2m_ctx*, int, double*, long long*) { return S2M_ERR_NCCL; }
+extern "C" int s2m_shard_unique_id(void* id128) {
+  if (!id128) return S2M_ERR_ARG;
+  if (!nccl::load()) return S2M_ERR_NCCL;
+  nccl::UniqueId id;
+  if (nccl::GetUniqueId(&id) != 0) return S2M_ERR_NCCL;
+  std::memcpy(id128, &id, sizeof(id));
+  return S2M_OK;
+}
+extern "C" int s2m_shard_init(s2m_ctx* ctx, const void* id128) {
+  if (!ctx || !id128 || ctx->P.shard_world <= 1) return S2M_ERR_ARG;
+  if (!nccl::load()) { ctx->err = "libnccl.so.2 not found"; return S2M_ERR_NCCL; }
+  CK(cudaSetDevice(ctx->P.device));
+  nccl::UniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  const int rc = nccl::CommInitRank(&ctx->comm, ctx->P.shard_world, id, ctx->P.shard_rank);
+  if (rc != 0) { ctx->err = std::string("ncclCommInitRank: ") + (nccl::GetErrorString ? nccl::GetErrorString(rc) : "?"); ctx->comm = nullptr; return S2M_ERR_NCCL; }
+  return S2M_OK;
+}
+extern "C" int s2m_shard_profile(s2m_ctx* ctx, int reset, double* allreduce_ms_total, long long* count) {
+  if (!ctx) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i + 1 < ctx->ar_used; i += 2) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ar_pool[i], ctx->ar_pool[i + 1]) == cudaSuccess) { ctx->ar_ms += ms; ctx->ar_count++; }
+  }
+  ctx->ar_used = 0;
+  if (allreduce_ms_total) *allreduce_ms_total = ctx->ar_ms;
+  if (count) *count = ctx->ar_count;
+  if (reset) { ctx->ar_ms = 0; ctx->ar_count = 0; }
+  return S2M_OK;
+}

@@ -91,6 +91,10 @@ struct SlotOut {            // per slot, read back by the host after every call
 // All device pointers of one context (sizes are host-known capacities).
 struct Dev {
   int B, G;                     // slots, segments
+  int shard_world;              // >1: spatially sharded map (x-slabs per rank)
+  float shard_lo, shard_hi;     // this rank's slab in world x, [lo, hi)
+  double* shard_sums;           // [B][kPartial] per-rank sums awaiting the allreduce
+  int* shard_counts;            // [G] map points this rank owns in the valid block (allreduced for the guard)
   float inv_leaf[2];
   // ---- per call small tables (device copies of host arrays)
   FrameDesc* desc;              // [B]
@@ -159,6 +163,7 @@ int launch_query_order(const Dev& d, int n_ds, cudaStream_t s);
 int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s);
 int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s);
 int launch_count_candidates(const Dev& d, int blocks_per_slot, cudaStream_t s);
+int launch_lm_shard(const Dev& d, int outer, int after, cudaStream_t s);
 int launch_finish_pose(const Dev& d, cudaStream_t s);
 int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, bool check_pending, bool identity_pose,
                       cudaStream_t s);

@@ -206,6 +206,7 @@ __global__ void local_key_kernel(Dev d, int cur, int total_lp) {
   if (l < d.loc_off[g * (kCols + 1) + kCols]) {
     const float4 p = d.st_pt[cur][d.st_base[g] + local_to_store(d, g, l)];
     const FrameDesc& fd = d.desc[seg_slot(d, g)];
+    if (d.shard_world > 1 && p.x >= d.shard_lo && p.x < d.shard_hi) atomicAdd(d.shard_counts + g, 1);
     const int rx = (int)floorf(p.x) - fd.origin[0], ry = (int)floorf(p.y) - fd.origin[1],
               rz = (int)floorf(p.z) - fd.origin[2];
     if ((unsigned)rx > 255u || (unsigned)ry > 255u || (unsigned)rz > 255u) set_err(d, -4);
@@ -570,6 +571,55 @@ __device__ __forceinline__ void slot_counts(const Dev& d, int slot, int& dc0, in
 // K4: fused association.  One thread per down-sampled scan point; a block walks
 // tiles of kTile points of one slot (grid.x blocks per slot, grid.y = slots).
 // ----------------------------------------------------------------------------
+// LM tails: run by the last block of a slot (unsharded) or by lm_shard_kernel after the
+// allreduce of the 32 sums (sharded map).  `red` = reduced sums in shared memory.
+__device__ __forceinline__ void lm_tail_begin(const Dev& d, int slot, int outer, const double* red, LmState* Ls) {
+  lm_load(Ls, d.lm + slot);
+  if (threadIdx.x == 0) {
+    Sums28 S;
+    for (int i = 0; i < 28; ++i) S.v[i] = red[i];
+    SlotOut& o = d.out[slot];
+    o.n_edge[outer] = (int)red[28]; o.n_plane[outer] = (int)red[29];
+    if (outer == 0) { o.cand[0] = (double)d.scanned[2 * slot]; o.cand[1] = (double)d.scanned[2 * slot + 1]; }
+    double x0[7];
+    for (int i = 0; i < 7; ++i) x0[i] = Ls->x[i];
+    lm_begin(*Ls, x0, S, (int)red[28] + (int)red[29], 4);
+    o.lm_iters[outer] = Ls->iteration; o.lm_term[outer] = Ls->termination;
+    o.cost_initial[outer] = Ls->initial_cost; o.cost_final[outer] = Ls->final_cost;
+  }
+  lm_store(d.lm + slot, Ls);
+}
+__device__ __forceinline__ void lm_tail_after(const Dev& d, int slot, int outer, const double* red, LmState* Ls) {
+  lm_load(Ls, d.lm + slot);
+  if (threadIdx.x == 0) {
+    Sums28 S;
+    for (int i = 0; i < 28; ++i) S.v[i] = red[i];
+    lm_after_eval(*Ls, S, 4);
+    SlotOut& o = d.out[slot];
+    o.lm_iters[outer] = Ls->iteration; o.lm_term[outer] = Ls->termination;
+    o.cost_final[outer] = Ls->final_cost;
+  }
+  lm_store(d.lm + slot, Ls);
+}
+// sharded map: the per-rank sums wait in d.shard_sums for the allreduce
+__device__ __forceinline__ void shard_publish(const Dev& d, int slot, const double* red) {
+  if (threadIdx.x < kPartial) d.shard_sums[(size_t)slot * kPartial + threadIdx.x] = red[threadIdx.x];
+}
+__global__ void lm_shard_kernel(Dev d, int outer, int after) {
+  const int slot = blockIdx.x;
+  if (!d.out[slot].optimized) return;
+  __shared__ double red[kPartial];
+  __shared__ LmState Ls;
+  if (after) {
+    const LmState& L = d.lm[slot];
+    if (L.done || !L.have_candidate) return;
+  }
+  if (threadIdx.x < kPartial) red[threadIdx.x] = d.shard_sums[(size_t)slot * kPartial + threadIdx.x];
+  __syncthreads();
+  if (after) lm_tail_after(d, slot, outer, red, &Ls);
+  else lm_tail_begin(d, slot, outer, red, &Ls);
+}
+
 // ----------------------------------------------------------------------------
 // K4 = two back-to-back kernels over the same tiles of 128 queries (walked in map-cell
 // order, d.qperm):
@@ -605,6 +655,12 @@ __global__ void __launch_bounds__(kTile, S2M_K4A_MINB) knn_kernel(Dev d, int out
     const float4 p = d.ds_pts[di];
     float w[3];
     xf_point(pose, p.x, p.y, p.z, w);
+    if (d.shard_world > 1 && !(w[0] >= d.shard_lo && w[0] < d.shard_hi)) {
+      // sharded map: this query is answered by the rank whose x-slab holds it
+      d.nbr[6 * (size_t)pos_q] = -1;
+      d.rec_valid[di] = 0;
+      continue;
+    }
     Knn5 r;
     const int visited = knn5_cells(d, cls ? d.B + slot : slot, origin, w[0], w[1], w[2], r, stage);
     if (cls) visited_s += (unsigned long long)visited; else visited_c += (unsigned long long)visited;
@@ -717,21 +773,9 @@ __global__ void __launch_bounds__(kTile, S2M_K4B_MINB) fit_kernel(Dev d, int out
   if (!block_is_last(d.ticket + slot, nwork)) return;
   // ---- last block of this slot: reduce and start the LM solve (row S) ----
   sum_partials(d, slot, nwork, red);
+  if (d.shard_world > 1) { shard_publish(d, slot, red); return; }
   __shared__ LmState Ls;
-  lm_load(&Ls, d.lm + slot);
-  if (threadIdx.x == 0) {
-    Sums28 S;
-    for (int i = 0; i < 28; ++i) S.v[i] = red[i];
-    SlotOut& o = d.out[slot];
-    o.n_edge[outer] = (int)red[28]; o.n_plane[outer] = (int)red[29];
-    if (outer == 0) { o.cand[0] = (double)d.scanned[2 * slot]; o.cand[1] = (double)d.scanned[2 * slot + 1]; }
-    double x0[7];
-    for (int i = 0; i < 7; ++i) x0[i] = Ls.x[i];
-    lm_begin(Ls, x0, S, (int)red[28] + (int)red[29], 4);
-    o.lm_iters[outer] = Ls.iteration; o.lm_term[outer] = Ls.termination;
-    o.cost_initial[outer] = Ls.initial_cost; o.cost_final[outer] = Ls.final_cost;
-  }
-  lm_store(d.lm + slot, &Ls);
+  lm_tail_begin(d, slot, outer, red, &Ls);
 }
 
 // ----------------------------------------------------------------------------
@@ -775,17 +819,9 @@ __global__ void __launch_bounds__(kTile, 4) evaluate_kernel(Dev d, int outer) {
   acc_store(A, d.partials + ((size_t)slot * d.max_tiles + blockIdx.x) * kPartial);
   if (!block_is_last(d.ticket + slot, nwork)) return;
   sum_partials(d, slot, nwork, red);
+  if (d.shard_world > 1) { shard_publish(d, slot, red); return; }
   __shared__ LmState Ls;
-  lm_load(&Ls, d.lm + slot);
-  if (threadIdx.x == 0) {
-    Sums28 S;
-    for (int i = 0; i < 28; ++i) S.v[i] = red[i];
-    lm_after_eval(Ls, S, 4);
-    SlotOut& o = d.out[slot];
-    o.lm_iters[outer] = Ls.iteration; o.lm_term[outer] = Ls.termination;
-    o.cost_final[outer] = Ls.final_cost;
-  }
-  lm_store(d.lm + slot, &Ls);
+  lm_tail_after(d, slot, outer, red, &Ls);
 }
 
 __global__ void guard_kernel(Dev d) {
@@ -794,7 +830,10 @@ __global__ void guard_kernel(Dev d) {
   const FrameDesc& fd = d.desc[s];
   SlotOut& o = d.out[s];
   // laserMapping.cpp:555
-  const int opt = fd.active && fd.allow_opt && o.n_local[0] > 10 && o.n_local[1] > 50;
+  // sharded map: the guard looks at the whole map = sum over ranks of the points each rank owns
+  const int mc = d.shard_world > 1 ? d.shard_counts[s] : o.n_local[0];
+  const int ms = d.shard_world > 1 ? d.shard_counts[d.B + s] : o.n_local[1];
+  const int opt = fd.active && fd.allow_opt && mc > 10 && ms > 50;
   o.optimized = opt;
   for (int k = 0; k < 2; ++k) {
     o.n_edge[k] = o.n_plane[k] = 0; o.lm_iters[k] = 0; o.lm_term[k] = 0;
@@ -850,7 +889,15 @@ __global__ void delta_key_kernel(Dev d, int front, int n_delta, bool identity_po
       else xf_point(d.out[seg_slot(d, g)].pose, p.x, p.y, p.z, w);
       d.dl_pt[di] = make_float4(w[0], w[1], w[2], p.w);
       const int ci = cube_of((double)w[0]), cj = cube_of((double)w[1]), ck = cube_of((double)w[2]);
-      if (fd.active && in_box(ci, cj, ck, fd.win_lo, fd.win_hi)) {  // laserMapping.cpp:753-755
+      bool mine = true;
+      if (d.shard_world > 1) {
+        // membership is decided per VOXEL (all points of a voxel go to the same ranks, so centroids
+        // agree across ranks): keep it if its x-extent touches [lo - 1 m, hi + 1 m]
+        const float leaf = 1.0f / d.inv_leaf[seg_cls(d, g)];
+        const float vx = floorf(xfmul(w[0], d.inv_leaf[seg_cls(d, g)]));
+        mine = (vx + 1.0f) * leaf >= d.shard_lo - 1.01f && vx * leaf <= d.shard_hi + 1.01f;
+      }
+      if (mine && fd.active && in_box(ci, cj, ck, fd.win_lo, fd.win_hi)) {  // laserMapping.cpp:753-755
         if (!cube_in_range(ci, cj, ck)) set_err(d, -4);
         if (in_box(ci, cj, ck, fd.val_lo, fd.val_hi))
           key = delta_key(g, fd, ci, cj, ck, 0, voxel_payload(d, seg_cls(d, g), w[0], w[1], w[2], ci, cj, ck));
@@ -1088,6 +1135,7 @@ int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, cuda
   int k = 0;
   range_kernel<<<d.G, 32, 0, s>>>(d, cur); ++k;
   cudaMemsetAsync(d.hash_tab, 0xFF, sizeof(unsigned long long) * (size_t)hash_total, s);
+  if (d.shard_world > 1) cudaMemsetAsync(d.shard_counts, 0, sizeof(int) * d.G, s);
   if (total_lp > 0) {
     local_key_kernel<<<cdiv(total_lp, 256), 256, 0, s>>>(d, cur, total_lp); ++k;
     size_t tb = d.cub_tmp_bytes;
@@ -1123,6 +1171,10 @@ int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bo
     fit_kernel<false><<<gb, kTile, 0, s>>>(d, outer);
   }
   return 2;
+}
+int launch_lm_shard(const Dev& d, int outer, int after, cudaStream_t s) {
+  lm_shard_kernel<<<d.B, kTile, 0, s>>>(d, outer, after);
+  return 1;
 }
 int launch_count_candidates(const Dev& d, int blocks_per_slot, cudaStream_t s) {
   if (blocks_per_slot <= 0) return 0;
