@@ -110,7 +110,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def result(self):
         if not self.samples:
@@ -213,6 +213,77 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------
+def make_worlds_distributed(n_frames, rank, world):
+    """Each rank ray-casts its share of the N_WORLDS worlds, then all ranks exchange them."""
+    if world == 1:
+        return make_worlds(n_frames, rank, os.cpu_count() or 1)
+    import harness
+    import torch.distributed as dist
+    mine = {}
+    for w in range(rank, N_WORLDS, world):
+        seed = 20261018 + w
+        truth = harness.trajectory(seed, n_frames, 1.0)
+        frames = [harness.features(SENSOR, harness.scan(seed, SENSOR, truth[f], f, 0.02)) for f in range(n_frames)]
+        mine[w] = (seed, truth, frames)
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    merged = {}
+    for p in parts:
+        merged.update(p)
+    return [merged[w] for w in range(N_WORLDS)]
+
+
+class Lane:
+    """One context (S sequences) driven by one host thread on its own CUDA stream."""
+
+    def __init__(self, pkg, torch, worlds, S, variant, n_frames, local_rank, args, host_buffers):
+        self.torch, self.S, self.n_frames = torch, S, n_frames
+        odo = slot_odometry(worlds, S, variant)
+        steps = [pack_step(worlds, S, f) for f in range(n_frames)]
+        self.q_all = np.array([[odo[s][f, :4] for s in range(S)] for f in range(n_frames)])
+        self.t_all = np.array([[odo[s][f, 4:] for s in range(S)] for f in range(n_frames)])
+        self.host = host_buffers
+        if host_buffers:
+            self.steps = [(torch.from_numpy(c).pin_memory(), co, torch.from_numpy(su).pin_memory(), so) for c, co, su, so in steps]
+        else:
+            self.steps = [(torch.from_numpy(c).cuda(), co, torch.from_numpy(su).cuda(), so) for c, co, su, so in steps]
+        self.h2d = float(np.mean([c.nbytes + su.nbytes for c, _, su, _ in steps[PREFILL + args.warmup:]]))
+        max_c = max(int(np.diff(st[1]).max()) for st in steps)
+        max_s = max(int(np.diff(st[3]).max()) for st in steps)
+        self.stream = torch.cuda.Stream()  # a real stream: the library launches on it, the events time it
+        self.R = pkg.Registrar(LINE_RES, PLANE_RES, device=local_rank, batch=S, cap_corner_in=max_c + 64,
+                               cap_surf_in=max_s + 64, cap_map_corner=args.cap_map_corner, cap_map_surf=args.cap_map_surf)
+        self.R.set_stream(self.stream.cuda_stream)
+        self.events = None
+
+    def step(self, f):
+        c, co, su, so = self.steps[f]
+        if self.host:  # the reference-facing call with HOST buffers: H2D + D2H inside
+            return self.R.register_batch_ptr(c.data_ptr(), co, su.data_ptr(), so, self.q_all[f], self.t_all[f], False)
+        return self.R.register_batch_ptr(c.data_ptr(), co, su.data_ptr(), so, self.q_all[f], self.t_all[f], True)
+
+    def run(self, f0, f1, timed):
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            for f in range(f0, f1):
+                self.step(f)
+            e1.record(self.stream)
+        if timed:
+            self.events = (e0, e1)
+
+    def close(self):
+        self.R.close()
+        self.steps = None
+
+
+def run_lanes(lanes, f0, f1, timed):
+    th = [threading.Thread(target=l.run, args=(f0, f1, timed)) for l in lanes]
+    [t.start() for t in th]
+    [t.join() for t in th]
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -223,149 +294,101 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    S = args.seqs
+    S, C = args.seqs, args.ctx
     n_frames = PREFILL + args.warmup + args.steps
-    cores = os.cpu_count() or 1
     t_gen = time.perf_counter()
-    worlds = make_worlds(n_frames, rank, max(1, cores // world))
-    odo = slot_odometry(worlds, S, rank)
+    worlds = make_worlds_distributed(n_frames, rank, world)
     t_gen = time.perf_counter() - t_gen
-    steps = [pack_step(worlds, S, f) for f in range(n_frames)]
-    q_all = np.array([[odo[s][f, :4] for s in range(S)] for f in range(n_frames)])
-    t_all = np.array([[odo[s][f, 4:] for s in range(S)] for f in range(n_frames)])
-    max_c = max(int(np.diff(st[1]).max()) for st in steps)
-    max_s = max(int(np.diff(st[3]).max()) for st in steps)
-    stream = torch.cuda.Stream()  # a real (non-default) stream: the library launches on it, the events time it
-    torch.cuda.set_stream(stream)
-
-    def make_ctx():
-        R = pkg.Registrar(LINE_RES, PLANE_RES, device=local_rank, batch=S, cap_corner_in=max_c + 64,
-                          cap_surf_in=max_s + 64, cap_map_corner=args.cap_map_corner, cap_map_surf=args.cap_map_surf)
-        R.set_stream(stream.cuda_stream)
-        return R
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
-    def timed_loop(R, call, sampler=None):
-        for f in range(PREFILL + args.warmup):
-            call(R, f)
+    def timed_arm(host_buffers, sampler=None):
+        lanes = [Lane(pkg, torch, worlds, S, rank * C + c, n_frames, local_rank, args, host_buffers) for c in range(C)]
+        run_lanes(lanes, 0, PREFILL + args.warmup, False)  # untimed: map prefill + warm-up steps
         barrier()
         if sampler:
             sampler.start()
-        evs = []
-        l0 = R.launch_count()
+        l0 = sum(l.R.launch_count() for l in lanes)
         wall0 = time.perf_counter()
-        for f in range(PREFILL + args.warmup, n_frames):
-            flush.fill_(f & 0xFF)  # evict L2 between steps (untimed)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            call(R, f)
-            e1.record(stream)
-            evs.append((e0, e1))
+        run_lanes(lanes, PREFILL + args.warmup, n_frames, True)
         barrier()
         wall = time.perf_counter() - wall0
         if sampler:
             sampler.stop_flag = True
-        ms = sum(a.elapsed_time(b) for a, b in evs)
+        ms = max(a.elapsed_time(b) for a, b in (l.events for l in lanes))  # lanes run concurrently
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, R.launch_count() - l0, wall
+        launches = sum(l.R.launch_count() for l in lanes) - l0
+        h2d = sum(l.h2d for l in lanes)
+        stats = [lanes[0].R.batch_stats[s] for s in range(S)]
+        shape = {k: float(np.mean([getattr(st, k) for st in stats])) for k in
+                 ("n_corner_in", "n_surf_in", "n_corner_ds", "n_surf_ds", "n_map_corner", "n_map_surf")}
+        shape["n_edge"] = float(np.mean([st.n_edge[1] for st in stats]))
+        shape["n_plane"] = float(np.mean([st.n_plane[1] for st in stats]))
+        for l in lanes:
+            l.close()
+        torch.cuda.empty_cache()
+        return ms, launches, wall, h2d, shape
 
-    # ---- arm 1: inputs resident in HBM -------------------------------------------------------
-    dev_steps = [(torch.from_numpy(c).cuda(), co, torch.from_numpy(s).cuda(), so) for c, co, s, so in steps]
-
-    def call_dev(R, f):
-        c, co, s, so = dev_steps[f]
-        return R.register_batch(c.data_ptr(), co, s.data_ptr(), so, q_all[f], t_all[f], device_ptrs=True)
-
-    R = make_ctx()
     sampler = ClockSampler(local_rank)
-    R.set_profiling(False)
-    # profile K4 only inside the timed steps: enable after warm-up via a wrapper
-    state = {"armed": False}
+    ms_dev, launches, wall_dev, _, shape = timed_arm(False, sampler)      # arm 1: inputs resident in HBM
+    ms_e2e, _, wall_e2e, h2d, _ = timed_arm(True)                         # arm 2: pinned host buffers, end to end
 
-    def call_dev_prof(R, f):
-        if f == PREFILL + args.warmup and not state["armed"]:
-            R.set_profiling(True)
-            R.k4_profile(reset=True)
-            state["armed"] = True
-        return call_dev(R, f)
-
-    ms_dev, launches, wall_dev = timed_loop(R, call_dev_prof, sampler)
-    k4_ms, k4_n, k4_bytes = R.k4_profile(reset=False)
-    phases = R.phase_profile(reset=True)
-    stats = [R.batch_stats[s] for s in range(S)]
-    shape = {"Nc_in": float(np.mean([st.n_corner_in for st in stats])), "Ns_in": float(np.mean([st.n_surf_in for st in stats])),
-             "Nc": float(np.mean([st.n_corner_ds for st in stats])), "Ns": float(np.mean([st.n_surf_ds for st in stats])),
-             "Mc": float(np.mean([st.n_map_corner for st in stats])), "Ms": float(np.mean([st.n_map_surf for st in stats])),
-             "n_edge": float(np.mean([st.n_edge[1] for st in stats])), "n_plane": float(np.mean([st.n_plane[1] for st in stats]))}
-    R.close()
-    del dev_steps
-    torch.cuda.empty_cache()
-
-    # ---- arm 2: end to end from pinned host buffers ----------------------------------------------
-    pin_steps = []
-    for c, co, s, so in steps:
-        pc, ps = torch.from_numpy(c).pin_memory(), torch.from_numpy(s).pin_memory()
-        pin_steps.append((pc, co, ps, so))
-
-    def call_host(R, f):
-        pc, co, ps, so = pin_steps[f]
-        fn = R.L.s2m_register_batch
-        B = R.batch
-        qo, to = np.zeros((B, 4)), np.zeros((B, 3))
-        q, t = np.ascontiguousarray(q_all[f]), np.ascontiguousarray(t_all[f])
-        rc = fn(R.h, pc.data_ptr(), co.ctypes.data, ps.data_ptr(), so.ctypes.data, q.ctypes.data, t.ctypes.data,
-                None, qo.ctypes.data, to.ctypes.data, ctypes.cast(R._bstats, ctypes.c_void_p), R._status.ctypes.data)
-        R._check(rc)
-        return qo, to
-
-    R2 = make_ctx()
-    ms_e2e, _, wall_e2e = timed_loop(R2, call_host)
-    R2.close()
-    h2d = float(np.mean([steps[f][0].nbytes + steps[f][2].nbytes for f in range(PREFILL + args.warmup, n_frames)]))
-    h2d += 64 * 128  # per-step descriptor block (poses, windows, offsets) -- order of magnitude
-    d2h = float(S * 168 + 4)  # poses + per-slot counters + error flag read back every step
+    # arm 3 (untimed for the headline): one context with profiling on -> K4 roofline and phase split
+    prof_steps = min(args.steps, 6)
+    lane = Lane(pkg, torch, worlds, S, rank * C, PREFILL + args.warmup + prof_steps, local_rank, args, False)
+    lane.run(0, PREFILL + args.warmup, False)
+    torch.cuda.synchronize()
+    lane.R.set_profiling(True)
+    lane.R.k4_profile(reset=True)
+    lane.run(PREFILL + args.warmup, PREFILL + args.warmup + prof_steps, False)
+    k4_ms, k4_n, k4_bytes = lane.R.k4_profile(reset=False)
+    phases = lane.R.phase_profile(reset=True)
+    lane.close()
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return 0
-    regs = world * S * args.steps
+    regs = world * C * S * args.steps
     value = regs / (ms_dev * 1e-3)
     e2e_value = regs / (ms_e2e * 1e-3)
     peak, peak_src = measured_peak()
     ach = (k4_bytes / max(k4_n, 1)) / (1e-3 * k4_ms / max(k4_n, 1)) / 1e9 if k4_ms > 0 else 0.0
     traffic = k4_traffic()
+    d2h = float(C * (S * 168 + 4))  # poses + per-slot counters + error flag read back every step
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "hdl64_batch_replay", "sensor": "HDL-64 synthetic 64x1900 (121600 rays/sweep)",
-                   "line_res": LINE_RES, "plane_res": PLANE_RES, "sequences_per_gpu": S, "distinct_worlds": N_WORLDS,
-                   "prefill_frames": PREFILL, "registrations_per_step": world * S, "parallelism": "replicas-of-sequences x%d" % world,
-                   "l2": "flushed between steps (256 MiB write outside the per-step event pairs)",
-                   "timing": "CUDA events per step on the launching stream, summed; max over ranks",
+                   "line_res": LINE_RES, "plane_res": PLANE_RES, "sequences_per_gpu": C * S, "contexts_per_gpu": C,
+                   "sequences_per_context": S, "distinct_worlds": N_WORLDS, "prefill_frames": PREFILL,
+                   "registrations_per_step": world * C * S, "parallelism": "independent sequences x%d GPUs, no collective" % world,
+                   "l2": "no flush: each step touches >300 MB per context (maps, sort buffers, clouds), larger than the 126 MB L2",
+                   "timing": "CUDA events around the K steps on each context's stream (contexts run concurrently); max over contexts and ranks",
                    "per_registration_mean": shape, "datagen_s": round(t_gen, 1),
-                   "phase_ms_per_step": {k: round(v / args.steps, 4) for k, v in phases.items()},
+                   "phase_ms_per_step_single_context": {k: round(v / prof_steps, 4) for k, v in phases.items()},
                    "host_wall_ms_per_step": round(1e3 * wall_dev / args.steps, 3)},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d + C * 64 * 128, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "associate_kernel (K4: transform+kNN5+PCA/QR+residual/J+Huber+reduce)",
+        "roofline": {"bound": "hbm", "kernel": "association = knn_kernel + fit_kernel (transform + exact kNN5 + edge PCA / plane QR + residual/J + Huber + reduce)",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                      "bytes_per_launch_algorithmic": k4_bytes / max(k4_n, 1), "launches": int(k4_n),
-                     "avg_launch_us": 1e3 * k4_ms / max(k4_n, 1),
+                     "avg_launch_us": 1e3 * k4_ms / max(k4_n, 1), "slots_per_launch": S,
+                     "measured": "CUDA events on the launching stream, single context, profiling pass",
                      "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
                      "traffic_source": traffic.get("source") if traffic else None},
         "clocks": sampler.result(),
     }
     if world == 1 and not args.no_cpu_baseline:
+        odo = slot_odometry(worlds, N_WORLDS, 0)
         line["cpu_baseline"] = cpu_baseline(worlds, odo, n_frames)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -376,10 +399,11 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seqs", type=int, default=64, help="independent sequences per GPU (<=64)")
+    ap.add_argument("--seqs", type=int, default=64, help="independent sequences per context (<=64)")
+    ap.add_argument("--ctx", type=int, default=3, help="contexts per GPU, each on its own stream / host thread")
     ap.add_argument("--cap-map-corner", type=int, default=1 << 17)
     ap.add_argument("--cap-map-surf", type=int, default=1 << 17)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -200,6 +200,19 @@ class Registrar:
         self._check(rc)
         return self._status.copy(), qo, to
 
+    def register_batch_ptr(self, corner_ptr, corner_off, surf_ptr, surf_off, q_wodom, t_wodom, device):
+        """Raw-pointer variant (ints): host pointers -> s2m_register_batch, device pointers -> _dev."""
+        B = self.batch
+        co, so = np.ascontiguousarray(corner_off, np.int32), np.ascontiguousarray(surf_off, np.int32)
+        q, t = _f64(q_wodom).reshape(B, 4), _f64(t_wodom).reshape(B, 3)
+        qo, to = np.zeros((B, 4)), np.zeros((B, 3))
+        fn = self.L.s2m_register_batch_dev if device else self.L.s2m_register_batch
+        rc = fn(self.h, ctypes.c_void_p(int(corner_ptr)), co.ctypes.data, ctypes.c_void_p(int(surf_ptr)), so.ctypes.data,
+                q.ctypes.data, t.ctypes.data, None, qo.ctypes.data, to.ctypes.data,
+                ctypes.cast(self._bstats, ctypes.c_void_p), self._status.ctypes.data)
+        self._check(rc)
+        return self._status, qo, to
+
     @property
     def batch_stats(self):
         return self._bstats
