@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 METRIC = "scan_to_map_registrations_per_s"
 UNIT = "registrations/s"
 N_WORLDS = 8          # distinct synthetic worlds/trajectories (BASELINE config 4: 8 sequences)
-PREFILL = 20          # untimed frames that build each sequence's map before warm-up
+PREFILL = int(os.environ.get("S2M_BENCH_PREFILL", 20))  # untimed frames that build each sequence's map before warm-up
 SENSOR = "HDL64"
 LINE_RES, PLANE_RES = 0.4, 0.8  # aloam_velodyne_HDL_64.launch:11-12
 
@@ -46,16 +46,17 @@ def env_int(name, default):
 def make_worlds(n_frames, rank, threads):
     """N_WORLDS replayable HDL-64 sequences: truth poses + per-frame (corner, surf) clouds."""
     import harness
-    worlds = []
-    for w in range(N_WORLDS):
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(w):
         seed = 20261018 + w
         truth = harness.trajectory(seed, n_frames, 1.0)
-        frames = []
-        for f in range(n_frames):
-            xyz = harness.scan(seed, SENSOR, truth[f], f, 0.02)
-            frames.append(harness.features(SENSOR, xyz))
-        worlds.append((seed, truth, frames))
-    return worlds
+        frames = [harness.features(SENSOR, harness.scan(seed, SENSOR, truth[f], f, 0.02)) for f in range(n_frames)]
+        return (seed, truth, frames)
+
+    harness.lib()
+    with ThreadPoolExecutor(max_workers=min(N_WORLDS, max(1, threads))) as ex:  # ctypes releases the GIL
+        return list(ex.map(one, range(N_WORLDS)))
 
 
 def slot_odometry(worlds, n_slots, rank):

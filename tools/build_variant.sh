@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: tools_build_variant.sh <name> <extra nvcc flags...>  -> sc-a-loam_b200/csrc/variants/libs2m_<name>.so
 set -e
-cd "$(dirname "$0")/sc-a-loam_b200/csrc"
+cd "$(dirname "$0")/../sc-a-loam_b200/csrc"
 name=$1; shift
 mkdir -p variants
 F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-O3"

@@ -1,7 +1,7 @@
 """Experiment: C contexts x S sequences on one GPU, driven by C host threads on C streams."""
 import sys, os, time, threading
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from __graft_entry__ import load_package
 pkg = load_package()
