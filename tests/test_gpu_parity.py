@@ -28,6 +28,16 @@ def seq_vlp(built):
     return harness.sequence(7, "VLP16", 10, step_m=0.5)
 
 
+@pytest.fixture(scope="module")
+def seq_os1(built):
+    return harness.sequence(13, "OS1-64", 8)
+
+
+def pick(sensor, seq_hdl, seq_vlp, seq_os1):
+    # launch-file parameters: HDL-64 0.4/0.8, VLP-16 0.2/0.4, OS1-64 (MulRan) 0.4/0.8
+    return {"hdl": (seq_hdl, 0.4, 0.8), "vlp": (seq_vlp, 0.2, 0.4), "os1": (seq_os1, 0.4, 0.8)}[sensor]
+
+
 def run_oracle(seq, n, line, plane, **kw):
     truth, odom, frames = seq
     O = oracle.Oracle(line, plane, **kw)
@@ -63,10 +73,10 @@ def test_first_frame_takes_guard_path(s2m, seq_hdl):
     assert rc == 0 and R.stats.optimized == 1
 
 
-@pytest.mark.parametrize("sensor", ["hdl", "vlp"])
-def test_map_evolution_bit_exact_without_optimisation(s2m, seq_hdl, seq_vlp, sensor):
+@pytest.mark.parametrize("sensor", ["hdl", "vlp", "os1"])
+def test_map_evolution_bit_exact_without_optimisation(s2m, seq_hdl, seq_vlp, seq_os1, sensor):
     """Rows B, C, V, I, W with pose = guess on both sides: maps stay bit-identical frame after frame."""
-    seq, line, plane = (seq_hdl, 0.4, 0.8) if sensor == "hdl" else (seq_vlp, 0.2, 0.4)
+    seq, line, plane = pick(sensor, seq_hdl, seq_vlp, seq_os1)
     truth, odom, frames = seq
     R = s2m.Registrar(line, plane, skip_optimization=True)
     O = oracle.Oracle(line, plane, skip_optimization=True)
@@ -150,10 +160,10 @@ def test_registration_matches_oracle_on_uploaded_map(s2m, seq_hdl):
     assert np.linalg.norm(tg - to) < 1e-8  # what we actually observe
 
 
-@pytest.mark.parametrize("sensor", ["hdl", "vlp"])
-def test_stream_poses_within_tolerance(s2m, seq_hdl, seq_vlp, sensor):
+@pytest.mark.parametrize("sensor", ["hdl", "vlp", "os1"])
+def test_stream_poses_within_tolerance(s2m, seq_hdl, seq_vlp, seq_os1, sensor):
     """N-frame replay, each side on its own map: per-scan poses agree within the north_star tolerance."""
-    seq, line, plane = (seq_hdl, 0.4, 0.8) if sensor == "hdl" else (seq_vlp, 0.2, 0.4)
+    seq, line, plane = pick(sensor, seq_hdl, seq_vlp, seq_os1)
     truth, odom, frames = seq
     n = len(frames)
     O, poses_o = run_oracle(seq, n, line, plane)
@@ -168,6 +178,41 @@ def test_stream_poses_within_tolerance(s2m, seq_hdl, seq_vlp, sensor):
         assert np.linalg.norm(t - truth[n - 1, 4:]) < np.linalg.norm(odom[n - 1, 4:] - truth[n - 1, 4:])
     qc, tc = R.correction()
     assert abs(np.linalg.norm(qc) - 1) < 1e-9
+
+
+def test_perturbed_initial_guesses_against_a_mature_map(s2m, built):
+    """SURVEY 8d "T_init distribution": truth o perturbation (U(-0.2,0.2) m, U(-1,1) deg per axis, and a
+    second set at 0.5 m / 3 deg) against a map built from 40 frames at the true poses. Both sides start
+    from the same uploaded map; poses must agree within tolerance for every draw."""
+    from conftest import quat_mul
+    truth, odom, frames = harness.sequence(20261018, "HDL64", 44)
+    B = oracle.Oracle(0.4, 0.8, skip_optimization=True)
+    for f in range(40):
+        B.register(frames[f][0], frames[f][1], truth[f, :4], truth[f, 4:])
+    cm, sm = B.get_map(0), B.get_map(1)
+    assert len(cm) + len(sm) > 40000
+    rng = np.random.default_rng(20261018)
+    worst_t = worst_r = 0.0
+    for trial, (dt, dr) in enumerate([(0.2, 1.0)] * 4 + [(0.5, 3.0)] * 2):
+        f = 40 + trial % 4
+        rv = np.deg2rad(rng.uniform(-dr, dr, 3))
+        a = np.linalg.norm(rv)
+        dq = np.r_[np.sin(a / 2) * rv / a, np.cos(a / 2)]
+        q0 = quat_mul(truth[f, :4], dq)
+        t0 = truth[f, 4:] + rng.uniform(-dt, dt, 3)
+        R = s2m.Registrar(0.4, 0.8)
+        O = oracle.Oracle(0.4, 0.8)
+        R.map_upload(cm, sm)
+        O.map_upload(cm, sm)
+        rg, qg, tg = R.register(frames[f][0], frames[f][1], q0, t0)
+        ro, qo, to = O.register(frames[f][0], frames[f][1], q0, t0)
+        assert rg == ro == 0
+        assert list(R.stats.n_edge) == list(O.stats.n_edge) and list(R.stats.n_plane) == list(O.stats.n_plane)
+        worst_t = max(worst_t, float(np.linalg.norm(tg - to)))
+        worst_r = max(worst_r, rot_angle(qg, qo))
+        # the registration pulled the perturbed guess towards the truth
+        assert np.linalg.norm(tg - truth[f, 4:]) < 0.5 * np.linalg.norm(t0 - truth[f, 4:]) + 0.05
+    assert worst_t < TOL_T and worst_r < TOL_R, (worst_t, worst_r)
 
 
 def test_batch_slots_are_independent_and_identical_to_single(s2m, seq_hdl, seq_vlp):
