@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -210,6 +211,7 @@ static int create_impl(s2m_ctx* ctx) {
   std::memset(&d, 0, sizeof(d));
   const int B = P.batch, G = 2 * B;
   d.B = B; d.G = G;
+  d.use_qperm = getenv("S2M_QUERY_ORDER") ? atoi(getenv("S2M_QUERY_ORDER")) : 0;
   d.shard_world = P.shard_world;
   d.shard_lo = -INFINITY; d.shard_hi = INFINITY;
   if (P.shard_world > 1) {
@@ -466,14 +468,15 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
     const int nq = (ctx->h_dsoff[b + 1] - ctx->h_dsoff[b]) + (ctx->h_dsoff[B + b + 1] - ctx->h_dsoff[B + b]);
     tiles = std::max(tiles, (nq + kTile - 1) / kTile);
   }
-  k += launch_query_order(d, n_ds, s);
+  if (d.use_qperm) k += launch_query_order(d, n_ds, s);
   prof_mark(ctx, S2M_PHASE_INDEX);
   // one resident wave each: S2M_K4x_MINB blocks per SM shared by the B slots
   const int knn_blocks = std::max(1, std::min(tiles, (S2M_K4A_MINB * ctx->sm_count) / B));
   const int fit_blocks = std::max(1, std::min(tiles, (S2M_K4B_MINB * ctx->sm_count) / B));
   const int blocks = knn_blocks;
   // the evaluation kernel is a light streaming pass: about four records per thread
-  const int eval_blocks = std::max(1, std::min((tiles + 3) / 4, d.max_tiles));
+  const int eval_div = getenv("S2M_EVAL_DIV") ? atoi(getenv("S2M_EVAL_DIV")) : 8;
+  const int eval_blocks = std::max(1, std::min((tiles + eval_div - 1) / eval_div, d.max_tiles));
   for (int outer = 0; outer < 2; ++outer) {  // laserMapping.cpp:563
     if (ctx->profiling && outer == 0) {  // C-bar of the byte formula, outside the K4 event bracket
       launch_count_candidates(d, blocks, s);

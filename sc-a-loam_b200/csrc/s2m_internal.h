@@ -91,6 +91,7 @@ struct SlotOut {            // per slot, read back by the host after every call
 // All device pointers of one context (sizes are host-known capacities).
 struct Dev {
   int B, G;                     // slots, segments
+  int use_qperm;                // walk the queries in map-cell order (d.qperm) instead of scan order
   int shard_world;              // >1: spatially sharded map (x-slabs per rank)
   float shard_lo, shard_hi;     // this rank's slab in world x, [lo, hi)
   double* shard_sums;           // [B][kPartial] per-rank sums awaiting the allreduce

@@ -66,7 +66,7 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
 // bbox[g][0..2] = min (init 0xFFFFFFFF), bbox[g][3..5] = max (init 0), ordered-uint encoded
 __global__ void vox_bbox_kernel(Dev d, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int g = -1;
   uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
   if (i < n) {
@@ -74,19 +74,29 @@ __global__ void vox_bbox_kernel(Dev d, int n) {
     const float4 p = d.in_pts[i];
     mn[0] = mx[0] = f2ord(p.x); mn[1] = mx[1] = f2ord(p.y); mn[2] = mx[2] = f2ord(p.z);
   }
-  // warp-aggregate when the whole warp lies in one segment (the common case)
-  const int g0 = __shfl_sync(0xffffffffu, g, 0);
-  if (__all_sync(0xffffffffu, g == g0)) {
-    if (g0 < 0) return;
+  // segment of the first and of the last point of the block: equal => one reduction per block
+  __shared__ int gs[2];
+  __shared__ uint32_t sm[6][8];
+  if (threadIdx.x == 0) gs[0] = g;
+  const int last = min(n - 1 - (int)(blockIdx.x * blockDim.x), (int)blockDim.x - 1);
+  if ((int)threadIdx.x == last) gs[1] = g;
+  __syncthreads();
+  if (gs[0] == gs[1]) {
 #pragma unroll
     for (int k = 0; k < 3; ++k)
       for (int o = 16; o > 0; o >>= 1) {
         mn[k] = min(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
         mx[k] = max(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
       }
-    if (lane < 3) atomicMin(d.bbox + 6 * g0 + lane, mn[lane]);
-    else if (lane < 6) atomicMax(d.bbox + 6 * g0 + lane, mx[lane - 3]);
-  } else if (g >= 0) {
+    if (lane == 0) for (int k = 0; k < 3; ++k) { sm[k][wid] = mn[k]; sm[3 + k][wid] = mx[k]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      uint32_t v = sm[threadIdx.x][0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = threadIdx.x < 3 ? min(v, sm[threadIdx.x][w]) : max(v, sm[threadIdx.x][w]);
+      if (threadIdx.x < 3) atomicMin(d.bbox + 6 * gs[0] + threadIdx.x, v);
+      else atomicMax(d.bbox + 6 * gs[0] + threadIdx.x, v);
+    }
+  } else if (g >= 0) {  // block straddles a segment boundary (at most G of them)
 #pragma unroll
     for (int k = 0; k < 3; ++k) { atomicMin(d.bbox + 6 * g + k, mn[k]); atomicMax(d.bbox + 6 * g + 3 + k, mx[k]); }
   }
@@ -651,7 +661,7 @@ __global__ void __launch_bounds__(kTile, S2M_K4A_MINB) knn_kernel(Dev d, int out
     if (q >= nq) continue;
     const int cls = q >= nc;
     const int pos_q = cls ? ds0 + (q - nc) : dc0 + q;  // position in the packed, cell-ordered query list
-    const int di = (int)d.qperm[pos_q];
+    const int di = d.use_qperm ? (int)d.qperm[pos_q] : pos_q;
     const float4 p = d.ds_pts[di];
     float w[3];
     xf_point(pose, p.x, p.y, p.z, w);

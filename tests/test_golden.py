@@ -58,7 +58,7 @@ def test_cuda_knn_matches_reference_nanoflann_vectors(s2m, built):
     assert len(local) == len(mp)
     idx, d2 = R.debug_knn(1, centre, g["q_xyz"])
     gate = g["d2"][:, 4] < 1.0
-    assert gate.sum() > 1000 and np.array_equal(gate, d2[:, 4] < 1.0)
+    assert gate.sum() > 500 and np.array_equal(gate, d2[:, 4] < 1.0)
     assert np.array_equal(bits(d2[gate]), bits(g["d2"][gate]))
     # same neighbours; where float distances tie, the order inside the tie may differ from nanoflann's visit order
     got = np.sort(to_upload[idx[gate]], axis=1)
