@@ -257,8 +257,8 @@ static int create_impl(s2m_ctx* ctx) {
   rc |= dev_alloc(ctx, &d.nbr, (size_t)d.cap_in * 6); rc |= dev_alloc(ctx, &d.scanned, 2 * B);
   // cell tables: per segment a power of two >= 2 x entries, >= 1024
   long long hcap = 0;
-  for (int g = 0; g < G; ++g) hcap += next_pow2(std::max(1024, 2 * (g < B ? P.cap_map_corner : P.cap_map_surf)));
-  if (hcap >= (1ll << 31)) { ctx->err = "cell tables too large"; return S2M_ERR_ARG; }
+  for (int g = 0; g < G; ++g) hcap += next_pow2(std::max(1024, 4 * (g < B ? P.cap_map_corner : P.cap_map_surf)));
+  if (hcap >= (1ll << 31)) { ctx->err = "cell tables too large (4 entries per map point)"; return S2M_ERR_ARG; }
   ctx->hash_cap_total = (int)hcap;
   rc |= dev_alloc(ctx, &d.hash_tab, (size_t)hcap); rc |= dev_alloc(ctx, &d.hash_aux, (size_t)hcap);
   rc |= dev_alloc(ctx, &d.cs_off, G + 1);
@@ -394,7 +394,7 @@ static void fill_store_tables(s2m_ctx* ctx, int* total_lp, int* hash_total) {
   for (int g = 0; g < G; ++g) {
     const int n = ctx->slots[g < B ? g : g - B].n_store[g >= B];
     T.lp_off[g] = acc; acc += n;
-    T.hash_off[g] = hacc; hacc += next_pow2(std::max(1024, 2 * n));
+    T.hash_off[g] = hacc; hacc += next_pow2(std::max(1024, 4 * n));  // <= 3 entries per point: cells + virtual x-neighbours
   }
   T.lp_off[G] = acc; T.hash_off[G] = hacc;
   *total_lp = acc; *hash_total = hacc;
@@ -472,11 +472,9 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   prof_mark(ctx, S2M_PHASE_INDEX);
   // one resident wave each: S2M_K4x_MINB blocks per SM shared by the B slots
   const int knn_blocks = std::max(1, std::min(tiles, (S2M_K4A_MINB * ctx->sm_count) / B));
-  const int fit_blocks = std::max(1, std::min(tiles, (S2M_K4B_MINB * ctx->sm_count) / B));
+  const int fit_blocks = std::max(1, (tiles + kFitTilesPerBlock - 1) / kFitTilesPerBlock);
   const int blocks = knn_blocks;
-  // the evaluation kernel is a light streaming pass: about four records per thread
-  const int eval_div = getenv("S2M_EVAL_DIV") ? atoi(getenv("S2M_EVAL_DIV")) : 8;
-  const int eval_blocks = std::max(1, std::min((tiles + eval_div - 1) / eval_div, d.max_tiles));
+  const int eval_blocks = std::max(1, (tiles + kEvalTilesPerBlock - 1) / kEvalTilesPerBlock);
   for (int outer = 0; outer < 2; ++outer) {  // laserMapping.cpp:563
     if (ctx->profiling && outer == 0) {  // C-bar of the byte formula, outside the K4 event bracket
       launch_count_candidates(d, blocks, s);

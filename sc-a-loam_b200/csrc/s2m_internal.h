@@ -33,6 +33,8 @@ namespace s2m {
 #ifndef S2M_K4B_MINB
 #define S2M_K4B_MINB 4  // ... and the fit / residual kernel
 #endif
+constexpr int kFitTilesPerBlock = 2;   // tiles one fit_kernel block sums (fixed: keeps sums independent of the batch)
+constexpr int kEvalTilesPerBlock = 8;  // ... one evaluate_kernel block
 constexpr int kTile = 128;       // queries per block of the association / evaluation kernels
 constexpr int kPartial = 32;     // doubles per block partial: 28 sums, n_edge, n_plane, cand_corner, cand_surf
 constexpr int kCols = 25;        // (i,j) columns of the valid block

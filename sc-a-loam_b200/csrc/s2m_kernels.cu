@@ -232,12 +232,27 @@ __global__ void cs_off_kernel(Dev d, int total_lp) {
   d.cs_off[g] = lower_bound_u32(d.ckey2, total_lp, (uint32_t)g << 24);
 }
 
-// Cell table entry: [cell key:24][count3:10][start3:30].  (start3, count3) is the
-// contiguous run of d.cand holding the cell AND its two x-neighbours of the same
-// (y,z) row -- cell keys sort x-fastest, so one probe at the centre cell of a row
-// yields all three cells.  hash_aux[slot] = (points of the cell itself, exact
-// count3); read when count3 saturates (1023) or when the centre cell of a row is
-// empty and the two side cells are probed on their own.
+// Cell table entry: [cell key:24][count:10][start:30].  (start, count) is the contiguous
+// run of d.cand holding the cell AND its two x-neighbours of the same (y,z) row -- cell keys
+// sort x-fastest, so one probe at the centre cell of a row yields all three cells.  An EMPTY
+// cell with an occupied x-neighbour gets a "virtual" entry whose run is its neighbour(s)
+// (contiguous too, nothing lies between them), so a row is always exactly one probe.
+// hash_aux[slot] = (points of the cell itself, exact run length); read when the 10-bit count
+// saturates (1023) and by the profiling counter.
+__device__ __forceinline__ void cell_insert(const Dev& d, int g, uint32_t k24, int start, uint32_t count, uint32_t own) {
+  const unsigned long long entry = ((unsigned long long)k24 << 40) |
+                                   ((unsigned long long)(count < 1023u ? count : 1023u) << 30) |
+                                   (unsigned long long)start;
+  const int base = d.hash_off[g];
+  const uint32_t mask = (uint32_t)(d.hash_off[g + 1] - base) - 1u;
+  uint32_t s = cell_hash(k24) & mask;
+  for (;;) {
+    unsigned long long old = atomicCAS(d.hash_tab + base + s, kSentinel64, entry);
+    if (old == kSentinel64) break;
+    s = (s + 1) & mask;
+  }
+  d.hash_aux[base + s] = make_uint2(own, count);
+}
 __global__ void cand_build_kernel(Dev d, int cur, int total_lp) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total_lp) return;
@@ -249,33 +264,34 @@ __global__ void cand_build_kernel(Dev d, int cur, int total_lp) {
   d.cand[p] = make_float4(q.x, q.y, q.z, __int_as_float(l));
   d.inv[d.lp_off[g] + l] = p;  // local index -> position in d.cand
   if (p == 0 || d.ckey2[p - 1] != key) {
-    int e = p + 1;
-    while (e < total_lp && d.ckey2[e] == key) ++e;
+    // run of a key starting at position a (a < total_lp): its end
+    auto run_end = [&](int a) {
+      const uint32_t k = d.ckey2[a];
+      int e = a + 1;
+      while (e < total_lp && d.ckey2[e] == k) ++e;
+      return e;
+    };
+    const int e = run_end(p);
     const uint32_t own = (uint32_t)(e - p);
     const uint32_t rx = key & 255u;
-    int s3 = p, e3 = e;
-    if (rx > 0u && p > 0 && d.ckey2[p - 1] == key - 1u) {
-      s3 = p - 1;
-      while (s3 > 0 && d.ckey2[s3 - 1] == key - 1u) --s3;
-    }
-    if (rx < 255u && e < total_lp && d.ckey2[e] == key + 1u) {
-      e3 = e + 1;
-      while (e3 < total_lp && d.ckey2[e3] == key + 1u) ++e3;
-    }
-    const uint32_t count3 = (uint32_t)(e3 - s3);
     const uint32_t k24 = key & 0xFFFFFFu;
-    const unsigned long long entry = ((unsigned long long)k24 << 40) |
-                                     ((unsigned long long)(count3 < 1023u ? count3 : 1023u) << 30) |
-                                     (unsigned long long)s3;
-    const int base = d.hash_off[g];
-    const uint32_t mask = (uint32_t)(d.hash_off[g + 1] - base) - 1u;
-    uint32_t s = cell_hash(k24) & mask;
-    for (;;) {
-      unsigned long long old = atomicCAS(d.hash_tab + base + s, kSentinel64, entry);
-      if (old == kSentinel64) break;
-      s = (s + 1) & mask;
+    const bool has_l1 = rx > 0u && p > 0 && d.ckey2[p - 1] == key - 1u;
+    const bool has_r1 = rx < 255u && e < total_lp && d.ckey2[e] == key + 1u;
+    int s3 = p, e3 = e;
+    if (has_l1) { s3 = p - 1; while (s3 > 0 && d.ckey2[s3 - 1] == key - 1u) --s3; }
+    if (has_r1) e3 = run_end(e);
+    cell_insert(d, g, k24, s3, (uint32_t)(e3 - s3), own);
+    // virtual entry for the empty right neighbour: this cell + the cell two to the right
+    if (!has_r1 && rx < 255u) {
+      int ev = e;
+      if (rx < 254u && e < total_lp && d.ckey2[e] == key + 2u) ev = run_end(e);
+      cell_insert(d, g, k24 + 1u, p, (uint32_t)(ev - p), 0u);
     }
-    d.hash_aux[base + s] = make_uint2(own, count3);
+    // virtual entry for the empty left neighbour, unless the cell two to the left makes it (as ITS right neighbour)
+    if (!has_l1 && rx > 0u) {
+      const bool has_l2 = rx > 1u && p > 0 && d.ckey2[p - 1] == key - 2u;
+      if (!has_l2) cell_insert(d, g, k24 - 1u, p, own, 0u);
+    }
   }
 }
 
@@ -329,8 +345,7 @@ __device__ __forceinline__ void knn_scan_range(const float4* __restrict__ cand, 
 
 // per-thread staging of the nine row probes (one column per thread)
 struct KnnStage {
-  unsigned long long e[9][kTile];
-  uint32_t sl[9][kTile];
+  unsigned long long run[9][kTile];  // count << 32 | start of each row's candidate run (0 = none)
 };
 
 // Rows (dy,dz) of three x-adjacent cells are visited near to far; a row is skipped when
@@ -351,72 +366,56 @@ __device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[
   const int base = d.hash_off[g];
   const uint32_t mask = (uint32_t)(d.hash_off[g + 1] - base) - 1u;
   const unsigned long long* __restrict__ tab = d.hash_tab + base;
-  const bool cx_ok = (unsigned)cx <= 255u;
   const int t = threadIdx.x;
-  {  // phase 1: the nine centre-cell probes, issued back to back (independent loads)
-    uint32_t k24[9], sl[9];
-    unsigned long long e[9];
-#pragma unroll
-    for (int rr = 0; rr < 9; ++rr) {
-      const int z = cz + rr / 3 - 1, y = cy + rr % 3 - 1;
-      const bool ok = (unsigned)z <= 255u && (unsigned)y <= 255u && cx_ok;
-      k24[rr] = ((uint32_t)(z & 255) << 16) | ((uint32_t)(y & 255) << 8) | (uint32_t)(cx & 255);
-      sl[rr] = cell_hash(k24[rr]) & mask;
-      e[rr] = ok ? tab[sl[rr]] : kSentinel64;
-    }
-#pragma unroll
-    for (int rr = 0; rr < 9; ++rr) {
-      while (e[rr] != kSentinel64 && (uint32_t)(e[rr] >> 40) != k24[rr]) {
-        sl[rr] = (sl[rr] + 1) & mask;
-        e[rr] = tab[sl[rr]];
-      }
-      st.e[rr][t] = e[rr];
-      st.sl[rr][t] = sl[rr];
-    }
-  }
   // exact distances from the query to the cell's boundary planes (fractional parts are exact)
   const float fy = xfsub(qy, fly), fz = xfsub(qz, flz);
   const float gy = xfsub(1.0f, fy), gz = xfsub(1.0f, fz);
   const int sy = fy < 0.5f ? -1 : 1, sz = fz < 0.5f ? -1 : 1;  // side of the nearer boundary
+  // A query one cell outside the block in x still has one column of the block in range: probe
+  // that column (its run is a superset of what is needed, which keeps the search exact).
+  const int px = cx < 0 ? cx + 1 : (cx > 255 ? cx - 1 : cx);
+  const bool x_ok = (unsigned)px <= 255u;
+  {  // phase 1: the nine row probes issued back to back (independent loads), near-to-far order
+    uint32_t k24[9], sl[9];
+    unsigned long long e[9];
+#pragma unroll
+    for (int o = 0; o < 9; ++o) {
+      // order: centre, (sy,0), (0,sz), (sy,sz), (-sy,0), (0,-sz), (-sy,sz), (sy,-sz), (-sy,-sz)
+      const int dy = (o == 1 || o == 3 || o == 7) ? sy : ((o == 4 || o == 6 || o == 8) ? -sy : 0);
+      const int dz = (o == 2 || o == 3 || o == 6) ? sz : ((o == 5 || o == 7 || o == 8) ? -sz : 0);
+      const int z = cz + dz, y = cy + dy;
+      const bool ok = (unsigned)z <= 255u && (unsigned)y <= 255u && x_ok;
+      k24[o] = ((uint32_t)(z & 255) << 16) | ((uint32_t)(y & 255) << 8) | (uint32_t)(px & 255);
+      sl[o] = cell_hash(k24[o]) & mask;
+      e[o] = ok ? tab[sl[o]] : kSentinel64;
+    }
+#pragma unroll
+    for (int o = 0; o < 9; ++o) {
+      while (e[o] != kSentinel64 && (uint32_t)(e[o] >> 40) != k24[o]) {
+        sl[o] = (sl[o] + 1) & mask;
+        e[o] = tab[sl[o]];
+      }
+      unsigned long long rn = 0ull;
+      if (e[o] != kSentinel64) {
+        uint32_t c = (uint32_t)(e[o] >> 30) & 1023u;
+        if (c == 1023u) c = d.hash_aux[base + sl[o]].y;
+        rn = ((unsigned long long)c << 32) | (e[o] & 0x3FFFFFFFull);
+      }
+      st.run[o][t] = rn;
+    }
+  }
   // phase 2: rows near to far (one copy of the scan code; the staging lives in shared memory)
   int visited = 0;
 #pragma unroll 1
   for (int o = 0; o < 9; ++o) {
-    // order: centre, (sy,0), (0,sz), (sy,sz), (-sy,0), (0,-sz), (-sy,sz), (sy,-sz), (-sy,-sz)
-    const int dy = (o == 1 || o == 3 || o == 7) ? sy : ((o == 4 || o == 6 || o == 8) ? -sy : 0);
-    const int dz = (o == 2 || o == 3 || o == 6) ? sz : ((o == 5 || o == 7 || o == 8) ? -sz : 0);
-    const int z = cz + dz, y = cy + dy;
-    if ((unsigned)z > 255u || (unsigned)y > 255u || cx < -1 || cx > 256) continue;
-    const float by = dy == 0 ? 0.0f : (dy < 0 ? fy : gy), bz = dz == 0 ? 0.0f : (dz < 0 ? fz : gz);
-    const float bound = xfadd(xfmul(by, by), xfmul(bz, bz));
-    if (bound > knn_d2(r, 4)) continue;  // strict: a tie at the 5th distance may still win on the index
-    const int rr = (dz + 1) * 3 + (dy + 1);
-    const unsigned long long e = st.e[rr][t];
-    int start[2], count[2] = {0, 0};
-    if (e != kSentinel64) {
-      uint32_t c3 = (uint32_t)(e >> 30) & 1023u;
-      if (c3 == 1023u) c3 = d.hash_aux[base + st.sl[rr][t]].y;
-      start[0] = (int)(e & 0x3FFFFFFFull);
-      count[0] = (int)c3;
-    } else {
-      // centre cell empty: its x-neighbours on their own (the tail / head of their 3-cell runs)
-      const uint32_t row24 = ((uint32_t)z << 16) | ((uint32_t)y << 8);
-#pragma unroll
-      for (int side = 0; side < 2; ++side) {
-        const int x = cx + (side ? 1 : -1);
-        if ((unsigned)x > 255u) continue;
-        uint32_t s;
-        const unsigned long long en = cell_probe(tab, mask, row24 | (uint32_t)x, s);
-        if (en == kSentinel64) continue;
-        const uint2 ax = d.hash_aux[base + s];
-        start[side] = (int)(en & 0x3FFFFFFFull) + (side ? 0 : (int)(ax.y - ax.x));
-        count[side] = (int)ax.x;
-      }
-    }
-    visited += count[0] + count[1];
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h)
-      if (count[h] > 0) knn_scan_range(d.cand, start[h], count[h], qx, qy, qz, r);
+    const unsigned long long rn = st.run[o][t];
+    const int cnt = (int)(rn >> 32);
+    if (cnt == 0) continue;
+    const float by = (o == 0 || o == 2 || o == 5) ? 0.0f : ((o == 1 || o == 3 || o == 7) ? (sy < 0 ? fy : gy) : (sy < 0 ? gy : fy));
+    const float bz = (o == 0 || o == 1 || o == 4) ? 0.0f : ((o == 2 || o == 3 || o == 6) ? (sz < 0 ? fz : gz) : (sz < 0 ? gz : fz));
+    if (xfadd(xfmul(by, by), xfmul(bz, bz)) > knn_d2(r, 4)) continue;  // strict: a tie at the 5th distance may still win on the index
+    visited += cnt;
+    knn_scan_range(d.cand, (int)(uint32_t)rn, cnt, qx, qy, qz, r);
   }
   return visited;
 }
@@ -455,7 +454,7 @@ __device__ __forceinline__ int cells27_count(const Dev& d, int g, const int orig
         if ((unsigned)x > 255u || (unsigned)y > 255u || (unsigned)z > 255u) continue;
         uint32_t s;
         const unsigned long long e = cell_probe(d.hash_tab + base, mask, ((uint32_t)z << 16) | ((uint32_t)y << 8) | (uint32_t)x, s);
-        if (e != kSentinel64) n += (int)d.hash_aux[base + s].x;
+        if (e != kSentinel64) n += (int)d.hash_aux[base + s].x;  // 0 for virtual entries
       }
   return n;
 }
@@ -713,7 +712,9 @@ __global__ void __launch_bounds__(kTile, S2M_K4B_MINB) fit_kernel(Dev d, int out
   int dc0, nc, ds0, nq;
   slot_counts(d, slot, dc0, nc, ds0, nq);
   const int ntiles = (nq + kTile - 1) / kTile;
-  const int nwork = max(1, min((int)gridDim.x, ntiles));
+  // blocks per slot depend ONLY on the slot's own size, so the summation order (hence every bit of
+  // the pose) is the same whatever else shares the launch
+  const int nwork = max(1, (ntiles + kFitTilesPerBlock - 1) / kFitTilesPerBlock);
   if ((int)blockIdx.x >= nwork) return;
   __shared__ double pose[7];
   __shared__ BlockAcc A;
@@ -723,7 +724,7 @@ __global__ void __launch_bounds__(kTile, S2M_K4B_MINB) fit_kernel(Dev d, int out
   acc_zero(A);
   __syncthreads();
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile < ntiles; tile += nwork) {
     // ---- compaction of the gated queries of this tile (thread order => deterministic) ----
     const int q = tile * kTile + t;
     const int pos_q = q < nc ? dc0 + q : ds0 + (q - nc);
@@ -800,7 +801,7 @@ __global__ void __launch_bounds__(kTile, 4) evaluate_kernel(Dev d, int outer) {
   int dc0, nc, ds0, nq;
   slot_counts(d, slot, dc0, nc, ds0, nq);
   const int ntiles = (nq + kTile - 1) / kTile;
-  const int nwork = max(1, min((int)gridDim.x, ntiles));
+  const int nwork = max(1, (ntiles + kEvalTilesPerBlock - 1) / kEvalTilesPerBlock);  // see fit_kernel
   if ((int)blockIdx.x >= nwork) return;
   __shared__ double pose[7];
   __shared__ BlockAcc A;
@@ -812,7 +813,7 @@ __global__ void __launch_bounds__(kTile, 4) evaluate_kernel(Dev d, int outer) {
   Sums28 S;
   S.zero();
   double ne = 0.0, np = 0.0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile < ntiles; tile += nwork) {
     const int q = tile * kTile + threadIdx.x;
     const int di = q < nc ? dc0 + q : ds0 + (q - nc);
     if (q < nq && d.rec_valid[di]) {
