@@ -404,7 +404,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seqs", type=int, default=64, help="independent sequences per context (<=64)")
-    ap.add_argument("--ctx", type=int, default=3, help="contexts per GPU, each on its own stream / host thread")
+    ap.add_argument("--ctx", type=int, default=4, help="contexts per GPU, each on its own stream / host thread")
     ap.add_argument("--cap-map-corner", type=int, default=1 << 17)
     ap.add_argument("--cap-map-surf", type=int, default=1 << 17)
     ap.add_argument("--no-cpu-baseline", action="store_true")
