@@ -55,6 +55,7 @@ def lib():
         L.orc_get_local_map.argtypes = [vp, ci, vp, vp, ci]
         L.orc_get_map.argtypes = [vp, ci, vp, ci]
         L.orc_get_window.argtypes = [vp, vp]
+        L.orc_get_surround.argtypes = [vp, vp, ci]
         L.orc_debug_knn.argtypes = [vp, ci, vp, vp, ci, ci, vp, vp]
         L.orc_voxel_grid.argtypes = [vp, ci, cf, vp]
         L.orc_knn.argtypes = [vp, ci, vp, ci, ci, vp, vp]
@@ -127,6 +128,12 @@ class Oracle:
         n = self.L.orc_get_map(self.h, cls, None, 0)
         out = np.zeros((max(n, 1), 4), np.float32)
         self.L.orc_get_map(self.h, cls, out.ctypes.data, n)
+        return out[:n]
+
+    def surround(self):
+        n = self.L.orc_get_surround(self.h, None, 0)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        self.L.orc_get_surround(self.h, out.ctypes.data, n)
         return out[:n]
 
     def window(self):

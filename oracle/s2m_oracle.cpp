@@ -1323,6 +1323,19 @@ int orc_get_map(void* h, int cls, float* out, int cap) {
         }
   return n;
 }
+// /laser_cloud_surround as published every 5th frame (laserMapping.cpp:807-815): corner then
+// surf cloud of every valid cube of the last process() call.
+int orc_get_surround(void* h, float* out, int cap) {
+  auto* m = (orc::Mapper*)h;
+  int n = 0;
+  for (int v = 0; v < m->n_valid_; ++v)
+    for (int c = 0; c < 2; ++c)
+      for (auto& p : (c == 0 ? m->corner_ : m->surf_)[m->valid_[v]]) {
+        if (out && n < cap) std::memcpy(out + 4 * (size_t)n, &p, 16);
+        ++n;
+      }
+  return n;
+}
 void orc_get_window(void* h, int cen[3]) {
   auto* m = (orc::Mapper*)h;
   cen[0] = m->cenW; cen[1] = m->cenH; cen[2] = m->cenD;

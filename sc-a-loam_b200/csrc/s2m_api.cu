@@ -85,6 +85,8 @@ struct s2m_ctx {
   int* h_err = nullptr;          // pinned
   int* h_dsoff = nullptr;        // pinned [G+1]: down-sampled counts read back mid-frame
   cudaEvent_t ev_ds = nullptr;
+  uint32_t* h_bbox = nullptr;    // pinned [G][6]: boxes of the incoming clouds (ordered-uint encoding)
+  cudaEvent_t ev_bbox = nullptr;
   LmState* lm_trace = nullptr;   // [2][B] device
   LmState* h_lm = nullptr;       // pinned [2][B]
   std::vector<void*> allocs;
@@ -193,6 +195,8 @@ extern "C" void s2m_destroy(s2m_ctx* ctx) {
   if (ctx->h_err) cudaFreeHost(ctx->h_err);
   if (ctx->h_dsoff) cudaFreeHost(ctx->h_dsoff);
   if (ctx->ev_ds) cudaEventDestroy(ctx->ev_ds);
+  if (ctx->h_bbox) cudaFreeHost(ctx->h_bbox);
+  if (ctx->ev_bbox) cudaEventDestroy(ctx->ev_bbox);
   if (ctx->h_lm) cudaFreeHost(ctx->h_lm);
   for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
   for (auto& e : ctx->ar_pool) cudaEventDestroy(e);
@@ -211,6 +215,13 @@ static int create_impl(s2m_ctx* ctx) {
   std::memset(&d, 0, sizeof(d));
   const int B = P.batch, G = 2 * B;
   d.B = B; d.G = G;
+  {
+    const float min_leaf = std::min(P.line_res, P.plane_res);
+    int nvox = (int)(50.0f / min_leaf) + 3, b = 1;
+    while ((1 << b) < nvox) ++b;
+    d.vox_bits = std::min(b, 11);
+    d.delta_pbits = std::max(3 * d.vox_bits, 18);
+  }
   d.use_qperm = getenv("S2M_QUERY_ORDER") ? atoi(getenv("S2M_QUERY_ORDER")) : 0;
   d.shard_world = P.shard_world;
   d.shard_lo = -INFINITY; d.shard_hi = INFINITY;
@@ -234,6 +245,8 @@ static int create_impl(s2m_ctx* ctx) {
   CK(cudaMallocHost((void**)&ctx->h_err, sizeof(int)));
   CK(cudaMallocHost((void**)&ctx->h_dsoff, sizeof(int) * (2 * kMaxBatch + 1)));
   CK(cudaEventCreateWithFlags(&ctx->ev_ds, cudaEventDisableTiming));
+  CK(cudaMallocHost((void**)&ctx->h_bbox, sizeof(uint32_t) * 6 * 2 * kMaxBatch));
+  CK(cudaEventCreateWithFlags(&ctx->ev_bbox, cudaEventDisableTiming));
   CK(cudaMallocHost((void**)&ctx->h_lm, sizeof(LmState) * 2 * B));
   std::memset(ctx->ht, 0, sizeof(HostTables));
   if (dev_alloc(ctx, &ctx->d_ht, 1)) return S2M_ERR_CUDA;
@@ -451,25 +464,47 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   // (about 4 blocks of 128 threads per SM over all slots), never more than the tiles
   long long k = 0;
   prof_mark(ctx, S2M_PHASE_INPUT);
-  k += launch_voxel_filter(d, total_in, s);
-  // the down-sampled counts come back while the local index is being built, so the
-  // later launches (query order, association grid, map update) use exact sizes
-  CK(cudaMemcpyAsync(ctx->h_dsoff, d.ds_off, sizeof(int) * (G + 1), cudaMemcpyDeviceToHost, s));
-  CK(cudaEventRecord(ctx->ev_ds, s));
-  prof_mark(ctx, S2M_PHASE_VOXEL);
+  // boxes of the incoming clouds first: they come back while the local index is being built and
+  // give the exact width of PCL's voxel index, i.e. the number of radix passes of the scan filter
+  k += launch_voxel_bbox(d, total_in, s);
+  CK(cudaMemcpyAsync(ctx->h_bbox, d.bbox, sizeof(uint32_t) * 6 * G, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(ctx->ev_bbox, s));
   k += launch_local_index(d, ctx->cur, total_lp, hash_total, s);
   const bool sharded = ctx->P.shard_world > 1;
   if (sharded) { int rs = shard_allreduce(ctx, d.shard_counts, (size_t)G, nccl::kInt32); if (rs != S2M_OK) return rs; }
   k += launch_guard(d, s);
-  CK(cudaEventSynchronize(ctx->ev_ds));
-  const int n_ds = ctx->h_dsoff[G];
-  tiles = 0;
-  for (int b = 0; b < B; ++b) {
-    const int nq = (ctx->h_dsoff[b + 1] - ctx->h_dsoff[b]) + (ctx->h_dsoff[B + b + 1] - ctx->h_dsoff[B + b]);
-    tiles = std::max(tiles, (nq + kTile - 1) / kTile);
-  }
-  if (d.use_qperm) k += launch_query_order(d, n_ds, s);
   prof_mark(ctx, S2M_PHASE_INDEX);
+  CK(cudaEventSynchronize(ctx->ev_bbox));
+  int key_bits = 1;
+  for (int g = 0; g < G && total_in > 0; ++g) {
+    const int cnt = T.in_off[g + 1] - T.in_off[g];
+    if (cnt == 0) continue;
+    auto ord2f = [](uint32_t u) { uint32_t b2 = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u; float f; std::memcpy(&f, &b2, 4); return f; };
+    const uint32_t* bb = ctx->h_bbox + 6 * g;
+    const float inv = d.inv_leaf[g >= B];
+    double cells = 1.0;
+    long long lin = 1;
+    for (int a2 = 0; a2 < 3; ++a2) {
+      const float mn = ord2f(bb[a2]), mx = ord2f(bb[3 + a2]);
+      cells *= (double)((long long)xfmul(xfsub(mx, mn), inv) + 1);             // PCL's overflow test
+      lin *= (long long)((int)floorf(xfmul(mx, inv)) - (int)floorf(xfmul(mn, inv)) + 1);  // div_b product
+    }
+    const long long span = cells > 2147483647.0 ? (long long)cnt : std::min<long long>(lin, 2147483647LL);
+    int bits = 1;
+    while ((1ll << bits) < span) ++bits;
+    key_bits = std::max(key_bits, bits);
+  }
+  key_bits = std::min(key_bits, 31);
+  k += launch_voxel_filter(d, total_in, key_bits, s);
+  // the down-sampled counts are needed on the host only for the map update (exact sort size): they
+  // come back while the association and the solves run
+  CK(cudaMemcpyAsync(ctx->h_dsoff, d.ds_off, sizeof(int) * (G + 1), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(ctx->ev_ds, s));
+  prof_mark(ctx, S2M_PHASE_VOXEL);
+  if (d.use_qperm) {  // optional cell ordering of the queries needs the exact count now
+    CK(cudaEventSynchronize(ctx->ev_ds));
+    k += launch_query_order(d, ctx->h_dsoff[G], s);
+  }
   // one resident wave each: S2M_K4x_MINB blocks per SM shared by the B slots
   const int knn_blocks = std::max(1, std::min(tiles, (S2M_K4A_MINB * ctx->sm_count) / B));
   const int fit_blocks = std::max(1, (tiles + kFitTilesPerBlock - 1) / kFitTilesPerBlock);
@@ -500,6 +535,8 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
       CK(cudaMemcpyAsync(ctx->lm_trace + (size_t)outer * B, d.lm, sizeof(LmState) * B, cudaMemcpyDeviceToDevice, s));
   }
   k += launch_finish_pose(d, s);
+  CK(cudaEventSynchronize(ctx->ev_ds));
+  const int n_ds = ctx->h_dsoff[G];
   k += launch_map_update(d, ctx->cur, n_ds, total_lp, check_pending, false, s);
   prof_mark(ctx, S2M_PHASE_UPDATE);
   ctx->launches += k;
@@ -799,29 +836,26 @@ extern "C" int s2m_debug_knn(s2m_ctx* ctx, int slot, int cls, const double centr
 }
 
 extern "C" int s2m_get_surround(s2m_ctx* ctx, int slot, float* out, int cap) {
-  if (!ctx || slot < 0 || slot >= ctx->d.B) return S2M_ERR_ARG;
+  if (!ctx || slot < 0 || slot >= ctx->d.B || cap < 0) return S2M_ERR_ARG;
   CK(cudaSetDevice(ctx->P.device));
-  // corner then surf of each valid cube, cubes in gather order (laserMapping.cpp:810-815)
-  std::vector<uint64_t> keys[2];
-  std::vector<float> pts[2];
-  for (int c = 0; c < 2; ++c) {
-    int rc = download_store(ctx, slot, c, keys[c], pts[c]);
-    if (rc != S2M_OK) return rc;
-  }
+  // corner then surf of each valid cube, cubes in gather order (laserMapping.cpp:810-815), gathered
+  // on the device from the valid block of the last registration; only the result crosses PCIe
+  Dev& d = ctx->d;
   const SlotHost& sh = ctx->slots[slot];
+  HostTables& T = *ctx->ht;
+  FrameDesc& fd = T.desc[slot];
+  for (int a2 = 0; a2 < 3; ++a2) { fd.val_lo[a2] = sh.val_lo[a2]; fd.val_hi[a2] = sh.val_hi[a2]; }
+  CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, ctx->stream));
+  const int room = std::min(cap, d.cap_sort);
+  ctx->launches += launch_surround(d, ctx->cur, slot, d.ins_pt, room, d.ticket, ctx->stream);
   int n = 0;
-  for (int ci = sh.val_lo[0]; ci <= sh.val_hi[0]; ++ci)
-    for (int cj = sh.val_lo[1]; cj <= sh.val_hi[1]; ++cj)
-      for (int ck = sh.val_lo[2]; ck <= sh.val_hi[2]; ++ck)
-        for (int c = 0; c < 2; ++c) {
-          const uint32_t cube = pack_cube(ci, cj, ck);
-          auto lo = std::lower_bound(keys[c].begin(), keys[c].end(), store_key(cube, 0, 0));
-          auto hi = std::lower_bound(keys[c].begin(), keys[c].end(), store_key(cube + 1, 0, 0));
-          for (auto it = lo; it != hi; ++it) {
-            if (out && n < cap) std::memcpy(out + 4 * (size_t)n, &pts[c][4 * (it - keys[c].begin())], 16);
-            ++n;
-          }
-        }
+  CK(cudaMemcpyAsync(&n, d.ticket, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemsetAsync(d.ticket, 0, sizeof(int), ctx->stream));
+  if (out && n > 0) {
+    CK(cudaMemcpyAsync(out, d.ins_pt, sizeof(float4) * (size_t)std::min(n, room), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   return n;
 }
 

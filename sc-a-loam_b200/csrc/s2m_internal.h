@@ -93,6 +93,8 @@ struct SlotOut {            // per slot, read back by the host after every call
 // All device pointers of one context (sizes are host-known capacities).
 struct Dev {
   int B, G;                     // slots, segments
+  int vox_bits;                 // bits of a voxel coordinate inside a cube (delta sort key)
+  int delta_pbits;              // payload bits of the delta sort key
   int use_qperm;                // walk the queries in map-cell order (d.qperm) instead of scan order
   int shard_world;              // >1: spatially sharded map (x-slabs per rank)
   float shard_lo, shard_hi;     // this rank's slab in world x, [lo, hi)
@@ -159,7 +161,8 @@ struct Dev {
 
 // launchers (s2m_kernels.cu); every one returns the number of kernels it launched
 size_t cub_temp_bytes(int cap_sort, int cap_lp);
-int launch_voxel_filter(const Dev& d, int total_in, cudaStream_t s);
+int launch_voxel_bbox(const Dev& d, int total_in, cudaStream_t s);
+int launch_voxel_filter(const Dev& d, int total_in, int key_bits, cudaStream_t s);
 int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, cudaStream_t s);
 int launch_guard(const Dev& d, cudaStream_t s);
 int launch_query_order(const Dev& d, int n_ds, cudaStream_t s);
@@ -174,5 +177,6 @@ int launch_knn_debug(const Dev& d, int slot, int cls, const float* d_q, int n, i
                      cudaStream_t s);
 int launch_transform_cloud(const double* d_pose7, const float4* in, float4* out, int n, cudaStream_t s);
 int launch_gather_local(const Dev& d, int cur, int g, float4* out, cudaStream_t s);
+int launch_surround(const Dev& d, int cur, int slot, float4* out, int cap, int* n_out, cudaStream_t s);
 
 }  // namespace s2m

@@ -106,7 +106,7 @@ __global__ void vox_bbox_init_kernel(Dev d) {
   if (i < 6 * d.G) d.bbox[i] = (i % 6) < 3 ? 0xFFFFFFFFu : 0u;
 }
 
-__global__ void vox_key_kernel(Dev d, int n) {
+__global__ void vox_key_kernel(Dev d, int n, int key_bits) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int g = find_seg(d.in_off, d.G, i);
@@ -131,7 +131,8 @@ __global__ void vox_key_kernel(Dev d, int n) {
     const int i2 = (int)(floorf(xfmul(p.z, inv)) - (float)m2);
     key = (uint64_t)((long long)i0 + (long long)i1 * d0 + (long long)i2 * d0 * d1) & 0x7FFFFFFFull;
   }
-  d.vkey[i] = ((uint64_t)g << 31) | key;
+  if (key >> key_bits) set_err(d, -4);  // the host derived key_bits from the same boxes
+  d.vkey[i] = ((uint64_t)g << key_bits) | key;
   d.vval[i] = (uint32_t)i;
 }
 
@@ -871,17 +872,19 @@ __global__ void finish_pose_kernel(Dev d) {
 __device__ __forceinline__ bool in_box(int ci, int cj, int ck, const int lo[3], const int hi[3]) {
   return ci >= lo[0] && ci <= hi[0] && cj >= lo[1] && cj <= hi[1] && ck >= lo[2] && ck <= hi[2];
 }
-__device__ __forceinline__ uint64_t delta_key(int g, const FrameDesc& fd, int ci, int cj, int ck, uint32_t pend,
+__device__ __forceinline__ uint64_t delta_key(const Dev& d, int g, const FrameDesc& fd, int ci, int cj, int ck, uint32_t pend,
                                               uint64_t payload) {
   const uint32_t rel = (uint32_t)(((ci - fd.win_lo[0]) * kWinJ + (cj - fd.win_lo[1])) * kWinK + (ck - fd.win_lo[2]));
-  return ((uint64_t)g << 47) | ((uint64_t)rel << 34) | ((uint64_t)pend << 33) | (payload & 0x1FFFFFFFFull);
+  const int P = d.delta_pbits;
+  return ((uint64_t)g << (14 + P)) | ((uint64_t)rel << (1 + P)) | ((uint64_t)pend << P) | (payload & ((1ull << P) - 1ull));
 }
 __device__ __forceinline__ uint64_t voxel_payload(const Dev& d, int cls, float x, float y, float z, int ci, int cj,
                                                   int ck) {
   const float inv = d.inv_leaf[cls];
   const int vx = voxel_rel(x, ci, inv), vy = voxel_rel(y, cj, inv), vz = voxel_rel(z, ck, inv);
-  if ((unsigned)vx > 2047u || (unsigned)vy > 2047u || (unsigned)vz > 2047u) set_err(d, -4);
-  return ((uint64_t)(vz & 2047) << 22) | ((uint64_t)(vy & 2047) << 11) | (uint64_t)(vx & 2047);
+  const int b = d.vox_bits;
+  if ((unsigned)vx >= (1u << b) || (unsigned)vy >= (1u << b) || (unsigned)vz >= (1u << b)) set_err(d, -4);
+  return ((uint64_t)vz << (2 * b)) | ((uint64_t)vy << b) | (uint64_t)vx;  // compact (sort key only)
 }
 
 __global__ void delta_key_kernel(Dev d, int front, int n_delta, bool identity_pose) {
@@ -911,9 +914,9 @@ __global__ void delta_key_kernel(Dev d, int front, int n_delta, bool identity_po
       if (mine && fd.active && in_box(ci, cj, ck, fd.win_lo, fd.win_hi)) {  // laserMapping.cpp:753-755
         if (!cube_in_range(ci, cj, ck)) set_err(d, -4);
         if (in_box(ci, cj, ck, fd.val_lo, fd.val_hi))
-          key = delta_key(g, fd, ci, cj, ck, 0, voxel_payload(d, seg_cls(d, g), w[0], w[1], w[2], ci, cj, ck));
+          key = delta_key(d, g, fd, ci, cj, ck, 0, voxel_payload(d, seg_cls(d, g), w[0], w[1], w[2], ci, cj, ck));
         else
-          key = delta_key(g, fd, ci, cj, ck, 1, fd.seq_base[seg_cls(d, g)] + (unsigned long long)(di - d.ds_off[g]));
+          key = delta_key(d, g, fd, ci, cj, ck, 1, (unsigned long long)(di - d.ds_off[g]));  // arrival offset inside this frame
         val = (uint32_t)di;
       }
     }
@@ -957,7 +960,7 @@ __global__ void pending_gather_kernel(Dev d, int cur) {
       const int src = d.st_base[g] + lo_s[c] + j;
       const float4 p = d.st_pt[cur][src];
       const int pos = d.lp_off[g] + off_s[c] + j;
-      d.vkey[pos] = delta_key(g, fd, ci, cj, ck, 0, voxel_payload(d, seg_cls(d, g), p.x, p.y, p.z, ci, cj, ck));
+      d.vkey[pos] = delta_key(d, g, fd, ci, cj, ck, 0, voxel_payload(d, seg_cls(d, g), p.x, p.y, p.z, ci, cj, ck));
       d.vval[pos] = 0x80000000u | (uint32_t)src;
     }
   }
@@ -975,13 +978,20 @@ __global__ void delta_reduce_kernel(Dev d, int cur, int n_delta) {
   const uint64_t key = d.vkey2[p];
   if (key == kSentinel64) return;
   const int r = (int)d.scan[p];
-  const int g = (int)(key >> 47);
+  const int P = d.delta_pbits, vb = d.vox_bits;
+  const int g = (int)(key >> (14 + P));
   const FrameDesc& fd = d.desc[seg_slot(d, g)];
-  const int rel = (int)((key >> 34) & 0x1FFF);
+  const int rel = (int)((key >> (1 + P)) & 0x1FFF);
+  const uint32_t pend = (uint32_t)((key >> P) & 1);
+  const uint64_t pl = key & ((1ull << P) - 1ull);
+  // store payload: arrival number (raw) or the 3 x 11-bit voxel coordinate inside the cube (filtered)
+  const uint64_t vm = (1ull << vb) - 1ull;
+  const uint64_t store_pl = pend ? fd.seq_base[seg_cls(d, g)] + pl
+                                 : (((pl >> (2 * vb)) & vm) << 22) | (((pl >> vb) & vm) << 11) | (pl & vm);
   const int ci = fd.win_lo[0] + rel / (kWinJ * kWinK), cj = fd.win_lo[1] + (rel / kWinK) % kWinJ,
             ck = fd.win_lo[2] + rel % kWinK;
-  const uint64_t wkey = store_key(pack_cube(ci, cj, ck), (uint32_t)((key >> 33) & 1), key & 0x1FFFFFFFFull);
-  if ((key >> 33) & 1) {  // raw point for a cube outside the valid block: stays raw
+  const uint64_t wkey = store_key(pack_cube(ci, cj, ck), pend, store_pl);
+  if (pend) {  // raw point for a cube outside the valid block: stays raw
     d.ins_key[r] = wkey;
     d.ins_pt[r] = delta_point(d, cur, d.vval2[p]);
     return;
@@ -1028,7 +1038,7 @@ __global__ void ins_compact_kernel(Dev d, int n) {
 __global__ void ins_off_kernel(Dev d, int n_delta) {
   const int g = threadIdx.x + blockIdx.x * blockDim.x;
   if (g > d.G) return;
-  const int pos = lower_bound_u64(d.vkey2, n_delta, (uint64_t)g << 47);
+  const int pos = lower_bound_u64(d.vkey2, n_delta, (uint64_t)g << (14 + d.delta_pbits));
   const int run = (int)d.scan[pos];  // scan has n_delta+1 entries
   d.run_off[g] = (int)d.ascan[run];  // ascan here = exclusive scan of insert flags over runs
 }
@@ -1107,6 +1117,39 @@ __global__ void gather_local_kernel(Dev d, int cur, int g, float4* __restrict__ 
   out[l] = d.st_pt[cur][d.st_base[g] + local_to_store(d, g, l)];
 }
 
+// Row X, /laser_cloud_surround (laserMapping.cpp:807-815): corner then surf cloud of every valid
+// cube, cubes in gather order. One block: 150 (cube, class) ranges by binary search, a scan, a copy.
+__global__ void surround_kernel(Dev d, int cur, int slot, float4* __restrict__ out, int cap, int* __restrict__ n_out) {
+  __shared__ int lo_s[2 * kValidCubes], off_s[2 * kValidCubes + 1];
+  const FrameDesc& fd = d.desc[slot];
+  const int t = threadIdx.x;
+  if (t < 2 * kValidCubes) {
+    const int c = t >> 1, cls = t & 1, g = cls * d.B + slot;
+    const int ci = fd.val_lo[0] + c / 15, cj = fd.val_lo[1] + (c / 3) % 5, ck = fd.val_lo[2] + c % 3;
+    int lo = 0, len = 0;
+    if (ci <= fd.val_hi[0] && cj <= fd.val_hi[1] && ck <= fd.val_hi[2]) {
+      const uint64_t* keys = d.st_key[cur] + d.st_base[g];
+      const uint32_t cube = pack_cube(ci, cj, ck);
+      lo = lower_bound_u64(keys, d.st_n[g], store_key(cube, 0, 0));
+      len = lower_bound_u64(keys, d.st_n[g], store_key(cube + 1, 0, 0)) - lo;
+    }
+    lo_s[t] = lo;
+    off_s[t + 1] = len;
+  }
+  __syncthreads();
+  if (t == 0) {
+    off_s[0] = 0;
+    for (int k = 0; k < 2 * kValidCubes; ++k) off_s[k + 1] += off_s[k];
+    *n_out = off_s[2 * kValidCubes];
+  }
+  __syncthreads();
+  for (int r = 0; r < 2 * kValidCubes; ++r) {
+    const int g = (r & 1) * d.B + slot, len = off_s[r + 1] - off_s[r];
+    for (int j = t; j < len; j += blockDim.x)
+      if (off_s[r] + j < cap) out[off_s[r] + j] = d.st_pt[cur][d.st_base[g] + lo_s[r] + j];
+  }
+}
+
 // ----------------------------------------------------------------------------
 // launchers
 // ----------------------------------------------------------------------------
@@ -1123,16 +1166,24 @@ size_t cub_temp_bytes(int cap_sort, int cap_lp) {
   return std::max(std::max(a, b), std::max(c, e)) + 256;
 }
 
-int launch_voxel_filter(const Dev& d, int n, cudaStream_t s) {
+int launch_voxel_bbox(const Dev& d, int n, cudaStream_t s) {
   int k = 0;
   if (n > 0) {
     vox_bbox_init_kernel<<<cdiv(6 * d.G, 256), 256, 0, s>>>(d); ++k;
     vox_bbox_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n); ++k;
-    vox_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n); ++k;
+  }
+  return k;
+}
+// key_bits: width of PCL's linear voxel index over all segments (<= 31), known from the boxes;
+// the segment number sits right above it, so the sort covers key_bits + log2(segments) bits
+int launch_voxel_filter(const Dev& d, int n, int key_bits, cudaStream_t s) {
+  int k = 0;
+  if (n > 0) {
+    vox_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n, key_bits); ++k;
     size_t tb = d.cub_tmp_bytes;
     int gbits = 1;
     while ((1 << gbits) < d.G) ++gbits;
-    cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n, 0, 31 + gbits, s);
+    cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n, 0, key_bits + gbits, s);
   }
   head_flag_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(d.vkey2, d.flag, n); ++k;
   size_t tb = d.cub_tmp_bytes;
@@ -1222,7 +1273,7 @@ int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, bool check_
     int gbits = 1;
     while ((1 << gbits) < d.G) ++gbits;
     // the sentinel is all ones inside the sorted bit range too, so it stays at the end
-    cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n_delta, 0, 47 + gbits, s);
+    cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n_delta, 0, 14 + d.delta_pbits + gbits, s);
   }
   head_flag_kernel<<<cdiv(n_delta + 1, 256), 256, 0, s>>>(d.vkey2, d.flag, n_delta); ++k;
   size_t tb = d.cub_tmp_bytes;
@@ -1254,6 +1305,10 @@ int launch_knn_debug(const Dev& d, int slot, int cls, const float* d_q, int n, i
 int launch_transform_cloud(const double* d_pose7, const float4* in, float4* out, int n, cudaStream_t s) {
   if (n <= 0) return 0;
   transform_cloud_kernel<<<cdiv(n, 256), 256, 0, s>>>(d_pose7, in, out, n);
+  return 1;
+}
+int launch_surround(const Dev& d, int cur, int slot, float4* out, int cap, int* n_out, cudaStream_t s) {
+  surround_kernel<<<1, 512, 0, s>>>(d, cur, slot, out, cap, n_out);
   return 1;
 }
 int launch_gather_local(const Dev& d, int cur, int g, float4* out, cudaStream_t s) {

@@ -90,6 +90,8 @@ def test_map_evolution_bit_exact_without_optimisation(s2m, seq_hdl, seq_vlp, seq
                 got, want = R.map_download(cls), O.get_map(cls)
                 assert got.shape == want.shape, (f, cls, got.shape, want.shape)
                 assert np.array_equal(bits(got), bits(want)), (f, cls)
+    sg, so = R.surround(), O.surround()  # row X: /laser_cloud_surround, gathered on the device
+    assert sg.shape == so.shape and np.array_equal(bits(sg), bits(so))
     lm_g, lm_o = R.local_map(1, odom[7, 4:]), O.local_map(1, odom[7, 4:])
     assert np.array_equal(bits(lm_g), bits(lm_o))
 
