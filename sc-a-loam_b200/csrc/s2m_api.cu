@@ -496,15 +496,19 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   }
   key_bits = std::min(key_bits, 31);
   k += launch_voxel_filter(d, total_in, key_bits, s);
-  // the down-sampled counts are needed on the host only for the map update (exact sort size): they
-  // come back while the association and the solves run
+  // exact down-sampled counts size the association / evaluation grids and the map update; the short
+  // wait is hidden by the other contexts sharing the GPU
   CK(cudaMemcpyAsync(ctx->h_dsoff, d.ds_off, sizeof(int) * (G + 1), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(ctx->ev_ds, s));
   prof_mark(ctx, S2M_PHASE_VOXEL);
-  if (d.use_qperm) {  // optional cell ordering of the queries needs the exact count now
-    CK(cudaEventSynchronize(ctx->ev_ds));
-    k += launch_query_order(d, ctx->h_dsoff[G], s);
+  CK(cudaEventSynchronize(ctx->ev_ds));
+  const int n_ds = ctx->h_dsoff[G];
+  tiles = 0;
+  for (int b = 0; b < B; ++b) {
+    const int nq = (ctx->h_dsoff[b + 1] - ctx->h_dsoff[b]) + (ctx->h_dsoff[B + b + 1] - ctx->h_dsoff[B + b]);
+    tiles = std::max(tiles, (nq + kTile - 1) / kTile);
   }
+  if (d.use_qperm) k += launch_query_order(d, n_ds, s);
   // one resident wave each: S2M_K4x_MINB blocks per SM shared by the B slots
   const int knn_blocks = std::max(1, std::min(tiles, (S2M_K4A_MINB * ctx->sm_count) / B));
   const int fit_blocks = std::max(1, (tiles + kFitTilesPerBlock - 1) / kFitTilesPerBlock);
@@ -535,8 +539,6 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
       CK(cudaMemcpyAsync(ctx->lm_trace + (size_t)outer * B, d.lm, sizeof(LmState) * B, cudaMemcpyDeviceToDevice, s));
   }
   k += launch_finish_pose(d, s);
-  CK(cudaEventSynchronize(ctx->ev_ds));
-  const int n_ds = ctx->h_dsoff[G];
   k += launch_map_update(d, ctx->cur, n_ds, total_lp, check_pending, false, s);
   prof_mark(ctx, S2M_PHASE_UPDATE);
   ctx->launches += k;

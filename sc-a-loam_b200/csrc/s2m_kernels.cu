@@ -143,18 +143,26 @@ __global__ void head_flag_kernel(const uint64_t* __restrict__ keys, uint32_t* __
   flag[p] = (p < n) && (p == 0 || keys[p] != keys[p - 1]);
 }
 
-__global__ void vox_centroid_kernel(Dev d, int n) {
+// positions of the run heads, compacted (rank r -> first sorted position of voxel r)
+__global__ void vox_heads_kernel(Dev d, int n) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n || !d.flag[p]) return;
-  const uint64_t key = d.vkey2[p];
+  d.vval[d.scan[p]] = (uint32_t)p;  // vval (the unsorted value buffer) is free after the sort
+}
+// one thread per voxel: sequential float sums in (stable) sorted order, like pcl::VoxelGrid
+__global__ void vox_centroid_kernel(Dev d, int n) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_runs = (int)d.scan[n];
+  if (r >= n_runs) return;
+  const int p = (int)d.vval[r];
+  const int e = r + 1 < n_runs ? (int)d.vval[r + 1] : n;
   float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-  int e = p;
-  for (; e < n && d.vkey2[e] == key; ++e) {  // sequential float sums in (stable) sorted order
-    const float4 q = d.in_pts[d.vval2[e]];
+  for (int j = p; j < e; ++j) {
+    const float4 q = d.in_pts[d.vval2[j]];
     sx = xfadd(sx, q.x); sy = xfadd(sy, q.y); sz = xfadd(sz, q.z); si = xfadd(si, q.w);
   }
   const float c = (float)(e - p);
-  d.ds_pts[d.scan[p]] = make_float4(xfdiv(sx, c), xfdiv(sy, c), xfdiv(sz, c), xfdiv(si, c));
+  d.ds_pts[r] = make_float4(xfdiv(sx, c), xfdiv(sy, c), xfdiv(sz, c), xfdiv(si, c));
 }
 
 __global__ void ds_off_kernel(Dev d, int n) {
@@ -1188,7 +1196,10 @@ int launch_voxel_filter(const Dev& d, int n, int key_bits, cudaStream_t s) {
   head_flag_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(d.vkey2, d.flag, n); ++k;
   size_t tb = d.cub_tmp_bytes;
   cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.flag, d.scan, n + 1, s);
-  if (n > 0) { vox_centroid_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n); ++k; }
+  if (n > 0) {
+    vox_heads_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n); ++k;
+    vox_centroid_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n); ++k;  // n >= number of voxels; surplus threads exit
+  }
   ds_off_kernel<<<cdiv(d.G + 1, 128), 128, 0, s>>>(d, n); ++k;
   return k;
 }
