@@ -180,6 +180,8 @@ int s2m_phase_profile(s2m_ctx* ctx, int reset, double ms[S2M_N_PHASES]);
  * of the 28-double normal-equation block per evaluation.  nccl_unique_id is the
  * 128-byte ncclUniqueId obtained on rank 0 with s2m_shard_unique_id. */
 int s2m_shard_unique_id(void* id128);
+/* world-x interval [lo, hi) a rank owns (needs no GPU; used by the CPU multi-process tests) */
+int s2m_shard_slab(int rank, int world, float* x_lo, float* x_hi);
 int s2m_shard_init(s2m_ctx* ctx, const void* id128);
 int s2m_shard_profile(s2m_ctx* ctx, int reset, double* allreduce_ms_total, long long* count);
 

@@ -28,7 +28,7 @@ EXPORTS = [
     "s2m_register", "s2m_register_batch", "s2m_register_batch_dev", "s2m_get_correction",
     "s2m_transform_cloud", "s2m_map_upload", "s2m_map_download", "s2m_get_local_map", "s2m_get_surround",
     "s2m_get_window", "s2m_debug_knn", "s2m_trace_cloud", "s2m_trace_knn", "s2m_trace_lm",
-    "s2m_launch_count", "s2m_set_profiling", "s2m_k4_profile", "s2m_phase_profile", "s2m_shard_unique_id", "s2m_shard_init",
+    "s2m_launch_count", "s2m_set_profiling", "s2m_k4_profile", "s2m_phase_profile", "s2m_shard_unique_id", "s2m_shard_slab", "s2m_shard_init",
     "s2m_shard_profile",
 ]
 
@@ -97,10 +97,20 @@ def load_library(path=LIB_PATH):
     L.s2m_k4_profile.argtypes = [vp, ci, vp, vp, vp]
     L.s2m_phase_profile.argtypes = [vp, ci, vp]
     L.s2m_shard_unique_id.argtypes = [vp]
+    L.s2m_shard_slab.argtypes = [ci, ci, vp, vp]
     L.s2m_shard_init.argtypes = [vp, vp]
     L.s2m_shard_profile.argtypes = [vp, ci, vp, vp]
     _lib = L
     return L
+
+
+def shard_slab(rank, world):
+    """[lo, hi) of world x owned by `rank` in a `world`-way sharded map (no GPU needed)."""
+    lo, hi = ctypes.c_float(), ctypes.c_float()
+    rc = load_library().s2m_shard_slab(rank, world, ctypes.byref(lo), ctypes.byref(hi))
+    if rc != 0:
+        raise S2MError("bad shard rank/world")
+    return lo.value, hi.value
 
 
 def default_params():

@@ -224,14 +224,7 @@ static int create_impl(s2m_ctx* ctx) {
   }
   d.use_qperm = getenv("S2M_QUERY_ORDER") ? atoi(getenv("S2M_QUERY_ORDER")) : 0;
   d.shard_world = P.shard_world;
-  d.shard_lo = -INFINITY; d.shard_hi = INFINITY;
-  if (P.shard_world > 1) {
-    // contiguous slabs of cube columns of the initial window (world cube columns -10..10) per rank
-    const int lo_col = -10 + (kWinI * P.shard_rank) / P.shard_world;
-    const int hi_col = -10 + (kWinI * (P.shard_rank + 1)) / P.shard_world;
-    if (P.shard_rank > 0) d.shard_lo = (float)(50.0 * lo_col - 25.0);
-    if (P.shard_rank < P.shard_world - 1) d.shard_hi = (float)(50.0 * hi_col - 25.0);
-  }
+  s2m_shard_slab(P.shard_rank, P.shard_world, &d.shard_lo, &d.shard_hi);
   d.inv_leaf[0] = 1.0f / P.line_res;   // pcl::VoxelGrid::setLeafSize: inverse_leaf_size = 1 / leaf (float)
   d.inv_leaf[1] = 1.0f / P.plane_res;
   const long long cap_in = (long long)B * ((long long)P.cap_corner_in + P.cap_surf_in);
@@ -946,6 +939,19 @@ extern "C" int s2m_phase_profile(s2m_ctx* ctx, int reset, double ms[S2M_N_PHASES
 }
 
 // ---- sharded-map mode: not wired in this build ------------------------------------
+// Slab of world x owned by `rank`: contiguous cube columns of the initial window (world cube
+// columns -10..10, laserMapping.cpp:74-79), the first and last slab open-ended. No GPU needed.
+extern "C" int s2m_shard_slab(int rank, int world, float* x_lo, float* x_hi) {
+  if (world < 1 || rank < 0 || rank >= world || !x_lo || !x_hi) return S2M_ERR_ARG;
+  *x_lo = -INFINITY; *x_hi = INFINITY;
+  if (world > 1) {
+    const int lo_col = -10 + (kWinI * rank) / world;
+    const int hi_col = -10 + (kWinI * (rank + 1)) / world;
+    if (rank > 0) *x_lo = (float)(50.0 * lo_col - 25.0);
+    if (rank < world - 1) *x_hi = (float)(50.0 * hi_col - 25.0);
+  }
+  return S2M_OK;
+}
 extern "C" int s2m_shard_unique_id(void* id128) {
   if (!id128) return S2M_ERR_ARG;
   if (!nccl::load()) return S2M_ERR_NCCL;
