@@ -235,9 +235,10 @@ def make_worlds_distributed(n_frames, rank, world):
 
 
 class Lane:
-    """One context (S sequences) driven by one host thread on its own CUDA stream."""
+    """One context holding S sequences split over `lanes` concurrent lanes (own stream + host thread
+    each, inside the library): one C-ABI call per step advances all of them."""
 
-    def __init__(self, pkg, torch, worlds, S, variant, n_frames, local_rank, args, host_buffers):
+    def __init__(self, pkg, torch, worlds, S, lanes, variant, n_frames, local_rank, args, host_buffers):
         self.torch, self.S, self.n_frames = torch, S, n_frames
         odo = slot_odometry(worlds, S, variant)
         steps = [pack_step(worlds, S, f) for f in range(n_frames)]
@@ -251,25 +252,35 @@ class Lane:
         self.h2d = float(np.mean([c.nbytes + su.nbytes for c, _, su, _ in steps[PREFILL + args.warmup:]]))
         max_c = max(int(np.diff(st[1]).max()) for st in steps)
         max_s = max(int(np.diff(st[3]).max()) for st in steps)
-        self.stream = torch.cuda.Stream()  # a real stream: the library launches on it, the events time it
-        self.R = pkg.Registrar(LINE_RES, PLANE_RES, device=local_rank, batch=S, cap_corner_in=max_c + 64,
+        self.stream = torch.cuda.Stream()  # a real stream: the library fences its lanes on it, the events time it
+        self.R = pkg.Registrar(LINE_RES, PLANE_RES, device=local_rank, batch=S, lanes=lanes, cap_corner_in=max_c + 64,
                                cap_surf_in=max_s + 64, cap_map_corner=args.cap_map_corner, cap_map_surf=args.cap_map_surf)
         self.R.set_stream(self.stream.cuda_stream)
         self.events = None
+        self.pipelined = lanes >= 1 and not args.no_pipeline
 
     def step(self, f):
         c, co, su, so = self.steps[f]
-        if self.host:  # the reference-facing call with HOST buffers: H2D + D2H inside
-            return self.R.register_batch_ptr(c.data_ptr(), co, su.data_ptr(), so, self.q_all[f], self.t_all[f], False)
-        return self.R.register_batch_ptr(c.data_ptr(), co, su.data_ptr(), so, self.q_all[f], self.t_all[f], True)
+        # host_buffers: the reference-facing call with HOST buffers (H2D + D2H inside); else device pointers
+        return self.R.register_batch_ptr(c.data_ptr(), co, su.data_ptr(), so, self.q_all[f], self.t_all[f], not self.host)
 
     def run(self, f0, f1, timed):
         torch = self.torch
         with torch.cuda.stream(self.stream):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(self.stream)
-            for f in range(f0, f1):
-                self.step(f)
+            if self.pipelined:
+                # two frames in flight: the copy of frame f+1 overlaps the registration of frame f
+                for f in range(f0, f1):
+                    if f - f0 >= 2:
+                        self.R.wait()
+                    c, co, su, so = self.steps[f]
+                    self.R.submit(c.data_ptr(), co, su.data_ptr(), so, self.q_all[f], self.t_all[f], device=not self.host)
+                for _ in range(min(2, f1 - f0)):
+                    self.R.wait()
+            else:
+                for f in range(f0, f1):
+                    self.step(f)
             e1.record(self.stream)
         if timed:
             self.events = (e0, e1)
@@ -277,12 +288,6 @@ class Lane:
     def close(self):
         self.R.close()
         self.steps = None
-
-
-def run_lanes(lanes, f0, f1, timed):
-    th = [threading.Thread(target=l.run, args=(f0, f1, timed)) for l in lanes]
-    [t.start() for t in th]
-    [t.join() for t in th]
 
 
 def run_ours(args, rank, world, local_rank):
@@ -307,26 +312,27 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
 
     def timed_arm(host_buffers, sampler=None):
-        lanes = [Lane(pkg, torch, worlds, S, rank * C + c, n_frames, local_rank, args, host_buffers) for c in range(C)]
-        run_lanes(lanes, 0, PREFILL + args.warmup, False)  # untimed: map prefill + warm-up steps
+        lane = Lane(pkg, torch, worlds, C * S, C, rank, n_frames, local_rank, args, host_buffers)
+        lane.run(0, PREFILL + args.warmup, False)  # untimed: map prefill + warm-up steps
         barrier()
         if sampler:
             sampler.start()
-        l0 = sum(l.R.launch_count() for l in lanes)
+        l0 = lane.R.launch_count()
         wall0 = time.perf_counter()
-        run_lanes(lanes, PREFILL + args.warmup, n_frames, True)
+        lane.run(PREFILL + args.warmup, n_frames, True)
         barrier()
         wall = time.perf_counter() - wall0
         if sampler:
             sampler.stop_flag = True
-        ms = max(a.elapsed_time(b) for a, b in (l.events for l in lanes))  # lanes run concurrently
+        ms = lane.events[0].elapsed_time(lane.events[1])
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        launches = sum(l.R.launch_count() for l in lanes) - l0
-        h2d = sum(l.h2d for l in lanes)
-        stats = [lanes[0].R.batch_stats[s] for s in range(S)]
+        launches = lane.R.launch_count() - l0
+        h2d = lane.h2d
+        stats = [lane.R.batch_stats[s] for s in range(C * S)]
+        lanes = [lane]
         shape = {k: float(np.mean([getattr(st, k) for st in stats])) for k in
                  ("n_corner_in", "n_surf_in", "n_corner_ds", "n_surf_ds", "n_map_corner", "n_map_surf")}
         shape["n_edge"] = float(np.mean([st.n_edge[1] for st in stats]))
@@ -342,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
 
     # arm 3 (untimed for the headline): one context with profiling on -> K4 roofline and phase split
     prof_steps = min(args.steps, 6)
-    lane = Lane(pkg, torch, worlds, S, rank * C, PREFILL + args.warmup + prof_steps, local_rank, args, False)
+    lane = Lane(pkg, torch, worlds, S, 0, rank, PREFILL + args.warmup + prof_steps, local_rank, args, False)
     lane.run(0, PREFILL + args.warmup, False)
     torch.cuda.synchronize()
     lane.R.set_profiling(True)
@@ -368,13 +374,13 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "hdl64_batch_replay", "sensor": "HDL-64 synthetic 64x1900 (121600 rays/sweep)",
-                   "line_res": LINE_RES, "plane_res": PLANE_RES, "sequences_per_gpu": C * S, "contexts_per_gpu": C,
-                   "sequences_per_context": S, "distinct_worlds": N_WORLDS, "prefill_frames": PREFILL,
+                   "line_res": LINE_RES, "plane_res": PLANE_RES, "sequences_per_gpu": C * S, "lanes_per_gpu": C,
+                   "sequences_per_lane": S, "distinct_worlds": N_WORLDS, "prefill_frames": PREFILL,
                    "registrations_per_step": world * C * S, "parallelism": "independent sequences x%d GPUs, no collective" % world,
                    "l2": "no flush: each step touches >300 MB per context (maps, sort buffers, clouds), larger than the 126 MB L2",
-                   "timing": "CUDA events around the K steps on each context's stream (contexts run concurrently); max over contexts and ranks",
+                   "timing": "CUDA events around the K steps on the caller's stream (the library fences its lanes on it); max over ranks",
                    "per_registration_mean": shape, "datagen_s": round(t_gen, 1),
-                   "phase_ms_per_step_single_context": {k: round(v / prof_steps, 4) for k, v in phases.items()},
+                   "phase_ms_per_step_single_lane": {k: round(v / prof_steps, 4) for k, v in phases.items()},
                    "host_wall_ms_per_step": round(1e3 * wall_dev / args.steps, 3)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d + C * 64 * 128, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
@@ -403,8 +409,9 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seqs", type=int, default=64, help="independent sequences per context (<=64)")
-    ap.add_argument("--ctx", type=int, default=4, help="contexts per GPU, each on its own stream / host thread")
+    ap.add_argument("--seqs", type=int, default=64, help="independent sequences per lane (<=64)")
+    ap.add_argument("--no-pipeline", action="store_true", help="synchronous batch calls instead of submit/wait with two frames in flight")
+    ap.add_argument("--ctx", "--lanes", dest="ctx", type=int, default=4, help="concurrent lanes per GPU inside the one context")
     ap.add_argument("--cap-map-corner", type=int, default=1 << 17)
     ap.add_argument("--cap-map-surf", type=int, default=1 << 17)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -55,6 +55,9 @@ typedef struct s2m_params {
   int trace;             /* debug: keep per-query kNN results of the last call */
   int shard_rank;        /* sharded-map mode: this GPU's rank, 0 when unsharded */
   int shard_world;       /* sharded-map mode: number of GPUs, 1 when unsharded */
+  int lanes;             /* 0: plain context (<= 64 slots, work issued on the caller's thread).
+                            >= 1: the slots are split over this many concurrent lanes (own stream + host
+                            thread each, <= 64 slots per lane) and s2m_register_batch_submit/_wait work */
 } s2m_params;
 
 /* Per-registration statistics (the reference's commented-out printf lines,
@@ -105,6 +108,21 @@ int s2m_register_batch_dev(s2m_ctx* ctx, const float* d_corner_xyzi, const int* 
                            const float* d_surf_xyzi, const int* surf_off, const double* q_wodom,
                            const double* t_wodom, const int* active, double* q_w_out,
                            double* t_w_out, s2m_stats* stats, int* status);
+
+/* Asynchronous pair of the batch call, multi-lane contexts only (params.lanes >= 1).
+ * submit enqueues one frame of every slot and returns at once; wait completes the
+ * OLDEST frame in flight (returns its error code; its outputs are then written).
+ * At most two frames may be in flight: the host->device copy of frame f+1 then overlaps
+ * the registration of frame f, which is how the node's callback queue
+ * (laserMapping.cpp:232-306 pops the next message while the last one is still being
+ * published) maps onto a copy engine.  Offsets, poses and `active` are copied at submit;
+ * the clouds and the output arrays must stay valid until the matching wait.
+ * device_ptrs != 0: the clouds are device pointers (as s2m_register_batch_dev). */
+int s2m_register_batch_submit(s2m_ctx* ctx, const float* corner_xyzi, const int* corner_off,
+                              const float* surf_xyzi, const int* surf_off, const double* q_wodom,
+                              const double* t_wodom, const int* active, double* q_w_out,
+                              double* t_w_out, s2m_stats* stats, int* status, int device_ptrs);
+int s2m_register_batch_wait(s2m_ctx* ctx);
 
 /* wmap<-wodom correction kept by transformUpdate() (laserMapping.cpp:149-153);
  * the shim's high-rate odometry relay (:198-230) composes with it on the host. */

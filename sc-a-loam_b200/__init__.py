@@ -25,7 +25,8 @@ S2M_MAP_TOO_SMALL = 1
 # every symbol include/s2m.h declares (tests check the library exports all of them)
 EXPORTS = [
     "s2m_default_params", "s2m_create", "s2m_destroy", "s2m_strerror", "s2m_last_error", "s2m_set_stream",
-    "s2m_register", "s2m_register_batch", "s2m_register_batch_dev", "s2m_get_correction",
+    "s2m_register", "s2m_register_batch", "s2m_register_batch_dev", "s2m_register_batch_submit",
+    "s2m_register_batch_wait", "s2m_get_correction",
     "s2m_transform_cloud", "s2m_map_upload", "s2m_map_download", "s2m_get_local_map", "s2m_get_surround",
     "s2m_get_window", "s2m_debug_knn", "s2m_trace_cloud", "s2m_trace_knn", "s2m_trace_lm",
     "s2m_launch_count", "s2m_set_profiling", "s2m_k4_profile", "s2m_phase_profile", "s2m_shard_unique_id", "s2m_shard_slab", "s2m_shard_init",
@@ -38,7 +39,7 @@ class Params(ctypes.Structure):
                 ("batch", ctypes.c_int), ("cap_corner_in", ctypes.c_int), ("cap_surf_in", ctypes.c_int),
                 ("cap_map_corner", ctypes.c_int), ("cap_map_surf", ctypes.c_int),
                 ("skip_optimization", ctypes.c_int), ("trace", ctypes.c_int),
-                ("shard_rank", ctypes.c_int), ("shard_world", ctypes.c_int)]
+                ("shard_rank", ctypes.c_int), ("shard_world", ctypes.c_int), ("lanes", ctypes.c_int)]
 
 
 class Stats(ctypes.Structure):
@@ -80,6 +81,8 @@ def load_library(path=LIB_PATH):
     L.s2m_register.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp, vp, vp]
     L.s2m_register_batch.argtypes = [vp] + [vp] * 11
     L.s2m_register_batch_dev.argtypes = [vp] + [vp] * 11
+    L.s2m_register_batch_submit.argtypes = [vp] + [vp] * 11 + [ctypes.c_int]
+    L.s2m_register_batch_wait.argtypes = [vp]
     L.s2m_get_correction.argtypes = [vp, ci, vp, vp]
     L.s2m_transform_cloud.argtypes = [vp, ci, vp, ci, vp]
     L.s2m_map_upload.argtypes = [vp, ci, vp, ci, vp, ci]
@@ -137,7 +140,7 @@ class Registrar:
 
     def __init__(self, line_res=0.4, plane_res=0.8, device=0, batch=1, cap_corner_in=16384,
                  cap_surf_in=131072, cap_map_corner=1 << 19, cap_map_surf=1 << 20,
-                 skip_optimization=False, trace=False, shard_rank=0, shard_world=1):
+                 skip_optimization=False, trace=False, shard_rank=0, shard_world=1, lanes=0):
         self.L = load_library()
         p = default_params()
         p.line_res, p.plane_res, p.device, p.batch = line_res, plane_res, device, batch
@@ -145,6 +148,7 @@ class Registrar:
         p.cap_map_corner, p.cap_map_surf = cap_map_corner, cap_map_surf
         p.skip_optimization, p.trace = int(skip_optimization), int(trace)
         p.shard_rank, p.shard_world = shard_rank, shard_world
+        p.lanes = lanes
         self.params = p
         self.batch = batch
         h = ctypes.c_void_p()
@@ -156,6 +160,7 @@ class Registrar:
         self.stats = Stats()
         self._bstats = (Stats * batch)()
         self._status = np.zeros(batch, np.int32)
+        self._jobs = []
 
     def close(self):
         if getattr(self, "h", None):
@@ -222,6 +227,29 @@ class Registrar:
                 ctypes.cast(self._bstats, ctypes.c_void_p), self._status.ctypes.data)
         self._check(rc)
         return self._status, qo, to
+
+    def submit(self, corner_ptr, corner_off, surf_ptr, surf_off, q_wodom, t_wodom, device=False):
+        """Asynchronous batch call (lanes >= 1): raw pointers (ints) to the packed clouds, which must stay
+        valid until the matching wait().  At most two frames in flight."""
+        B = self.batch
+        job = dict(co=np.ascontiguousarray(corner_off, np.int32), so=np.ascontiguousarray(surf_off, np.int32),
+                   q=_f64(q_wodom).reshape(B, 4), t=_f64(t_wodom).reshape(B, 3), qo=np.zeros((B, 4)), to=np.zeros((B, 3)),
+                   status=np.zeros(B, np.int32), stats=(Stats * B)())
+        rc = self.L.s2m_register_batch_submit(self.h, ctypes.c_void_p(int(corner_ptr)), job["co"].ctypes.data,
+                                              ctypes.c_void_p(int(surf_ptr)), job["so"].ctypes.data, job["q"].ctypes.data,
+                                              job["t"].ctypes.data, None, job["qo"].ctypes.data, job["to"].ctypes.data,
+                                              ctypes.cast(job["stats"], ctypes.c_void_p), job["status"].ctypes.data,
+                                              1 if device else 0)
+        self._check(rc)
+        self._jobs.append(job)
+
+    def wait(self):
+        """Completes the oldest submitted frame -> (status[B], q_w[B,4], t_w[B,3])."""
+        rc = self.L.s2m_register_batch_wait(self.h)
+        job = self._jobs.pop(0)
+        self._check(rc)
+        ctypes.memmove(self._bstats, job["stats"], ctypes.sizeof(self._bstats))
+        return job["status"], job["qo"], job["to"]
 
     @property
     def batch_stats(self):

@@ -13,6 +13,12 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -73,8 +79,82 @@ static bool load() {
 }
 }  // namespace nccl
 
+// One host thread per lane of a multi-lane context (see s2m_params.lanes); jobs run in order.
+struct LaneWorker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::deque<std::function<void()>> q;
+  long long submitted = 0, completed = 0;
+  bool quit = false;
+  void start(int device) {
+    th = std::thread([this, device] {
+      cudaSetDevice(device);
+      for (;;) {
+        std::function<void()> j;
+        {
+          std::unique_lock<std::mutex> lk(m);
+          cv.wait(lk, [&] { return !q.empty() || quit; });
+          if (q.empty()) return;
+          j = std::move(q.front());
+          q.pop_front();
+        }
+        j();
+        {
+          std::lock_guard<std::mutex> lk(m);
+          ++completed;
+        }
+        cv.notify_all();
+      }
+    });
+  }
+  long long submit(std::function<void()> j) {
+    std::lock_guard<std::mutex> lk(m);
+    q.push_back(std::move(j));
+    cv.notify_all();
+    return ++submitted;
+  }
+  void wait(long long ticket) {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return completed >= ticket; });
+  }
+  void stop() {
+    { std::lock_guard<std::mutex> lk(m); quit = true; }
+    cv.notify_all();
+    if (th.joinable()) th.join();
+  }
+};
+
+// one frame in flight on a multi-lane context
+struct PendingFrame {
+  std::vector<std::vector<int>> co, so;  // per lane, rebased offsets
+  std::vector<double> q, t;
+  std::vector<int> active;
+  bool has_active = false;
+  double *q_out = nullptr, *t_out = nullptr;
+  s2m_stats* stats = nullptr;
+  int* status = nullptr;
+  std::vector<int> rcs;
+  std::vector<long long> tickets;
+  int evslot = 0;
+};
+
 struct s2m_ctx {
   s2m_params P;
+  // multi-lane context: the slots are split over `children` (each a complete context with its own
+  // stream, buffers and host thread); the fields below this block are unused in the parent
+  std::vector<s2m_ctx*> children;
+  std::vector<LaneWorker*> workers;
+  std::vector<cudaEvent_t> lane_done;   // [2 frames in flight][lanes]
+  cudaEvent_t lane_start[2] = {nullptr, nullptr};
+  std::deque<std::unique_ptr<PendingFrame>> in_flight;
+  int frame_seq = 0;
+  int lane_batch = 0;
+  // leaf: double-buffered incoming clouds so the copy of the next frame overlaps this frame's work
+  float4* in_buf[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr};
+  int stage_next = 0;
   Dev d;
   int cur = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -134,6 +214,17 @@ static void prof_resolve(s2m_ctx* ctx) {
   ctx->ev_used = 0;
 }
 
+// multi-lane contexts forward per-slot calls to the lane that holds the slot
+#define ROUTE_SLOT(expr)                                                          \
+  if (ctx && !ctx->children.empty()) {                                            \
+    if (slot < 0 || slot >= ctx->P.batch) return S2M_ERR_ARG;                     \
+    s2m_ctx* ch = ctx->children[slot / ctx->lane_batch];                          \
+    slot = slot % ctx->lane_batch;                                                \
+    const int rc_ = (expr);                                                       \
+    if (rc_ < 0) ctx->err = ch->err;                                              \
+    return rc_;                                                                   \
+  }
+
 #define CK(call)                                                                         \
   do {                                                                                   \
     cudaError_t e_ = (call);                                                             \
@@ -169,6 +260,7 @@ extern "C" void s2m_default_params(s2m_params* p) {
   p->cap_map_corner = 1 << 20;
   p->cap_map_surf = 1 << 21;
   p->shard_world = 1;
+  p->lanes = 0;
 }
 
 extern "C" const char* s2m_strerror(int code) {
@@ -185,9 +277,19 @@ extern "C" const char* s2m_strerror(int code) {
 }
 extern "C" const char* s2m_last_error(s2m_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+static int parent_wait(s2m_ctx* ctx);
 extern "C" void s2m_destroy(s2m_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->P.device);
+  while (!ctx->in_flight.empty()) parent_wait(ctx);
+  for (LaneWorker* w : ctx->workers) { w->stop(); delete w; }
+  for (s2m_ctx* ch : ctx->children) s2m_destroy(ch);
+  for (cudaEvent_t e : ctx->lane_done) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->lane_start[i]) cudaEventDestroy(ctx->lane_start[i]);
+    if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (void* p : ctx->allocs) cudaFree(p);
   if (ctx->ht) cudaFreeHost(ctx->ht);
@@ -210,6 +312,8 @@ static int create_impl(s2m_ctx* ctx) {
   CK(cudaSetDevice(P.device));
   CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, P.device));
+  CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
   ctx->stream = ctx->own_stream;
   Dev& d = ctx->d;
   std::memset(&d, 0, sizeof(d));
@@ -247,7 +351,8 @@ static int create_impl(s2m_ctx* ctx) {
 
   int rc = 0;
   rc |= dev_alloc(ctx, &d.st_base, G); rc |= dev_alloc(ctx, &d.st_cap, G);
-  rc |= dev_alloc(ctx, &d.in_pts, d.cap_in);
+  rc |= dev_alloc(ctx, &ctx->in_buf[0], d.cap_in); rc |= dev_alloc(ctx, &ctx->in_buf[1], d.cap_in);
+  d.in_pts = ctx->in_buf[0];
   rc |= dev_alloc(ctx, &d.vkey, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.vkey2, d.cap_sort + 1);
   rc |= dev_alloc(ctx, &d.vval, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.vval2, d.cap_sort + 1);
   rc |= dev_alloc(ctx, &d.flag, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.scan, d.cap_sort + 1);
@@ -310,7 +415,7 @@ static int create_impl(s2m_ctx* ctx) {
 extern "C" int s2m_create(const s2m_params* p, s2m_ctx** out) {
   if (!p || !out) return S2M_ERR_ARG;
   *out = nullptr;
-  if (p->batch < 1 || p->batch > kMaxBatch || !(p->line_res > 0.03f) || !(p->plane_res > 0.03f) ||
+  if (p->batch < 1 || p->lanes < 0 || p->lanes > 64 || p->batch > 64 * kMaxBatch || !(p->line_res > 0.03f) || !(p->plane_res > 0.03f) ||
       p->cap_corner_in < 1 || p->cap_surf_in < 1 || p->cap_map_corner < 1 || p->cap_map_surf < 1)
     return S2M_ERR_ARG;
   int ndev = 0;
@@ -318,7 +423,42 @@ extern "C" int s2m_create(const s2m_params* p, s2m_ctx** out) {
   s2m_ctx* ctx = new s2m_ctx();
   ctx->P = *p;
   if (ctx->P.shard_world < 1) ctx->P.shard_world = 1;
-  if (ctx->P.shard_rank < 0 || ctx->P.shard_rank >= ctx->P.shard_world) { delete ctx; return S2M_ERR_ARG; }
+  {  // lanes: slots split over independent sub-contexts that run concurrently inside one call
+    int lanes = std::max(0, p->lanes);
+    if (p->batch > kMaxBatch) lanes = std::max(lanes, (p->batch + kMaxBatch - 1) / kMaxBatch);
+    lanes = std::min(lanes, p->batch);
+    if (lanes >= 1) {
+      ctx->lane_batch = (p->batch + lanes - 1) / lanes;
+      int rc = S2M_OK;
+      for (int i = 0; i * ctx->lane_batch < p->batch && rc == S2M_OK; ++i) {
+        s2m_params cp = *p;
+        cp.lanes = 0;
+        cp.batch = std::min(ctx->lane_batch, p->batch - i * ctx->lane_batch);
+        s2m_ctx* ch = nullptr;
+        rc = s2m_create(&cp, &ch);
+        if (rc == S2M_OK) ctx->children.push_back(ch);
+      }
+      if (rc == S2M_OK && (cudaSetDevice(p->device) != cudaSuccess ||
+                           cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&ctx->lane_start[0], cudaEventDisableTiming) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&ctx->lane_start[1], cudaEventDisableTiming) != cudaSuccess))
+        rc = S2M_ERR_CUDA;
+      if (rc != S2M_OK) { s2m_destroy(ctx); return rc; }
+      ctx->stream = ctx->own_stream;
+      for (size_t i = 0; i < 2 * ctx->children.size(); ++i) {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        ctx->lane_done.push_back(e);
+      }
+      for (size_t i = 0; i < ctx->children.size(); ++i) {
+        LaneWorker* w = new LaneWorker();
+        w->start(p->device);
+        ctx->workers.push_back(w);
+      }
+      *out = ctx;
+      return S2M_OK;
+    }
+  }
   int rc = create_impl(ctx);
   if (rc != S2M_OK) {
     fprintf(stderr, "s2m_create: %s\n", ctx->err.c_str());
@@ -337,7 +477,12 @@ extern "C" int s2m_set_stream(s2m_ctx* ctx, void* cuda_stream) {
   return S2M_OK;
 }
 
-extern "C" long long s2m_launch_count(s2m_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" long long s2m_launch_count(s2m_ctx* ctx) {
+  if (!ctx) return 0;
+  long long n = ctx->launches;
+  for (s2m_ctx* ch : ctx->children) n += ch->launches;
+  return n;
+}
 
 // ---- sharded map: allreduce of the per-rank sums (latency-bound: 32 doubles per slot) ----------
 static int shard_allreduce(s2m_ctx* ctx, void* buf, size_t count, int dtype) {
@@ -608,19 +753,118 @@ static int check_offsets(s2m_ctx* ctx, const int* corner_off, const int* surf_of
   return S2M_OK;
 }
 
+// leaf: enqueue the copy of one frame's clouds into the next staging buffer (copy stream)
+static int leaf_stage(s2m_ctx* ctx, const float* corner, const int* corner_off, const float* surf, const int* surf_off,
+                      cudaMemcpyKind kind, cudaStream_t cs, cudaEvent_t after, int* stage_out) {
+  const int B = ctx->d.B;
+  const long long NC = corner_off[B], NS = surf_off[B];
+  if (corner_off[0] != 0 || surf_off[0] != 0 || NC < 0 || NS < 0) { ctx->err = "offset arrays must start at 0"; return S2M_ERR_ARG; }
+  if (NC + NS > ctx->d.cap_in) { ctx->err = "incoming clouds larger than the context's input capacity"; return S2M_ERR_CAPACITY; }
+  const int st = ctx->stage_next;
+  ctx->stage_next ^= 1;
+  if (after) CK(cudaStreamWaitEvent(cs, after, 0));
+  if (NC > 0) CK(cudaMemcpyAsync(ctx->in_buf[st], corner, sizeof(float4) * (size_t)NC, kind, cs));
+  if (NS > 0) CK(cudaMemcpyAsync(ctx->in_buf[st] + NC, surf, sizeof(float4) * (size_t)NS, kind, cs));
+  CK(cudaEventRecord(ctx->ev_in[st], cs));
+  *stage_out = st;
+  return S2M_OK;
+}
+// leaf: run one frame on the clouds staged in buffer `st`
+static int leaf_run(s2m_ctx* ctx, int st, const int* corner_off, const int* surf_off, const double* q_wodom,
+                    const double* t_wodom, const int* active, double* q_out, double* t_out, s2m_stats* stats, int* status) {
+  CK(cudaSetDevice(ctx->P.device));
+  int rc = check_offsets(ctx, corner_off, surf_off);
+  if (rc != S2M_OK) return rc;
+  ctx->d.in_pts = ctx->in_buf[st];
+  prof_mark(ctx, -1);
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[st], 0));
+  return run_frame(ctx, corner_off, surf_off, q_wodom, t_wodom, active, q_out, t_out, stats, status);
+}
+
+static int parent_wait(s2m_ctx* ctx) {
+  if (ctx->in_flight.empty()) { ctx->err = "no frame in flight"; return S2M_ERR_ARG; }
+  std::unique_ptr<PendingFrame> pf = std::move(ctx->in_flight.front());
+  ctx->in_flight.pop_front();
+  const int L = (int)ctx->children.size();
+  int rc_all = S2M_OK;
+  for (int i = 0; i < L; ++i) {
+    ctx->workers[i]->wait(pf->tickets[i]);
+    cudaStreamWaitEvent(ctx->stream, ctx->lane_done[pf->evslot * L + i], 0);
+    if (pf->rcs[i] < 0 && rc_all == S2M_OK) { rc_all = pf->rcs[i]; ctx->err = ctx->children[i]->err; }
+  }
+  return rc_all;
+}
+
+// every lane advances its slots on its own stream and host thread; the caller's stream is fenced
+// on both sides so events recorded around submit ... wait bracket all the work
+static int parent_submit(s2m_ctx* ctx, const float* corner, const int* corner_off, const float* surf, const int* surf_off,
+                         const double* q_wodom, const double* t_wodom, const int* active, double* q_out, double* t_out,
+                         s2m_stats* stats, int* status, cudaMemcpyKind kind) {
+  if (ctx->in_flight.size() >= 2) { ctx->err = "at most two frames may be in flight: call s2m_register_batch_wait first"; return S2M_ERR_ARG; }
+  const int L = (int)ctx->children.size(), Bl = ctx->lane_batch, B = ctx->P.batch;
+  std::unique_ptr<PendingFrame> pf(new PendingFrame());
+  pf->evslot = ctx->frame_seq++ & 1;
+  pf->co.resize(L); pf->so.resize(L); pf->rcs.assign(L, S2M_OK); pf->tickets.assign(L, 0);
+  pf->q.assign(q_wodom, q_wodom + 4 * (size_t)B); pf->t.assign(t_wodom, t_wodom + 3 * (size_t)B);
+  pf->has_active = active != nullptr;
+  if (active) pf->active.assign(active, active + B);
+  pf->q_out = q_out; pf->t_out = t_out; pf->stats = stats; pf->status = status;
+  CK(cudaEventRecord(ctx->lane_start[pf->evslot], ctx->stream));
+  PendingFrame* P = pf.get();
+  for (int i = 0; i < L; ++i) {
+    s2m_ctx* ch = ctx->children[i];
+    const int b0 = i * Bl, nb = ch->P.batch;
+    P->co[i].resize(nb + 1); P->so[i].resize(nb + 1);
+    for (int b = 0; b <= nb; ++b) { P->co[i][b] = corner_off[b0 + b] - corner_off[b0]; P->so[i][b] = surf_off[b0 + b] - surf_off[b0]; }
+    int st = 0;
+    int rc = leaf_stage(ch, corner ? corner + 4 * (size_t)corner_off[b0] : nullptr, P->co[i].data(),
+                        surf ? surf + 4 * (size_t)surf_off[b0] : nullptr, P->so[i].data(), kind, ch->copy_stream,
+                        ctx->lane_start[P->evslot], &st);
+    if (rc != S2M_OK) P->rcs[i] = rc;
+    cudaEvent_t done = ctx->lane_done[P->evslot * L + i];
+    P->tickets[i] = ctx->workers[i]->submit([=]() {
+      if (P->rcs[i] == S2M_OK)
+        P->rcs[i] = leaf_run(ch, st, P->co[i].data(), P->so[i].data(), P->q.data() + 4 * b0, P->t.data() + 3 * b0,
+                             P->has_active ? P->active.data() + b0 : nullptr, P->q_out + 4 * b0, P->t_out + 3 * b0,
+                             P->stats ? P->stats + b0 : nullptr, P->status ? P->status + b0 : nullptr);
+      cudaEventRecord(done, ch->stream);
+    });
+  }
+  ctx->in_flight.push_back(std::move(pf));
+  return S2M_OK;
+}
+
 static int register_batch_impl(s2m_ctx* ctx, const float* corner, const int* corner_off, const float* surf,
                                const int* surf_off, const double* q_wodom, const double* t_wodom, const int* active,
                                double* q_out, double* t_out, s2m_stats* stats, int* status, cudaMemcpyKind kind) {
   if (!ctx || !corner_off || !surf_off || !q_wodom || !t_wodom || !q_out || !t_out) return S2M_ERR_ARG;
   CK(cudaSetDevice(ctx->P.device));
-  int rc = check_offsets(ctx, corner_off, surf_off);
+  if (!ctx->children.empty()) {
+    if (!ctx->in_flight.empty()) { ctx->err = "frames still in flight: wait for them before a synchronous call"; return S2M_ERR_ARG; }
+    int rc = parent_submit(ctx, corner, corner_off, surf, surf_off, q_wodom, t_wodom, active, q_out, t_out, stats, status, kind);
+    if (rc != S2M_OK) return rc;
+    return parent_wait(ctx);
+  }
+  int st = 0;
+  int rc = leaf_stage(ctx, corner, corner_off, surf, surf_off, kind, ctx->stream, nullptr, &st);
   if (rc != S2M_OK) return rc;
-  const int B = ctx->d.B;
-  const int NC = corner_off[B], NS = surf_off[B];
-  prof_mark(ctx, -1);
-  if (NC > 0) CK(cudaMemcpyAsync(ctx->d.in_pts, corner, sizeof(float4) * (size_t)NC, kind, ctx->stream));
-  if (NS > 0) CK(cudaMemcpyAsync(ctx->d.in_pts + NC, surf, sizeof(float4) * (size_t)NS, kind, ctx->stream));
-  return run_frame(ctx, corner_off, surf_off, q_wodom, t_wodom, active, q_out, t_out, stats, status);
+  return leaf_run(ctx, st, corner_off, surf_off, q_wodom, t_wodom, active, q_out, t_out, stats, status);
+}
+
+extern "C" int s2m_register_batch_submit(s2m_ctx* ctx, const float* corner, const int* corner_off, const float* surf,
+                                         const int* surf_off, const double* q_wodom, const double* t_wodom,
+                                         const int* active, double* q_out, double* t_out, s2m_stats* stats, int* status,
+                                         int device_ptrs) {
+  if (!ctx || !corner_off || !surf_off || !q_wodom || !t_wodom || !q_out || !t_out) return S2M_ERR_ARG;
+  if (ctx->children.empty()) { ctx->err = "the asynchronous pair needs a multi-lane context (s2m_params.lanes >= 1)"; return S2M_ERR_ARG; }
+  CK(cudaSetDevice(ctx->P.device));
+  return parent_submit(ctx, corner, corner_off, surf, surf_off, q_wodom, t_wodom, active, q_out, t_out, stats, status,
+                       device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice);
+}
+extern "C" int s2m_register_batch_wait(s2m_ctx* ctx) {
+  if (!ctx || ctx->children.empty()) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  return parent_wait(ctx);
 }
 
 extern "C" int s2m_register_batch(s2m_ctx* ctx, const float* corner, const int* corner_off, const float* surf,
@@ -640,6 +884,7 @@ extern "C" int s2m_register_batch_dev(s2m_ctx* ctx, const float* corner, const i
 extern "C" int s2m_register(s2m_ctx* ctx, const float* corner, int nc, const float* surf, int ns,
                             const double q_wodom[4], const double t_wodom[3], double q_out[4], double t_out[3],
                             s2m_stats* stats) {
+  if (ctx && !ctx->children.empty()) return s2m_register(ctx->children[0], corner, nc, surf, ns, q_wodom, t_wodom, q_out, t_out, stats);
   if (!ctx || nc < 0 || ns < 0) return S2M_ERR_ARG;
   const int B = ctx->d.B;
   std::vector<int> co(B + 1, nc), so(B + 1, ns), act(B, 0);
@@ -658,18 +903,21 @@ extern "C" int s2m_register(s2m_ctx* ctx, const float* corner, int nc, const flo
 }
 
 extern "C" int s2m_get_correction(s2m_ctx* ctx, int slot, double q[4], double t[3]) {
+  ROUTE_SLOT(s2m_get_correction(ch, slot, q, t));
   if (!ctx || slot < 0 || slot >= ctx->d.B) return S2M_ERR_ARG;
   std::memcpy(q, ctx->slots[slot].q_wmap_wodom, 32);
   std::memcpy(t, ctx->slots[slot].t_wmap_wodom, 24);
   return S2M_OK;
 }
 extern "C" int s2m_get_window(s2m_ctx* ctx, int slot, int cen[3]) {
+  ROUTE_SLOT(s2m_get_window(ch, slot, cen));
   if (!ctx || slot < 0 || slot >= ctx->d.B) return S2M_ERR_ARG;
   std::memcpy(cen, ctx->slots[slot].cen, 12);
   return S2M_OK;
 }
 
 extern "C" int s2m_transform_cloud(s2m_ctx* ctx, int slot, const float* in, int n, float* out) {
+  ROUTE_SLOT(s2m_transform_cloud(ch, slot, in, n, out));
   if (!ctx || slot < 0 || slot >= ctx->d.B || n < 0) return S2M_ERR_ARG;
   if (n > ctx->d.cap_sort) return S2M_ERR_CAPACITY;
   if (n == 0) return S2M_OK;
@@ -685,6 +933,7 @@ extern "C" int s2m_transform_cloud(s2m_ctx* ctx, int slot, const float* in, int 
 
 // ---- map access ---------------------------------------------------------------
 extern "C" int s2m_map_upload(s2m_ctx* ctx, int slot, const float* corner, int nc, const float* surf, int ns) {
+  ROUTE_SLOT(s2m_map_upload(ch, slot, corner, nc, surf, ns));
   if (!ctx || slot < 0 || slot >= ctx->d.B || nc < 0 || ns < 0) return S2M_ERR_ARG;
   if (nc > ctx->P.cap_map_corner || ns > ctx->P.cap_map_surf || nc + ns > ctx->d.cap_in) return S2M_ERR_CAPACITY;
   CK(cudaSetDevice(ctx->P.device));
@@ -758,6 +1007,7 @@ static int download_store(s2m_ctx* ctx, int slot, int cls, std::vector<uint64_t>
 }
 
 extern "C" int s2m_map_download(s2m_ctx* ctx, int slot, int cls, float* out, int cap) {
+  ROUTE_SLOT(s2m_map_download(ch, slot, cls, out, cap));
   if (!ctx || slot < 0 || slot >= ctx->d.B || cls < 0 || cls > 1) return S2M_ERR_ARG;
   CK(cudaSetDevice(ctx->P.device));
   std::vector<uint64_t> keys;
@@ -785,6 +1035,7 @@ static int prepare_local(s2m_ctx* ctx, int slot, const double centre_t[3], int* 
 }
 
 extern "C" int s2m_get_local_map(s2m_ctx* ctx, int slot, int cls, const double centre_t[3], float* out, int cap) {
+  ROUTE_SLOT(s2m_get_local_map(ch, slot, cls, centre_t, out, cap));
   if (!ctx || slot < 0 || slot >= ctx->d.B || cls < 0 || cls > 1 || !centre_t) return S2M_ERR_ARG;
   CK(cudaSetDevice(ctx->P.device));
   int total_lp, hash_total;
@@ -805,6 +1056,7 @@ extern "C" int s2m_get_local_map(s2m_ctx* ctx, int slot, int cls, const double c
 
 extern "C" int s2m_debug_knn(s2m_ctx* ctx, int slot, int cls, const double centre_t[3], const float* q_xyz, int n,
                              int32_t* idx5, float* d2_5) {
+  ROUTE_SLOT(s2m_debug_knn(ch, slot, cls, centre_t, q_xyz, n, idx5, d2_5));
   if (!ctx || slot < 0 || slot >= ctx->d.B || cls < 0 || cls > 1 || !centre_t || n < 0) return S2M_ERR_ARG;
   if ((size_t)n * 5 > (size_t)ctx->d.cap_sort) return S2M_ERR_CAPACITY;
   CK(cudaSetDevice(ctx->P.device));
@@ -831,6 +1083,7 @@ extern "C" int s2m_debug_knn(s2m_ctx* ctx, int slot, int cls, const double centr
 }
 
 extern "C" int s2m_get_surround(s2m_ctx* ctx, int slot, float* out, int cap) {
+  ROUTE_SLOT(s2m_get_surround(ch, slot, out, cap));
   if (!ctx || slot < 0 || slot >= ctx->d.B || cap < 0) return S2M_ERR_ARG;
   CK(cudaSetDevice(ctx->P.device));
   // corner then surf of each valid cube, cubes in gather order (laserMapping.cpp:810-815), gathered
@@ -864,6 +1117,7 @@ static int seg_ds_range(s2m_ctx* ctx, int slot, int cls, int* off, int* n) {
   return S2M_OK;
 }
 extern "C" int s2m_trace_cloud(s2m_ctx* ctx, int slot, int cls, float* out, int cap) {
+  ROUTE_SLOT(s2m_trace_cloud(ch, slot, cls, out, cap));
   if (!ctx || slot < 0 || slot >= ctx->d.B || cls < 0 || cls > 1) return S2M_ERR_ARG;
   CK(cudaSetDevice(ctx->P.device));
   int off, n;
@@ -877,6 +1131,7 @@ extern "C" int s2m_trace_cloud(s2m_ctx* ctx, int slot, int cls, float* out, int 
 }
 extern "C" int s2m_trace_knn(s2m_ctx* ctx, int slot, int outer, int cls, int32_t* idx5, float* d2_5, uint8_t* used,
                              int cap) {
+  ROUTE_SLOT(s2m_trace_knn(ch, slot, outer, cls, idx5, d2_5, used, cap));
   if (!ctx || !ctx->P.trace || slot < 0 || slot >= ctx->d.B || cls < 0 || cls > 1 || outer < 0 || outer > 1) return S2M_ERR_ARG;
   CK(cudaSetDevice(ctx->P.device));
   int off, n;
@@ -894,6 +1149,7 @@ extern "C" int s2m_trace_knn(s2m_ctx* ctx, int slot, int outer, int cls, int32_t
 }
 extern "C" int s2m_trace_lm(s2m_ctx* ctx, int slot, int outer, double pose7[7], double sums28[28], double iters24[24],
                             int* n_iter, int* termination) {
+  ROUTE_SLOT(s2m_trace_lm(ch, slot, outer, pose7, sums28, iters24, n_iter, termination));
   if (!ctx || !ctx->P.trace || slot < 0 || slot >= ctx->d.B || outer < 0 || outer > 1) return S2M_ERR_ARG;
   CK(cudaSetDevice(ctx->P.device));
   LmState* h = ctx->h_lm;
@@ -910,11 +1166,27 @@ extern "C" int s2m_trace_lm(s2m_ctx* ctx, int slot, int outer, double pose7[7], 
 // ---- profiling ------------------------------------------------------------------
 extern "C" int s2m_set_profiling(s2m_ctx* ctx, int on) {
   if (!ctx) return S2M_ERR_ARG;
+  for (s2m_ctx* ch : ctx->children) s2m_set_profiling(ch, on);
   ctx->profiling = on != 0;
   return S2M_OK;
 }
 extern "C" int s2m_k4_profile(s2m_ctx* ctx, int reset, double* ms_total, long long* launches, double* alg_bytes) {
   if (!ctx) return S2M_ERR_ARG;
+  if (!ctx->children.empty()) {  // sums over the lanes
+    double ms = 0, by = 0;
+    long long n = 0;
+    for (s2m_ctx* ch : ctx->children) {
+      double m1 = 0, b1 = 0;
+      long long n1 = 0;
+      int rc = s2m_k4_profile(ch, reset, &m1, &n1, &b1);
+      if (rc != S2M_OK) return rc;
+      ms += m1; by += b1; n += n1;
+    }
+    if (ms_total) *ms_total = ms;
+    if (launches) *launches = n;
+    if (alg_bytes) *alg_bytes = by;
+    return S2M_OK;
+  }
   CK(cudaSetDevice(ctx->P.device));
   prof_resolve(ctx);
   if (ms_total) *ms_total = ctx->phase_ms[S2M_PHASE_ASSOCIATE];
@@ -928,6 +1200,16 @@ extern "C" int s2m_k4_profile(s2m_ctx* ctx, int reset, double* ms_total, long lo
 }
 extern "C" int s2m_phase_profile(s2m_ctx* ctx, int reset, double ms[S2M_N_PHASES]) {
   if (!ctx || !ms) return S2M_ERR_ARG;
+  if (!ctx->children.empty()) {  // sums over the lanes
+    for (int i = 0; i < S2M_N_PHASES; ++i) ms[i] = 0;
+    for (s2m_ctx* ch : ctx->children) {
+      double m1[S2M_N_PHASES];
+      int rc = s2m_phase_profile(ch, reset, m1);
+      if (rc != S2M_OK) return rc;
+      for (int i = 0; i < S2M_N_PHASES; ++i) ms[i] += m1[i];
+    }
+    return S2M_OK;
+  }
   CK(cudaSetDevice(ctx->P.device));
   prof_resolve(ctx);
   for (int i = 0; i < S2M_N_PHASES; ++i) ms[i] = ctx->phase_ms[i];
@@ -961,7 +1243,7 @@ extern "C" int s2m_shard_unique_id(void* id128) {
   return S2M_OK;
 }
 extern "C" int s2m_shard_init(s2m_ctx* ctx, const void* id128) {
-  if (!ctx || !id128 || ctx->P.shard_world <= 1) return S2M_ERR_ARG;
+  if (!ctx || !id128 || ctx->P.shard_world <= 1 || !ctx->children.empty()) return S2M_ERR_ARG;
   if (!nccl::load()) { ctx->err = "libnccl.so.2 not found"; return S2M_ERR_NCCL; }
   CK(cudaSetDevice(ctx->P.device));
   nccl::UniqueId id;

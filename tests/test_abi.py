@@ -23,8 +23,8 @@ def test_library_exports_every_symbol(s2m, built):
 
 
 def test_struct_sizes(s2m, built):
-    # s2m_params: 2 floats + 10 ints; s2m_stats: 15 ints (+pad) + 4 doubles
-    assert ctypes.sizeof(s2m.Params) == 48
+    # s2m_params: 2 floats + 11 ints; s2m_stats: 15 ints (+pad) + 4 doubles
+    assert ctypes.sizeof(s2m.Params) == 52
     assert ctypes.sizeof(s2m.Stats) == 96
     p = s2m.default_params()
     assert abs(p.line_res - 0.4) < 1e-7 and abs(p.plane_res - 0.8) < 1e-7 and p.batch == 1

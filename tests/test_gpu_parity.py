@@ -217,12 +217,13 @@ def test_perturbed_initial_guesses_against_a_mature_map(s2m, built):
     assert worst_t < TOL_T and worst_r < TOL_R, (worst_t, worst_r)
 
 
-def test_batch_slots_are_independent_and_identical_to_single(s2m, seq_hdl, seq_vlp):
-    """register_batch over 3 slots == 3 single-slot contexts, bit for bit (no cross-talk)."""
+@pytest.mark.parametrize("lanes", [0, 1, 2, 3])
+def test_batch_slots_are_independent_and_identical_to_single(s2m, seq_hdl, seq_vlp, lanes):
+    """register_batch over 3 slots (plain context, or 1, 2, 3 concurrent lanes) == 3 single-slot contexts, bit for bit."""
     truth, odom, frames = seq_hdl
     n = 6
     B = 3
-    RB = s2m.Registrar(0.4, 0.8, batch=B, cap_map_corner=1 << 17, cap_map_surf=1 << 18)
+    RB = s2m.Registrar(0.4, 0.8, batch=B, lanes=lanes, cap_map_corner=1 << 17, cap_map_surf=1 << 18)
     singles = [s2m.Registrar(0.4, 0.8, cap_map_corner=1 << 17, cap_map_surf=1 << 18) for _ in range(B)]
     for f in range(n):
         # slot b replays the sequence with a lag of b frames (different inputs per slot, ragged sizes)
@@ -241,6 +242,45 @@ def test_batch_slots_are_independent_and_identical_to_single(s2m, seq_hdl, seq_v
             rc, q1, t1 = singles[b].register(frames[fr[b]][0], frames[fr[b]][1], odom[fr[b], :4], odom[fr[b], 4:])
             assert st[b] == rc
             assert np.array_equal(qo[b], q1) and np.array_equal(to[b], t1), (f, b)
+
+
+def test_submit_wait_pipeline_matches_synchronous_calls(s2m, seq_hdl):
+    """s2m_register_batch_submit/_wait with two frames in flight (the copy of frame f+1 overlapping frame f)
+    returns, frame by frame, the bits of the synchronous calls; a third submit is refused; a plain
+    context refuses the pair."""
+    truth, odom, frames = seq_hdl
+    n, B = 6, 2
+    kw = dict(cap_map_corner=1 << 17, cap_map_surf=1 << 18)
+    RA = s2m.Registrar(0.4, 0.8, batch=B, lanes=2, **kw)
+    RS = s2m.Registrar(0.4, 0.8, batch=B, lanes=0, **kw)
+    packed = []
+    for f in range(n):
+        fr = [f, max(f - 1, 0)]
+        corner = np.ascontiguousarray(np.concatenate([frames[i][0] for i in fr]), np.float32)
+        surf = np.ascontiguousarray(np.concatenate([frames[i][1] for i in fr]), np.float32)
+        co = np.cumsum([0] + [len(frames[i][0]) for i in fr]).astype(np.int32)
+        so = np.cumsum([0] + [len(frames[i][1]) for i in fr]).astype(np.int32)
+        packed.append((corner, co, surf, so, np.array([odom[i, :4] for i in fr]), np.array([odom[i, 4:] for i in fr])))
+    want = [RS.register_batch(*p) for p in packed]
+    got = []
+    for f, (corner, co, surf, so, q, t) in enumerate(packed):
+        if f >= 2:
+            got.append(RA.wait())
+        RA.submit(corner.ctypes.data, co, surf.ctypes.data, so, q, t)
+    with pytest.raises(s2m.S2MError):
+        c, co, su, so, q, t = packed[-1]
+        RA.submit(c.ctypes.data, co, su.ctypes.data, so, q, t)      # two already in flight
+    got.append(RA.wait())
+    got.append(RA.wait())
+    for f in range(n):
+        assert np.array_equal(got[f][0], want[f][0])
+        assert np.array_equal(got[f][1], want[f][1]) and np.array_equal(got[f][2], want[f][2]), f
+    for cls in (0, 1):
+        for b in range(B):
+            assert np.array_equal(bits(RA.map_download(cls, b)), bits(RS.map_download(cls, b)))
+    with pytest.raises(s2m.S2MError):
+        c, co, su, so, q, t = packed[0]
+        RS.submit(c.ctypes.data, co, su.ctypes.data, so, q, t)
 
 
 def test_window_shift_and_eviction(s2m, built):
