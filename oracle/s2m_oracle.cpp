@@ -9,7 +9,12 @@
 // Eigen 3.3 / Ceres 1.12-2.1, none of which is installed here.
 // What IS pinned: the kNN part is checked against the KD-tree the reference
 // vendors (include/scancontext/nanoflann.hpp, built into oracle/_ref by
-// oracle/Makefile) and against brute force.
+// oracle/Makefile) and against brute force.  One end-to-end anchor on the
+// reference's OWN OUTPUT exists, at centimetre (not bit) level: the real OS1-64
+// scans and saved poses under utils/sample_data/KAIST03 -- this restatement,
+// given the map those poses produce, pulls guesses perturbed by 0.2 m / 1 deg
+// back to within 6 cm / 0.45 deg of the pose the reference saved
+// (tests/golden/make_kaist03.py, tests/test_golden.py).
 //
 // What follows the reference line by line (file = /root/reference/src/laserMapping.cpp):
 //   A  transformAssociateToMap            :143-147      -> Mapper::associate_to_map

@@ -2,6 +2,8 @@
 
 knn_nanoflann.npz holds answers of the KD-tree vendored in the reference tree
 (include/scancontext/nanoflann.hpp) -- produced by reference code in the authoring container.
+kaist03.npz (tests/golden/make_kaist03.py) is derived from the REAL OS1-64 scans and saved poses the
+reference ships under utils/sample_data/KAIST03 -- output of the reference pipeline itself.
 The others pin the oracle's outputs at the commit that generated them."""
 import os
 
@@ -41,6 +43,45 @@ def test_oracle_stream_matches_golden(built):
                st.n_plane[0], st.n_plane[1], st.lm_iters[0], st.lm_iters[1]]
         assert got == list(g["counters"][f])
         assert np.abs(np.r_[q, t] - g["poses"][f]).max() < 1e-12
+
+
+def rot_deg(qa, qb):
+    d = abs(float(np.dot(qa / np.linalg.norm(qa), qb / np.linalg.norm(qb))))
+    return np.rad2deg(2.0 * np.arccos(min(1.0, d)))
+
+
+KAIST_TOL_M, KAIST_TOL_DEG = 0.06, 0.45   # decimetre-level anchor, not bit parity
+
+
+def replay_kaist03(reg, upload):
+    """Real scans 10..14 registered, from perturbed guesses, against the map the reference's own saved
+    poses produce for scans 0..9; returns the poses and checks them against the poses the reference saved."""
+    g = np.load(os.path.join(G, "kaist03.npz"))
+    assert upload(g["map_corner"], g["map_surf"]) == 0
+    out = []
+    for i, k in enumerate(g["frames"]):
+        rc, q, t = reg(g["corner_%d" % k], g["surf_%d" % k], g["guess_q"][i], g["guess_t"][i])
+        assert rc == 0
+        before = np.linalg.norm(g["guess_t"][i] - g["ref_t"][i])
+        after = np.linalg.norm(t - g["ref_t"][i])
+        assert after < KAIST_TOL_M and after < 0.3 * before, (k, before, after)
+        assert rot_deg(q, g["ref_q"][i]) < KAIST_TOL_DEG, k
+        out.append(np.r_[q, t])
+    return g, np.array(out)
+
+
+def test_oracle_registers_real_kaist03_scans_onto_the_reference_poses(built):
+    O = oracle.Oracle(0.4, 0.8)
+    g, poses = replay_kaist03(O.register, O.map_upload)
+    assert np.abs(poses - np.c_[g["oracle_q"], g["oracle_t"]]).max() < 1e-12
+
+
+@pytest.mark.gpu
+def test_cuda_registers_real_kaist03_scans_onto_the_reference_poses(s2m, built):
+    R = s2m.Registrar(0.4, 0.8)
+    g, poses = replay_kaist03(R.register, R.map_upload)
+    assert np.linalg.norm(poses[:, 4:] - g["oracle_t"], axis=1).max() < 1e-4
+    assert np.abs(poses[:, :4] - g["oracle_q"]).max() < 1e-5
 
 
 @pytest.mark.gpu
