@@ -35,6 +35,7 @@ extern "C" {
 #define S2M_ERR_CAPACITY (-3) /* an input or the map exceeded the capacities given at create */
 #define S2M_ERR_RANGE (-4)    /* coordinates outside the supported lattice range */
 #define S2M_ERR_NCCL (-5)
+#define S2M_ERR_IO (-6)       /* a checkpoint / PCD file could not be read or written */
 
 typedef struct s2m_ctx s2m_ctx;
 
@@ -123,6 +124,21 @@ int s2m_register_batch_submit(s2m_ctx* ctx, const float* corner_xyzi, const int*
                               const double* t_wodom, const int* active, double* q_w_out,
                               double* t_w_out, s2m_stats* stats, int* status, int device_ptrs);
 int s2m_register_batch_wait(s2m_ctx* ctx);
+
+/* --- map checkpoint ---------------------------------------------------
+ * PCD v0.7 binary, FIELDS x y z intensity, float32: the layout pcl::io::savePCDFileBinary
+ * produces for PointXYZI (laserPosegraphOptimization.cpp:695) and the reference ships under
+ * utils/sample_data/<seq>/Scans/ (188-byte header for 5-digit counts, 16 B per point).  Host-only helpers.
+ * s2m_pcd_read returns the number of points in the file and copies min(n, cap) of them. */
+int s2m_pcd_write(const char* path, const float* xyzi, int n);
+int s2m_pcd_read(const char* path, float* xyzi_out, int cap);
+/* The reference keeps its map only in RAM; these two make the node resumable.  save writes
+ * <prefix>.corner.pcd, <prefix>.surf.pcd and <prefix>.state (window centre laserMapping.cpp:74-76
+ * and the wmap<-wodom correction :116-117, hex floats).  load restores them into `slot`; a context
+ * that continues from a checkpoint produces the bits of the uninterrupted run.  load returns the
+ * number of points that fell outside the restored window (0 for this library's own files). */
+int s2m_checkpoint_save(s2m_ctx* ctx, int slot, const char* prefix);
+int s2m_checkpoint_load(s2m_ctx* ctx, int slot, const char* prefix);
 
 /* wmap<-wodom correction kept by transformUpdate() (laserMapping.cpp:149-153);
  * the shim's high-rate odometry relay (:198-230) composes with it on the host. */

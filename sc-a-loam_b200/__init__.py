@@ -27,7 +27,8 @@ EXPORTS = [
     "s2m_default_params", "s2m_create", "s2m_destroy", "s2m_strerror", "s2m_last_error", "s2m_set_stream",
     "s2m_register", "s2m_register_batch", "s2m_register_batch_dev", "s2m_register_batch_submit",
     "s2m_register_batch_wait", "s2m_get_correction",
-    "s2m_transform_cloud", "s2m_map_upload", "s2m_map_download", "s2m_get_local_map", "s2m_get_surround",
+    "s2m_transform_cloud", "s2m_map_upload", "s2m_map_download", "s2m_pcd_write", "s2m_pcd_read", "s2m_checkpoint_save",
+    "s2m_checkpoint_load", "s2m_get_local_map", "s2m_get_surround",
     "s2m_get_window", "s2m_debug_knn", "s2m_trace_cloud", "s2m_trace_knn", "s2m_trace_lm",
     "s2m_launch_count", "s2m_set_profiling", "s2m_k4_profile", "s2m_phase_profile", "s2m_shard_unique_id", "s2m_shard_slab", "s2m_shard_init",
     "s2m_shard_profile",
@@ -87,6 +88,10 @@ def load_library(path=LIB_PATH):
     L.s2m_transform_cloud.argtypes = [vp, ci, vp, ci, vp]
     L.s2m_map_upload.argtypes = [vp, ci, vp, ci, vp, ci]
     L.s2m_map_download.argtypes = [vp, ci, ci, vp, ci]
+    L.s2m_pcd_write.argtypes = [ctypes.c_char_p, vp, ci]
+    L.s2m_pcd_read.argtypes = [ctypes.c_char_p, vp, ci]
+    L.s2m_checkpoint_save.argtypes = [vp, ci, ctypes.c_char_p]
+    L.s2m_checkpoint_load.argtypes = [vp, ci, ctypes.c_char_p]
     L.s2m_get_local_map.argtypes = [vp, ci, ci, vp, vp, ci]
     L.s2m_get_surround.argtypes = [vp, ci, vp, ci]
     L.s2m_get_window.argtypes = [vp, ci, vp]
@@ -114,6 +119,25 @@ def shard_slab(rank, world):
     if rc != 0:
         raise S2MError("bad shard rank/world")
     return lo.value, hi.value
+
+
+def pcd_write(path, xyzi):
+    """PCD v0.7 binary x y z intensity float32, as the reference's savePCDFileBinary writes it (no GPU needed)."""
+    a = _f32(xyzi).reshape(-1, 4)
+    rc = load_library().s2m_pcd_write(os.fsencode(path), a.ctypes.data, len(a))
+    if rc != 0:
+        raise S2MError("cannot write %s" % path)
+
+
+def pcd_read(path):
+    L = load_library()
+    n = L.s2m_pcd_read(os.fsencode(path), None, 0)
+    if n < 0:
+        raise S2MError("cannot read %s" % path)
+    out = np.zeros((max(n, 1), 4), np.float32)
+    if L.s2m_pcd_read(os.fsencode(path), out.ctypes.data, n) != n:
+        raise S2MError("cannot read %s" % path)
+    return out[:n]
 
 
 def default_params():
@@ -282,6 +306,13 @@ class Registrar:
         out = np.zeros((max(n, 1), 4), np.float32)
         self._check(self.L.s2m_map_download(self.h, slot, cls, out.ctypes.data, n))
         return out[:n]
+
+    def checkpoint_save(self, prefix, slot=0):
+        self._check(self.L.s2m_checkpoint_save(self.h, slot, os.fsencode(prefix)))
+
+    def checkpoint_load(self, prefix, slot=0):
+        """-> number of points that fell outside the restored window"""
+        return self._check(self.L.s2m_checkpoint_load(self.h, slot, os.fsencode(prefix)))
 
     def local_map(self, cls, centre_t, slot=0):
         c = _f64(centre_t)

@@ -272,6 +272,7 @@ extern "C" const char* s2m_strerror(int code) {
     case S2M_ERR_CAPACITY: return "capacity exceeded";
     case S2M_ERR_RANGE: return "coordinates outside the supported lattice range";
     case S2M_ERR_NCCL: return "NCCL error";
+    case S2M_ERR_IO: return "file could not be read or written";
     default: return "unknown";
   }
 }
@@ -1021,6 +1022,104 @@ extern "C" int s2m_map_download(s2m_ctx* ctx, int slot, int cls, float* out, int
     ++n;
   }
   return n;
+}
+
+// ---- PCD v0.7 binary, FIELDS x y z intensity (float32): the layout pcl::io::savePCDFileBinary
+// writes for PointXYZI (laserPosegraphOptimization.cpp:695) and the reference ships under
+// utils/sample_data/*/Scans. Host-only helpers; no device is touched.
+extern "C" int s2m_pcd_write(const char* path, const float* xyzi, int n) {
+  if (!path || n < 0 || (n > 0 && !xyzi)) return S2M_ERR_ARG;
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return S2M_ERR_IO;
+  std::fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\n"
+                  "TYPE F F F F\nCOUNT 1 1 1 1\nWIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n", n, n);
+  const size_t w = n ? std::fwrite(xyzi, 16, (size_t)n, f) : 0;
+  const int bad = std::fclose(f);
+  return (w == (size_t)n && !bad) ? S2M_OK : S2M_ERR_IO;
+}
+// returns the number of points in the file (copies min(n, cap) of them), or an error
+extern "C" int s2m_pcd_read(const char* path, float* xyzi, int cap) {
+  if (!path || cap < 0) return S2M_ERR_ARG;
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return S2M_ERR_IO;
+  char line[256];
+  long long points = -1;
+  bool fields_ok = false, sizes_ok = false, types_ok = false, binary = false;
+  while (std::fgets(line, sizeof line, f)) {
+    if (!std::strncmp(line, "FIELDS", 6)) fields_ok = !std::strncmp(line, "FIELDS x y z intensity", 22);
+    else if (!std::strncmp(line, "SIZE", 4)) sizes_ok = !std::strncmp(line, "SIZE 4 4 4 4", 12);
+    else if (!std::strncmp(line, "TYPE", 4)) types_ok = !std::strncmp(line, "TYPE F F F F", 12);
+    else if (!std::strncmp(line, "POINTS", 6)) points = std::atoll(line + 6);
+    else if (!std::strncmp(line, "DATA", 4)) { binary = !std::strncmp(line, "DATA binary", 11) && line[11] != '_'; break; }
+  }
+  int rc;
+  if (!fields_ok || !sizes_ok || !types_ok || !binary || points < 0 || points > 0x7fffffffLL) rc = S2M_ERR_IO;
+  else {
+    const size_t want = (size_t)std::min<long long>(points, cap);
+    rc = (want == 0 || (xyzi && std::fread(xyzi, 16, want, f) == want)) ? (int)points : S2M_ERR_IO;
+  }
+  std::fclose(f);
+  return rc;
+}
+
+// Checkpoint of one slot: <prefix>.corner.pcd, <prefix>.surf.pcd (the map, rows I/W state) and
+// <prefix>.state (window centre :74-76, wmap<-wodom correction :116-117, as hex floats).
+extern "C" int s2m_checkpoint_save(s2m_ctx* ctx, int slot, const char* prefix) {
+  if (!ctx || !prefix) return S2M_ERR_ARG;
+  const std::string base(prefix);
+  for (int cls = 0; cls < 2; ++cls) {
+    const int n = s2m_map_download(ctx, slot, cls, nullptr, 0);
+    if (n < 0) return n;
+    std::vector<float> pts(4 * (size_t)std::max(n, 1));
+    int rc = s2m_map_download(ctx, slot, cls, pts.data(), n);
+    if (rc < 0) return rc;
+    rc = s2m_pcd_write((base + (cls ? ".surf.pcd" : ".corner.pcd")).c_str(), pts.data(), n);
+    if (rc != S2M_OK) { ctx->err = "cannot write the checkpoint PCD"; return rc; }
+  }
+  int cen[3];
+  double q[4], t[3];
+  int rc = s2m_get_window(ctx, slot, cen);
+  if (rc == S2M_OK) rc = s2m_get_correction(ctx, slot, q, t);
+  if (rc != S2M_OK) return rc;
+  FILE* f = std::fopen((base + ".state").c_str(), "w");
+  if (!f) { ctx->err = "cannot write the checkpoint state"; return S2M_ERR_IO; }
+  std::fprintf(f, "s2m-checkpoint 1\ncen %d %d %d\nq_wmap_wodom %a %a %a %a\nt_wmap_wodom %a %a %a\n", cen[0], cen[1], cen[2],
+               q[0], q[1], q[2], q[3], t[0], t[1], t[2]);
+  return std::fclose(f) ? S2M_ERR_IO : S2M_OK;
+}
+static int restore_state(s2m_ctx* ctx, int slot, const int cen[3], const double q[4], const double t[3]) {
+  ROUTE_SLOT(restore_state(ch, slot, cen, q, t));
+  if (!ctx || slot < 0 || slot >= ctx->d.B) return S2M_ERR_ARG;
+  SlotHost& sh = ctx->slots[slot];
+  std::memcpy(sh.cen, cen, 12);
+  std::memcpy(sh.q_wmap_wodom, q, 32);
+  std::memcpy(sh.t_wmap_wodom, t, 24);
+  return S2M_OK;
+}
+// returns the number of points that fell outside the restored window (0 for a checkpoint of this library)
+extern "C" int s2m_checkpoint_load(s2m_ctx* ctx, int slot, const char* prefix) {
+  if (!ctx || !prefix) return S2M_ERR_ARG;
+  const std::string base(prefix);
+  FILE* f = std::fopen((base + ".state").c_str(), "r");
+  if (!f) { ctx->err = "cannot read the checkpoint state"; return S2M_ERR_IO; }
+  int ver = 0, cen[3];
+  double q[4], t[3];
+  const int got = std::fscanf(f, "s2m-checkpoint %d cen %d %d %d q_wmap_wodom %la %la %la %la t_wmap_wodom %la %la %la", &ver, &cen[0],
+                              &cen[1], &cen[2], &q[0], &q[1], &q[2], &q[3], &t[0], &t[1], &t[2]);
+  std::fclose(f);
+  if (got != 11 || ver != 1) { ctx->err = "malformed checkpoint state"; return S2M_ERR_IO; }
+  std::vector<float> pts[2];
+  int n[2];
+  for (int cls = 0; cls < 2; ++cls) {
+    const std::string path = base + (cls ? ".surf.pcd" : ".corner.pcd");
+    n[cls] = s2m_pcd_read(path.c_str(), nullptr, 0);
+    if (n[cls] < 0) { ctx->err = "cannot read the checkpoint PCD"; return n[cls]; }
+    pts[cls].resize(4 * (size_t)std::max(n[cls], 1));
+    if (s2m_pcd_read(path.c_str(), pts[cls].data(), n[cls]) != n[cls]) { ctx->err = "cannot read the checkpoint PCD"; return S2M_ERR_IO; }
+  }
+  int rc = restore_state(ctx, slot, cen, q, t);
+  if (rc != S2M_OK) return rc;
+  return s2m_map_upload(ctx, slot, pts[0].data(), n[0], pts[1].data(), n[1]);
 }
 
 // prepares the descriptor of `slot` for a sensor at centre_t (rows B, C) and uploads the tables

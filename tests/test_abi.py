@@ -53,3 +53,36 @@ def test_product_never_touches_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "orc_" not in txt and "libs2m_oracle" not in txt, f
+
+
+PCD_HEADER_37101 = (b"# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\n"
+                    b"TYPE F F F F\nCOUNT 1 1 1 1\nWIDTH 37101\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS 37101\nDATA binary\n")
+
+
+def test_pcd_layout_is_the_reference_sample_layout(s2m, built, tmp_path):
+    """s2m_pcd_write emits, byte for byte, the 188-byte header of the reference's shipped
+    utils/sample_data/KAIST03/Scans/000000.pcd (37101 points) followed by 16 B per point;
+    s2m_pcd_read gives the floats back. Host-only: no GPU involved."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    pts = rng.normal(size=(37101, 4)).astype(np.float32)
+    path = str(tmp_path / "a.pcd")
+    s2m.pcd_write(path, pts)
+    raw = open(path, "rb").read()
+    assert len(PCD_HEADER_37101) == 188 and raw[:188] == PCD_HEADER_37101 and len(raw) == 188 + 16 * 37101
+    assert np.array_equal(s2m.pcd_read(path).view(np.uint32), pts.view(np.uint32))
+    s2m.pcd_write(path, np.zeros((0, 4), np.float32))
+    assert len(s2m.pcd_read(path)) == 0
+    import pytest
+    with pytest.raises(s2m.S2MError):
+        s2m.pcd_read(str(tmp_path / "missing.pcd"))
+    open(path, "wb").write(PCD_HEADER_37101.replace(b"DATA binary", b"DATA ascii"))
+    with pytest.raises(s2m.S2MError):
+        s2m.pcd_read(path)
+    # the reference's own files, when the tree is mounted (authoring container only)
+    sample = "/root/reference/utils/sample_data/KAIST03/Scans/000000.pcd"
+    if os.path.exists(sample):
+        got = s2m.pcd_read(sample)
+        raw = open(sample, "rb").read()
+        assert raw[:188] == PCD_HEADER_37101
+        assert np.array_equal(got.view(np.uint32), np.frombuffer(raw[188:188 + 16 * 37101], np.uint32).reshape(-1, 4))

@@ -2,6 +2,8 @@
 
 Bars (BASELINE.json north_star): kNN indices and float distances bit-exact; poses within
 1e-4 m / 1e-5 rad of the reference-path restatement (observed agreement is ~1e-9)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -281,6 +283,33 @@ def test_submit_wait_pipeline_matches_synchronous_calls(s2m, seq_hdl):
     with pytest.raises(s2m.S2MError):
         c, co, su, so, q, t = packed[0]
         RS.submit(c.ctypes.data, co, su.ctypes.data, so, q, t)
+
+
+def test_checkpoint_resume_reproduces_the_uninterrupted_run(s2m, seq_hdl, tmp_path):
+    """s2m_checkpoint_save after frame 3, s2m_checkpoint_load into a new context (slot 1 of a batch of 2):
+    frames 4..7 give the bits of the run that never stopped; so does the map at the end."""
+    truth, odom, frames = seq_hdl
+    kw = dict(cap_map_corner=1 << 17, cap_map_surf=1 << 18)
+    A = s2m.Registrar(0.4, 0.8, **kw)
+    for f in range(4):
+        A.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+    prefix = str(tmp_path / "ckpt")
+    A.checkpoint_save(prefix)
+    for ext in (".corner.pcd", ".surf.pcd", ".state"):
+        assert os.path.getsize(prefix + ext) > 0
+    assert len(s2m.pcd_read(prefix + ".surf.pcd")) == len(A.map_download(1))
+    Bc = s2m.Registrar(0.4, 0.8, batch=2, **kw)
+    assert Bc.checkpoint_load(prefix, slot=1) == 0
+    assert np.array_equal(Bc.window(1), A.window()) and np.array_equal(Bc.correction(1)[1], A.correction()[1])
+    e = np.zeros((0, 4), np.float32)
+    for f in range(4, 8):
+        rc, q, t = A.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+        co, so = np.array([0, 0, len(frames[f][0])], np.int32), np.array([0, 0, len(frames[f][1])], np.int32)
+        st, qb, tb = Bc.register_batch(frames[f][0], co, frames[f][1], so, np.tile(odom[f, :4], (2, 1)), np.tile(odom[f, 4:], (2, 1)),
+                                       active=[0, 1])
+        assert st[1] == rc and np.array_equal(qb[1], q) and np.array_equal(tb[1], t), f
+    for cls in (0, 1):
+        assert np.array_equal(bits(A.map_download(cls)), bits(Bc.map_download(cls, 1)))
 
 
 def test_window_shift_and_eviction(s2m, built):
