@@ -366,7 +366,7 @@ static int create_impl(s2m_ctx* ctx) {
   rc |= dev_alloc(ctx, &d.ckey, ccap); rc |= dev_alloc(ctx, &d.ckey2, ccap);
   rc |= dev_alloc(ctx, &d.cval, ccap); rc |= dev_alloc(ctx, &d.cval2, ccap);
   rc |= dev_alloc(ctx, &d.cand, d.cap_lp); rc |= dev_alloc(ctx, &d.qperm, d.cap_in); rc |= dev_alloc(ctx, &d.inv, d.cap_lp);
-  rc |= dev_alloc(ctx, &d.nbr, (size_t)d.cap_in * 6); rc |= dev_alloc(ctx, &d.scanned, 2 * B);
+  rc |= dev_alloc(ctx, &d.nbr, (size_t)d.cap_in * 6); rc |= dev_alloc(ctx, &d.scanned, 2 * B); rc |= dev_alloc(ctx, &d.knn_ticket, 1);
   // cell tables: per segment a power of two >= 2 x entries, >= 1024
   long long hcap = 0;
   for (int g = 0; g < G; ++g) hcap += next_pow2(std::max(1024, 4 * (g < B ? P.cap_map_corner : P.cap_map_surf)));
@@ -406,6 +406,7 @@ static int create_impl(s2m_ctx* ctx) {
   CK(cudaMemset(d.st_n_new, 0, sizeof(int) * G));
   CK(cudaMemset(d.err_flag, 0, sizeof(int)));
   CK(cudaMemset(d.ticket, 0, sizeof(int) * B));
+  CK(cudaMemset(d.knn_ticket, 0, sizeof(int)));
   CK(cudaMemset(d.out, 0, sizeof(SlotOut) * B));
   CK(cudaMemset(d.lm, 0, sizeof(LmState) * B));
   CK(cudaMemset(d.ds_off, 0, sizeof(int) * (G + 1)));
@@ -643,15 +644,18 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   CK(cudaEventSynchronize(ctx->ev_ds));
   const int n_ds = ctx->h_dsoff[G];
   tiles = 0;
+  int chunks = 0;  // 32-query work units of knn_kernel over all slots
   for (int b = 0; b < B; ++b) {
     const int nq = (ctx->h_dsoff[b + 1] - ctx->h_dsoff[b]) + (ctx->h_dsoff[B + b + 1] - ctx->h_dsoff[B + b]);
     tiles = std::max(tiles, (nq + kTile - 1) / kTile);
+    chunks += (nq + 31) / 32;
   }
+  d.count_scanned = ctx->profiling ? 1 : 0;
   if (d.use_qperm) k += launch_query_order(d, n_ds, s);
   // one resident wave each: S2M_K4x_MINB blocks per SM shared by the B slots
-  const int knn_blocks = std::max(1, std::min(tiles, (S2M_K4A_MINB * ctx->sm_count) / B));
+  const int knn_blocks = std::max(1, std::min((chunks + kTile / 32 - 1) / (kTile / 32), S2M_K4A_MINB * ctx->sm_count));
   const int fit_blocks = std::max(1, (tiles + kFitTilesPerBlock - 1) / kFitTilesPerBlock);
-  const int blocks = knn_blocks;
+  const int blocks = std::max(1, std::min(tiles, (S2M_K4A_MINB * ctx->sm_count) / B));
   const int eval_blocks = std::max(1, (tiles + kEvalTilesPerBlock - 1) / kEvalTilesPerBlock);
   for (int outer = 0; outer < 2; ++outer) {  // laserMapping.cpp:563
     if (ctx->profiling && outer == 0) {  // C-bar of the byte formula, outside the K4 event bracket

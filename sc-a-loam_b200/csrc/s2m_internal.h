@@ -129,7 +129,9 @@ struct Dev {
   int* inv;                     // [cap_lp] local index -> position in cand (packed by lp_off)
   uint32_t* qperm;              // [cap_in] query order of the association kernel (packed ds indices)
   int* nbr;                     // [cap_in][6] K4a -> K4b: ds index (or -1 when gated out) + 5 neighbour positions
-  unsigned long long* scanned;  // [B][2] candidate points actually scanned (statistics)
+  unsigned long long* scanned;  // [B][2] candidate points actually scanned (statistics, profiling only)
+  int* knn_ticket;              // next 32-query work unit of knn_kernel (re-armed by fit_kernel)
+  int count_scanned;            // profiling: maintain `scanned`
   unsigned long long* hash_tab; // cell tables
   uint2* hash_aux;              // per table slot: (points of the cell itself, exact 3-cell count)
   int* cs_off;                  // [G+1] first sorted position of each segment

@@ -650,63 +650,95 @@ __global__ void lm_shard_kernel(Dev d, int outer, int after) {
 // ----------------------------------------------------------------------------
 template <bool kTrace>
 __global__ void __launch_bounds__(kTile, S2M_K4A_MINB) knn_kernel(Dev d, int outer) {
-  const int slot = blockIdx.y;
-  if (!d.out[slot].optimized) return;
-  int dc0, nc, ds0, nq;
-  slot_counts(d, slot, dc0, nc, ds0, nq);
-  const int ntiles = (nq + kTile - 1) / kTile;
-  __shared__ double pose[7];
-  __shared__ int origin[3];
+  // Work unit = 32 consecutive queries of one slot, taken by a WARP from a device-wide ticket:
+  // the trip counts of the search vary a lot between queries, so static tiles leave most of a
+  // block (and the tail of the grid) idle. The results do not depend on who computes them.
   __shared__ KnnStage stage;
-  __shared__ unsigned long long cand_s[2];
-  if (threadIdx.x < 7) pose[threadIdx.x] = d.lm[slot].x[threadIdx.x];
-  if (threadIdx.x < 3) origin[threadIdx.x] = d.desc[slot].origin[threadIdx.x];
-  if (threadIdx.x < 2) cand_s[threadIdx.x] = 0ull;
-  __syncthreads();
-  unsigned long long visited_c = 0, visited_s = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int q = tile * kTile + threadIdx.x;
-    if (q >= nq) continue;
-    const int cls = q >= nc;
-    const int pos_q = cls ? ds0 + (q - nc) : dc0 + q;  // position in the packed, cell-ordered query list
-    const int di = d.use_qperm ? (int)d.qperm[pos_q] : pos_q;
-    const float4 p = d.ds_pts[di];
-    float w[3];
-    xf_point(pose, p.x, p.y, p.z, w);
-    if (d.shard_world > 1 && !(w[0] >= d.shard_lo && w[0] < d.shard_hi)) {
-      // sharded map: this query is answered by the rank whose x-slab holds it
-      d.nbr[6 * (size_t)pos_q] = -1;
-      d.rec_valid[di] = 0;
-      continue;
-    }
-    Knn5 r;
-    const int visited = knn5_cells(d, cls ? d.B + slot : slot, origin, w[0], w[1], w[2], r, stage);
-    if (cls) visited_s += (unsigned long long)visited; else visited_c += (unsigned long long)visited;
-    const bool gate = knn_d2(r, 4) < 1.0f;  // laserMapping.cpp:585 / :653
-    int* nb = d.nbr + 6 * (size_t)pos_q;
-    nb[0] = gate ? di : -1;
+  __shared__ int chunk_off[kMaxBatch + 1];
+  const int B = d.B, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {  // chunks per slot (none for a slot that is not optimised this frame), prefix-summed
+    int c[2], incl[2];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) nb[1 + k] = knn_idx(r, k);  // local indices; K4b maps them to d.cand
-    d.rec_valid[di] = 0;
-    if (kTrace) {
-      const size_t o = ((size_t)outer * d.cap_in + di);
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const bool have = r.key[k] != kKnnInit;
-        d.tr_idx[5 * o + k] = have ? knn_idx(r, k) : -1;
-        d.tr_d2[5 * o + k] = have ? knn_d2(r, k) : INFINITY;
+    for (int h = 0; h < 2; ++h) {
+      const int sl = 32 * h + lane;
+      c[h] = 0;
+      if (sl < B && d.out[sl].optimized) {
+        int dc0, nc, ds0, nq;
+        slot_counts(d, sl, dc0, nc, ds0, nq);
+        c[h] = (nq + 31) >> 5;
       }
-      d.tr_used[o] = 0;
+      incl[h] = c[h];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl[h], o);
+        if (lane >= o) incl[h] += v;
+      }
+    }
+    const int first = __shfl_sync(0xffffffffu, incl[0], 31);
+    if (lane == 0) chunk_off[0] = 0;
+    chunk_off[1 + lane] = incl[0];
+    if (32 + lane < kMaxBatch) chunk_off[33 + lane] = first + incl[1];
+  }
+  __syncthreads();
+  const int total = chunk_off[B];
+  for (;;) {
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(d.knn_ticket, 1);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (chunk >= total) break;
+    int slot = 0, hi = B;  // chunk_off[slot] <= chunk < chunk_off[hi]
+    while (hi - slot > 1) {
+      const int mid = (slot + hi) >> 1;
+      if (chunk_off[mid] <= chunk) slot = mid; else hi = mid;
+    }
+    int dc0, nc, ds0, nq;
+    slot_counts(d, slot, dc0, nc, ds0, nq);
+    const int q = ((chunk - chunk_off[slot]) << 5) + lane;
+    int visited = 0, cls = 0;
+    if (q < nq) {
+      cls = q >= nc;
+      const int pos_q = cls ? ds0 + (q - nc) : dc0 + q;  // position in the packed query list
+      const int di = d.use_qperm ? (int)d.qperm[pos_q] : pos_q;
+      const float4 p = d.ds_pts[di];
+      float w[3];
+      xf_point(d.lm[slot].x, p.x, p.y, p.z, w);
+      if (d.shard_world > 1 && !(w[0] >= d.shard_lo && w[0] < d.shard_hi)) {
+        // sharded map: this query is answered by the rank whose x-slab holds it
+        d.nbr[6 * (size_t)pos_q] = -1;
+        d.rec_valid[di] = 0;
+      } else {
+        const int origin[3] = {d.desc[slot].origin[0], d.desc[slot].origin[1], d.desc[slot].origin[2]};
+        Knn5 r;
+        visited = knn5_cells(d, cls ? B + slot : slot, origin, w[0], w[1], w[2], r, stage);
+        const bool gate = knn_d2(r, 4) < 1.0f;  // laserMapping.cpp:585 / :653
+        int* nb = d.nbr + 6 * (size_t)pos_q;
+        nb[0] = gate ? di : -1;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) nb[1 + k] = knn_idx(r, k);  // local indices; K4b maps them to d.cand
+        d.rec_valid[di] = 0;
+        if (kTrace) {
+          const size_t o = ((size_t)outer * d.cap_in + di);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const bool have = r.key[k] != kKnnInit;
+            d.tr_idx[5 * o + k] = have ? knn_idx(r, k) : -1;
+            d.tr_d2[5 * o + k] = have ? knn_d2(r, k) : INFINITY;
+          }
+          d.tr_used[o] = 0;
+        }
+      }
+    }
+    if (d.count_scanned) {  // scanned-candidate counters (profiling only)
+      int vc = cls ? 0 : visited, vs = cls ? visited : 0;
+      for (int o = 16; o > 0; o >>= 1) {
+        vc += __shfl_down_sync(0xffffffffu, vc, o);
+        vs += __shfl_down_sync(0xffffffffu, vs, o);
+      }
+      if (lane == 0) {
+        if (vc) atomicAdd(d.scanned + 2 * slot, (unsigned long long)vc);
+        if (vs) atomicAdd(d.scanned + 2 * slot + 1, (unsigned long long)vs);
+      }
     }
   }
-  // scanned-candidate counters (statistics only)
-  for (int o = 16; o > 0; o >>= 1) {
-    visited_c += __shfl_down_sync(0xffffffffu, visited_c, o);
-    visited_s += __shfl_down_sync(0xffffffffu, visited_s, o);
-  }
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&cand_s[0], visited_c); atomicAdd(&cand_s[1], visited_s); }
-  __syncthreads();
-  if (threadIdx.x < 2 && cand_s[threadIdx.x]) atomicAdd(d.scanned + 2 * slot + threadIdx.x, cand_s[threadIdx.x]);
 }
 
 struct TileXfer {
@@ -717,6 +749,7 @@ struct TileXfer {
 template <bool kTrace>
 __global__ void __launch_bounds__(kTile, S2M_K4B_MINB) fit_kernel(Dev d, int outer) {
   const int slot = blockIdx.y;
+  if (blockIdx.x == 0 && slot == 0 && threadIdx.x == 0) *d.knn_ticket = 0;  // K4a finished: re-arm its work ticket
   if (!d.out[slot].optimized) return;
   int dc0, nc, ds0, nq;
   slot_counts(d, slot, dc0, nc, ds0, nq);
@@ -1234,8 +1267,8 @@ int launch_guard(const Dev& d, cudaStream_t s) {
 }
 int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s) {
   if (knn_blocks <= 0 || fit_blocks <= 0) return 0;
-  if (outer == 0) cudaMemsetAsync(d.scanned, 0, sizeof(unsigned long long) * 2 * d.B, s);
-  dim3 ga(knn_blocks, d.B), gb(fit_blocks, d.B);
+  if (outer == 0 && d.count_scanned) cudaMemsetAsync(d.scanned, 0, sizeof(unsigned long long) * 2 * d.B, s);
+  dim3 ga(knn_blocks), gb(fit_blocks, d.B);
   if (trace) {
     knn_kernel<true><<<ga, kTile, 0, s>>>(d, outer);
     fit_kernel<true><<<gb, kTile, 0, s>>>(d, outer);
