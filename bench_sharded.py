@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--map-side", type=int, default=2000, help="ground lattice points per side")
     ap.add_argument("--map-spacing", type=float, default=0.5)
+    ap.add_argument("--cap-map-surf", type=int, default=1 << 23, help="surf capacity of the window (points)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -55,7 +56,7 @@ def main():
     corner, surf = giant_map(args.map_side, args.map_spacing, 5)
     n_bg = len(corner) + len(surf)
     R = pkg.Registrar(0.4, 0.8, device=local, cap_corner_in=max(1 << 14, len(corner)), cap_surf_in=max(1 << 17, len(surf)),
-                      cap_map_corner=1 << 21, cap_map_surf=1 << 23, shard_rank=rank, shard_world=world)
+                      cap_map_corner=1 << 21, cap_map_surf=max(args.cap_map_surf, len(surf) + (1 << 20)), shard_rank=rank, shard_world=world)
     if world > 1:
         ids = [pkg.Registrar.shard_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)

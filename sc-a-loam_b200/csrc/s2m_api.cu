@@ -48,6 +48,7 @@ struct HostTables {  // one pinned block, copied to the device in one go
   FrameDesc desc[kMaxBatch];
   int in_off[2 * kMaxBatch + 1];
   int lp_off[2 * kMaxBatch + 1];
+  int so_off[2 * kMaxBatch + 1];
   int hash_off[2 * kMaxBatch + 1];
 };
 
@@ -166,6 +167,7 @@ struct s2m_ctx {
   int* h_dsoff = nullptr;        // pinned [G+1]: down-sampled counts read back mid-frame
   cudaEvent_t ev_ds = nullptr;
   uint32_t* h_bbox = nullptr;    // pinned [G][6]: boxes of the incoming clouds (ordered-uint encoding)
+  int* h_lpcnt = nullptr;        // pinned [G]: local-map sizes of this frame
   cudaEvent_t ev_bbox = nullptr;
   LmState* lm_trace = nullptr;   // [2][B] device
   LmState* h_lm = nullptr;       // pinned [2][B]
@@ -299,6 +301,7 @@ extern "C" void s2m_destroy(s2m_ctx* ctx) {
   if (ctx->h_dsoff) cudaFreeHost(ctx->h_dsoff);
   if (ctx->ev_ds) cudaEventDestroy(ctx->ev_ds);
   if (ctx->h_bbox) cudaFreeHost(ctx->h_bbox);
+  if (ctx->h_lpcnt) cudaFreeHost(ctx->h_lpcnt);
   if (ctx->ev_bbox) cudaEventDestroy(ctx->ev_bbox);
   if (ctx->h_lm) cudaFreeHost(ctx->h_lm);
   for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
@@ -344,11 +347,12 @@ static int create_impl(s2m_ctx* ctx) {
   CK(cudaMallocHost((void**)&ctx->h_dsoff, sizeof(int) * (2 * kMaxBatch + 1)));
   CK(cudaEventCreateWithFlags(&ctx->ev_ds, cudaEventDisableTiming));
   CK(cudaMallocHost((void**)&ctx->h_bbox, sizeof(uint32_t) * 6 * 2 * kMaxBatch));
+  CK(cudaMallocHost((void**)&ctx->h_lpcnt, sizeof(int) * 2 * kMaxBatch));
   CK(cudaEventCreateWithFlags(&ctx->ev_bbox, cudaEventDisableTiming));
   CK(cudaMallocHost((void**)&ctx->h_lm, sizeof(LmState) * 2 * B));
   std::memset(ctx->ht, 0, sizeof(HostTables));
   if (dev_alloc(ctx, &ctx->d_ht, 1)) return S2M_ERR_CUDA;
-  d.desc = ctx->d_ht->desc; d.in_off = ctx->d_ht->in_off; d.lp_off = ctx->d_ht->lp_off; d.hash_off = ctx->d_ht->hash_off;
+  d.desc = ctx->d_ht->desc; d.in_off = ctx->d_ht->in_off; d.lp_off = ctx->d_ht->lp_off; d.so_off = ctx->d_ht->so_off; d.hash_off = ctx->d_ht->hash_off;
 
   int rc = 0;
   rc |= dev_alloc(ctx, &d.st_base, G); rc |= dev_alloc(ctx, &d.st_cap, G);
@@ -361,7 +365,7 @@ static int create_impl(s2m_ctx* ctx) {
   rc |= dev_alloc(ctx, &d.ds_pts, d.cap_in); rc |= dev_alloc(ctx, &d.ds_off, G + 1);
   for (int b = 0; b < 2; ++b) { rc |= dev_alloc(ctx, &d.st_key[b], d.cap_lp); rc |= dev_alloc(ctx, &d.st_pt[b], d.cap_lp); }
   rc |= dev_alloc(ctx, &d.st_n, G); rc |= dev_alloc(ctx, &d.st_n_new, G);
-  rc |= dev_alloc(ctx, &d.rng_start, G * kCols); rc |= dev_alloc(ctx, &d.loc_off, G * (kCols + 1));
+  rc |= dev_alloc(ctx, &d.rng_start, G * kCols); rc |= dev_alloc(ctx, &d.loc_off, G * (kCols + 1)); rc |= dev_alloc(ctx, &d.lp_cnt, G);
   const size_t ccap = (size_t)std::max(d.cap_lp, d.cap_in);
   rc |= dev_alloc(ctx, &d.ckey, ccap); rc |= dev_alloc(ctx, &d.ckey2, ccap);
   rc |= dev_alloc(ctx, &d.cval, ccap); rc |= dev_alloc(ctx, &d.cval2, ccap);
@@ -546,10 +550,10 @@ static void fill_store_tables(s2m_ctx* ctx, int* total_lp, int* hash_total) {
   int acc = 0, hacc = 0;
   for (int g = 0; g < G; ++g) {
     const int n = ctx->slots[g < B ? g : g - B].n_store[g >= B];
-    T.lp_off[g] = acc; acc += n;
+    T.lp_off[g] = T.so_off[g] = acc; acc += n;
     T.hash_off[g] = hacc; hacc += next_pow2(std::max(1024, 4 * n));  // <= 3 entries per point: cells + virtual x-neighbours
   }
-  T.lp_off[G] = acc; T.hash_off[G] = hacc;
+  T.lp_off[G] = T.so_off[G] = acc; T.hash_off[G] = hacc;
   *total_lp = acc; *hash_total = hacc;
 }
 
@@ -598,23 +602,37 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   }
   int total_lp, hash_total;
   fill_store_tables(ctx, &total_lp, &hash_total);
+  const int total_store = total_lp;
   CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, s));
 
   // blocks per slot of the association / evaluation kernels: enough to fill the GPU
   // (about 4 blocks of 128 threads per SM over all slots), never more than the tiles
   long long k = 0;
   prof_mark(ctx, S2M_PHASE_INPUT);
-  // boxes of the incoming clouds first: they come back while the local index is being built and
-  // give the exact width of PCL's voxel index, i.e. the number of radix passes of the scan filter
+  // Two small results come back before the bulk of the frame is enqueued: the boxes of the incoming
+  // clouds (exact width of PCL's voxel index = radix passes of the scan filter) and the sizes of the
+  // local maps (25 ranges of the sorted store), so the cell index costs O(local map), not O(store).
+  // The round trip is hidden by the other lanes sharing the GPU.
   k += launch_voxel_bbox(d, total_in, s);
+  k += launch_local_ranges(d, ctx->cur, s);
   CK(cudaMemcpyAsync(ctx->h_bbox, d.bbox, sizeof(uint32_t) * 6 * G, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->h_lpcnt, d.lp_cnt, sizeof(int) * G, cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(ctx->ev_bbox, s));
-  k += launch_local_index(d, ctx->cur, total_lp, hash_total, s);
+  CK(cudaEventSynchronize(ctx->ev_bbox));
+  total_lp = hash_total = 0;
+  for (int g = 0; g < G; ++g) {
+    const int n = ctx->h_lpcnt[g];
+    T.lp_off[g] = total_lp; total_lp += n;
+    T.hash_off[g] = hash_total; hash_total += next_pow2(std::max(1024, 4 * n));  // <= 3 entries per point: cells + virtual x-neighbours
+  }
+  T.lp_off[G] = total_lp; T.hash_off[G] = hash_total;
+  CK(cudaMemcpyAsync(ctx->d_ht->lp_off, T.lp_off, sizeof(int) * (G + 1), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->d_ht->hash_off, T.hash_off, sizeof(int) * (G + 1), cudaMemcpyHostToDevice, s));
+  k += launch_local_index(d, ctx->cur, total_lp, hash_total, true, s);
   const bool sharded = ctx->P.shard_world > 1;
   if (sharded) { int rs = shard_allreduce(ctx, d.shard_counts, (size_t)G, nccl::kInt32); if (rs != S2M_OK) return rs; }
   k += launch_guard(d, s);
   prof_mark(ctx, S2M_PHASE_INDEX);
-  CK(cudaEventSynchronize(ctx->ev_bbox));
   int key_bits = 1;
   for (int g = 0; g < G && total_in > 0; ++g) {
     const int cnt = T.in_off[g + 1] - T.in_off[g];
@@ -682,7 +700,7 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
       CK(cudaMemcpyAsync(ctx->lm_trace + (size_t)outer * B, d.lm, sizeof(LmState) * B, cudaMemcpyDeviceToDevice, s));
   }
   k += launch_finish_pose(d, s);
-  k += launch_map_update(d, ctx->cur, n_ds, total_lp, check_pending, false, s);
+  k += launch_map_update(d, ctx->cur, n_ds, total_lp, total_store, check_pending, false, s);
   prof_mark(ctx, S2M_PHASE_UPDATE);
   ctx->launches += k;
   int rc = finish_call(ctx);
@@ -974,7 +992,7 @@ extern "C" int s2m_map_upload(s2m_ctx* ctx, int slot, const float* corner, int n
   CK(cudaMemcpyAsync(d.ds_off, dsoff.data(), sizeof(int) * (G + 1), cudaMemcpyHostToDevice, s));
   if (nc) CK(cudaMemcpyAsync(d.ds_pts, corner, sizeof(float4) * (size_t)nc, cudaMemcpyHostToDevice, s));
   if (ns) CK(cudaMemcpyAsync(d.ds_pts + nc, surf, sizeof(float4) * (size_t)ns, cudaMemcpyHostToDevice, s));
-  ctx->launches += launch_map_update(d, ctx->cur, nc + ns, total_lp, false, true, s);
+  ctx->launches += launch_map_update(d, ctx->cur, nc + ns, total_lp, total_lp, false, true, s);
   int rc = finish_call(ctx);
   if (rc != S2M_OK) return rc;
   ctx->cur ^= 1;
@@ -1144,7 +1162,7 @@ extern "C" int s2m_get_local_map(s2m_ctx* ctx, int slot, int cls, const double c
   int total_lp, hash_total;
   int rc = prepare_local(ctx, slot, centre_t, &total_lp, &hash_total);
   if (rc != S2M_OK) return rc;
-  ctx->launches += launch_local_index(ctx->d, ctx->cur, total_lp, hash_total, ctx->stream);
+  ctx->launches += launch_local_index(ctx->d, ctx->cur, total_lp, hash_total, false, ctx->stream);
   const int g = cls * ctx->d.B + slot;
   ctx->launches += launch_gather_local(ctx->d, ctx->cur, g, ctx->d.ins_pt, ctx->stream);
   rc = finish_call(ctx);
@@ -1168,7 +1186,7 @@ extern "C" int s2m_debug_knn(s2m_ctx* ctx, int slot, int cls, const double centr
   if (rc != S2M_OK) return rc;
   Dev& d = ctx->d;
   cudaStream_t s = ctx->stream;
-  ctx->launches += launch_local_index(d, ctx->cur, total_lp, hash_total, s);
+  ctx->launches += launch_local_index(d, ctx->cur, total_lp, hash_total, false, s);
   // scratch: queries in dl_pt/ins_pt area, results in vval (int32) and flag (float bits)
   float* dq = (float*)d.ins_pt;
   int32_t* didx = (int32_t*)d.vval;

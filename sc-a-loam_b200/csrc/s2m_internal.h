@@ -27,6 +27,9 @@
 
 namespace s2m {
 
+#ifndef S2M_K4A_PREFETCH
+#define S2M_K4A_PREFETCH 0  // 0 off, 1 prefetch.global.L2, 2 prefetch.global.L1 of each row's candidates at probe time
+#endif
 #ifndef S2M_K4A_MINB
 #define S2M_K4A_MINB 8  // resident blocks per SM the kNN kernel is compiled for
 #endif
@@ -104,7 +107,8 @@ struct Dev {
   // ---- per call small tables (device copies of host arrays)
   FrameDesc* desc;              // [B]
   int* in_off;                  // [G+1] packed offsets of the incoming clouds
-  int* lp_off;                  // [G+1] packed offsets of the local/store index space (host upper bounds)
+  int* lp_off;                  // [G+1] packed offsets of the local maps (exact in a frame: sizes are read back)
+  int* so_off;                  // [G+1] packed offsets of the whole stores (merge index space)
   int* st_base;                 // [G]   base of each segment in the store arrays
   int* st_cap;                  // [G]
   int* hash_off;                // [G+1] base of each segment's cell table
@@ -124,6 +128,7 @@ struct Dev {
   // ---- local map + cell index
   int* rng_start;               // [G][25]
   int* loc_off;                 // [G][26]
+  int* lp_cnt;                  // [G] points of the local map (read back: sizes the index exactly)
   uint32_t *ckey, *ckey2, *cval, *cval2;  // [cap_lp]
   float4* cand;                 // [cap_lp] cell-sorted local points, w = local index bits
   int* inv;                     // [cap_lp] local index -> position in cand (packed by lp_off)
@@ -165,7 +170,8 @@ struct Dev {
 size_t cub_temp_bytes(int cap_sort, int cap_lp);
 int launch_voxel_bbox(const Dev& d, int total_in, cudaStream_t s);
 int launch_voxel_filter(const Dev& d, int total_in, int key_bits, cudaStream_t s);
-int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, cudaStream_t s);
+int launch_local_ranges(const Dev& d, int cur, cudaStream_t s);
+int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, bool ranges_done, cudaStream_t s);
 int launch_guard(const Dev& d, cudaStream_t s);
 int launch_query_order(const Dev& d, int n_ds, cudaStream_t s);
 int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s);
@@ -173,7 +179,7 @@ int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s
 int launch_count_candidates(const Dev& d, int blocks_per_slot, cudaStream_t s);
 int launch_lm_shard(const Dev& d, int outer, int after, cudaStream_t s);
 int launch_finish_pose(const Dev& d, cudaStream_t s);
-int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, bool check_pending, bool identity_pose,
+int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_store, bool check_pending, bool identity_pose,
                       cudaStream_t s);
 int launch_knn_debug(const Dev& d, int slot, int cls, const float* d_q, int n, int32_t* d_idx, float* d_d2,
                      cudaStream_t s);

@@ -201,6 +201,7 @@ __global__ void range_kernel(Dev d, int cur) {
   }
   if (c == kCols - 1) {
     d.loc_off[g * (kCols + 1) + kCols] = incl;
+    d.lp_cnt[g] = incl;
     d.out[seg_slot(d, g)].n_local[seg_cls(d, g)] = incl;
   }
 }
@@ -409,6 +410,17 @@ __device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[
         uint32_t c = (uint32_t)(e[o] >> 30) & 1023u;
         if (c == 1023u) c = d.hash_aux[base + sl[o]].y;
         rn = ((unsigned long long)c << 32) | (e[o] & 0x3FFFFFFFull);
+#if S2M_K4A_PREFETCH
+        // the row's candidates start their trip from HBM now, while the other probes resolve
+        const float4* pf = d.cand + (uint32_t)(e[o] & 0x3FFFFFFFull);
+#if S2M_K4A_PREFETCH == 1
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        if (c > 8u) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 8));
+#else
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+        if (c > 8u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 8));
+#endif
+#endif
       }
       st.run[o][t] = rn;
     }
@@ -1090,13 +1102,13 @@ __device__ __forceinline__ bool entry_dead(const FrameDesc& fd, uint64_t key) {
   if (!in_box(ci, cj, ck, fd.win_lo, fd.win_hi)) return true;           // cube left the window (:346-347 ...)
   return key_pending(key) && in_box(ci, cj, ck, fd.val_lo, fd.val_hi);  // raw point merged by this re-filter
 }
-__global__ void alive_flag_kernel(Dev d, int cur, int total_lp) {
+__global__ void alive_flag_kernel(Dev d, int cur, int total_store) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > total_lp) return;
+  if (i > total_store) return;
   uint32_t f = 0;
-  if (i < total_lp) {
-    const int g = find_seg(d.lp_off, d.G, i);
-    const int l = i - d.lp_off[g];
+  if (i < total_store) {
+    const int g = find_seg(d.so_off, d.G, i);
+    const int l = i - d.so_off[g];
     if (l < d.st_n[g]) {
       const FrameDesc& fd = d.desc[seg_slot(d, g)];
       f = fd.active ? !entry_dead(fd, d.st_key[cur][d.st_base[g] + l]) : 1u;
@@ -1104,15 +1116,15 @@ __global__ void alive_flag_kernel(Dev d, int cur, int total_lp) {
   }
   d.aflag[i] = f;
 }
-__global__ void merge_old_kernel(Dev d, int cur, int total_lp) {
+__global__ void merge_old_kernel(Dev d, int cur, int total_store) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total_lp || !d.aflag[i]) return;
-  const int g = find_seg(d.lp_off, d.G, i);
-  const int l = i - d.lp_off[g];
+  if (i >= total_store || !d.aflag[i]) return;
+  const int g = find_seg(d.so_off, d.G, i);
+  const int l = i - d.so_off[g];
   const int src = d.st_base[g] + l;
   const uint64_t key = d.st_key[cur][src];
   const int io = d.run_off[g], nins = d.run_off[g + 1] - io;
-  const int pos = (int)(d.ascan[i] - d.ascan[d.lp_off[g]]) + lower_bound_u64(d.ins_ckey + io, nins, key);
+  const int pos = (int)(d.ascan[i] - d.ascan[d.so_off[g]]) + lower_bound_u64(d.ins_ckey + io, nins, key);
   if (pos >= d.st_cap[g]) { set_err(d, -3); return; }
   d.st_key[cur ^ 1][d.st_base[g] + pos] = key;
   d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.st_pt[cur][src];
@@ -1123,7 +1135,7 @@ __global__ void merge_new_kernel(Dev d, int cur, int n_max) {
   const int g = find_seg(d.run_off, d.G, j);
   const uint64_t key = d.ins_ckey[j];
   const int lb = lower_bound_u64(d.st_key[cur] + d.st_base[g], d.st_n[g], key);
-  const int pos = (j - d.run_off[g]) + (int)(d.ascan[d.lp_off[g] + lb] - d.ascan[d.lp_off[g]]);
+  const int pos = (j - d.run_off[g]) + (int)(d.ascan[d.so_off[g] + lb] - d.ascan[d.so_off[g]]);
   if (pos >= d.st_cap[g]) { set_err(d, -3); return; }
   d.st_key[cur ^ 1][d.st_base[g] + pos] = key;
   d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.ins_cpt[j];
@@ -1131,7 +1143,7 @@ __global__ void merge_new_kernel(Dev d, int cur, int n_max) {
 __global__ void store_count_kernel(Dev d) {
   const int g = threadIdx.x + blockIdx.x * blockDim.x;
   if (g >= d.G) return;
-  const int n = (int)(d.ascan[d.lp_off[g + 1]] - d.ascan[d.lp_off[g]]) + (d.run_off[g + 1] - d.run_off[g]);
+  const int n = (int)(d.ascan[d.so_off[g + 1]] - d.ascan[d.so_off[g]]) + (d.run_off[g + 1] - d.run_off[g]);
   if (n > d.st_cap[g]) set_err(d, -3);
   d.st_n_new[g] = min(n, d.st_cap[g]);
   d.out[seg_slot(d, g)].n_store[seg_cls(d, g)] = n;
@@ -1237,9 +1249,13 @@ int launch_voxel_filter(const Dev& d, int n, int key_bits, cudaStream_t s) {
   return k;
 }
 
-int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, cudaStream_t s) {
+int launch_local_ranges(const Dev& d, int cur, cudaStream_t s) {
+  range_kernel<<<d.G, 32, 0, s>>>(d, cur);
+  return 1;
+}
+int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, bool ranges_done, cudaStream_t s) {
   int k = 0;
-  range_kernel<<<d.G, 32, 0, s>>>(d, cur); ++k;
+  if (!ranges_done) k += launch_local_ranges(d, cur, s);
   cudaMemsetAsync(d.hash_tab, 0xFF, sizeof(unsigned long long) * (size_t)hash_total, s);
   if (d.shard_world > 1) cudaMemsetAsync(d.shard_counts, 0, sizeof(int) * d.G, s);
   if (total_lp > 0) {
@@ -1300,8 +1316,10 @@ int launch_finish_pose(const Dev& d, cudaStream_t s) {
   return 1;
 }
 
-int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, bool check_pending, bool identity_pose,
-                      cudaStream_t s) {
+// total_lp: points of the local maps (d.lp_off spacing, the pending-point staging area);
+// total_store: entries of the whole stores (d.so_off spacing, the merge)
+int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_store, bool check_pending,
+                      bool identity_pose, cudaStream_t s) {
   const int total_in = n_ds;  // exact number of down-sampled points (host read it back)
   int k = 0;
   const int front = check_pending ? total_lp : 0;
@@ -1331,10 +1349,10 @@ int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, bool check_
   if (n_delta > 0) { ins_compact_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, n_delta); ++k; }
   ins_off_kernel<<<cdiv(d.G + 1, 128), 128, 0, s>>>(d, n_delta); ++k;
   // survivors of the old store
-  alive_flag_kernel<<<cdiv(total_lp + 1, 256), 256, 0, s>>>(d, cur, total_lp); ++k;
+  alive_flag_kernel<<<cdiv(total_store + 1, 256), 256, 0, s>>>(d, cur, total_store); ++k;
   tb = d.cub_tmp_bytes;
-  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.aflag, d.ascan, total_lp + 1, s);
-  if (total_lp > 0) { merge_old_kernel<<<cdiv(total_lp, 256), 256, 0, s>>>(d, cur, total_lp); ++k; }
+  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.aflag, d.ascan, total_store + 1, s);
+  if (total_store > 0) { merge_old_kernel<<<cdiv(total_store, 256), 256, 0, s>>>(d, cur, total_store); ++k; }
   if (n_delta > 0) { merge_new_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, cur, n_delta); ++k; }
   store_count_kernel<<<cdiv(d.G, 128), 128, 0, s>>>(d); ++k;
   return k;
