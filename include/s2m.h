@@ -219,6 +219,45 @@ int s2m_shard_slab(int rank, int world, float* x_lo, float* x_hi);
 int s2m_shard_init(s2m_ctx* ctx, const void* id128);
 int s2m_shard_profile(s2m_ctx* ctx, int reset, double* allreduce_ms_total, long long* count);
 
+/* --- feature extraction ----------------------------------------------
+ * scanRegistration.cpp:116-454 (laserCloudHandler) for a batch of raw sweeps: the five clouds
+ * the node publishes -- /velodyne_cloud_2 (ring-major, intensity = ring + 0.1 * relative time),
+ * /laser_cloud_sharp, /laser_cloud_less_sharp, /laser_cloud_flat, /laser_cloud_less_flat
+ * (:415-446).  laserMapping consumes less_sharp / less_flat / full (relayed unchanged by
+ * laserOdometry.cpp:574-590).  The results stay on the device until the next extract, so they
+ * can be handed to s2m_register_batch_dev without leaving HBM. */
+#define S2M_SENSOR_HDL64 0 /* LIDAR_TYPE / N_SCANS pairs of scanRegistration.cpp:172-208 */
+#define S2M_SENSOR_VLP16 1
+#define S2M_SENSOR_OS1_64 2
+#define S2M_SENSOR_HDL32 3
+#define S2M_FX_FULL 0
+#define S2M_FX_SHARP 1
+#define S2M_FX_LESS_SHARP 2
+#define S2M_FX_FLAT 3
+#define S2M_FX_LESS_FLAT 4
+typedef struct s2m_fx s2m_fx;
+typedef struct s2m_fx_params {
+  int device;
+  int batch;            /* sweeps per call */
+  int cap_points;       /* max raw points of one sweep */
+  int sensor;           /* S2M_SENSOR_* */
+  double minimum_range; /* the node's minimum_range parameter (:458) */
+} s2m_fx_params;
+int s2m_fx_create(const s2m_fx_params* p, s2m_fx** out);
+void s2m_fx_destroy(s2m_fx* fx);
+const char* s2m_fx_last_error(s2m_fx* fx);
+/* xyz: packed float[3*n] raw points of the B sweeps in arrival order (host, or device if
+ * device_input != 0); off[B+1]: sweep offsets in points (host). */
+int s2m_fx_extract(s2m_fx* fx, const float* xyz, const int* off, int device_input);
+/* per-sweep offsets (B+1, in points) of output `which` of the last extract */
+int s2m_fx_offsets(s2m_fx* fx, int which, int* off_out);
+/* packed xyzi of output `which` over all sweeps -> host; returns the number of points
+ * (out may be NULL to query) */
+int s2m_fx_download(s2m_fx* fx, int which, float* out_xyzi, int cap_points_total);
+/* device pointer to the same packed xyzi (valid until the next extract / destroy) */
+const float* s2m_fx_device_cloud(s2m_fx* fx, int which);
+long long s2m_fx_launch_count(s2m_fx* fx);
+
 #ifdef __cplusplus
 }
 #endif

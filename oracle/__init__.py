@@ -28,8 +28,8 @@ class Stats(ctypes.Structure):
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "s2m_oracle.cpp")
-    stale = (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < os.path.getmtime(src)
+    srcs = [os.path.join(_HERE, f) for f in ("s2m_oracle.cpp", "scan_registration.cpp")]
+    stale = (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < max(os.path.getmtime(f) for f in srcs)
     if force or stale or (os.path.exists("/root/reference") and not os.path.exists(_REF)):
         subprocess.check_call(["make", "-C", _HERE, "CXX=g++"], stdout=subprocess.DEVNULL)
     return _LIB
@@ -180,6 +180,33 @@ def voxel_grid(pts, leaf):
     out = np.zeros((max(len(pts), 1), 4), np.float32)
     n = lib().orc_voxel_grid(pts.ctypes.data, len(pts), leaf, out.ctypes.data)
     return out[:n]
+
+
+SENSORS = {"HDL64": 0, "VLP16": 1, "OS1-64": 2, "HDL32": 3}
+FEATURE_CLOUDS = ("full", "sharp", "less_sharp", "flat", "less_flat")
+
+
+def scan_registration(sensor, xyz, minimum_range, tie_rule=0):
+    """scanRegistration.cpp:116-454 restated: raw sweep (n,3) -> dict of the five clouds it publishes
+    (full = /velodyne_cloud_2, sharp, less_sharp, flat, less_flat), each (m,4) xyzi."""
+    xyz = _f32(xyz).reshape(-1, 3)
+    cap = max(len(xyz), 1)
+    bufs = [np.zeros((cap, 4), np.float32) for _ in FEATURE_CLOUDS]
+    cnt = [ctypes.c_int() for _ in FEATURE_CLOUDS]
+    args = []
+    for b, c in zip(bufs, cnt):
+        args += [ctypes.c_void_p(b.ctypes.data), ctypes.byref(c)]
+    rc = lib().orc_scan_registration(SENSORS[sensor], ctypes.c_double(minimum_range), ctypes.c_void_p(xyz.ctypes.data), len(xyz),
+                                     tie_rule, cap, *args)
+    assert rc == 0
+    return {k: b[:c.value].copy() for k, b, c in zip(FEATURE_CLOUDS, bufs, cnt)}
+
+
+def ring_of(sensor, xyz):
+    xyz = _f32(xyz).reshape(-1, 3)
+    out = np.zeros(len(xyz), np.int32)
+    lib().orc_ring_of(SENSORS[sensor], ctypes.c_void_p(xyz.ctypes.data), len(xyz), ctypes.c_void_p(out.ctypes.data))
+    return out
 
 
 def knn(map_xyzi, q_xyz, method=0):

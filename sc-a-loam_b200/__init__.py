@@ -32,6 +32,8 @@ EXPORTS = [
     "s2m_get_window", "s2m_debug_knn", "s2m_trace_cloud", "s2m_trace_knn", "s2m_trace_lm",
     "s2m_launch_count", "s2m_set_profiling", "s2m_k4_profile", "s2m_phase_profile", "s2m_shard_unique_id", "s2m_shard_slab", "s2m_shard_init",
     "s2m_shard_profile",
+    "s2m_fx_create", "s2m_fx_destroy", "s2m_fx_last_error", "s2m_fx_extract", "s2m_fx_offsets", "s2m_fx_download",
+    "s2m_fx_device_cloud", "s2m_fx_launch_count",
 ]
 
 
@@ -88,6 +90,18 @@ def load_library(path=LIB_PATH):
     L.s2m_transform_cloud.argtypes = [vp, ci, vp, ci, vp]
     L.s2m_map_upload.argtypes = [vp, ci, vp, ci, vp, ci]
     L.s2m_map_download.argtypes = [vp, ci, ci, vp, ci]
+    L.s2m_fx_create.argtypes = [vp, vp]
+    L.s2m_fx_destroy.argtypes = [vp]
+    L.s2m_fx_destroy.restype = None
+    L.s2m_fx_last_error.argtypes = [vp]
+    L.s2m_fx_last_error.restype = ctypes.c_char_p
+    L.s2m_fx_extract.argtypes = [vp, vp, vp, ci]
+    L.s2m_fx_offsets.argtypes = [vp, ci, vp]
+    L.s2m_fx_download.argtypes = [vp, ci, vp, ci]
+    L.s2m_fx_device_cloud.argtypes = [vp, ci]
+    L.s2m_fx_device_cloud.restype = vp
+    L.s2m_fx_launch_count.argtypes = [vp]
+    L.s2m_fx_launch_count.restype = ctypes.c_longlong
     L.s2m_pcd_write.argtypes = [ctypes.c_char_p, vp, ci]
     L.s2m_pcd_read.argtypes = [ctypes.c_char_p, vp, ci]
     L.s2m_checkpoint_save.argtypes = [vp, ci, ctypes.c_char_p]
@@ -119,6 +133,73 @@ def shard_slab(rank, world):
     if rc != 0:
         raise S2MError("bad shard rank/world")
     return lo.value, hi.value
+
+
+class FxParams(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int), ("batch", ctypes.c_int), ("cap_points", ctypes.c_int), ("sensor", ctypes.c_int),
+                ("minimum_range", ctypes.c_double)]
+
+
+SENSORS = {"HDL64": 0, "VLP16": 1, "OS1-64": 2, "HDL32": 3}
+FX_CLOUDS = {"full": 0, "sharp": 1, "less_sharp": 2, "flat": 3, "less_flat": 4}
+
+
+class FeatureExtractor:
+    """scanRegistration.cpp:116-454 for a batch of raw sweeps on the device (include/s2m.h, s2m_fx_*)."""
+
+    def __init__(self, sensor, minimum_range, batch=1, cap_points=1 << 17, device=0):
+        self.L = load_library()
+        p = FxParams(device, batch, cap_points, SENSORS[sensor], float(minimum_range))
+        h = ctypes.c_void_p()
+        rc = self.L.s2m_fx_create(ctypes.byref(p), ctypes.byref(h))
+        if rc != 0:
+            raise S2MError("s2m_fx_create: %s (no CUDA device? the product has no CPU path)" % self.L.s2m_strerror(rc).decode())
+        self.h, self.batch = h, batch
+
+    def close(self):
+        if self.h:
+            self.L.s2m_fx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise S2MError("%s: %s" % (self.L.s2m_strerror(rc).decode(), self.L.s2m_fx_last_error(self.h).decode()))
+        return rc
+
+    def extract(self, xyz, off, device=False):
+        """xyz: packed (n,3) float32 host array (or a raw device pointer if device); off: B+1 sweep offsets."""
+        off = np.ascontiguousarray(off, np.int32)
+        assert len(off) == self.batch + 1
+        if device:
+            ptr = ctypes.c_void_p(int(xyz))
+        else:
+            xyz = _f32(xyz).reshape(-1, 3)
+            ptr = ctypes.c_void_p(xyz.ctypes.data)
+        self._check(self.L.s2m_fx_extract(self.h, ptr, off.ctypes.data, 1 if device else 0))
+
+    def offsets(self, which):
+        off = np.zeros(self.batch + 1, np.int32)
+        self._check(self.L.s2m_fx_offsets(self.h, FX_CLOUDS[which], off.ctypes.data))
+        return off
+
+    def cloud(self, which):
+        """-> (packed (m,4) xyzi over all sweeps, per-sweep offsets)"""
+        n = self._check(self.L.s2m_fx_download(self.h, FX_CLOUDS[which], None, 0))
+        out = np.zeros((max(n, 1), 4), np.float32)
+        self._check(self.L.s2m_fx_download(self.h, FX_CLOUDS[which], out.ctypes.data, n))
+        return out[:n], self.offsets(which)
+
+    def device_cloud(self, which):
+        return self.L.s2m_fx_device_cloud(self.h, FX_CLOUDS[which])
+
+    def launch_count(self):
+        return self.L.s2m_fx_launch_count(self.h)
 
 
 def pcd_write(path, xyzi):

@@ -33,7 +33,7 @@ def _nvcc():
 
 
 def build_cuda(force=False, verbose=False):
-    cu = [os.path.join(CSRC, f) for f in ("s2m_kernels.cu", "s2m_api.cu")]
+    cu = [os.path.join(CSRC, f) for f in ("s2m_kernels.cu", "s2m_api.cu", "s2m_fx.cu")]
     deps = cu + [os.path.join(CSRC, f) for f in ("s2m_math.cuh", "s2m_internal.h")] + \
         [os.path.join(HERE, "..", "include", "s2m.h")]
     objs = []
