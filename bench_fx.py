@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""bench_fx.py -- SURVEY 8f row N2: feature extraction (scanRegistration.cpp:116-454) on the device.
+
+A secondary measurement (the driver's contract lives in bench.py). One step = s2m_fx_extract over a
+batch of synthetic HDL-64 sweeps (harness/, 121 600 rays each). Reports sweeps/s with the raw sweeps
+resident in HBM, end to end from pinned host memory (H2D of the raw points inside; the feature clouds
+stay on the device, where the mapping call consumes them), and again with the three clouds the
+mapping node subscribes to copied back to the host. The CPU restatement (oracle/) is timed beside it
+on one core. CUDA events on the library's stream are not exposed, so the timed region is bracketed
+by torch.cuda.synchronize() + perf_counter around K calls (each call ends with a stream sync itself).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic sweeps (tiled over the batch)")
+    ap.add_argument("--cpu-sweeps", type=int, default=40)
+    args = ap.parse_args()
+    import torch
+    import harness
+    import oracle
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench_fx.py: no CUDA device; the product has no CPU path")
+    sensor, mr = "HDL64", harness.LAUNCH["HDL64"]["minimum_range"]
+    tr = harness.trajectory(20261018, args.distinct)
+    base = [harness.scan(20261018, sensor, tr[f], f) for f in range(args.distinct)]
+    sw = [base[b % args.distinct] for b in range(args.batch)]
+    off = np.cumsum([0] + [len(x) for x in sw]).astype(np.int32)
+    host = torch.from_numpy(np.concatenate(sw)).pin_memory()
+    dev = host.cuda()
+    F = pkg.FeatureExtractor(sensor, mr, batch=args.batch, cap_points=max(len(x) for x in sw) + 64)
+
+    def run(src, device, download):
+        for _ in range(args.warmup):
+            F.extract(src.data_ptr() if device else src.numpy(), off, device=device)
+        torch.cuda.synchronize()
+        l0 = F.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            F.extract(src.data_ptr() if device else src.numpy(), off, device=device)
+            if download:
+                for k in ("full", "less_sharp", "less_flat"):
+                    F.cloud(k)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return args.batch * args.steps / dt, 1e3 * dt / args.steps, (F.launch_count() - l0) // args.steps
+
+    v_dev, ms_dev, launches = run(dev, True, False)
+    v_h2d, ms_h2d, _ = run(host, False, False)
+    v_all, ms_all, _ = run(host, False, True)
+    sizes = {k: int(F.offsets(k)[-1]) for k in ("full", "sharp", "less_sharp", "flat", "less_flat")}
+    # parity spot check against the oracle on the first sweep (the checker, not the thing measured)
+    want = oracle.scan_registration(sensor, sw[0], mr)
+    ok = True
+    for k in want:
+        got, o = F.cloud(k)
+        ok = ok and np.array_equal(got[o[0]:o[1]].view(np.uint32), want[k].view(np.uint32))
+    t0 = time.perf_counter()
+    for i in range(args.cpu_sweeps):
+        oracle.scan_registration(sensor, base[i % args.distinct], mr)
+    cpu = args.cpu_sweeps / (time.perf_counter() - t0)
+    n_raw = int(off[-1])
+    alg_bytes = 12 * n_raw + 16 * (sizes["full"] + sizes["sharp"] + sizes["less_sharp"] + sizes["flat"] + sizes["less_flat"])
+    peak = 6541.8
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    print(json.dumps({
+        "workload": "hdl64_feature_extraction", "metric": "sweeps_per_s", "value": v_dev, "ms_per_step": ms_dev,
+        "batch": args.batch, "steps": args.steps, "raw_points_per_step": n_raw, "points_out_per_step": sizes,
+        "e2e_h2d_only": {"value": v_h2d, "ms_per_step": ms_h2d, "h2d_bytes_per_step": 12 * n_raw},
+        "e2e_with_download": {"value": v_all, "ms_per_step": ms_all,
+                              "d2h_bytes_per_step": 16 * (sizes["full"] + sizes["less_sharp"] + sizes["less_flat"])},
+        "gpu_launches_per_step": int(launches), "bit_identical_to_oracle": bool(ok),
+        "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms_dev * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg_bytes / (ms_dev * 1e-3) / 1e9 / peak,
+                     "bytes_per_step_algorithmic": alg_bytes, "note": "12 B per raw point read once + 16 B per output point written once; whole pipeline, host-timed"},
+        "cpu_baseline": {"value": cpu, "unit": "sweeps/s", "cores": 1, "kind": "port",
+                         "sample": "%d sweeps, oracle/scan_registration.cpp on one core" % args.cpu_sweeps}}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

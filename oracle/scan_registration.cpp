@@ -68,6 +68,7 @@ int ring_of(int sensor, const Pt& p) {
   const float planar = p.x * p.x + p.y * p.y;
   const float angle = (float)(::atan((double)p.z / ::sqrt((double)planar)) * 180 / M_PI);
   const int lines = scan_lines(sensor);
+  if (!(angle == angle)) return -1;  // x = y = z = 0 (only with minimum_range 0): int(NaN) is INT_MIN on x86, i.e. dropped
   int id;
   if (sensor == VLP16) {
     id = int((angle + 15) / 2 + 0.5);

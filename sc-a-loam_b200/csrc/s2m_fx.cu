@@ -122,6 +122,7 @@ __global__ void sweep_kernel(Dev d) {
 __device__ __forceinline__ int ring_of(int sensor, float x, float y, float z) {
   const float planar = xfadd(xfmul(x, x), xfmul(y, y));
   const float angle = (float)xddiv(xdmul(atan(xddiv((double)z, sqrt((double)planar))), 180.0), kPi);
+  if (!(angle == angle)) return -1;  // x = y = z = 0 with minimum_range 0: int(NaN) is INT_MIN on x86, i.e. dropped
   int id;
   if (sensor == S2M_SENSOR_VLP16) {
     id = (int)xdadd((double)xfmul(xfadd(angle, 15.0f), 0.5f), 0.5);
@@ -146,21 +147,74 @@ __device__ __forceinline__ float ori_first_half(float y, float x, float start) {
   else if ((double)ori > xdadd((double)start, kPi * 3 / 2)) ori = (float)xdsub((double)ori, 2 * kPi);
   return ori;
 }
+// FP32 screening of the two decisions of ring_kernel.  The exact arithmetic above is FP64
+// (atan, sqrt, two divisions, atan2 per point) and would make this kernel FP64-pipe bound; the
+// decisions only depend on which side of a threshold a value falls, so a float estimate settles
+// every point that is not within a (generous) margin of a threshold and the exact path runs for
+// the rest.  Float error of the estimates is < 5e-5 in the units compared; margins are 2e-3 / 1e-4.
+__device__ __forceinline__ bool ring_fast(int sensor, float x, float y, float z, int& id) {
+  const float planar = x * x + y * y;
+  if (!(planar > 0.0f)) return false;
+  const float a = atanf(z / sqrtf(planar)) * 57.29577951f;
+  const float m = 2e-3f;
+  float u;
+  int lim;
+  if (sensor == S2M_SENSOR_VLP16) { u = (a + 15.0f) * 0.5f + 0.5f; lim = 15; }
+  else if (sensor == S2M_SENSOR_HDL32) { u = (a + 30.66666667f) * 0.75f; lim = 31; }
+  else if (sensor == S2M_SENSOR_HDL64) {
+    if (fabsf(a + 8.83f) < m || fabsf(a - 2.0f) < m || fabsf(a + 24.33f) < m) return false;
+    if (a > 2.0f || a < -24.33f) { id = -1; return true; }
+    u = a >= -8.83f ? (2.0f - a) * 3.0f + 0.5f : 32.0f + truncf((-8.83f - a) * 2.0f + 0.5f) + 0.5f;
+    if (a < -8.83f) {  // the integer part comes from the inner expression
+      const float v = (-8.83f - a) * 2.0f + 0.5f;
+      if (fabsf(v - rintf(v)) < m) return false;
+    }
+    lim = 50;
+  } else { u = (a + 22.5f) * 0.5f + 0.5f; lim = 63; }
+  if (!(fabsf(u) < 1e6f) || fabsf(u - rintf(u)) < m) return false;
+  const int t = (int)u;
+  id = (t > lim || t < 0) ? -1 : t;
+  return true;
+}
+__device__ __forceinline__ bool half_fast(float y, float x, float start, bool& past) {
+  const float pi = 3.14159265f, m = 1e-4f;
+  float o = -atan2f(y, x);
+  const float lo = start - 0.5f * pi, hi = start + 1.5f * pi;
+  if (fabsf(o - lo) < m || fabsf(o - hi) < m) return false;
+  if (o < lo) o += 2.0f * pi;
+  else if (o > hi) o -= 2.0f * pi;
+  const float dlt = o - start;
+  if (fabsf(dlt - pi) < m) return false;
+  past = dlt > pi;
+  return true;
+}
 __global__ void ring_kernel(Dev d, int n) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n || j >= d.voff[d.B]) return;
-  const int b = find_off(d.voff, d.B, j);
-  int id = -1;
-  if (d.ok[b]) {
-    const size_t s = 3 * (size_t)d.vidx[j];
-    const float x = d.xyz[s], y = d.xyz[s + 1], z = d.xyz[s + 2];
-    id = ring_of(d.sensor, x, y, z);
-    if (id >= 0) {
-      const float start = d.ori[2 * b];
-      if ((double)xfsub(ori_first_half(y, x, start), start) > kPi) atomicMin(d.jstar + b, j);
+  const bool live = j < n && j < d.voff[d.B];
+  int b = -1, cand = INT_MAX;  // cand: this point is past the half turn (:232-235)
+  if (live) {
+    b = find_off(d.voff, d.B, j);
+    int id = -1;
+    if (d.ok[b]) {
+      const size_t s = 3 * (size_t)d.vidx[j];
+      const float x = d.xyz[s], y = d.xyz[s + 1], z = d.xyz[s + 2];
+      if (!ring_fast(d.sensor, x, y, z, id)) id = ring_of(d.sensor, x, y, z);
+      if (id >= 0) {
+        const float start = d.ori[2 * b];
+        bool past;
+        if (!half_fast(y, x, start, past)) past = (double)xfsub(ori_first_half(y, x, start), start) > kPi;
+        if (past) cand = j;
+      }
     }
+    d.ring[j] = id;
   }
-  d.ring[j] = id;
+  // Half of every sweep qualifies, all aimed at one word per sweep: reduce inside the warp first
+  // (lanes of the sweep of lane 0; a warp straddling two sweeps lets the others go alone) and look
+  // at the current value before touching the atomic.
+  const int b0 = __shfl_sync(0xffffffffu, b, 0);
+  const int m = __reduce_min_sync(0xffffffffu, b == b0 ? cand : INT_MAX);
+  if ((threadIdx.x & 31) == 0 && b0 >= 0 && m < *(volatile int*)(d.jstar + b0)) atomicMin(d.jstar + b0, m);
+  if (live && b != b0 && cand < *(volatile int*)(d.jstar + b)) atomicMin(d.jstar + b, cand);
 }
 // relative time -> intensity (:218-253); sort key = sweep * 64 + ring
 __global__ void time_kernel(Dev d, int n) {
@@ -296,7 +350,8 @@ __global__ void __launch_bounds__(32 * kWarps) select_kernel(Dev d) {
       int largest = 0, n_less = 0, n_sharp = 0, n_flat = 0;
       for (int k = n - 1; k >= 0; --k) {  // :305-356
         const int li = sp - rs + (int)(uint32_t)buf[k];
-        if ((st[li] & 1) || !((double)__uint_as_float((uint32_t)(buf[k] >> 32)) > 0.1)) continue;
+        if (!((double)__uint_as_float((uint32_t)(buf[k] >> 32)) > 0.1)) break;  // ascending order: nothing below can pass either
+        if (st[li] & 1) continue;
         ++largest;
         if (largest <= kSharp) {
           st[li] |= 2 << 2;
@@ -314,7 +369,8 @@ __global__ void __launch_bounds__(32 * kWarps) select_kernel(Dev d) {
       int smallest = 0;
       for (int k = 0; k < n; ++k) {  // :358-394
         const int li = sp - rs + (int)(uint32_t)buf[k];
-        if ((st[li] & 1) || !((double)__uint_as_float((uint32_t)(buf[k] >> 32)) < 0.1)) continue;
+        if (!((double)__uint_as_float((uint32_t)(buf[k] >> 32)) < 0.1)) break;  // nothing above can pass either
+        if (st[li] & 1) continue;
         st[li] |= 3 << 2;
         d.i_flat[sec * kFlat + n_flat++] = rs + li;
         if (++smallest >= kFlat) break;

@@ -89,6 +89,37 @@ def test_cuda_features_bit_identical_to_oracle(s2m, built, sensor, batch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("sensor", ["VLP16", "HDL32", "HDL64", "OS1-64"])
+def test_cuda_ring_and_time_rules_at_the_bucket_edges(s2m, built, sensor):
+    """Adversarial sweep: elevation angles packed around every ring-bucket edge of the sensor's rule
+    (:168-213) at offsets from 1e-7 to 1e-2 degrees, azimuths covering the half-turn and wrap-around
+    thresholds of the relative-time rule (:218-250).  The device screens these decisions in FP32 and
+    falls back to the exact FP64 path near a threshold: the ring-major cloud must still be the oracle's."""
+    rng = np.random.default_rng(42)
+    edges = {"VLP16": np.arange(-16.0, 17.0, 2.0), "HDL32": np.arange(-92.0 / 3, 12.0, 4.0 / 3),
+             "HDL64": np.r_[2.0 - (np.arange(0, 34) - 0.5) / 3.0, -8.83 - (np.arange(0, 33) - 0.5) / 2.0, 2.0, -8.83, -24.33],
+             "OS1-64": np.arange(-23.5, 107.0, 2.0)}[sensor]
+    offs = np.r_[0.0, np.geomspace(1e-7, 1e-2, 12), -np.geomspace(1e-7, 1e-2, 12)]
+    elev = np.deg2rad((edges[:, None] + offs[None, :]).ravel())
+    elev = np.tile(elev, 12)
+    n = len(elev)
+    az0 = 0.3
+    # one clockwise turn; extra samples right at the half turn and at the end of the sweep
+    az = az0 - np.sort(np.r_[rng.uniform(0, 2 * np.pi + 0.02, n - 60), np.pi + np.linspace(-3e-4, 3e-4, 30),
+                             2 * np.pi + np.linspace(-3e-4, 3e-4, 30)])
+    rng.shuffle(elev)
+    rad = rng.uniform(5.0, 40.0, n)
+    xyz = np.c_[rad * np.cos(elev) * np.cos(az), rad * np.cos(elev) * np.sin(az), rad * np.sin(elev)].astype(np.float32)
+    want = oracle.scan_registration(sensor, xyz, 0.1)
+    assert len(want["full"]) > 0.3 * n
+    F = s2m.FeatureExtractor(sensor, 0.1, batch=1, cap_points=n + 16)
+    F.extract(xyz, np.array([0, n], np.int32))
+    for k in CLOUDS:
+        got, _ = F.cloud(k)
+        assert got.shape == want[k].shape and np.array_equal(bits(got), bits(want[k])), k
+
+
+@pytest.mark.gpu
 def test_cuda_features_degenerate_sweeps(s2m, built):
     F = s2m.FeatureExtractor("VLP16", 0.1, batch=3, cap_points=40000)
     good = sweeps("VLP16", 3, 1)[0]
