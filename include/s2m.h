@@ -219,6 +219,22 @@ int s2m_shard_slab(int rank, int world, float* x_lo, float* x_hi);
 int s2m_shard_init(s2m_ctx* ctx, const void* id128);
 int s2m_shard_profile(s2m_ctx* ctx, int reset, double* allreduce_ms_total, long long* count);
 
+/* --- scan-to-scan odometry --------------------------------------------
+ * laserOdometry.cpp:220-591 with DISTORTION 0: per sweep, the sharp / flat points are matched against
+ * the previous sweep's less-sharp / less-flat clouds (exact nearest neighbour :303/:392, ring-
+ * constrained second / third neighbours :313-357/:401-452), LidarEdgeFactor + LidarPlaneFactor
+ * (lidarFactor.hpp:12-104), HuberLoss(0.1), two passes of a 4-iteration Ceres solve (:277, :495-500),
+ * then q_w_curr / t_w_curr are advanced (:504-505).  `batch` independent sequences per context; the
+ * four clouds of each are packed with B+1 offsets, host pointers or (device_ptrs != 0) device pointers,
+ * e.g. straight from s2m_fx_device_cloud.  The first call of a slot only initialises (:267-271).
+ * The context is an s2m_ctx: s2m_destroy, s2m_last_error, s2m_launch_count, s2m_trace_knn apply. */
+int s2m_odom_create(int device, int batch, int cap_sharp, int cap_flat, int cap_less_sharp,
+                    int cap_less_flat, int trace, s2m_ctx** out);
+int s2m_odom_step_batch(s2m_ctx* ctx, const float* sharp, const int* sharp_off, const float* flat,
+                        const int* flat_off, const float* less_sharp, const int* less_sharp_off,
+                        const float* less_flat, const int* less_flat_off, int device_ptrs,
+                        double* q_w_out, double* t_w_out, double* para_out, int* counts_out);
+
 /* --- feature extraction ----------------------------------------------
  * scanRegistration.cpp:116-454 (laserCloudHandler) for a batch of raw sweeps: the five clouds
  * the node publishes -- /velodyne_cloud_2 (ring-major, intensity = ring + 0.1 * relative time),

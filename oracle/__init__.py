@@ -182,6 +182,46 @@ def voxel_grid(pts, leaf):
     return out[:n]
 
 
+class Odometer:
+    """laserOdometry.cpp:220-591 restated (DISTORTION 0): feed the four feature clouds of each sweep."""
+
+    def __init__(self):
+        L = lib()
+        L.orc_odom_create.restype = ctypes.c_void_p
+        L.orc_odom_destroy.argtypes = [ctypes.c_void_p]
+        self.L, self.h = L, ctypes.c_void_p(L.orc_odom_create())
+        self.counts = np.zeros(4, np.int32)
+        self.para = np.zeros(7)
+        self._n = (0, 0)
+
+    def __del__(self):
+        try:
+            self.L.orc_odom_destroy(self.h)
+        except Exception:
+            pass
+
+    def step(self, sharp, flat, less_sharp, less_flat):
+        """-> (q_w_curr[4] x,y,z,w, t_w_curr[3]); self.para = (q_last_curr, t_last_curr), self.counts =
+        [corner pass 0, corner pass 1, plane pass 0, plane pass 1]"""
+        a = [_f32(x).reshape(-1, 4) for x in (sharp, flat, less_sharp, less_flat)]
+        q, t = np.zeros(4), np.zeros(3)
+        args = []
+        for x in a:
+            args += [ctypes.c_void_p(x.ctypes.data), len(x)]
+        self.L.orc_odom_step(self.h, *args, ctypes.c_void_p(q.ctypes.data), ctypes.c_void_p(t.ctypes.data),
+                             ctypes.c_void_p(self.para.ctypes.data), ctypes.c_void_p(self.counts.ctypes.data))
+        self._n = (len(a[0]), len(a[1]))
+        return q, t
+
+    def trace(self, opt):
+        """correspondence indices of pass `opt` of the last step: edge (n_sharp,2), plane (n_flat,3); -1 = none"""
+        e = np.full((self._n[0], 2), -1, np.int32)
+        p = np.full((self._n[1], 3), -1, np.int32)
+        if self.counts.sum() or True:
+            self.L.orc_odom_trace(self.h, opt, ctypes.c_void_p(e.ctypes.data), ctypes.c_void_p(p.ctypes.data))
+        return e, p
+
+
 SENSORS = {"HDL64": 0, "VLP16": 1, "OS1-64": 2, "HDL32": 3}
 FEATURE_CLOUDS = ("full", "sharp", "less_sharp", "flat", "less_flat")
 

@@ -33,6 +33,8 @@
 //   O  2 outer iterations                 :563
 //   I  map insertion                      :737-784
 //   W  re-filter of the valid cubes       :788-802
+// Also here: laserOdometry.cpp:220-591 with lidarFactor.hpp:57-104 -> class Odometer
+// (three-point PlaneFactor, exact 1-NN, ring-constrained second / third neighbours, same LM).
 //
 // Numbered assumptions about upstream libraries:
 //   A1 pcl::VoxelGrid 1.8: float inverse leaf, floor(p*inv) lattice, key order x
@@ -652,13 +654,39 @@ struct PlaneNormFactor {  // lidarFactor.hpp:106-138
   }
 };
 
+struct PlaneFactor {  // lidarFactor.hpp:57-104 (laserOdometry's plane factor: three points of the last sweep)
+  double cp[3], lpj[3], ljm[3], s;
+  void set(const double cp_[3], const double j[3], const double l[3], const double m[3], double s_) {
+    const double a[3] = {j[0] - l[0], j[1] - l[1], j[2] - l[2]}, b[3] = {j[0] - m[0], j[1] - m[1], j[2] - m[2]};
+    double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};  // :64
+    const double z = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];  // Eigen normalize(): divide by the norm when squaredNorm > 0
+    if (z > 0.0) { const double inv = std::sqrt(z); for (int k = 0; k < 3; ++k) n[k] /= inv; }
+    for (int k = 0; k < 3; ++k) { cp[k] = cp_[k]; lpj[k] = j[k]; ljm[k] = n[k]; }
+    s = s_;
+  }
+  template <typename T>
+  bool operator()(const T* q, const T* t, T* residual) const {
+    T cpT[3] = {T(cp[0]), T(cp[1]), T(cp[2])};
+    T q_last_curr[4] = {q[0], q[1], q[2], q[3]};
+    T q_identity[4] = {T(0.0), T(0.0), T(0.0), T(1.0)};
+    T qs[4];
+    quat_slerp(q_identity, T(s), q_last_curr, qs);
+    T lp[3];
+    quat_rotate(qs, cpT, lp);
+    for (int i = 0; i < 3; ++i) lp[i] = lp[i] + T(s) * t[i];
+    residual[0] = (lp[0] - T(lpj[0])) * T(ljm[0]) + (lp[1] - T(lpj[1])) * T(ljm[1]) + (lp[2] - T(lpj[2])) * T(ljm[2]);
+    return true;
+  }
+};
+
 // =========================================================================
 // A5/A6. Problem, evaluation, trust-region LM with dense QR
 // =========================================================================
 struct Block {
-  int kind;  // 0 edge (3 residuals), 1 plane (1 residual)
+  int kind;  // 0 edge (3 residuals), 1 plane-norm (1 residual), 2 three-point plane (1 residual)
   EdgeFactor e;
   PlaneNormFactor p;
+  PlaneFactor p3;
 };
 
 struct IterLog { double cost, cost_change, radius, step_norm, model_change; int accepted; };
@@ -718,10 +746,10 @@ double evaluate(const std::vector<Block>& blocks, const double x[7], std::vector
       Jet q[4], t[3], rj[3];
       for (int i = 0; i < 4; ++i) q[i] = Jet(x[i], i);
       for (int i = 0; i < 3; ++i) t[i] = Jet(x[4 + i], 4 + i);
-      if (b.kind == 0) b.e(q, t, rj); else b.p(q, t, rj);
+      if (b.kind == 0) b.e(q, t, rj); else if (b.kind == 1) b.p(q, t, rj); else b.p3(q, t, rj);
       for (int k = 0; k < nr; ++k) { r[k] = rj[k].a; for (int i = 0; i < 7; ++i) J7[k][i] = rj[k].v[i]; }
     } else {
-      if (b.kind == 0) b.e(x, x + 4, r); else b.p(x, x + 4, r);
+      if (b.kind == 0) b.e(x, x + 4, r); else if (b.kind == 1) b.p(x, x + 4, r); else b.p3(x, x + 4, r);
     }
     double s = 0;
     for (int k = 0; k < nr; ++k) s += r[k] * r[k];
@@ -1223,11 +1251,136 @@ int Mapper::process(const Cloud& corner_last, const Cloud& surf_last, const doub
   return status;
 }
 
+// =========================================================================
+// laserOdometry.cpp:220-591 restated (scan-to-scan odometry).
+// DISTORTION = 0 (:57), so s = 1 everywhere and TransformToStart (:108-126) is q*p + t.
+// nearestKSearch(., 1, ...) (:303, :392): exact nearest neighbour; canonical tie rule (d2, index).
+// =========================================================================
+class Odometer {
+ public:
+  double para[7] = {0, 0, 0, 1, 0, 0, 0};   // para_q (x,y,z,w), para_t (:94-95): q_last_curr, t_last_curr
+  Quat q_w{0, 0, 0, 1};                      // q_w_curr, t_w_curr (:90-91)
+  double t_w[3] = {0, 0, 0};
+  bool inited = false;                       // systemInited (:67)
+  Cloud corner_last, surf_last;              // laserCloudCornerLast / SurfLast (:83-84)
+  int n_corner[2] = {0, 0}, n_plane[2] = {0, 0};
+  std::vector<int> tr_edge[2], tr_plane[2];  // per optimisation pass: closest / second / third index per query (-1 none)
+  SolveLog lm[2];
+
+  static int nearest(const Cloud& c, const float q[3], float* d2) {
+    int best = -1;
+    float bd = INFINITY;
+    for (size_t i = 0; i < c.size(); ++i) {
+      const float dx = q[0] - c[i].x, dy = q[1] - c[i].y, dz = q[2] - c[i].z;
+      const float d = dx * dx + dy * dy + dz * dz;
+      if (d < bd) { bd = d; best = (int)i; }
+    }
+    *d2 = bd;
+    return best;
+  }
+  void to_start(const Pt& p, float out[3]) const {  // :108-126 with s = 1
+    const double v[3] = {(double)p.x, (double)p.y, (double)p.z};
+    double r[3];
+    quat_rotate(para, v, r);
+    for (int k = 0; k < 3; ++k) out[k] = (float)(r[k] + para[4 + k]);
+  }
+  static float sq(const Pt& p, const float s[3]) {  // :322-327: float expression
+    return (p.x - s[0]) * (p.x - s[0]) + (p.y - s[1]) * (p.y - s[1]) + (p.z - s[2]) * (p.z - s[2]);
+  }
+  void step(const Cloud& sharp, const Cloud& flat, const Cloud& less_sharp, const Cloud& less_flat) {
+    const double kDistSq = 25, kNearby = 2.5;  // :63-64
+    n_corner[0] = n_corner[1] = n_plane[0] = n_plane[1] = 0;
+    for (int o = 0; o < 2; ++o) { tr_edge[o].clear(); tr_plane[o].clear(); lm[o] = SolveLog(); }
+    if (!inited) {
+      inited = true;  // :267-271
+    } else {
+      for (int opt = 0; opt < 2; ++opt) {  // :277
+        std::vector<Block> blocks;
+        for (const Pt& p : sharp) {  // :300-385
+          float sel[3], d2;
+          to_start(p, sel);
+          const int c = corner_last.empty() ? -1 : nearest(corner_last, sel, &d2);
+          int closest = -1, second = -1;
+          if (c >= 0 && d2 < kDistSq) {
+            closest = c;
+            const int id = int(corner_last[c].i);
+            double best = kDistSq;
+            for (int j = c + 1; j < (int)corner_last.size(); ++j) {
+              if (int(corner_last[j].i) <= id) continue;
+              if (int(corner_last[j].i) > id + kNearby) break;
+              const double d = sq(corner_last[j], sel);
+              if (d < best) { best = d; second = j; }
+            }
+            for (int j = c - 1; j >= 0; --j) {
+              if (int(corner_last[j].i) >= id) continue;
+              if (int(corner_last[j].i) < id - kNearby) break;
+              const double d = sq(corner_last[j], sel);
+              if (d < best) { best = d; second = j; }
+            }
+          }
+          tr_edge[opt].push_back(closest); tr_edge[opt].push_back(second);
+          if (second >= 0) {
+            Block b;
+            b.kind = 0;
+            const Pt &a = corner_last[closest], &bb = corner_last[second];
+            b.e.cp[0] = p.x; b.e.cp[1] = p.y; b.e.cp[2] = p.z;
+            b.e.lpa[0] = a.x; b.e.lpa[1] = a.y; b.e.lpa[2] = a.z;
+            b.e.lpb[0] = bb.x; b.e.lpb[1] = bb.y; b.e.lpb[2] = bb.z;
+            b.e.s = 1.0;
+            blocks.push_back(b);
+            n_corner[opt]++;
+          }
+        }
+        for (const Pt& p : flat) {  // :388-486
+          float sel[3], d2;
+          to_start(p, sel);
+          const int c = surf_last.empty() ? -1 : nearest(surf_last, sel, &d2);
+          int closest = -1, second = -1, third = -1;
+          if (c >= 0 && d2 < kDistSq) {
+            closest = c;
+            const int id = int(surf_last[c].i);
+            double best2 = kDistSq, best3 = kDistSq;
+            for (int j = c + 1; j < (int)surf_last.size(); ++j) {
+              if (int(surf_last[j].i) > id + kNearby) break;
+              const double d = sq(surf_last[j], sel);
+              if (int(surf_last[j].i) <= id && d < best2) { best2 = d; second = j; }
+              else if (int(surf_last[j].i) > id && d < best3) { best3 = d; third = j; }
+            }
+            for (int j = c - 1; j >= 0; --j) {
+              if (int(surf_last[j].i) < id - kNearby) break;
+              const double d = sq(surf_last[j], sel);
+              if (int(surf_last[j].i) >= id && d < best2) { best2 = d; second = j; }
+              else if (int(surf_last[j].i) < id && d < best3) { best3 = d; third = j; }
+            }
+          }
+          tr_plane[opt].push_back(closest); tr_plane[opt].push_back(second); tr_plane[opt].push_back(third);
+          if (second >= 0 && third >= 0) {
+            Block b;
+            b.kind = 2;
+            const double cp[3] = {p.x, p.y, p.z};
+            const Pt &a = surf_last[closest], &l = surf_last[second], &m = surf_last[third];
+            const double pj[3] = {a.x, a.y, a.z}, pl[3] = {l.x, l.y, l.z}, pm[3] = {m.x, m.y, m.z};
+            b.p3.set(cp, pj, pl, pm, 1.0);
+            blocks.push_back(b);
+            n_plane[opt]++;
+          }
+        }
+        solve_trust_region(blocks, para, 4, &lm[opt]);  // :495-500
+      }
+      // :504-505
+      double r[3];
+      const double qq[4] = {q_w.x, q_w.y, q_w.z, q_w.w};
+      quat_rotate(qq, para + 4, r);
+      for (int k = 0; k < 3; ++k) t_w[k] = t_w[k] + r[k];
+      q_w = quat_mul(q_w, Quat{para[0], para[1], para[2], para[3]});
+    }
+    corner_last = less_sharp;  // :556-562
+    surf_last = less_flat;
+  }
+};
+
 }  // namespace orc
 
-// =========================================================================
-// C ABI (mirrors include/s2m.h so tests drive both with the same inputs)
-// =========================================================================
 extern "C" {
 
 typedef struct orc_stats {
@@ -1497,4 +1650,24 @@ int orc_trace_lm(void* h, int outer, double pose7[7], double sums28[28], double 
   return 0;
 }
 
+
+// ----- scan-to-scan odometry (row N3) -----
+void* orc_odom_create() { return new orc::Odometer(); }
+void orc_odom_destroy(void* h) { delete (orc::Odometer*)h; }
+// one sweep's four feature clouds -> q_w_curr (x,y,z,w), t_w_curr, para (q_last_curr, t_last_curr), counts[4]
+void orc_odom_step(void* h, const float* sharp, int n_sharp, const float* flat, int n_flat, const float* less_sharp,
+                   int n_ls, const float* less_flat, int n_lf, double q_w[4], double t_w[3], double para[7], int counts[4]) {
+  orc::Odometer& O = *(orc::Odometer*)h;
+  O.step(to_cloud(sharp, n_sharp), to_cloud(flat, n_flat), to_cloud(less_sharp, n_ls), to_cloud(less_flat, n_lf));
+  q_w[0] = O.q_w.x; q_w[1] = O.q_w.y; q_w[2] = O.q_w.z; q_w[3] = O.q_w.w;
+  for (int k = 0; k < 3; ++k) t_w[k] = O.t_w[k];
+  for (int k = 0; k < 7; ++k) para[k] = O.para[k];
+  counts[0] = O.n_corner[0]; counts[1] = O.n_corner[1]; counts[2] = O.n_plane[0]; counts[3] = O.n_plane[1];
+}
+// correspondences of optimisation pass `opt` of the last step: edge[2*n_sharp], plane[3*n_flat]
+void orc_odom_trace(void* h, int opt, int32_t* edge, int32_t* plane) {
+  orc::Odometer& O = *(orc::Odometer*)h;
+  std::memcpy(edge, O.tr_edge[opt].data(), O.tr_edge[opt].size() * sizeof(int32_t));
+  std::memcpy(plane, O.tr_plane[opt].data(), O.tr_plane[opt].size() * sizeof(int32_t));
+}
 }  // extern "C"

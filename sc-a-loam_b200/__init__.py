@@ -32,6 +32,7 @@ EXPORTS = [
     "s2m_get_window", "s2m_debug_knn", "s2m_trace_cloud", "s2m_trace_knn", "s2m_trace_lm",
     "s2m_launch_count", "s2m_set_profiling", "s2m_k4_profile", "s2m_phase_profile", "s2m_shard_unique_id", "s2m_shard_slab", "s2m_shard_init",
     "s2m_shard_profile",
+    "s2m_odom_create", "s2m_odom_step_batch",
     "s2m_fx_create", "s2m_fx_destroy", "s2m_fx_last_error", "s2m_fx_extract", "s2m_fx_offsets", "s2m_fx_download",
     "s2m_fx_device_cloud", "s2m_fx_launch_count",
 ]
@@ -90,6 +91,8 @@ def load_library(path=LIB_PATH):
     L.s2m_transform_cloud.argtypes = [vp, ci, vp, ci, vp]
     L.s2m_map_upload.argtypes = [vp, ci, vp, ci, vp, ci]
     L.s2m_map_download.argtypes = [vp, ci, ci, vp, ci]
+    L.s2m_odom_create.argtypes = [ci, ci, ci, ci, ci, ci, ci, vp]
+    L.s2m_odom_step_batch.argtypes = [vp] + [vp] * 8 + [ci] + [vp] * 4
     L.s2m_fx_create.argtypes = [vp, vp]
     L.s2m_fx_destroy.argtypes = [vp]
     L.s2m_fx_destroy.restype = None
@@ -133,6 +136,74 @@ def shard_slab(rank, world):
     if rc != 0:
         raise S2MError("bad shard rank/world")
     return lo.value, hi.value
+
+
+class Odometer:
+    """laserOdometry.cpp:220-591 for `batch` independent sequences on the device (include/s2m.h, s2m_odom_*)."""
+
+    def __init__(self, batch=1, cap_sharp=4096, cap_flat=8192, cap_less_sharp=1 << 14, cap_less_flat=1 << 16, device=0,
+                 trace=False):
+        self.L = load_library()
+        h = ctypes.c_void_p()
+        rc = self.L.s2m_odom_create(device, batch, cap_sharp, cap_flat, cap_less_sharp, cap_less_flat, 1 if trace else 0,
+                                    ctypes.byref(h))
+        if rc != 0:
+            raise S2MError("s2m_odom_create: %s (no CUDA device? the product has no CPU path)" % self.L.s2m_strerror(rc).decode())
+        self.h, self.batch = h, batch
+        self.para = np.zeros((batch, 7))
+        self.counts = np.zeros((batch, 4), np.int32)
+
+    def close(self):
+        if self.h:
+            self.L.s2m_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise S2MError("%s: %s" % (self.L.s2m_strerror(rc).decode(), self.L.s2m_last_error(self.h).decode()))
+        return rc
+
+    def step_batch(self, sharp, sharp_off, flat, flat_off, less_sharp, ls_off, less_flat, lf_off, device_ptrs=False):
+        """four packed xyzi clouds (host arrays, or raw device pointers if device_ptrs) with B+1 offsets each
+        -> (q_w_curr[B,4], t_w_curr[B,3]); self.para[B,7], self.counts[B,4]"""
+        B = self.batch
+        offs = [np.ascontiguousarray(o, np.int32) for o in (sharp_off, flat_off, ls_off, lf_off)]
+        assert all(len(o) == B + 1 for o in offs)
+        if device_ptrs:
+            ptrs = [ctypes.c_void_p(int(x)) for x in (sharp, flat, less_sharp, less_flat)]
+        else:
+            keep = [_f32(x).reshape(-1, 4) for x in (sharp, flat, less_sharp, less_flat)]
+            ptrs = [ctypes.c_void_p(x.ctypes.data) for x in keep]
+        q, t = np.zeros((B, 4)), np.zeros((B, 3))
+        rc = self.L.s2m_odom_step_batch(self.h, ptrs[0], offs[0].ctypes.data, ptrs[1], offs[1].ctypes.data, ptrs[2],
+                                        offs[2].ctypes.data, ptrs[3], offs[3].ctypes.data, 1 if device_ptrs else 0,
+                                        q.ctypes.data, t.ctypes.data, self.para.ctypes.data, self.counts.ctypes.data)
+        self._check(rc)
+        return q, t
+
+    def step(self, sharp, flat, less_sharp, less_flat):
+        """single sequence, host arrays -> (q_w_curr[4], t_w_curr[3])"""
+        a = [_f32(x).reshape(-1, 4) for x in (sharp, flat, less_sharp, less_flat)]
+        q, t = self.step_batch(a[0], [0, len(a[0])], a[1], [0, len(a[1])], a[2], [0, len(a[2])], a[3], [0, len(a[3])])
+        return q[0], t[0]
+
+    def trace(self, outer, cls, slot=0, cap=1 << 16):
+        """correspondences of pass `outer` for the sharp (cls 0) / flat (cls 1) queries of the last step:
+        (idx[n,3] = closest, second, third index into the previous cloud or -1, used[n])"""
+        idx = np.zeros((cap, 5), np.int32)
+        d2 = np.zeros((cap, 5), np.float32)
+        used = np.zeros(cap, np.uint8)
+        n = self._check(self.L.s2m_trace_knn(self.h, slot, outer, cls, idx.ctypes.data, d2.ctypes.data, used.ctypes.data, cap))
+        return idx[:n, :3].copy(), used[:n].astype(bool)
+
+    def launch_count(self):
+        return self.L.s2m_launch_count(self.h)
 
 
 class FxParams(ctypes.Structure):

@@ -160,6 +160,11 @@ struct s2m_ctx {
   int cur = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   std::vector<SlotHost> slots;
+  // scan-to-scan odometry contexts (s2m_odom_create): per-slot state of laserOdometry.cpp:67, :90-95
+  struct OdomHost { bool inited = false; double q_w[4] = {0, 0, 0, 1}, t_w[3] = {0, 0, 0}, para[7] = {0, 0, 0, 1, 0, 0, 0}; };
+  std::vector<OdomHost> odom;
+  bool is_odom = false;
+  long long od_cap = 0;  // points d.od_last can hold
   HostTables* ht = nullptr;      // pinned
   HostTables* d_ht = nullptr;    // device copy (desc/in_off/lp_off/hash_off point into it)
   SlotOut* h_out = nullptr;      // pinned
@@ -1281,6 +1286,110 @@ extern "C" int s2m_trace_lm(s2m_ctx* ctx, int slot, int outer, double pose7[7], 
   std::memcpy(iters24, h->it_log, 24 * 8);
   *n_iter = h->iteration;
   *termination = h->termination;
+  return S2M_OK;
+}
+
+// ---- scan-to-scan odometry (laserOdometry.cpp:220-591) ----------------------
+extern "C" int s2m_odom_create(int device, int batch, int cap_sharp, int cap_flat, int cap_less_sharp, int cap_less_flat,
+                               int trace, s2m_ctx** out) {
+  if (!out || batch < 1 || batch > kMaxBatch || cap_sharp < 1 || cap_flat < 1 || cap_less_sharp < 1 || cap_less_flat < 1)
+    return S2M_ERR_ARG;
+  s2m_params P;
+  s2m_default_params(&P);
+  P.device = device; P.batch = batch; P.trace = trace;
+  P.cap_corner_in = cap_sharp; P.cap_surf_in = cap_flat;
+  P.cap_map_corner = 1024; P.cap_map_surf = 1024;  // the map store of a mapping context is not used here
+  s2m_ctx* ctx = nullptr;
+  int rc = s2m_create(&P, &ctx);
+  if (rc != S2M_OK) return rc;
+  ctx->is_odom = true;
+  ctx->odom.resize(batch);
+  ctx->od_cap = (long long)batch * ((long long)cap_less_sharp + cap_less_flat);
+  if (dev_alloc(ctx, &ctx->d.od_last, (size_t)ctx->od_cap) || dev_alloc(ctx, &ctx->d.od_last_off, 2 * batch + 1) ||
+      cudaMemset(ctx->d.od_last_off, 0, sizeof(int) * (2 * batch + 1)) != cudaSuccess) {
+    s2m_destroy(ctx);
+    return S2M_ERR_CUDA;
+  }
+  *out = ctx;
+  return S2M_OK;
+}
+
+// One sweep of every slot: sharp / flat are the queries, less_sharp / less_flat become the next call's
+// targets (:556-566).  Outputs per slot: q_w_curr, t_w_curr (:504-505), optionally para (q_last_curr,
+// t_last_curr) and counts[4] = corner correspondences of pass 0, 1, plane correspondences of pass 0, 1.
+extern "C" int s2m_odom_step_batch(s2m_ctx* ctx, const float* sharp, const int* sharp_off, const float* flat,
+                                   const int* flat_off, const float* less_sharp, const int* ls_off,
+                                   const float* less_flat, const int* lf_off, int device_ptrs, double* q_w_out,
+                                   double* t_w_out, double* para_out, int* counts_out) {
+  if (!ctx || !ctx->is_odom || !sharp_off || !flat_off || !ls_off || !lf_off || !q_w_out || !t_w_out) return S2M_ERR_ARG;
+  CK(cudaSetDevice(ctx->P.device));
+  Dev& d = ctx->d;
+  const int B = d.B, G = d.G;
+  HostTables& T = *ctx->ht;
+  cudaStream_t s = ctx->stream;
+  const cudaMemcpyKind kind = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  int rc = check_offsets(ctx, sharp_off, flat_off);
+  if (rc != S2M_OK) return rc;
+  if (ls_off[0] != 0 || lf_off[0] != 0 || (long long)ls_off[B] + lf_off[B] > ctx->od_cap) {
+    ctx->err = "less-sharp / less-flat clouds exceed the context capacity";
+    return S2M_ERR_CAPACITY;
+  }
+  const int NC = sharp_off[B], NS = flat_off[B];
+  int tiles = 0;
+  bool any = false;
+  for (int b = 0; b < B; ++b) {
+    FrameDesc& fd = T.desc[b];
+    fd.active = ctx->odom[b].inited ? 1 : 0;  // the first sweep only initialises (:267-271)
+    fd.allow_opt = 1;
+    std::memcpy(fd.pose, ctx->odom[b].para, sizeof(fd.pose));
+    any = any || fd.active;
+    const int nq = (sharp_off[b + 1] - sharp_off[b]) + (flat_off[b + 1] - flat_off[b]);
+    tiles = std::max(tiles, (nq + kTile - 1) / kTile);
+  }
+  long long k = 0;
+  CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d.ds_off, T.in_off, sizeof(int) * (G + 1), cudaMemcpyHostToDevice, s));
+  if (NC > 0) CK(cudaMemcpyAsync(d.ds_pts, sharp, sizeof(float4) * (size_t)NC, kind, s));
+  if (NS > 0) CK(cudaMemcpyAsync(d.ds_pts + NC, flat, sizeof(float4) * (size_t)NS, kind, s));
+  k += launch_odom_guard(d, s);
+  if (any) {
+    const int eval_blocks = std::max(1, (tiles + kEvalTilesPerBlock - 1) / kEvalTilesPerBlock);
+    for (int outer = 0; outer < 2; ++outer) {  // :277
+      k += launch_odom_associate(d, outer, std::max(tiles, 1), ctx->P.trace != 0, s);
+      for (int it = 0; it < 4; ++it) k += launch_evaluate(d, outer, eval_blocks, s);  // max_num_iterations = 4 (:497)
+    }
+  }
+  k += launch_finish_pose(d, s);
+  ctx->launches += k;
+  rc = finish_call(ctx);
+  if (rc != S2M_OK) return rc;
+  for (int b = 0; b < B; ++b) {
+    s2m_ctx::OdomHost& o = ctx->odom[b];
+    const SlotOut& so = ctx->h_out[b];
+    if (o.inited) {
+      std::memcpy(o.para, so.pose, sizeof(o.para));
+      double r[3], qn[4];
+      quat_rotate_exact(o.q_w, o.para[4], o.para[5], o.para[6], r);  // t_w_curr = t_w_curr + q_w_curr * t_last_curr
+      for (int i = 0; i < 3; ++i) o.t_w[i] = xdadd(o.t_w[i], r[i]);
+      quat_mul_exact(o.q_w, o.para, qn);                              // q_w_curr = q_w_curr * q_last_curr
+      std::memcpy(o.q_w, qn, sizeof(qn));
+    }
+    o.inited = true;
+    std::memcpy(q_w_out + 4 * b, o.q_w, 32);
+    std::memcpy(t_w_out + 3 * b, o.t_w, 24);
+    if (para_out) std::memcpy(para_out + 7 * b, o.para, 56);
+    if (counts_out) {
+      counts_out[4 * b] = so.n_edge[0]; counts_out[4 * b + 1] = so.n_edge[1];
+      counts_out[4 * b + 2] = so.n_plane[0]; counts_out[4 * b + 3] = so.n_plane[1];
+    }
+  }
+  // this sweep's less-sharp / less-flat clouds are the next call's targets (:556-562)
+  std::vector<int> lo(2 * B + 1);
+  for (int b = 0; b <= B; ++b) { lo[b] = ls_off[b]; lo[B + b] = ls_off[B] + lf_off[b]; }
+  CK(cudaMemcpyAsync(d.od_last_off, lo.data(), sizeof(int) * (2 * B + 1), cudaMemcpyHostToDevice, s));
+  if (ls_off[B] > 0) CK(cudaMemcpyAsync(d.od_last, less_sharp, sizeof(float4) * (size_t)ls_off[B], kind, s));
+  if (lf_off[B] > 0) CK(cudaMemcpyAsync(d.od_last + ls_off[B], less_flat, sizeof(float4) * (size_t)lf_off[B], kind, s));
+  CK(cudaStreamSynchronize(s));
   return S2M_OK;
 }
 

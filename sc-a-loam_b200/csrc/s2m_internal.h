@@ -136,6 +136,8 @@ struct Dev {
   int* nbr;                     // [cap_in][6] K4a -> K4b: ds index (or -1 when gated out) + 5 neighbour positions
   unsigned long long* scanned;  // [B][2] candidate points actually scanned (statistics, profiling only)
   int* knn_ticket;              // next 32-query work unit of knn_kernel (re-armed by fit_kernel)
+  float4* od_last;              // odometry: less-sharp / less-flat clouds of the previous sweep, class-major
+  int* od_last_off;             // [2B+1]
   int count_scanned;            // profiling: maintain `scanned`
   unsigned long long* hash_tab; // cell tables
   uint2* hash_aux;              // per table slot: (points of the cell itself, exact 3-cell count)
@@ -178,6 +180,8 @@ int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bo
 int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s);
 int launch_count_candidates(const Dev& d, int blocks_per_slot, cudaStream_t s);
 int launch_lm_shard(const Dev& d, int outer, int after, cudaStream_t s);
+int launch_odom_guard(const Dev& d, cudaStream_t s);
+int launch_odom_associate(const Dev& d, int outer, int tiles, bool trace, cudaStream_t s);
 int launch_finish_pose(const Dev& d, cudaStream_t s);
 int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_store, bool check_pending, bool identity_pose,
                       cudaStream_t s);

@@ -889,6 +889,185 @@ __global__ void __launch_bounds__(kTile, 4) evaluate_kernel(Dev d, int outer) {
   lm_tail_after(d, slot, outer, red, &Ls);
 }
 
+// ----------------------------------------------------------------------------
+// Scan-to-scan odometry (laserOdometry.cpp:277-505): the queries are the
+// sharp / flat points of the current sweep, the targets the less-sharp / less-flat clouds of
+// the previous one (d.od_last, ring-major as the feature extraction left them).  Per query:
+// TransformToStart (:108-126 with s = 1: q*p + t), exact nearest neighbour (block-cooperative
+// sweep over the previous cloud through shared memory; order (d2, index)), the ring-constrained
+// second (and third) neighbour walks of :313-357 / :401-452, then the same residual / Jacobian /
+// Huber accumulation, block reduction and LM start as the mapping association: an edge factor
+// (lp-a) x (lp-b) / |a-b| is (lp - a) x u with u = (a-b)/|a-b|; the three-point plane factor
+// (lidarFactor.hpp:57-104) is n.lp + d with n = normalize((j-l) x (j-m)), d = -n.j.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float odom_sq(const float4 p, const float sel[3]) {  // the float expression of :322-327
+  const float dx = xfsub(p.x, sel[0]), dy = xfsub(p.y, sel[1]), dz = xfsub(p.z, sel[2]);
+  return xfadd(xfadd(xfmul(dx, dx), xfmul(dy, dy)), xfmul(dz, dz));
+}
+template <bool kTrace>
+__global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer) {
+  const int slot = blockIdx.y;
+  if (!d.out[slot].optimized) return;
+  int dc0, nc, ds0, nq;
+  slot_counts(d, slot, dc0, nc, ds0, nq);
+  const int nwork = max(1, (nq + kTile - 1) / kTile);  // one tile per block; depends only on the slot's own size
+  if ((int)blockIdx.x >= nwork) return;
+  __shared__ double pose[7];
+  __shared__ BlockAcc A;
+  __shared__ float4 stage[kTile];
+  __shared__ double red[kPartial];
+  if (threadIdx.x < 7) pose[threadIdx.x] = d.lm[slot].x[threadIdx.x];
+  acc_zero(A);
+  __syncthreads();
+  const int t = threadIdx.x, tile = blockIdx.x;
+  const int q = tile * kTile + t;
+  const bool live = q < nq;
+  const int cls = q >= nc;
+  const int di = cls ? ds0 + (q - nc) : dc0 + q;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  float sel[3] = {0.f, 0.f, 0.f};
+  if (live) {
+    p = d.ds_pts[di];
+    xf_point(pose, p.x, p.y, p.z, sel);
+  }
+  // ---- exact nearest neighbour in the previous sweep's cloud of the query's class (:303, :392) ----
+  int best_i = -1;
+  float best_d = INFINITY;
+  for (int c = 0; c < 2; ++c) {
+    const bool present = c == 0 ? (tile * kTile < nc) : ((tile + 1) * kTile > nc && tile * kTile < nq);  // block-uniform
+    if (!present) continue;
+    const int l0 = d.od_last_off[c * d.B + slot], ln = d.od_last_off[c * d.B + slot + 1] - l0;
+    for (int base = 0; base < ln; base += kTile) {
+      __syncthreads();
+      if (base + t < ln) stage[t] = d.od_last[l0 + base + t];
+      __syncthreads();
+      if (live && cls == c) {
+        const int m = min(kTile, ln - base);
+        for (int k = 0; k < m; ++k) {
+          const float4 s4 = stage[k];
+          const float dd = dist2(sel[0], sel[1], sel[2], s4.x, s4.y, s4.z);
+          if (dd < best_d) { best_d = dd; best_i = base + k; }
+        }
+      }
+    }
+  }
+  // ---- ring-constrained neighbours and the factor ----
+  Sums28 S;
+  S.zero();
+  double ne = 0.0, np = 0.0;
+  int second = -1, third = -1;
+  bool used = false;
+  double rec[6] = {0, 0, 0, 0, 0, 0};
+  if (live && best_i >= 0 && (double)best_d < 25.0) {  // DISTANCE_SQ_THRESHOLD (:63)
+    const int l0 = d.od_last_off[cls * d.B + slot], ln = d.od_last_off[cls * d.B + slot + 1] - l0;
+    const float4* __restrict__ last = d.od_last + l0;
+    const float4 a = last[best_i];
+    const int id = (int)a.w;
+    const double hi = (double)id + 2.5, lo = (double)id - 2.5;  // NEARBY_SCAN (:64)
+    if (cls == 0) {
+      double best = 25.0;
+      for (int j = best_i + 1; j < ln; ++j) {  // :313-334
+        const float4 c4 = last[j];
+        const int sid = (int)c4.w;
+        if (sid <= id) continue;
+        if ((double)sid > hi) break;
+        const double dd = (double)odom_sq(c4, sel);
+        if (dd < best) { best = dd; second = j; }
+      }
+      for (int j = best_i - 1; j >= 0; --j) {  // :337-357
+        const float4 c4 = last[j];
+        const int sid = (int)c4.w;
+        if (sid >= id) continue;
+        if ((double)sid < lo) break;
+        const double dd = (double)odom_sq(c4, sel);
+        if (dd < best) { best = dd; second = j; }
+      }
+      if (second >= 0) {
+        const float4 b = last[second];
+        const double e[3] = {(double)a.x - (double)b.x, (double)a.y - (double)b.y, (double)a.z - (double)b.z};
+        const double inv = 1.0 / sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        rec[0] = a.x; rec[1] = a.y; rec[2] = a.z;
+        rec[3] = e[0] * inv; rec[4] = e[1] * inv; rec[5] = e[2] * inv;
+        const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
+        accum_edge(S, pose, cp, rec, rec + 3);
+        ne = 1.0;
+        used = true;
+      }
+    } else {
+      double best2 = 25.0, best3 = 25.0;
+      for (int j = best_i + 1; j < ln; ++j) {  // :401-424
+        const float4 c4 = last[j];
+        const int sid = (int)c4.w;
+        if ((double)sid > hi) break;
+        const double dd = (double)odom_sq(c4, sel);
+        if (sid <= id && dd < best2) { best2 = dd; second = j; }
+        else if (sid > id && dd < best3) { best3 = dd; third = j; }
+      }
+      for (int j = best_i - 1; j >= 0; --j) {  // :427-452
+        const float4 c4 = last[j];
+        const int sid = (int)c4.w;
+        if ((double)sid < lo) break;
+        const double dd = (double)odom_sq(c4, sel);
+        if (sid >= id && dd < best2) { best2 = dd; second = j; }
+        else if (sid < id && dd < best3) { best3 = dd; third = j; }
+      }
+      if (second >= 0 && third >= 0) {
+        const float4 l = last[second], m = last[third];
+        const double u[3] = {(double)a.x - (double)l.x, (double)a.y - (double)l.y, (double)a.z - (double)l.z};
+        const double v[3] = {(double)a.x - (double)m.x, (double)a.y - (double)m.y, (double)a.z - (double)m.z};
+        double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+        const double z = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+        if (z > 0.0) { const double nn = sqrt(z); n[0] /= nn; n[1] /= nn; n[2] /= nn; }
+        rec[0] = n[0]; rec[1] = n[1]; rec[2] = n[2];
+        rec[3] = -(n[0] * (double)a.x + n[1] * (double)a.y + n[2] * (double)a.z);
+        const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
+        accum_plane(S, pose, cp, rec, rec[3]);
+        np = 1.0;
+        used = true;
+      }
+    }
+  }
+  if (live) {
+    if (used) {
+      double2* ro = reinterpret_cast<double2*>(d.rec + 6 * (size_t)di);
+      ro[0] = make_double2(rec[0], rec[1]);
+      ro[1] = make_double2(rec[2], rec[3]);
+      ro[2] = make_double2(rec[4], rec[5]);
+    }
+    d.rec_valid[di] = used ? 1 : 0;
+    if (kTrace) {
+      const size_t o = (size_t)outer * d.cap_in + di;
+      const bool gate = best_i >= 0 && (double)best_d < 25.0;
+      d.tr_idx[5 * o] = gate ? best_i : -1; d.tr_idx[5 * o + 1] = second; d.tr_idx[5 * o + 2] = third;
+      d.tr_idx[5 * o + 3] = d.tr_idx[5 * o + 4] = -1;
+      d.tr_d2[5 * o] = best_d;
+      d.tr_used[o] = used;
+    }
+  }
+  acc_add(A, S, ne, np, 0.0, 0.0);
+  acc_store(A, d.partials + ((size_t)slot * d.max_tiles + blockIdx.x) * kPartial);
+  if (!block_is_last(d.ticket + slot, nwork)) return;
+  sum_partials(d, slot, nwork, red);
+  __shared__ LmState Ls;
+  lm_tail_begin(d, slot, outer, red, &Ls);
+}
+// start of an odometry step: which slots solve, LM state from the previous relative motion (para_q, para_t)
+__global__ void odom_guard_kernel(Dev d) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= d.B) return;
+  const FrameDesc& fd = d.desc[s];
+  SlotOut& o = d.out[s];
+  o.optimized = fd.active && fd.allow_opt;
+  for (int k = 0; k < 2; ++k) {
+    o.n_edge[k] = o.n_plane[k] = 0; o.lm_iters[k] = 0; o.lm_term[k] = 0;
+    o.cost_initial[k] = o.cost_final[k] = 0.0; o.cand[k] = 0.0;
+  }
+  LmState& L = d.lm[s];
+  for (int i = 0; i < 7; ++i) L.x[i] = L.xc[i] = fd.pose[i];
+  L.done = !o.optimized; L.have_candidate = 0; L.iteration = 0;
+  d.ticket[s] = 0;
+}
+
 __global__ void guard_kernel(Dev d) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= d.B) return;
@@ -1309,6 +1488,17 @@ int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s
   if (blocks_per_slot <= 0) return 0;
   dim3 grid(blocks_per_slot, d.B);
   evaluate_kernel<<<grid, kTile, 0, s>>>(d, outer);
+  return 1;
+}
+int launch_odom_guard(const Dev& d, cudaStream_t s) {
+  odom_guard_kernel<<<cdiv(d.B, 64), 64, 0, s>>>(d);
+  return 1;
+}
+int launch_odom_associate(const Dev& d, int outer, int tiles, bool trace, cudaStream_t s) {
+  if (tiles <= 0) return 0;
+  dim3 grid(tiles, d.B);
+  if (trace) odom_associate_kernel<true><<<grid, kTile, 0, s>>>(d, outer);
+  else odom_associate_kernel<false><<<grid, kTile, 0, s>>>(d, outer);
   return 1;
 }
 int launch_finish_pose(const Dev& d, cudaStream_t s) {
