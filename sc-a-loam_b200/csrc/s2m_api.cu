@@ -165,6 +165,8 @@ struct s2m_ctx {
   std::vector<OdomHost> odom;
   bool is_odom = false;
   long long od_cap = 0;  // points d.od_last can hold
+  void* od_tmp = nullptr;
+  size_t od_tmp_bytes = 0;
   HostTables* ht = nullptr;      // pinned
   HostTables* d_ht = nullptr;    // device copy (desc/in_off/lp_off/hash_off point into it)
   SlotOut* h_out = nullptr;      // pinned
@@ -1305,8 +1307,17 @@ extern "C" int s2m_odom_create(int device, int batch, int cap_sharp, int cap_fla
   ctx->is_odom = true;
   ctx->odom.resize(batch);
   ctx->od_cap = (long long)batch * ((long long)cap_less_sharp + cap_less_flat);
-  if (dev_alloc(ctx, &ctx->d.od_last, (size_t)ctx->od_cap) || dev_alloc(ctx, &ctx->d.od_last_off, 2 * batch + 1) ||
-      cudaMemset(ctx->d.od_last_off, 0, sizeof(int) * (2 * batch + 1)) != cudaSuccess) {
+  const size_t oc = (size_t)ctx->od_cap;
+  bool bad = dev_alloc(ctx, &ctx->d.od_last, oc) || dev_alloc(ctx, &ctx->d.od_last_off, 2 * batch + 1) ||
+             dev_alloc(ctx, &ctx->d.od_sorted, oc) || dev_alloc(ctx, &ctx->d.od_key, oc) || dev_alloc(ctx, &ctx->d.od_key2, oc) ||
+             dev_alloc(ctx, &ctx->d.od_val, oc) || dev_alloc(ctx, &ctx->d.od_val2, oc);
+  if (!bad) {
+    ctx->od_tmp_bytes = odom_sort_temp_bytes(ctx->d, (int)oc);
+    char* tmp = nullptr;
+    bad = dev_alloc(ctx, &tmp, ctx->od_tmp_bytes) != 0;
+    ctx->od_tmp = tmp;
+  }
+  if (bad || cudaMemset(ctx->d.od_last_off, 0, sizeof(int) * (2 * batch + 1)) != cudaSuccess) {
     s2m_destroy(ctx);
     return S2M_ERR_CUDA;
   }
@@ -1389,6 +1400,7 @@ extern "C" int s2m_odom_step_batch(s2m_ctx* ctx, const float* sharp, const int* 
   CK(cudaMemcpyAsync(d.od_last_off, lo.data(), sizeof(int) * (2 * B + 1), cudaMemcpyHostToDevice, s));
   if (ls_off[B] > 0) CK(cudaMemcpyAsync(d.od_last, less_sharp, sizeof(float4) * (size_t)ls_off[B], kind, s));
   if (lf_off[B] > 0) CK(cudaMemcpyAsync(d.od_last + ls_off[B], less_flat, sizeof(float4) * (size_t)lf_off[B], kind, s));
+  ctx->launches += launch_odom_sort(d, ls_off[B] + lf_off[B], ctx->od_tmp, ctx->od_tmp_bytes, s);
   CK(cudaStreamSynchronize(s));
   return S2M_OK;
 }

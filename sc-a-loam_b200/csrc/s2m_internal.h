@@ -138,6 +138,9 @@ struct Dev {
   int* knn_ticket;              // next 32-query work unit of knn_kernel (re-armed by fit_kernel)
   float4* od_last;              // odometry: less-sharp / less-flat clouds of the previous sweep, class-major
   int* od_last_off;             // [2B+1]
+  float4* od_sorted;            // the same clouds ordered by x inside each segment, .w = index in od_last's segment
+  unsigned long long *od_key, *od_key2;
+  uint32_t *od_val, *od_val2;
   int count_scanned;            // profiling: maintain `scanned`
   unsigned long long* hash_tab; // cell tables
   uint2* hash_aux;              // per table slot: (points of the cell itself, exact 3-cell count)
@@ -180,6 +183,8 @@ int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bo
 int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s);
 int launch_count_candidates(const Dev& d, int blocks_per_slot, cudaStream_t s);
 int launch_lm_shard(const Dev& d, int outer, int after, cudaStream_t s);
+int launch_odom_sort(const Dev& d, int n, void* tmp, size_t tmp_bytes, cudaStream_t s);
+size_t odom_sort_temp_bytes(const Dev& d, int n);
 int launch_odom_guard(const Dev& d, cudaStream_t s);
 int launch_odom_associate(const Dev& d, int outer, int tiles, bool trace, cudaStream_t s);
 int launch_finish_pose(const Dev& d, cudaStream_t s);

@@ -914,7 +914,6 @@ __global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer)
   if ((int)blockIdx.x >= nwork) return;
   __shared__ double pose[7];
   __shared__ BlockAcc A;
-  __shared__ float4 stage[kTile];
   __shared__ double red[kPartial];
   if (threadIdx.x < 7) pose[threadIdx.x] = d.lm[slot].x[threadIdx.x];
   acc_zero(A);
@@ -931,57 +930,134 @@ __global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer)
     xf_point(pose, p.x, p.y, p.z, sel);
   }
   // ---- exact nearest neighbour in the previous sweep's cloud of the query's class (:303, :392) ----
+  // d.od_sorted holds each previous cloud ordered by x (.w = index in the ring-major cloud): start at the
+  // query's x and walk outwards; a side is finished once dx*dx alone exceeds the best distance (the float
+  // sum (dx*dx + dy*dy) + dz*dz can never be smaller than dx*dx), so the answer is the exact minimum of
+  // (d2, index) over the whole cloud.
   int best_i = -1;
   float best_d = INFINITY;
-  for (int c = 0; c < 2; ++c) {
-    const bool present = c == 0 ? (tile * kTile < nc) : ((tile + 1) * kTile > nc && tile * kTile < nq);  // block-uniform
-    if (!present) continue;
-    const int l0 = d.od_last_off[c * d.B + slot], ln = d.od_last_off[c * d.B + slot + 1] - l0;
-    for (int base = 0; base < ln; base += kTile) {
-      __syncthreads();
-      if (base + t < ln) stage[t] = d.od_last[l0 + base + t];
-      __syncthreads();
-      if (live && cls == c) {
-        const int m = min(kTile, ln - base);
-        for (int k = 0; k < m; ++k) {
-          const float4 s4 = stage[k];
-          const float dd = dist2(sel[0], sel[1], sel[2], s4.x, s4.y, s4.z);
-          if (dd < best_d) { best_d = dd; best_i = base + k; }
+  if (live) {
+    const int l0 = d.od_last_off[cls * d.B + slot], ln = d.od_last_off[cls * d.B + slot + 1] - l0;
+    const float4* __restrict__ sp = d.od_sorted + l0;
+    int lo = 0, hi = ln;
+    while (lo < hi) {  // first sorted position with x >= sel.x
+      const int mid = (lo + hi) >> 1;
+      if (sp[mid].x < sel[0]) lo = mid + 1; else hi = mid;
+    }
+    int up = lo, dn = lo - 1;
+    bool more_up = up < ln, more_dn = dn >= 0;
+    while (more_up || more_dn) {
+      if (more_up) {
+        const float4 c4 = sp[up];
+        const float dx = xfsub(sel[0], c4.x);
+        if (xfmul(dx, dx) > best_d) more_up = false;
+        else {
+          const float dd = dist2(sel[0], sel[1], sel[2], c4.x, c4.y, c4.z);
+          const int idx = __float_as_int(c4.w);
+          if (dd < best_d || (dd == best_d && idx < best_i)) { best_d = dd; best_i = idx; }
+          more_up = ++up < ln;
+        }
+      }
+      if (more_dn) {
+        const float4 c4 = sp[dn];
+        const float dx = xfsub(sel[0], c4.x);
+        if (xfmul(dx, dx) > best_d) more_dn = false;
+        else {
+          const float dd = dist2(sel[0], sel[1], sel[2], c4.x, c4.y, c4.z);
+          const int idx = __float_as_int(c4.w);
+          if (dd < best_d || (dd == best_d && idx < best_i)) { best_d = dd; best_i = idx; }
+          more_dn = --dn >= 0;
         }
       }
     }
   }
-  // ---- ring-constrained neighbours and the factor ----
+  // ---- ring-constrained neighbours (:313-357, :401-452) ----
+  // The reference walks the previous cloud point by point from the closest one, forwards until the ring
+  // number exceeds id + 2.5 and backwards until it drops below id - 2.5, keeping running minima with a
+  // strict "<".  Here the WARP walks for one query at a time, 32 consecutive points per step (coalesced),
+  // a ballot reproduces the sequential break, and the minima are reduced with the walk's own tie rule
+  // (forwards: lowest index; backwards: highest index, and only if strictly closer than the forward one).
+  const bool gate = live && best_i >= 0 && (double)best_d < 25.0;  // DISTANCE_SQ_THRESHOLD (:63)
+  int second = -1, third = -1;
+  {
+    const int lane = t & 31;
+    const unsigned full = 0xffffffffu;
+    for (unsigned todo = __ballot_sync(full, gate); todo; todo &= todo - 1) {
+      const int src = __ffs(todo) - 1;
+      const int qcls = __shfl_sync(full, cls, src), qbest = __shfl_sync(full, best_i, src);
+      const float qs[3] = {__shfl_sync(full, sel[0], src), __shfl_sync(full, sel[1], src), __shfl_sync(full, sel[2], src)};
+      const int l0 = d.od_last_off[qcls * d.B + slot], ln = d.od_last_off[qcls * d.B + slot + 1] - l0;
+      const float4* __restrict__ last = d.od_last + l0;
+      const int id = (int)last[qbest].w;
+      const double hi = (double)id + 2.5, lo = (double)id - 2.5;  // NEARBY_SCAN (:64)
+      float f2 = 25.0f, f3 = 25.0f, b2 = 25.0f, b3 = 25.0f;
+      int fi2 = -1, fi3 = -1, bi2 = -1, bi3 = -1;
+      for (int base = qbest + 1; base < ln; base += 32) {  // increasing scan line
+        const int j = base + lane;
+        bool brk = false, c2 = false, c3 = false;
+        float dd = 0.0f;
+        if (j < ln) {
+          const float4 c4 = last[j];
+          const int sid = (int)c4.w;
+          brk = (double)sid > hi;
+          dd = odom_sq(c4, qs);
+          if (qcls == 0) c2 = sid > id;
+          else { c2 = sid <= id; c3 = sid > id; }
+        }
+        const unsigned bb = __ballot_sync(full, brk);
+        if (bb == 0u || lane < __ffs(bb) - 1) {
+          if (c2 && dd < f2) { f2 = dd; fi2 = j; }
+          if (c3 && dd < f3) { f3 = dd; fi3 = j; }
+        }
+        if (bb) break;
+      }
+      for (int base = qbest - 1; base >= 0; base -= 32) {  // decreasing scan line
+        const int j = base - lane;
+        bool brk = false, c2 = false, c3 = false;
+        float dd = 0.0f;
+        if (j >= 0) {
+          const float4 c4 = last[j];
+          const int sid = (int)c4.w;
+          brk = (double)sid < lo;
+          dd = odom_sq(c4, qs);
+          if (qcls == 0) c2 = sid < id;
+          else { c2 = sid >= id; c3 = sid < id; }
+        }
+        const unsigned bb = __ballot_sync(full, brk);
+        if (bb == 0u || lane < __ffs(bb) - 1) {
+          if (c2 && dd < b2) { b2 = dd; bi2 = j; }
+          if (c3 && dd < b3) { b3 = dd; bi3 = j; }
+        }
+        if (bb) break;
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        float od; int oi;
+        od = __shfl_xor_sync(full, f2, o); oi = __shfl_xor_sync(full, fi2, o);
+        if (oi >= 0 && (od < f2 || (od == f2 && (fi2 < 0 || oi < fi2)))) { f2 = od; fi2 = oi; }
+        od = __shfl_xor_sync(full, f3, o); oi = __shfl_xor_sync(full, fi3, o);
+        if (oi >= 0 && (od < f3 || (od == f3 && (fi3 < 0 || oi < fi3)))) { f3 = od; fi3 = oi; }
+        od = __shfl_xor_sync(full, b2, o); oi = __shfl_xor_sync(full, bi2, o);
+        if (oi >= 0 && (od < b2 || (od == b2 && (bi2 < 0 || oi > bi2)))) { b2 = od; bi2 = oi; }
+        od = __shfl_xor_sync(full, b3, o); oi = __shfl_xor_sync(full, bi3, o);
+        if (oi >= 0 && (od < b3 || (od == b3 && (bi3 < 0 || oi > bi3)))) { b3 = od; bi3 = oi; }
+      }
+      if (lane == src) {
+        second = (bi2 >= 0 && b2 < f2) ? bi2 : fi2;
+        third = (bi3 >= 0 && b3 < f3) ? bi3 : fi3;
+      }
+    }
+  }
+  // ---- the factor ----
   Sums28 S;
   S.zero();
   double ne = 0.0, np = 0.0;
-  int second = -1, third = -1;
   bool used = false;
   double rec[6] = {0, 0, 0, 0, 0, 0};
-  if (live && best_i >= 0 && (double)best_d < 25.0) {  // DISTANCE_SQ_THRESHOLD (:63)
-    const int l0 = d.od_last_off[cls * d.B + slot], ln = d.od_last_off[cls * d.B + slot + 1] - l0;
+  if (gate) {
+    const int l0 = d.od_last_off[cls * d.B + slot];
     const float4* __restrict__ last = d.od_last + l0;
     const float4 a = last[best_i];
-    const int id = (int)a.w;
-    const double hi = (double)id + 2.5, lo = (double)id - 2.5;  // NEARBY_SCAN (:64)
     if (cls == 0) {
-      double best = 25.0;
-      for (int j = best_i + 1; j < ln; ++j) {  // :313-334
-        const float4 c4 = last[j];
-        const int sid = (int)c4.w;
-        if (sid <= id) continue;
-        if ((double)sid > hi) break;
-        const double dd = (double)odom_sq(c4, sel);
-        if (dd < best) { best = dd; second = j; }
-      }
-      for (int j = best_i - 1; j >= 0; --j) {  // :337-357
-        const float4 c4 = last[j];
-        const int sid = (int)c4.w;
-        if (sid >= id) continue;
-        if ((double)sid < lo) break;
-        const double dd = (double)odom_sq(c4, sel);
-        if (dd < best) { best = dd; second = j; }
-      }
       if (second >= 0) {
         const float4 b = last[second];
         const double e[3] = {(double)a.x - (double)b.x, (double)a.y - (double)b.y, (double)a.z - (double)b.z};
@@ -994,23 +1070,6 @@ __global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer)
         used = true;
       }
     } else {
-      double best2 = 25.0, best3 = 25.0;
-      for (int j = best_i + 1; j < ln; ++j) {  // :401-424
-        const float4 c4 = last[j];
-        const int sid = (int)c4.w;
-        if ((double)sid > hi) break;
-        const double dd = (double)odom_sq(c4, sel);
-        if (sid <= id && dd < best2) { best2 = dd; second = j; }
-        else if (sid > id && dd < best3) { best3 = dd; third = j; }
-      }
-      for (int j = best_i - 1; j >= 0; --j) {  // :427-452
-        const float4 c4 = last[j];
-        const int sid = (int)c4.w;
-        if ((double)sid < lo) break;
-        const double dd = (double)odom_sq(c4, sel);
-        if (sid >= id && dd < best2) { best2 = dd; second = j; }
-        else if (sid < id && dd < best3) { best3 = dd; third = j; }
-      }
       if (second >= 0 && third >= 0) {
         const float4 l = last[second], m = last[third];
         const double u[3] = {(double)a.x - (double)l.x, (double)a.y - (double)l.y, (double)a.z - (double)l.z};
@@ -1037,7 +1096,6 @@ __global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer)
     d.rec_valid[di] = used ? 1 : 0;
     if (kTrace) {
       const size_t o = (size_t)outer * d.cap_in + di;
-      const bool gate = best_i >= 0 && (double)best_d < 25.0;
       d.tr_idx[5 * o] = gate ? best_i : -1; d.tr_idx[5 * o + 1] = second; d.tr_idx[5 * o + 2] = third;
       d.tr_idx[5 * o + 3] = d.tr_idx[5 * o + 4] = -1;
       d.tr_d2[5 * o] = best_d;
@@ -1050,6 +1108,22 @@ __global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer)
   sum_partials(d, slot, nwork, red);
   __shared__ LmState Ls;
   lm_tail_begin(d, slot, outer, red, &Ls);
+}
+// previous clouds ordered by x for the nearest-neighbour walk: key = [segment][ordered bits of x]
+__global__ void odom_sort_key_kernel(Dev d, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = find_seg(d.od_last_off, 2 * d.B, i);
+  d.od_key[i] = ((unsigned long long)g << 32) | f2ord(d.od_last[i].x);
+  d.od_val[i] = (uint32_t)(i - d.od_last_off[g]);
+}
+__global__ void odom_gather_sorted_kernel(Dev d, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = (int)(d.od_key2[i] >> 32);
+  const uint32_t l = d.od_val2[i];
+  const float4 p = d.od_last[d.od_last_off[g] + l];
+  d.od_sorted[i] = make_float4(p.x, p.y, p.z, __int_as_float((int)l));
 }
 // start of an odometry step: which slots solve, LM state from the previous relative motion (para_q, para_t)
 __global__ void odom_guard_kernel(Dev d) {
@@ -1489,6 +1563,20 @@ int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s
   dim3 grid(blocks_per_slot, d.B);
   evaluate_kernel<<<grid, kTile, 0, s>>>(d, outer);
   return 1;
+}
+int launch_odom_sort(const Dev& d, int n, void* tmp, size_t tmp_bytes, cudaStream_t s) {
+  if (n <= 0) return 0;
+  odom_sort_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n);
+  int bits = 1;
+  while ((1 << bits) < 2 * d.B) ++bits;
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d.od_key, d.od_key2, d.od_val, d.od_val2, n, 0, 32 + bits, s);
+  odom_gather_sorted_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n);
+  return 2;
+}
+size_t odom_sort_temp_bytes(const Dev& d, int n) {
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, d.od_key, d.od_key2, d.od_val, d.od_val2, n, 0, 40, (cudaStream_t)0);
+  return tb;
 }
 int launch_odom_guard(const Dev& d, cudaStream_t s) {
   odom_guard_kernel<<<cdiv(d.B, 64), 64, 0, s>>>(d);
