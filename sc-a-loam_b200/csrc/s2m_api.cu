@@ -1308,8 +1308,7 @@ extern "C" int s2m_odom_create(int device, int batch, int cap_sharp, int cap_fla
   ctx->odom.resize(batch);
   ctx->od_cap = (long long)batch * ((long long)cap_less_sharp + cap_less_flat);
   const size_t oc = (size_t)ctx->od_cap;
-  bool bad = dev_alloc(ctx, &ctx->d.od_last, oc) || dev_alloc(ctx, &ctx->d.od_last_off, 2 * batch + 1) ||
-             dev_alloc(ctx, &ctx->d.od_sorted, oc) || dev_alloc(ctx, &ctx->d.od_key, oc) || dev_alloc(ctx, &ctx->d.od_key2, oc) ||
+  bool bad = dev_alloc(ctx, &ctx->d.od_sorted, oc) || dev_alloc(ctx, &ctx->d.od_key, oc) || dev_alloc(ctx, &ctx->d.od_key2, oc) ||
              dev_alloc(ctx, &ctx->d.od_val, oc) || dev_alloc(ctx, &ctx->d.od_val2, oc);
   if (!bad) {
     ctx->od_tmp_bytes = odom_sort_temp_bytes(ctx->d, (int)oc);
@@ -1317,6 +1316,10 @@ extern "C" int s2m_odom_create(int device, int batch, int cap_sharp, int cap_fla
     bad = dev_alloc(ctx, &tmp, ctx->od_tmp_bytes) != 0;
     ctx->od_tmp = tmp;
   }
+  bad = bad || dev_alloc(ctx, &ctx->d.od_last, oc) || dev_alloc(ctx, &ctx->d.od_last_off, 2 * batch + 1) ||
+                   dev_alloc(ctx, &ctx->d.od_meta, 2 * (oc / 32 + 2 * (size_t)batch + 1)) ||
+                   dev_alloc(ctx, &ctx->d.od_chunk_off, 2 * batch + 1) ||
+                   cudaMemset(ctx->d.od_chunk_off, 0, sizeof(int) * (2 * batch + 1)) != cudaSuccess;
   if (bad || cudaMemset(ctx->d.od_last_off, 0, sizeof(int) * (2 * batch + 1)) != cudaSuccess) {
     s2m_destroy(ctx);
     return S2M_ERR_CUDA;
@@ -1395,12 +1398,15 @@ extern "C" int s2m_odom_step_batch(s2m_ctx* ctx, const float* sharp, const int* 
     }
   }
   // this sweep's less-sharp / less-flat clouds are the next call's targets (:556-562)
-  std::vector<int> lo(2 * B + 1);
+  std::vector<int> lo(2 * B + 1), co(2 * B + 1, 0);
   for (int b = 0; b <= B; ++b) { lo[b] = ls_off[b]; lo[B + b] = ls_off[B] + lf_off[b]; }
+  for (int g = 0; g < 2 * B; ++g) co[g + 1] = co[g] + (lo[g + 1] - lo[g] + 31) / 32;  // 32-point chunks per cloud
   CK(cudaMemcpyAsync(d.od_last_off, lo.data(), sizeof(int) * (2 * B + 1), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d.od_chunk_off, co.data(), sizeof(int) * (2 * B + 1), cudaMemcpyHostToDevice, s));
   if (ls_off[B] > 0) CK(cudaMemcpyAsync(d.od_last, less_sharp, sizeof(float4) * (size_t)ls_off[B], kind, s));
   if (lf_off[B] > 0) CK(cudaMemcpyAsync(d.od_last + ls_off[B], less_flat, sizeof(float4) * (size_t)lf_off[B], kind, s));
   ctx->launches += launch_odom_sort(d, ls_off[B] + lf_off[B], ctx->od_tmp, ctx->od_tmp_bytes, s);
+  ctx->launches += launch_odom_meta(d, co[2 * B], s);
   CK(cudaStreamSynchronize(s));
   return S2M_OK;
 }

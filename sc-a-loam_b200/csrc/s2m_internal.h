@@ -141,6 +141,8 @@ struct Dev {
   float4* od_sorted;            // the same clouds ordered by x inside each segment, .w = index in od_last's segment
   unsigned long long *od_key, *od_key2;
   uint32_t *od_val, *od_val2;
+  float4* od_meta;              // [chunks][2] box + ring range of every 32-point chunk of od_last
+  int* od_chunk_off;            // [2B+1]
   int count_scanned;            // profiling: maintain `scanned`
   unsigned long long* hash_tab; // cell tables
   uint2* hash_aux;              // per table slot: (points of the cell itself, exact 3-cell count)
@@ -185,6 +187,7 @@ int launch_count_candidates(const Dev& d, int blocks_per_slot, cudaStream_t s);
 int launch_lm_shard(const Dev& d, int outer, int after, cudaStream_t s);
 int launch_odom_sort(const Dev& d, int n, void* tmp, size_t tmp_bytes, cudaStream_t s);
 size_t odom_sort_temp_bytes(const Dev& d, int n);
+int launch_odom_meta(const Dev& d, int nchunks, cudaStream_t s);
 int launch_odom_guard(const Dev& d, cudaStream_t s);
 int launch_odom_associate(const Dev& d, int outer, int tiles, bool trace, cudaStream_t s);
 int launch_finish_pose(const Dev& d, cudaStream_t s);

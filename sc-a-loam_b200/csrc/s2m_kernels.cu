@@ -900,6 +900,13 @@ __global__ void __launch_bounds__(kTile, 4) evaluate_kernel(Dev d, int outer) {
 // (lp-a) x (lp-b) / |a-b| is (lp - a) x u with u = (a-b)/|a-b|; the three-point plane factor
 // (lidarFactor.hpp:57-104) is n.lp + d with n = normalize((j-l) x (j-m)), d = -n.j.
 // ----------------------------------------------------------------------------
+// lower bound of the float squared distance from `sel` to any point inside the box of a chunk
+__device__ __forceinline__ float chunk_bound(const float4 ma, const float4 mb, const float sel[3]) {
+  const float bx = fmaxf(0.0f, fmaxf(xfsub(ma.x, sel[0]), xfsub(sel[0], ma.w)));
+  const float by = fmaxf(0.0f, fmaxf(xfsub(ma.y, sel[1]), xfsub(sel[1], mb.x)));
+  const float bz = fmaxf(0.0f, fmaxf(xfsub(ma.z, sel[2]), xfsub(sel[2], mb.y)));
+  return xfadd(xfadd(xfmul(bx, bx), xfmul(by, by)), xfmul(bz, bz));
+}
 __device__ __forceinline__ float odom_sq(const float4 p, const float sel[3]) {  // the float expression of :322-327
   const float dx = xfsub(p.x, sel[0]), dy = xfsub(p.y, sel[1]), dz = xfsub(p.z, sel[2]);
   return xfadd(xfadd(xfmul(dx, dx), xfmul(dy, dy)), xfmul(dz, dz));
@@ -929,6 +936,11 @@ __global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer)
     p = d.ds_pts[di];
     xf_point(pose, p.x, p.y, p.z, sel);
   }
+  const int seg = cls * d.B + slot;
+  const int l0 = d.od_last_off[seg], ln = d.od_last_off[seg + 1] - l0;
+  const float4* __restrict__ last = d.od_last + l0;
+  // box + ring range of every 32-point chunk of the previous cloud (ring-major: a chunk is a short arc)
+  const float4* __restrict__ meta = d.od_meta + 2 * (size_t)d.od_chunk_off[seg];
   // ---- exact nearest neighbour in the previous sweep's cloud of the query's class (:303, :392) ----
   // d.od_sorted holds each previous cloud ordered by x (.w = index in the ring-major cloud): start at the
   // query's x and walk outwards; a side is finished once dx*dx alone exceeds the best distance (the float
@@ -937,7 +949,6 @@ __global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer)
   int best_i = -1;
   float best_d = INFINITY;
   if (live) {
-    const int l0 = d.od_last_off[cls * d.B + slot], ln = d.od_last_off[cls * d.B + slot + 1] - l0;
     const float4* __restrict__ sp = d.od_sorted + l0;
     int lo = 0, hi = ln;
     while (lo < hi) {  // first sorted position with x >= sel.x
@@ -972,79 +983,107 @@ __global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer)
     }
   }
   // ---- ring-constrained neighbours (:313-357, :401-452) ----
-  // The reference walks the previous cloud point by point from the closest one, forwards until the ring
-  // number exceeds id + 2.5 and backwards until it drops below id - 2.5, keeping running minima with a
-  // strict "<".  Here the WARP walks for one query at a time, 32 consecutive points per step (coalesced),
-  // a ballot reproduces the sequential break, and the minima are reduced with the walk's own tie rule
-  // (forwards: lowest index; backwards: highest index, and only if strictly closer than the forward one).
+  // The reference walks the previous cloud point by point from the closest one -- forwards until a
+  // ring number exceeds id + 2.5, backwards until one drops below id - 2.5 -- keeping running minima
+  // with a strict "<".  The result is the candidate of smallest distance, ties to the one met first.
+  // Here: (1) the two break positions are found exactly from the chunk ring ranges; (2) the most
+  // promising chunk per neighbour class gives an upper bound U of the final distance; (3) the walks run
+  // in the reference's order, stepping over every chunk whose bound cannot beat the running minimum
+  // (>=) or exceeds U (>): neither kind can hold the winner, and dropping losers never changes it.
   const bool gate = live && best_i >= 0 && (double)best_d < 25.0;  // DISTANCE_SQ_THRESHOLD (:63)
   int second = -1, third = -1;
-  {
-    const int lane = t & 31;
-    const unsigned full = 0xffffffffu;
-    for (unsigned todo = __ballot_sync(full, gate); todo; todo &= todo - 1) {
-      const int src = __ffs(todo) - 1;
-      const int qcls = __shfl_sync(full, cls, src), qbest = __shfl_sync(full, best_i, src);
-      const float qs[3] = {__shfl_sync(full, sel[0], src), __shfl_sync(full, sel[1], src), __shfl_sync(full, sel[2], src)};
-      const int l0 = d.od_last_off[qcls * d.B + slot], ln = d.od_last_off[qcls * d.B + slot + 1] - l0;
-      const float4* __restrict__ last = d.od_last + l0;
-      const int id = (int)last[qbest].w;
-      const double hi = (double)id + 2.5, lo = (double)id - 2.5;  // NEARBY_SCAN (:64)
-      float f2 = 25.0f, f3 = 25.0f, b2 = 25.0f, b3 = 25.0f;
-      int fi2 = -1, fi3 = -1, bi2 = -1, bi3 = -1;
-      for (int base = qbest + 1; base < ln; base += 32) {  // increasing scan line
-        const int j = base + lane;
-        bool brk = false, c2 = false, c3 = false;
-        float dd = 0.0f;
-        if (j < ln) {
+  if (gate) {
+    const int id = (int)last[best_i].w;
+    const int hi = id + 3, lo = id - 3;  // (double)sid > id + 2.5  <=>  sid >= id + 3 (NEARBY_SCAN, :64)
+    // (1) first index that stops each walk
+    int jend = ln, jbeg = -1;
+    for (int j = best_i + 1; j < ln;) {
+      const int c = j >> 5;
+      if (__float_as_int(meta[2 * c + 1].w) < hi) { j = 32 * c + 32; continue; }
+      const int je = min(32 * c + 32, ln);
+      for (; j < je; ++j)
+        if ((int)last[j].w >= hi) { jend = j; break; }
+      if (jend != ln) break;
+    }
+    for (int j = best_i - 1; j >= 0;) {
+      const int c = j >> 5;
+      if (__float_as_int(meta[2 * c + 1].z) > lo) { j = 32 * c - 1; continue; }
+      for (; j >= 32 * c; --j)
+        if ((int)last[j].w <= lo) { jbeg = j; break; }
+      if (jbeg != -1) break;
+    }
+    // class of a candidate: 2 = "second" neighbour, 3 = "third" (surf only), 0 = none
+    auto klass = [&](int j, int sid) -> int {
+      if (cls == 0) return (j > best_i ? sid > id : sid < id) ? 2 : 0;
+      return (j > best_i ? sid <= id : sid >= id) ? 2 : 3;
+    };
+    // which classes a chunk may hold, from its ring range (a chunk on one side of best_i only; the chunk
+    // of best_i itself may hold all)
+    auto chunk_may = [&](int c, int smin, int smax, bool& may2, bool& may3) {
+      const bool fwd = 32 * c > best_i, bwd = 32 * c + 31 < best_i;
+      if (cls == 0) { may2 = fwd ? smax > id : (bwd ? smin < id : true); may3 = false; }
+      else { may2 = fwd ? smin <= id : (bwd ? smax >= id : true); may3 = fwd ? smax > id : (bwd ? smin < id : true); }
+    };
+    // (2) upper bounds from the chunk of smallest bound that can hold each class
+    float U2 = INFINITY, U3 = INFINITY;
+    {
+      int s2 = -1, s3 = -1;
+      float lb2 = INFINITY, lb3 = INFINITY;
+      for (int c = (jbeg + 1) >> 5; c <= (jend - 1) >> 5; ++c) {
+        const float4 ma = meta[2 * c], mb = meta[2 * c + 1];
+        const float lb = chunk_bound(ma, mb, sel);
+        const int smin = __float_as_int(mb.z), smax = __float_as_int(mb.w);
+        bool may2, may3;
+        chunk_may(c, smin, smax, may2, may3);
+        if (may2 && lb < lb2) { lb2 = lb; s2 = c; }
+        if (may3 && lb < lb3) { lb3 = lb; s3 = c; }
+      }
+      for (int pass = 0; pass < 2; ++pass) {
+        const int c = pass ? s3 : s2;
+        if (c < 0 || (pass && s3 == s2)) continue;
+        const int ja = max(32 * c, jbeg + 1), je = min(32 * c + 32, jend);
+        for (int j = ja; j < je; ++j) {
+          if (j == best_i) continue;
           const float4 c4 = last[j];
-          const int sid = (int)c4.w;
-          brk = (double)sid > hi;
-          dd = odom_sq(c4, qs);
-          if (qcls == 0) c2 = sid > id;
-          else { c2 = sid <= id; c3 = sid > id; }
+          const int k = klass(j, (int)c4.w);
+          const float dd = odom_sq(c4, sel);
+          if (k == 2) U2 = fminf(U2, dd);
+          else if (k == 3) U3 = fminf(U3, dd);
         }
-        const unsigned bb = __ballot_sync(full, brk);
-        if (bb == 0u || lane < __ffs(bb) - 1) {
-          if (c2 && dd < f2) { f2 = dd; fi2 = j; }
-          if (c3 && dd < f3) { f3 = dd; fi3 = j; }
-        }
-        if (bb) break;
       }
-      for (int base = qbest - 1; base >= 0; base -= 32) {  // decreasing scan line
-        const int j = base - lane;
-        bool brk = false, c2 = false, c3 = false;
-        float dd = 0.0f;
-        if (j >= 0) {
-          const float4 c4 = last[j];
-          const int sid = (int)c4.w;
-          brk = (double)sid < lo;
-          dd = odom_sq(c4, qs);
-          if (qcls == 0) c2 = sid < id;
-          else { c2 = sid >= id; c3 = sid < id; }
-        }
-        const unsigned bb = __ballot_sync(full, brk);
-        if (bb == 0u || lane < __ffs(bb) - 1) {
-          if (c2 && dd < b2) { b2 = dd; bi2 = j; }
-          if (c3 && dd < b3) { b3 = dd; bi3 = j; }
-        }
-        if (bb) break;
+    }
+    // (3) the walks
+    float m2 = 25.0f, m3 = 25.0f;  // minPointSqDis2 / 3 (float values compared as double in the reference)
+    auto cannot_win = [&](int c) -> bool {
+      const float4 ma = meta[2 * c], mb = meta[2 * c + 1];
+      const float lb = chunk_bound(ma, mb, sel);
+      bool may2, may3;
+      chunk_may(c, __float_as_int(mb.z), __float_as_int(mb.w), may2, may3);
+      return (!may2 || lb >= m2 || lb > U2) && (!may3 || lb >= m3 || lb > U3);
+    };
+    for (int j = best_i + 1; j < jend;) {  // increasing scan line
+      if ((j & 31) == 0 || j == best_i + 1) {
+        const int c = j >> 5;
+        if (cannot_win(c)) { j = 32 * c + 32; continue; }
       }
-      for (int o = 16; o > 0; o >>= 1) {
-        float od; int oi;
-        od = __shfl_xor_sync(full, f2, o); oi = __shfl_xor_sync(full, fi2, o);
-        if (oi >= 0 && (od < f2 || (od == f2 && (fi2 < 0 || oi < fi2)))) { f2 = od; fi2 = oi; }
-        od = __shfl_xor_sync(full, f3, o); oi = __shfl_xor_sync(full, fi3, o);
-        if (oi >= 0 && (od < f3 || (od == f3 && (fi3 < 0 || oi < fi3)))) { f3 = od; fi3 = oi; }
-        od = __shfl_xor_sync(full, b2, o); oi = __shfl_xor_sync(full, bi2, o);
-        if (oi >= 0 && (od < b2 || (od == b2 && (bi2 < 0 || oi > bi2)))) { b2 = od; bi2 = oi; }
-        od = __shfl_xor_sync(full, b3, o); oi = __shfl_xor_sync(full, bi3, o);
-        if (oi >= 0 && (od < b3 || (od == b3 && (bi3 < 0 || oi > bi3)))) { b3 = od; bi3 = oi; }
+      const float4 c4 = last[j];
+      const int k = klass(j, (int)c4.w);
+      const float dd = odom_sq(c4, sel);
+      if (k == 2 && dd < m2) { m2 = dd; second = j; }
+      else if (k == 3 && dd < m3) { m3 = dd; third = j; }
+      ++j;
+    }
+    for (int j = best_i - 1; j > jbeg;) {  // decreasing scan line
+      if ((j & 31) == 31 || j == best_i - 1) {
+        const int c = j >> 5;
+        if (cannot_win(c)) { j = 32 * c - 1; continue; }
       }
-      if (lane == src) {
-        second = (bi2 >= 0 && b2 < f2) ? bi2 : fi2;
-        third = (bi3 >= 0 && b3 < f3) ? bi3 : fi3;
-      }
+      const float4 c4 = last[j];
+      const int k = klass(j, (int)c4.w);
+      const float dd = odom_sq(c4, sel);
+      if (k == 2 && dd < m2) { m2 = dd; second = j; }
+      else if (k == 3 && dd < m3) { m3 = dd; third = j; }
+      --j;
     }
   }
   // ---- the factor ----
@@ -1054,8 +1093,6 @@ __global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer)
   bool used = false;
   double rec[6] = {0, 0, 0, 0, 0, 0};
   if (gate) {
-    const int l0 = d.od_last_off[cls * d.B + slot];
-    const float4* __restrict__ last = d.od_last + l0;
     const float4 a = last[best_i];
     if (cls == 0) {
       if (second >= 0) {
@@ -1124,6 +1161,35 @@ __global__ void odom_gather_sorted_kernel(Dev d, int n) {
   const uint32_t l = d.od_val2[i];
   const float4 p = d.od_last[d.od_last_off[g] + l];
   d.od_sorted[i] = make_float4(p.x, p.y, p.z, __int_as_float((int)l));
+}
+// box + ring-number range of every 32-point chunk of the previous clouds (one warp per chunk):
+// meta[2c] = (min x, min y, min z, max x), meta[2c+1] = (max y, max z, bits of min ring, bits of max ring)
+__global__ void odom_meta_kernel(Dev d, int nchunks) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= nchunks) return;
+  const int g = find_seg(d.od_chunk_off, 2 * d.B, c);
+  const int j = 32 * (c - d.od_chunk_off[g]) + lane;
+  const int l0 = d.od_last_off[g], ln = d.od_last_off[g + 1] - l0;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  int smin = INT_MAX, smax = INT_MIN;
+  if (j < ln) {
+    const float4 p = d.od_last[l0 + j];
+    mn[0] = mx[0] = p.x; mn[1] = mx[1] = p.y; mn[2] = mx[2] = p.z;
+    smin = smax = (int)p.w;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+    smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+  }
+  if (lane == 0) {
+    d.od_meta[2 * (size_t)c] = make_float4(mn[0], mn[1], mn[2], mx[0]);
+    d.od_meta[2 * (size_t)c + 1] = make_float4(mx[1], mx[2], __int_as_float(smin), __int_as_float(smax));
+  }
 }
 // start of an odometry step: which slots solve, LM state from the previous relative motion (para_q, para_t)
 __global__ void odom_guard_kernel(Dev d) {
@@ -1577,6 +1643,11 @@ size_t odom_sort_temp_bytes(const Dev& d, int n) {
   size_t tb = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tb, d.od_key, d.od_key2, d.od_val, d.od_val2, n, 0, 40, (cudaStream_t)0);
   return tb;
+}
+int launch_odom_meta(const Dev& d, int nchunks, cudaStream_t s) {
+  if (nchunks <= 0) return 0;
+  odom_meta_kernel<<<cdiv(nchunks, 8), 256, 0, s>>>(d, nchunks);
+  return 1;
 }
 int launch_odom_guard(const Dev& d, cudaStream_t s) {
   odom_guard_kernel<<<cdiv(d.B, 64), 64, 0, s>>>(d);
