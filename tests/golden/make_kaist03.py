@@ -13,6 +13,8 @@ Content (float32 clouds are xyzi):
   guess_q, guess_t     : those poses perturbed by U(-0.2,0.2) m and U(-1,1) deg per axis (seed 20261018)
   oracle_q, oracle_t   : the oracle's registered poses from those guesses (stream: each frame is inserted
                          at its own registered pose before the next one)
+kaist03_scan10.npz: xyz of real scan 10 and the ring number the reference stored in its intensity channel
+(scanRegistration.cpp:251-252), for tests/test_scan_registration.py.
 The test then asserts (a) the oracle -- and the CUDA path -- pull every perturbed guess back to within
 6 cm / 0.45 deg of the pose the reference itself saved, and (b) CUDA == oracle to the usual tolerance.
 """
@@ -70,6 +72,11 @@ def main():
                guess_t=np.array(gt), oracle_q=np.array(oq), oracle_t=np.array(ot))
     path = os.path.join(HERE, "kaist03.npz")
     np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
+    # one real sweep for the feature-extraction tests: xyz of scan 10 in the order the reference stored it
+    raw = read_pcd(SRC + "Scans/000010.pcd")
+    path = os.path.join(HERE, "kaist03_scan10.npz")
+    np.savez_compressed(path, xyz=raw[:, :3].copy(), ring=np.rint(raw[:, 3]).astype(np.int8))
     print(path, os.path.getsize(path), "bytes")
 
 

@@ -64,6 +64,38 @@ def test_oracle_ring_rule_matches_rings_stored_by_the_reference(built, s2m):
     assert total == 765919
 
 
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kaist03_scan10.npz")
+
+
+def test_oracle_on_a_real_scan_of_the_reference(built):
+    """tests/golden/kaist03_scan10.npz: a real OS1-64 sweep the reference shipped, with the ring number the
+    reference's own scanRegistration stored per point.  The restated ring rule gives those rings; the
+    re-extracted ring-major cloud keeps the stored order; the feature counts have the documented caps."""
+    g = np.load(GOLD)
+    xyz, ring = g["xyz"], g["ring"].astype(np.int32)
+    assert np.array_equal(oracle.ring_of("OS1-64", xyz), ring)
+    A = oracle.scan_registration("OS1-64", xyz, 0.5)     # minimum_range of aloam_mulran.launch:9
+    assert len(A["full"]) == len(xyz) and np.array_equal(bits(A["full"][:, :3]), bits(xyz))   # already ring-major: stable
+    assert np.array_equal(np.rint(A["full"][:, 3]).astype(np.int32), ring)
+    rings = len(np.unique(ring))
+    assert 0 < len(A["sharp"]) <= 2 * 6 * rings and len(A["sharp"]) < len(A["less_sharp"]) <= 20 * 6 * rings
+    assert 0 < len(A["flat"]) <= 4 * 6 * rings and len(A["less_flat"]) > 5000
+
+
+@pytest.mark.gpu
+def test_cuda_features_on_a_real_scan_of_the_reference(s2m, built):
+    g = np.load(GOLD)
+    xyz = g["xyz"]
+    want = oracle.scan_registration("OS1-64", xyz, 0.5)
+    F = s2m.FeatureExtractor("OS1-64", 0.5, batch=1, cap_points=len(xyz) + 16)
+    F.extract(xyz, np.array([0, len(xyz)], np.int32))
+    for k in CLOUDS:
+        got, _ = F.cloud(k)
+        assert got.shape == want[k].shape and np.array_equal(bits(got), bits(want[k])), k
+    full, _ = F.cloud("full")
+    assert np.array_equal(np.rint(full[:, 3]).astype(np.int32), g["ring"].astype(np.int32))   # the rings the reference stored
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("sensor,batch", [("VLP16", 1), ("HDL64", 3), ("OS1-64", 2)])
 def test_cuda_features_bit_identical_to_oracle(s2m, built, sensor, batch):
