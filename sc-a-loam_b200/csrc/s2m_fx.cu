@@ -11,8 +11,8 @@
 //   ring numbers (+ first point past the half turn, atomicMin) -> intensities and sort keys
 //   stable radix sort by (sweep, ring) -> ring offsets -> ring-major cloud
 //   curvature + "gap to the previous point" flags
-//   one WARP per (sweep, ring): bitonic sort of each sector by (curvature, index) in shared
-//   memory, lane 0 walks the picks, the warp compacts the less-flat points and their box
+//   one WARP per (sweep, ring): every pick is a warp-wide arg-max / arg-min of (curvature, index) over
+//   the not yet suppressed points of the sector; the warp compacts the less-flat points and their box
 //   prefix sums of the pick counts -> packed sharp / less-sharp / flat clouds
 //   per-ring voxel keys -> stable radix sort -> one thread per voxel sums its run in order
 #include <cub/cub.cuh>
@@ -33,8 +33,6 @@ namespace fx {
 constexpr int kRings = 64;        // ring slots per sweep (N_SCANS <= 64, scanRegistration.cpp:470-480)
 constexpr int kSectors = 6;       // :295
 constexpr int kSecPerScan = kRings * kSectors;
-constexpr int kMaxSector = 512;   // points of one sector held in shared memory
-constexpr int kMaxRing = kSectors * kMaxSector;  // a sector then never exceeds kMaxSector - 1 points
 constexpr int kLess = 20, kSharp = 2, kFlat = 4;  // :317-327, :366
 constexpr int kWarps = 4;
 
@@ -56,6 +54,7 @@ struct Dev {
   float4* cloud;           // [cap] ring-major (= the "full" output)
   float* curv;             // [cap]
   unsigned char* gapf;     // [cap] distance^2 to the previous point of the cloud > 0.05
+  unsigned char* state;    // [cap] pick state of every cloud point (select_kernel)
   int *n_sharp, *n_less, *n_flat;        // [B*384+1]
   int *o_sharp, *o_less, *o_flat;        // exclusive scans
   int *i_sharp, *i_less, *i_flat;        // pick lists (cloud indices)
@@ -294,8 +293,11 @@ __global__ void curv_kernel(Dev d, int n) {
 }
 
 // ---- the picks (:292-413): one warp per (sweep, ring) ------------------------------------
-// state byte per ring point: bit0 picked, bit1 gap-to-previous, bits 2-3 label (1: less sharp,
-// 2: sharp, 3: flat)
+// state byte per cloud point (d.state): bit0 picked, bit1 gap-to-previous, bits 2-3 label (1: less sharp,
+// 2: sharp, 3: flat).  The reference sorts a sector by curvature and walks it from the top (then from the
+// bottom), skipping points a previous pick suppressed: the next point it takes is always the largest
+// (smallest) not-yet-suppressed one, so each pick is a warp-wide arg-max (arg-min) over the sector with
+// the key (curvature, index) -- the order of A8 -- and no sort and no size limit are needed.
 __device__ __forceinline__ void suppress(unsigned char* st, int li) {
   for (int l = 1; l <= 5; ++l) {
     if (st[li + l] & 2) break;
@@ -306,80 +308,89 @@ __device__ __forceinline__ void suppress(unsigned char* st, int li) {
     st[li + l] |= 1;
   }
 }
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = u > v ? u : v;
+  }
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = u < v ? u : v;
+  }
+  return v;
+}
 __global__ void __launch_bounds__(32 * kWarps) select_kernel(Dev d) {
-  __shared__ unsigned long long sbuf[kWarps][kMaxSector];
-  __shared__ unsigned char sstate[kWarps][kMaxRing];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rid = blockIdx.x * kWarps + w;
   if (rid >= d.B * kRings) return;
   const int rs = d.ring_off[rid], re = d.ring_off[rid + 1], len = re - rs;
   const int first = rs + 5, last = re - 6;
-  unsigned long long* buf = sbuf[w];
-  unsigned char* st = sstate[w];
-  if (last - first < 6 || len > kMaxRing) {  // :294, or a ring too long for the staging
+  if (last - first < 6) {  // :294
     if (lane < kSectors) d.n_sharp[rid * kSectors + lane] = d.n_less[rid * kSectors + lane] = d.n_flat[rid * kSectors + lane] = 0;
-    if (lane == 0) {
-      d.lf_cnt[rid] = 0;
-      if (len > kMaxRing) atomicCAS(d.err, 0, S2M_ERR_CAPACITY);
-    }
+    if (lane == 0) d.lf_cnt[rid] = 0;
     return;
   }
+  unsigned char* st = d.state + rs;
   for (int t = lane; t < len; t += 32) st[t] = d.gapf[rs + t] ? 2 : 0;
   __syncwarp();
   for (int j = 0; j < kSectors; ++j) {
     const int sp = first + (last - first) * j / 6, ep = first + (last - first) * (j + 1) / 6 - 1;
     const int n = ep - sp + 1;
-    int P = 32;
-    while (P < n) P <<= 1;
-    for (int t = lane; t < P; t += 32)
-      buf[t] = t < n ? (((unsigned long long)__float_as_uint(d.curv[sp + t]) << 32) | (uint32_t)t) : ~0ull;
-    __syncwarp();
-    for (int k = 2; k <= P; k <<= 1)
-      for (int jj = k >> 1; jj > 0; jj >>= 1) {
-        for (int t = lane; t < P; t += 32) {
-          const int u = t ^ jj;
-          if (u > t) {
-            const unsigned long long a = buf[t], c = buf[u];
-            if ((a > c) == ((t & k) == 0)) { buf[t] = c; buf[u] = a; }
-          }
+    const int sec = rid * kSectors + j;
+    const float* __restrict__ cv = d.curv + sp;
+    unsigned char* ss = st + (sp - rs);
+    int n_less = 0, n_sharp = 0, n_flat = 0;
+    for (int pick = 0; pick < kLess; ++pick) {  // :305-356
+      unsigned long long best = 0ull;
+      for (int t = lane; t < n; t += 32) {
+        const float c = cv[t];
+        if ((double)c > 0.1 && !(ss[t] & 1)) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | (uint32_t)t;
+          best = key > best ? key : best;
         }
-        __syncwarp();
       }
-    if (lane == 0) {
-      const int sec = rid * kSectors + j;
-      int largest = 0, n_less = 0, n_sharp = 0, n_flat = 0;
-      for (int k = n - 1; k >= 0; --k) {  // :305-356
-        const int li = sp - rs + (int)(uint32_t)buf[k];
-        if (!((double)__uint_as_float((uint32_t)(buf[k] >> 32)) > 0.1)) break;  // ascending order: nothing below can pass either
-        if (st[li] & 1) continue;
-        ++largest;
-        if (largest <= kSharp) {
+      best = warp_max_u64(best);
+      if (best == 0ull) break;
+      if (lane == 0) {
+        const int li = sp - rs + (int)(uint32_t)best;
+        if (pick < kSharp) {
           st[li] |= 2 << 2;
           d.i_sharp[sec * kSharp + n_sharp++] = rs + li;
-          d.i_less[sec * kLess + n_less++] = rs + li;
-        } else if (largest <= kLess) {
-          st[li] |= 1 << 2;
-          d.i_less[sec * kLess + n_less++] = rs + li;
         } else {
-          break;
+          st[li] |= 1 << 2;
         }
+        d.i_less[sec * kLess + n_less++] = rs + li;
         st[li] |= 1;
         suppress(st, li);
       }
-      int smallest = 0;
-      for (int k = 0; k < n; ++k) {  // :358-394
-        const int li = sp - rs + (int)(uint32_t)buf[k];
-        if (!((double)__uint_as_float((uint32_t)(buf[k] >> 32)) < 0.1)) break;  // nothing above can pass either
-        if (st[li] & 1) continue;
+      __syncwarp();
+    }
+    for (int pick = 0; pick < kFlat; ++pick) {  // :358-394
+      unsigned long long best = ~0ull;
+      for (int t = lane; t < n; t += 32) {
+        const float c = cv[t];
+        if ((double)c < 0.1 && !(ss[t] & 1)) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | (uint32_t)t;
+          best = key < best ? key : best;
+        }
+      }
+      best = warp_min_u64(best);
+      if (best == ~0ull) break;
+      if (lane == 0) {
+        const int li = sp - rs + (int)(uint32_t)best;
         st[li] |= 3 << 2;
         d.i_flat[sec * kFlat + n_flat++] = rs + li;
-        if (++smallest >= kFlat) break;
-        st[li] |= 1;
-        suppress(st, li);
+        if (pick < kFlat - 1) {  // the fourth flat point ends the walk before it is marked (:367-370)
+          st[li] |= 1;
+          suppress(st, li);
+        }
       }
-      d.n_sharp[sec] = n_sharp; d.n_less[sec] = n_less; d.n_flat[sec] = n_flat;
+      __syncwarp();
     }
-    __syncwarp();
+    if (lane == 0) { d.n_sharp[sec] = n_sharp; d.n_less[sec] = n_less; d.n_flat[sec] = n_flat; }
   }
   // less-flat points of the ring (:396-402): label <= 0 over first .. last-1, in position order
   int running = 0;
@@ -562,7 +573,7 @@ static int fx_create_impl(s2m_fx* fx) {
   rc |= fx_alloc(fx, &d.jstar, B); rc |= fx_alloc(fx, &d.ok, B); rc |= fx_alloc(fx, &d.ring, cap);
   rc |= fx_alloc(fx, &d.pts, cap); rc |= fx_alloc(fx, &d.key, cap); rc |= fx_alloc(fx, &d.key2, cap);
   rc |= fx_alloc(fx, &d.val, cap); rc |= fx_alloc(fx, &d.val2, cap); rc |= fx_alloc(fx, &d.ring_off, B * kRings + 1);
-  rc |= fx_alloc(fx, &d.cloud, cap); rc |= fx_alloc(fx, &d.curv, cap); rc |= fx_alloc(fx, &d.gapf, cap);
+  rc |= fx_alloc(fx, &d.cloud, cap); rc |= fx_alloc(fx, &d.curv, cap); rc |= fx_alloc(fx, &d.gapf, cap); rc |= fx_alloc(fx, &d.state, cap);
   const size_t ns = (size_t)B * kSecPerScan;
   rc |= fx_alloc(fx, &d.n_sharp, ns + 1); rc |= fx_alloc(fx, &d.n_less, ns + 1); rc |= fx_alloc(fx, &d.n_flat, ns + 1);
   rc |= fx_alloc(fx, &d.o_sharp, ns + 1); rc |= fx_alloc(fx, &d.o_less, ns + 1); rc |= fx_alloc(fx, &d.o_flat, ns + 1);
@@ -673,7 +684,7 @@ extern "C" int s2m_fx_extract(s2m_fx* fx, const float* xyz, const int* off, int 
   if (*fx->h_err != 0) {
     const int e = *fx->h_err;
     cudaMemsetAsync(d.err, 0, sizeof(int), s);
-    fx->err = e == S2M_ERR_CAPACITY ? "a ring holds more points than the sector staging supports" : "voxel lattice of a ring overflows 31 bits";
+    fx->err = "voxel lattice of a ring overflows 31 bits";
     return e;
   }
   fx->have = true;
