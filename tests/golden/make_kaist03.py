@@ -76,7 +76,8 @@ def main():
     # one real sweep for the feature-extraction tests: xyz of scan 10 in the order the reference stored it
     raw = read_pcd(SRC + "Scans/000010.pcd")
     path = os.path.join(HERE, "kaist03_scan10.npz")
-    np.savez_compressed(path, xyz=raw[:, :3].copy(), ring=np.rint(raw[:, 3]).astype(np.int8))
+    nxt = read_pcd(SRC + "Scans/000011.pcd")   # the following keyframe, for the odometry test
+    np.savez_compressed(path, xyz=raw[:, :3].copy(), ring=np.rint(raw[:, 3]).astype(np.int8), xyz_next=nxt[:, :3].copy())
     print(path, os.path.getsize(path), "bytes")
 
 

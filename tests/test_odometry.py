@@ -93,6 +93,33 @@ def test_cuda_odometry_matches_oracle(s2m, built, sensor, step):
 
 
 @pytest.mark.gpu
+def test_cuda_front_end_on_two_real_keyframes(s2m, built):
+    """two consecutive real OS1-64 keyframes of the reference (tests/golden/kaist03_scan10.npz): features and
+    odometry on the device against the restatements -- real ring populations (> 3000 points in a bucket),
+    real geometry."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kaist03_scan10.npz"))
+    F = s2m.FeatureExtractor("OS1-64", 0.5, batch=1, cap_points=40000)
+    D = s2m.Odometer(trace=True, cap_less_flat=1 << 16)
+    O = oracle.Odometer()
+    names = ("sharp", "flat", "less_sharp", "less_flat")
+    for xyz in (g["xyz"], g["xyz_next"]):
+        F.extract(xyz, np.array([0, len(xyz)], np.int32))
+        args = []
+        for k in names:
+            args += [F.device_cloud(k), F.offsets(k)]
+        qd, td = D.step_batch(*args, device_ptrs=True)
+        A = oracle.scan_registration("OS1-64", xyz, 0.5)
+        qo, to = O.step(*[A[k] for k in names])
+        assert list(D.counts[0]) == list(O.counts)
+    assert O.counts[0] > 100 and O.counts[2] > 50
+    for outer in range(2):
+        e, p = O.trace(outer)
+        assert np.array_equal(D.trace(outer, 0)[0][:, :2], e) and np.array_equal(D.trace(outer, 1)[0], p)
+    assert np.linalg.norm(td[0] - to) < TOL_T and rot_angle(qd[0], qo) < TOL_R
+    assert 0.3 < np.linalg.norm(to) < 2.0      # the keyframes are about 1 m apart
+
+
+@pytest.mark.gpu
 def test_cuda_odometry_batch_slots_are_independent(s2m, built):
     """two sequences in one context (the second lags one sweep) == two single contexts, bit for bit"""
     _, feats = features_stream("VLP16", 3, 5, 0.5)
