@@ -30,6 +30,9 @@ namespace s2m {
 #ifndef S2M_K4A_PREFETCH
 #define S2M_K4A_PREFETCH 0  // 0 off, 1 prefetch.global.L2, 2 prefetch.global.L1 of each row's candidates at probe time
 #endif
+#ifndef S2M_OD_MINB
+#define S2M_OD_MINB 6  // resident blocks per SM of odom_associate_kernel: latency-bound walks, more warps win (3.9 -> 3.0 ms)
+#endif
 #ifndef S2M_K4A_MINB
 #define S2M_K4A_MINB 8  // resident blocks per SM the kNN kernel is compiled for
 #endif

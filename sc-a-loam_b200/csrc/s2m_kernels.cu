@@ -912,7 +912,7 @@ __device__ __forceinline__ float odom_sq(const float4 p, const float sel[3]) {  
   return xfadd(xfadd(xfmul(dx, dx), xfmul(dy, dy)), xfmul(dz, dz));
 }
 template <bool kTrace>
-__global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer) {
+__global__ void __launch_bounds__(kTile, S2M_OD_MINB) odom_associate_kernel(Dev d, int outer) {
   const int slot = blockIdx.y;
   if (!d.out[slot].optimized) return;
   int dc0, nc, ds0, nq;
@@ -961,7 +961,7 @@ __global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer)
       if (more_up) {
         const float4 c4 = sp[up];
         const float dx = xfsub(sel[0], c4.x);
-        if (xfmul(dx, dx) > best_d) more_up = false;
+        if (xfmul(dx, dx) > fminf(best_d, 25.0f)) more_up = false;  // beyond 25 the gate fails anyway
         else {
           const float dd = dist2(sel[0], sel[1], sel[2], c4.x, c4.y, c4.z);
           const int idx = __float_as_int(c4.w);
@@ -972,7 +972,7 @@ __global__ void __launch_bounds__(kTile) odom_associate_kernel(Dev d, int outer)
       if (more_dn) {
         const float4 c4 = sp[dn];
         const float dx = xfsub(sel[0], c4.x);
-        if (xfmul(dx, dx) > best_d) more_dn = false;
+        if (xfmul(dx, dx) > fminf(best_d, 25.0f)) more_dn = false;
         else {
           const float dd = dist2(sel[0], sel[1], sel[2], c4.x, c4.y, c4.z);
           const int idx = __float_as_int(c4.w);
