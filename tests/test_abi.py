@@ -86,3 +86,16 @@ def test_pcd_layout_is_the_reference_sample_layout(s2m, built, tmp_path):
         raw = open(sample, "rb").read()
         assert raw[:188] == PCD_HEADER_37101
         assert np.array_equal(got.view(np.uint32), np.frombuffer(raw[188:188 + 16 * 37101], np.uint32).reshape(-1, 4))
+
+
+def test_plain_c_consumer_of_the_header(s2m, built, tmp_path):
+    """tests/c/abi_smoke.c includes include/s2m.h as C99, links libs2m.so and calls the host-only entry points."""
+    import subprocess
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(s2m.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", libdir, "-ls2m",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe, str(tmp_path / "t.pcd")], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "s2m_params 52 bytes, s2m_stats 96 bytes" in out.stdout
