@@ -358,3 +358,24 @@ def test_transform_cloud_bit_exact(s2m, seq_hdl):
     uv = uv + uv
     want = ((v + q[3] * uv) + np.cross(u, uv) + t).astype(np.float32)
     assert np.array_equal(bits(got[:, :3]), bits(want)) and np.array_equal(got[:, 3], pts[:, 3])
+
+
+def test_contexts_release_their_memory(s2m, built):
+    """create / use / destroy every kind of context a few times: device memory returns to where it was."""
+    import torch
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    rng = np.random.default_rng(1)
+    pts = np.c_[rng.uniform(-20, 20, (4000, 3)), np.zeros(4000)].astype(np.float32)
+    for rep in range(4):
+        R = s2m.Registrar(0.4, 0.8, batch=4, lanes=2)
+        R.register_batch(np.tile(pts[:500], (4, 1)), np.arange(5) * 500, np.tile(pts, (4, 1)), np.arange(5) * 4000,
+                         np.tile([0, 0, 0, 1.0], (4, 1)), np.zeros((4, 3)))
+        R.close()
+        F = s2m.FeatureExtractor("VLP16", 0.1, batch=2, cap_points=30000)
+        F.close()
+        D = s2m.Odometer(batch=2)
+        D.close()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20, (free0, free1)      # CUDA keeps a little for itself; a leak would be GBs
