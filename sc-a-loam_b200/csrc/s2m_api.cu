@@ -1294,7 +1294,8 @@ extern "C" int s2m_trace_lm(s2m_ctx* ctx, int slot, int outer, double pose7[7], 
 // ---- scan-to-scan odometry (laserOdometry.cpp:220-591) ----------------------
 extern "C" int s2m_odom_create(int device, int batch, int cap_sharp, int cap_flat, int cap_less_sharp, int cap_less_flat,
                                int trace, s2m_ctx** out) {
-  if (!out || batch < 1 || batch > kMaxBatch || cap_sharp < 1 || cap_flat < 1 || cap_less_sharp < 1 || cap_less_flat < 1)
+  if (!out || batch < 1 || batch > kMaxBatch || cap_sharp < 1 || cap_flat < 1 || cap_less_sharp < 1 || cap_less_flat < 1 ||
+      cap_less_sharp >= (1 << 24) || cap_less_flat >= (1 << 24) || cap_sharp + cap_flat >= (1 << 20))
     return S2M_ERR_ARG;
   s2m_params P;
   s2m_default_params(&P);
@@ -1309,7 +1310,10 @@ extern "C" int s2m_odom_create(int device, int batch, int cap_sharp, int cap_fla
   ctx->od_cap = (long long)batch * ((long long)cap_less_sharp + cap_less_flat);
   const size_t oc = (size_t)ctx->od_cap;
   bool bad = dev_alloc(ctx, &ctx->d.od_sorted, oc) || dev_alloc(ctx, &ctx->d.od_key, oc) || dev_alloc(ctx, &ctx->d.od_key2, oc) ||
-             dev_alloc(ctx, &ctx->d.od_val, oc) || dev_alloc(ctx, &ctx->d.od_val2, oc);
+             dev_alloc(ctx, &ctx->d.od_val, oc) || dev_alloc(ctx, &ctx->d.od_val2, oc) || dev_alloc(ctx, &ctx->d.od_ckey, oc) ||
+             dev_alloc(ctx, &ctx->d.od_corr, (size_t)ctx->d.cap_in) || dev_alloc(ctx, &ctx->d.od_bestd, (size_t)ctx->d.cap_in) ||
+             dev_alloc(ctx, &ctx->d.od_fb_list, (size_t)ctx->d.cap_in) || dev_alloc(ctx, &ctx->d.od_fb_cnt, 1) ||
+             dev_alloc(ctx, &ctx->d.od_first_ge, (size_t)2 * batch * 257) || dev_alloc(ctx, &ctx->d.od_last_le, (size_t)2 * batch * 257);
   if (!bad) {
     ctx->od_tmp_bytes = odom_sort_temp_bytes(ctx->d, (int)oc);
     char* tmp = nullptr;
@@ -1369,7 +1373,7 @@ extern "C" int s2m_odom_step_batch(s2m_ctx* ctx, const float* sharp, const int* 
   if (any) {
     const int eval_blocks = std::max(1, (tiles + kEvalTilesPerBlock - 1) / kEvalTilesPerBlock);
     for (int outer = 0; outer < 2; ++outer) {  // :277
-      k += launch_odom_associate(d, outer, std::max(tiles, 1), ctx->P.trace != 0, s);
+      k += launch_odom_associate(d, outer, std::max(tiles, 1), S2M_OD_FB * ctx->sm_count, ctx->P.trace != 0, s);  // latency-bound warps: many in flight
       for (int it = 0; it < 4; ++it) k += launch_evaluate(d, outer, eval_blocks, s);  // max_num_iterations = 4 (:497)
     }
   }

@@ -30,6 +30,9 @@ namespace s2m {
 #ifndef S2M_K4A_PREFETCH
 #define S2M_K4A_PREFETCH 0  // 0 off, 1 prefetch.global.L2, 2 prefetch.global.L1 of each row's candidates at probe time
 #endif
+#ifndef S2M_OD_FB
+#define S2M_OD_FB 32  // blocks per SM of odom_fallback_kernel (one warp per listed query, latency-bound)
+#endif
 #ifndef S2M_OD_MINB
 #define S2M_OD_MINB 6  // resident blocks per SM of odom_associate_kernel: latency-bound walks, more warps win (3.9 -> 3.0 ms)
 #endif
@@ -141,7 +144,13 @@ struct Dev {
   int* knn_ticket;              // next 32-query work unit of knn_kernel (re-armed by fit_kernel)
   float4* od_last;              // odometry: less-sharp / less-flat clouds of the previous sweep, class-major
   int* od_last_off;             // [2B+1]
-  float4* od_sorted;            // the same clouds ordered by x inside each segment, .w = index in od_last's segment
+  float4* od_sorted;            // the same clouds ordered by 1 m cell inside each segment, .w = index | ring << 24
+  uint32_t* od_ckey;            // cell key of every entry of od_sorted
+  int4* od_corr;                // [cap_in] per query: closest, second, third index (-1 none), pending flags
+  float* od_bestd;              // [cap_in] distance of the closest point
+  int* od_fb_list;              // [cap_in] queries the cell search could not settle
+  int* od_fb_cnt;
+  int *od_first_ge, *od_last_le;  // [2B][257] ring tables of the previous clouds (first index with ring >= r, last with ring < r)
   unsigned long long *od_key, *od_key2;
   uint32_t *od_val, *od_val2;
   float4* od_meta;              // [chunks][2] box + ring range of every 32-point chunk of od_last
@@ -192,7 +201,7 @@ int launch_odom_sort(const Dev& d, int n, void* tmp, size_t tmp_bytes, cudaStrea
 size_t odom_sort_temp_bytes(const Dev& d, int n);
 int launch_odom_meta(const Dev& d, int nchunks, cudaStream_t s);
 int launch_odom_guard(const Dev& d, cudaStream_t s);
-int launch_odom_associate(const Dev& d, int outer, int tiles, bool trace, cudaStream_t s);
+int launch_odom_associate(const Dev& d, int outer, int tiles, int fallback_blocks, bool trace, cudaStream_t s);
 int launch_finish_pose(const Dev& d, cudaStream_t s);
 int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_store, bool check_pending, bool identity_pose,
                       cudaStream_t s);

@@ -893,8 +893,7 @@ __global__ void __launch_bounds__(kTile, 4) evaluate_kernel(Dev d, int outer) {
 // Scan-to-scan odometry (laserOdometry.cpp:277-505): the queries are the
 // sharp / flat points of the current sweep, the targets the less-sharp / less-flat clouds of
 // the previous one (d.od_last, ring-major as the feature extraction left them).  Per query:
-// TransformToStart (:108-126 with s = 1: q*p + t), exact nearest neighbour (block-cooperative
-// sweep over the previous cloud through shared memory; order (d2, index)), the ring-constrained
+// TransformToStart (:108-126 with s = 1: q*p + t), exact nearest neighbour (order (d2, index)), the ring-constrained
 // second (and third) neighbour walks of :313-357 / :401-452, then the same residual / Jacobian /
 // Huber accumulation, block reduction and LM start as the mapping association: an edge factor
 // (lp-a) x (lp-b) / |a-b| is (lp - a) x u with u = (a-b)/|a-b|; the three-point plane factor
@@ -911,8 +910,320 @@ __device__ __forceinline__ float odom_sq(const float4 p, const float sel[3]) {  
   const float dx = xfsub(p.x, sel[0]), dy = xfsub(p.y, sel[1]), dz = xfsub(p.z, sel[2]);
   return xfadd(xfadd(xfmul(dx, dx), xfmul(dy, dy)), xfmul(dz, dz));
 }
+// Correspondence search in three kernels:
+//   odom_search_kernel    every query: 27 half-metre cells around the transformed point through a
+//                         cell-ordered copy of the previous cloud.  A nearest neighbour found closer than
+//                         0.5 m is THE nearest neighbour (everything outside the 27 cells is at least 0.5 m
+//                         away); likewise a second / third neighbour closer than 0.5 m.  Anything not
+//                         settled that way is appended to a list.
+//   odom_fallback_kernel  the listed queries, one warp each: exhaustive nearest neighbour with box bounds
+//                         per 32-point chunk, the reference's two walks 32 points per step.
+//   odom_fit_kernel       factors, Huber, the 28 sums, block reduction, start of the LM solve.
+constexpr int kOdNeedNN = 1, kOdNeedWalk = 2;
+constexpr int kOdSid = 256;  // ring numbers 0..255 (checked when the previous cloud is indexed)
+constexpr float kOdSettled = 0.25f;  // (cell size)^2: everything outside the 27 cells is at least one cell away
+constexpr int kOdBias = 512;  // cell coordinates are floor(2 x) + 512 in 0..1023: half-metre cells, +-256 m
+
+__device__ __forceinline__ int od_cell(float v) { return (int)floorf(xfmul(v, 2.0f)) + kOdBias; }  // 2 v is exact
+struct OdCloud {  // the previous cloud of one (class, slot)
+  int l0, ln;
+  const float4* last;      // ring-major, as received
+  const float4* meta;      // box + ring range per 32-point chunk
+  int nch;
+  const float4* sorted;    // cell-ordered copy, .w = index | ring << 24
+  const uint32_t* ckey;    // cell key of every entry of `sorted`
+  const int* first_ge;     // [kOdSid + 1] first index whose ring number is >= r (ln if none)
+  const int* last_le;      // [kOdSid + 1] last index whose ring number is <= r - 1 (-1 if none); entry r = rings < r
+};
+__device__ __forceinline__ OdCloud od_cloud(const Dev& d, int seg) {
+  OdCloud c;
+  c.l0 = d.od_last_off[seg]; c.ln = d.od_last_off[seg + 1] - c.l0;
+  c.last = d.od_last + c.l0;
+  const int c0 = d.od_chunk_off[seg];
+  c.meta = d.od_meta + 2 * (size_t)c0; c.nch = d.od_chunk_off[seg + 1] - c0;
+  c.sorted = d.od_sorted + c.l0; c.ckey = d.od_ckey + c.l0;
+  c.first_ge = d.od_first_ge + (size_t)seg * (kOdSid + 1); c.last_le = d.od_last_le + (size_t)seg * (kOdSid + 1);
+  return c;
+}
+// class of a candidate of the ring walks: 2 = "second" neighbour, 3 = "third" (surf only), 0 = none
+__device__ __forceinline__ int od_class(int cls, bool fwd, int sid, int id) {
+  if (cls == 0) return (fwd ? sid > id : sid < id) ? 2 : 0;
+  return (fwd ? sid <= id : sid >= id) ? 2 : 3;
+}
+// first index that stops each walk of the reference (:317-318, :340-341, :404-405, :430-431)
+__device__ __forceinline__ void od_breaks(const OdCloud& C, int best_i, int id, int& jbeg, int& jend) {
+  const int hi = id + 3, lo = id - 3;  // (double)sid > id + 2.5  <=>  sid >= id + 3 (NEARBY_SCAN, :64)
+  // tables: the first index anywhere with ring >= hi is the break if it lies behind best_i (likewise the last
+  // index with ring <= lo before it); only a cloud that is not ring-major there needs the search below
+  const int fg = hi > kOdSid ? C.ln : C.first_ge[max(hi, 0)];
+  const int ll = lo < 0 ? -1 : C.last_le[min(lo + 1, kOdSid)];
+  if (fg > best_i && ll < best_i) { jend = fg; jbeg = ll; return; }
+  jend = C.ln; jbeg = -1;
+  for (int j = best_i + 1; j < C.ln;) {
+    const int c = j >> 5;
+    if (__float_as_int(C.meta[2 * c + 1].w) < hi) { j = 32 * c + 32; continue; }
+    const int je = min(32 * c + 32, C.ln);
+    for (; j < je; ++j)
+      if ((int)C.last[j].w >= hi) { jend = j; break; }
+    if (jend != C.ln) break;
+  }
+  for (int j = best_i - 1; j >= 0;) {
+    const int c = j >> 5;
+    if (__float_as_int(C.meta[2 * c + 1].z) > lo) { j = 32 * c - 1; continue; }
+    for (; j >= 32 * c; --j)
+      if ((int)C.last[j].w <= lo) { jbeg = j; break; }
+    if (jbeg != -1) break;
+  }
+}
+__global__ void __launch_bounds__(kTile, S2M_OD_MINB) odom_search_kernel(Dev d) {
+  const int slot = blockIdx.y;
+  if (!d.out[slot].optimized) return;
+  int dc0, nc, ds0, nq;
+  slot_counts(d, slot, dc0, nc, ds0, nq);
+  const int q = blockIdx.x * kTile + threadIdx.x;
+  if (q >= nq) return;
+  const int cls = q >= nc;
+  const int di = cls ? ds0 + (q - nc) : dc0 + q;
+  const float4 p = d.ds_pts[di];
+  float sel[3];
+  xf_point(d.lm[slot].x, p.x, p.y, p.z, sel);
+  const OdCloud C = od_cloud(d, cls * d.B + slot);
+  int best_i = -1, second = -1, third = -1, flags = 0;
+  float best_d = INFINITY;
+  uint32_t best_w = 0;
+  const int cx = od_cell(sel[0]), cy = od_cell(sel[1]), cz = od_cell(sel[2]);
+  int rlo[9];
+  if (cx < 1 || cx > 1022 || cy < 1 || cy > 1022 || cz < 1 || cz > 1022) {
+    flags = kOdNeedNN;
+  } else {
+    // ---- nearest neighbour among the 27 cells (nine rows of three x-adjacent cells) ----
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const uint32_t klo = ((uint32_t)(cz + r / 3 - 1) << 20) | ((uint32_t)(cy + r % 3 - 1) << 10) | (uint32_t)(cx - 1);
+      int a = 0, b = C.ln;
+      while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (C.ckey[mid] < klo) a = mid + 1; else b = mid;
+      }
+      rlo[r] = a;
+      for (int e = a; e < C.ln && C.ckey[e] <= klo + 2u; ++e) {
+        const float4 c4 = C.sorted[e];
+        const float dd = dist2(sel[0], sel[1], sel[2], c4.x, c4.y, c4.z);
+        const uint32_t w = __float_as_uint(c4.w);
+        const int idx = (int)(w & 0xFFFFFFu);
+        if (dd < best_d || (dd == best_d && idx < best_i)) { best_d = dd; best_i = idx; best_w = w; }
+      }
+    }
+    if (!(best_i >= 0 && best_d < kOdSettled)) flags = kOdNeedNN;  // not settled: something outside the cells may be nearer
+  }
+  if (flags == 0) {  // (best_d < 1 implies the 25 gate of :306 / :394)
+    // ---- second / third neighbour among the same cells ----
+    const int id = (int)(best_w >> 24);
+    int jbeg, jend;
+    od_breaks(C, best_i, id, jbeg, jend);
+    float m2 = 25.0f, m3 = 25.0f;
+    int k2 = INT_MAX, k3 = INT_MAX;  // position in the reference's walk order of the current minima
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const uint32_t khi = (((uint32_t)(cz + r / 3 - 1) << 20) | ((uint32_t)(cy + r % 3 - 1) << 10) | (uint32_t)(cx - 1)) + 2u;
+      for (int e = rlo[r]; e < C.ln && C.ckey[e] <= khi; ++e) {
+        const float4 c4 = C.sorted[e];
+        const uint32_t w = __float_as_uint(c4.w);
+        const int j = (int)(w & 0xFFFFFFu);
+        if (j <= jbeg || j >= jend || j == best_i) continue;
+        const bool fwd = j > best_i;
+        const int k = od_class(cls, fwd, (int)(w >> 24), id);
+        if (k == 0) continue;
+        const float dd = odom_sq(c4, sel);
+        const int rank = fwd ? j - best_i : C.ln + best_i - j;
+        if (k == 2) { if (dd < m2 || (dd == m2 && rank < k2)) { m2 = dd; k2 = rank; second = j; } }
+        else if (dd < m3 || (dd == m3 && rank < k3)) { m3 = dd; k3 = rank; third = j; }
+      }
+    }
+    if (!(m2 < kOdSettled) || (cls == 1 && !(m3 < kOdSettled))) { flags = kOdNeedWalk; second = third = -1; }
+  }
+  d.od_corr[di] = make_int4(best_i, second, third, flags);
+  d.od_bestd[di] = best_d;
+  if (flags) d.od_fb_list[atomicAdd(d.od_fb_cnt, 1)] = (slot << 20) | q;
+}
+
+// One WARP per listed query: the chains of a thread-per-query fallback (tens of thousands of dependent
+// steps) would set the duration of the whole step.  Nearest neighbour: lanes test 32 chunk boxes at a time,
+// chunks that can still win are scanned 32 points per step.  Walks: the two ranges of the reference's walks
+// (up to the exact break positions), 32 consecutive points per step; minima reduced with the walk's tie rule
+// (forwards the lowest index, backwards the highest, and the backward one only if strictly closer).
+__device__ __forceinline__ float warp_min_f(float v) {  // v >= 0: the bit patterns order like the values
+  return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));
+}
+__global__ void __launch_bounds__(kTile) odom_fallback_kernel(Dev d) {
+  const int n = *d.od_fb_cnt;
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += (gridDim.x * blockDim.x) >> 5) {
+    const int item = d.od_fb_list[i];
+    const int slot = item >> 20, q = item & 0xFFFFF;
+    int dc0, nc, ds0, nq;
+    slot_counts(d, slot, dc0, nc, ds0, nq);
+    const int cls = q >= nc;
+    const int di = cls ? ds0 + (q - nc) : dc0 + q;
+    const float4 p = d.ds_pts[di];
+    float sel[3];
+    xf_point(d.lm[slot].x, p.x, p.y, p.z, sel);
+    const OdCloud C = od_cloud(d, cls * d.B + slot);
+    const int4 co = d.od_corr[di];
+    float best_d = d.od_bestd[di];
+    int best_i = co.x;
+    // second attempt through the cells: 5 x 5 x 5 half-metre cells = everything within 1 m, one row of five
+    // x-adjacent cells per lane
+    const int cx = od_cell(sel[0]), cy = od_cell(sel[1]), cz = od_cell(sel[2]);
+    const bool wide = cx >= 2 && cx <= 1021 && cy >= 2 && cy <= 1021 && cz >= 2 && cz <= 1021;
+    uint32_t row_hi = 0;
+    int row_lo = 0;
+    if (wide && lane < 25) {
+      const uint32_t klo = ((uint32_t)(cz + lane / 5 - 2) << 20) | ((uint32_t)(cy + lane % 5 - 2) << 10) | (uint32_t)(cx - 2);
+      int a = 0, b = C.ln;
+      while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (C.ckey[mid] < klo) a = mid + 1; else b = mid;
+      }
+      row_lo = a;
+      row_hi = klo + 4u;
+    }
+    const bool have_row = wide && lane < 25;
+    bool need_nn = (co.w & kOdNeedNN) != 0;
+    if (need_nn && wide) {
+      float ld = INFINITY;
+      int li = INT_MAX;
+      if (have_row)
+        for (int e = row_lo; e < C.ln && C.ckey[e] <= row_hi; ++e) {
+          const float4 c4 = C.sorted[e];
+          const float dd = dist2(sel[0], sel[1], sel[2], c4.x, c4.y, c4.z);
+          const int idx = (int)(__float_as_uint(c4.w) & 0xFFFFFFu);
+          if (dd < ld || (dd == ld && idx < li)) { ld = dd; li = idx; }
+        }
+      const float m = warp_min_f(ld);
+      if (m < 1.0f) {  // everything outside the block is at least 1 m away
+        best_d = m;
+        best_i = __reduce_min_sync(full, ld == m ? li : INT_MAX);
+        need_nn = false;
+      }
+    }
+    if (need_nn) {  // exhaustive: every chunk whose box can still hold the minimum
+      const float bound = fminf(best_d, 25.0f);
+      best_d = INFINITY; best_i = -1;
+      for (int cb = 0; cb < C.nch; cb += 32) {
+        const int c = cb + lane;
+        const float lb = c < C.nch ? chunk_bound(C.meta[2 * c], C.meta[2 * c + 1], sel) : INFINITY;
+        for (unsigned need = __ballot_sync(full, lb <= fminf(bound, best_d)); need; need &= need - 1) {
+          const int k = __ffs(need) - 1;
+          if (__shfl_sync(full, lb, k) > fminf(bound, best_d)) continue;
+          const int j = 32 * (cb + k) + lane;
+          float dd = INFINITY;
+          if (j < C.ln) { const float4 c4 = C.last[j]; dd = dist2(sel[0], sel[1], sel[2], c4.x, c4.y, c4.z); }
+          const float m = warp_min_f(dd);
+          if (m < best_d) {  // chunks come in index order: a later equal distance never replaces
+            best_d = m;
+            best_i = __reduce_min_sync(full, dd == m ? j : INT_MAX);
+          }
+        }
+      }
+    }
+    int second = -1, third = -1;
+    if (best_i >= 0 && (double)best_d < 25.0) {  // DISTANCE_SQ_THRESHOLD (:63)
+      const int id = (int)C.last[best_i].w;
+      int jbeg, jend;
+      od_breaks(C, best_i, id, jbeg, jend);
+      // second / third neighbour among the same 125 cells: settled if closer than 1 m
+      bool settled = false;
+      if (wide) {
+        float l2 = 25.0f, l3 = 25.0f;
+        int r2 = INT_MAX, r3 = INT_MAX, j2 = -1, j3 = -1;
+        if (have_row)
+          for (int e = row_lo; e < C.ln && C.ckey[e] <= row_hi; ++e) {
+            const float4 c4 = C.sorted[e];
+            const uint32_t w = __float_as_uint(c4.w);
+            const int j = (int)(w & 0xFFFFFFu);
+            if (j <= jbeg || j >= jend || j == best_i) continue;
+            const bool fwd = j > best_i;
+            const int k = od_class(cls, fwd, (int)(w >> 24), id);
+            if (k == 0) continue;
+            const float dd = odom_sq(c4, sel);
+            const int rank = fwd ? j - best_i : C.ln + best_i - j;  // position in the reference's walk order
+            if (k == 2) { if (dd < l2 || (dd == l2 && rank < r2)) { l2 = dd; r2 = rank; j2 = j; } }
+            else if (dd < l3 || (dd == l3 && rank < r3)) { l3 = dd; r3 = rank; j3 = j; }
+          }
+        const float m2 = warp_min_f(l2), m3 = warp_min_f(l3);
+        if (m2 < 1.0f && (cls == 0 || m3 < 1.0f)) {
+          const int q2 = __reduce_min_sync(full, l2 == m2 ? r2 : INT_MAX);
+          second = __reduce_max_sync(full, (l2 == m2 && r2 == q2) ? j2 : -1);
+          if (cls == 1) {
+            const int q3 = __reduce_min_sync(full, l3 == m3 ? r3 : INT_MAX);
+            third = __reduce_max_sync(full, (l3 == m3 && r3 == q3) ? j3 : -1);
+          }
+          settled = true;
+        }
+      }
+      float f2 = 25.0f, f3 = 25.0f, b2 = 25.0f, b3 = 25.0f;  // minPointSqDis2 / 3, forward and backward parts
+      int fi2 = -1, fi3 = -1, bi2 = -1, bi3 = -1;                // (warp-uniform)
+      // chunks of the two ranges, 32 boxes per step; a chunk is scanned only if its box bound is below the
+      // running minimum of a class its ring range can hold (a candidate has to be strictly closer to win)
+      for (int dir = 0; dir < 2 && !settled; ++dir) {
+        const int ca = dir == 0 ? (best_i + 1) >> 5 : (jbeg + 1) >> 5;
+        const int cz = dir == 0 ? (jend - 1) >> 5 : (best_i - 1) >> 5;
+        if ((dir == 0 && best_i + 1 >= jend) || (dir == 1 && best_i - 1 <= jbeg)) continue;
+        for (int step = 0; step * 32 <= cz - ca; ++step) {
+          const int c = dir == 0 ? ca + step * 32 + lane : cz - step * 32 - lane;  // walk order
+          float lb = INFINITY;
+          bool may2 = false, may3 = false;
+          if (c >= ca && c <= cz) {
+            const float4 ma = C.meta[2 * c], mb = C.meta[2 * c + 1];
+            lb = chunk_bound(ma, mb, sel);
+            const int smin = __float_as_int(mb.z), smax = __float_as_int(mb.w);
+            if (cls == 0) may2 = dir == 0 ? smax > id : smin < id;
+            else { may2 = dir == 0 ? smin <= id : smax >= id; may3 = dir == 0 ? smax > id : smin < id; }
+          }
+          const float t2 = dir == 0 ? f2 : fminf(f2, b2), t3 = dir == 0 ? f3 : fminf(f3, b3);
+          for (unsigned need = __ballot_sync(full, (may2 && lb < t2) || (may3 && lb < t3)); need; need &= need - 1) {
+            const int k = __ffs(need) - 1;
+            const int ck = __shfl_sync(full, c, k);
+            const float lbk = __shfl_sync(full, lb, k);
+            const float u2 = dir == 0 ? f2 : fminf(f2, b2), u3 = dir == 0 ? f3 : fminf(f3, b3);
+            if (!(lbk < u2) && !(lbk < u3)) continue;  // the minima moved since the ballot
+            const int j = 32 * ck + lane;
+            int kl = 0;
+            float dd = INFINITY;
+            if (j < C.ln && (dir == 0 ? (j > best_i && j < jend) : (j < best_i && j > jbeg))) {
+              const float4 c4 = C.last[j];
+              kl = od_class(cls, dir == 0, (int)c4.w, id);
+              dd = odom_sq(c4, sel);
+            }
+            const float m2 = warp_min_f(kl == 2 ? dd : INFINITY), m3 = warp_min_f(kl == 3 ? dd : INFINITY);
+            if (dir == 0) {  // first met = lowest index
+              if (m2 < f2) { f2 = m2; fi2 = __reduce_min_sync(full, (kl == 2 && dd == m2) ? j : INT_MAX); }
+              if (m3 < f3) { f3 = m3; fi3 = __reduce_min_sync(full, (kl == 3 && dd == m3) ? j : INT_MAX); }
+            } else {         // first met = highest index
+              if (m2 < b2) { b2 = m2; bi2 = __reduce_max_sync(full, (kl == 2 && dd == m2) ? j : -1); }
+              if (m3 < b3) { b3 = m3; bi3 = __reduce_max_sync(full, (kl == 3 && dd == m3) ? j : -1); }
+            }
+          }
+        }
+      }
+      if (!settled) {
+        second = (bi2 >= 0 && b2 < f2) ? bi2 : fi2;
+        third = (bi3 >= 0 && b3 < f3) ? bi3 : fi3;
+      }
+    } else {
+      best_i = -1;
+    }
+    if (lane == 0) {
+      d.od_corr[di] = make_int4(best_i, second, third, 0);
+      d.od_bestd[di] = best_d;
+    }
+  }
+}
+
 template <bool kTrace>
-__global__ void __launch_bounds__(kTile, S2M_OD_MINB) odom_associate_kernel(Dev d, int outer) {
+__global__ void __launch_bounds__(kTile, 4) odom_fit_kernel(Dev d, int outer) {
   const int slot = blockIdx.y;
   if (!d.out[slot].optimized) return;
   int dc0, nc, ds0, nq;
@@ -925,205 +1236,42 @@ __global__ void __launch_bounds__(kTile, S2M_OD_MINB) odom_associate_kernel(Dev 
   if (threadIdx.x < 7) pose[threadIdx.x] = d.lm[slot].x[threadIdx.x];
   acc_zero(A);
   __syncthreads();
-  const int t = threadIdx.x, tile = blockIdx.x;
-  const int q = tile * kTile + t;
+  const int q = blockIdx.x * kTile + threadIdx.x;
   const bool live = q < nq;
   const int cls = q >= nc;
   const int di = cls ? ds0 + (q - nc) : dc0 + q;
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-  float sel[3] = {0.f, 0.f, 0.f};
-  if (live) {
-    p = d.ds_pts[di];
-    xf_point(pose, p.x, p.y, p.z, sel);
-  }
-  const int seg = cls * d.B + slot;
-  const int l0 = d.od_last_off[seg], ln = d.od_last_off[seg + 1] - l0;
-  const float4* __restrict__ last = d.od_last + l0;
-  // box + ring range of every 32-point chunk of the previous cloud (ring-major: a chunk is a short arc)
-  const float4* __restrict__ meta = d.od_meta + 2 * (size_t)d.od_chunk_off[seg];
-  // ---- exact nearest neighbour in the previous sweep's cloud of the query's class (:303, :392) ----
-  // d.od_sorted holds each previous cloud ordered by x (.w = index in the ring-major cloud): start at the
-  // query's x and walk outwards; a side is finished once dx*dx alone exceeds the best distance (the float
-  // sum (dx*dx + dy*dy) + dz*dz can never be smaller than dx*dx), so the answer is the exact minimum of
-  // (d2, index) over the whole cloud.
-  int best_i = -1;
-  float best_d = INFINITY;
-  if (live) {
-    const float4* __restrict__ sp = d.od_sorted + l0;
-    int lo = 0, hi = ln;
-    while (lo < hi) {  // first sorted position with x >= sel.x
-      const int mid = (lo + hi) >> 1;
-      if (sp[mid].x < sel[0]) lo = mid + 1; else hi = mid;
-    }
-    int up = lo, dn = lo - 1;
-    bool more_up = up < ln, more_dn = dn >= 0;
-    while (more_up || more_dn) {
-      if (more_up) {
-        const float4 c4 = sp[up];
-        const float dx = xfsub(sel[0], c4.x);
-        if (xfmul(dx, dx) > fminf(best_d, 25.0f)) more_up = false;  // beyond 25 the gate fails anyway
-        else {
-          const float dd = dist2(sel[0], sel[1], sel[2], c4.x, c4.y, c4.z);
-          const int idx = __float_as_int(c4.w);
-          if (dd < best_d || (dd == best_d && idx < best_i)) { best_d = dd; best_i = idx; }
-          more_up = ++up < ln;
-        }
-      }
-      if (more_dn) {
-        const float4 c4 = sp[dn];
-        const float dx = xfsub(sel[0], c4.x);
-        if (xfmul(dx, dx) > fminf(best_d, 25.0f)) more_dn = false;
-        else {
-          const float dd = dist2(sel[0], sel[1], sel[2], c4.x, c4.y, c4.z);
-          const int idx = __float_as_int(c4.w);
-          if (dd < best_d || (dd == best_d && idx < best_i)) { best_d = dd; best_i = idx; }
-          more_dn = --dn >= 0;
-        }
-      }
-    }
-  }
-  // ---- ring-constrained neighbours (:313-357, :401-452) ----
-  // The reference walks the previous cloud point by point from the closest one -- forwards until a
-  // ring number exceeds id + 2.5, backwards until one drops below id - 2.5 -- keeping running minima
-  // with a strict "<".  The result is the candidate of smallest distance, ties to the one met first.
-  // Here: (1) the two break positions are found exactly from the chunk ring ranges; (2) the most
-  // promising chunk per neighbour class gives an upper bound U of the final distance; (3) the walks run
-  // in the reference's order, stepping over every chunk whose bound cannot beat the running minimum
-  // (>=) or exceeds U (>): neither kind can hold the winner, and dropping losers never changes it.
-  const bool gate = live && best_i >= 0 && (double)best_d < 25.0;  // DISTANCE_SQ_THRESHOLD (:63)
-  int second = -1, third = -1;
-  if (gate) {
-    const int id = (int)last[best_i].w;
-    const int hi = id + 3, lo = id - 3;  // (double)sid > id + 2.5  <=>  sid >= id + 3 (NEARBY_SCAN, :64)
-    // (1) first index that stops each walk
-    int jend = ln, jbeg = -1;
-    for (int j = best_i + 1; j < ln;) {
-      const int c = j >> 5;
-      if (__float_as_int(meta[2 * c + 1].w) < hi) { j = 32 * c + 32; continue; }
-      const int je = min(32 * c + 32, ln);
-      for (; j < je; ++j)
-        if ((int)last[j].w >= hi) { jend = j; break; }
-      if (jend != ln) break;
-    }
-    for (int j = best_i - 1; j >= 0;) {
-      const int c = j >> 5;
-      if (__float_as_int(meta[2 * c + 1].z) > lo) { j = 32 * c - 1; continue; }
-      for (; j >= 32 * c; --j)
-        if ((int)last[j].w <= lo) { jbeg = j; break; }
-      if (jbeg != -1) break;
-    }
-    // class of a candidate: 2 = "second" neighbour, 3 = "third" (surf only), 0 = none
-    auto klass = [&](int j, int sid) -> int {
-      if (cls == 0) return (j > best_i ? sid > id : sid < id) ? 2 : 0;
-      return (j > best_i ? sid <= id : sid >= id) ? 2 : 3;
-    };
-    // which classes a chunk may hold, from its ring range (a chunk on one side of best_i only; the chunk
-    // of best_i itself may hold all)
-    auto chunk_may = [&](int c, int smin, int smax, bool& may2, bool& may3) {
-      const bool fwd = 32 * c > best_i, bwd = 32 * c + 31 < best_i;
-      if (cls == 0) { may2 = fwd ? smax > id : (bwd ? smin < id : true); may3 = false; }
-      else { may2 = fwd ? smin <= id : (bwd ? smax >= id : true); may3 = fwd ? smax > id : (bwd ? smin < id : true); }
-    };
-    // (2) upper bounds from the chunk of smallest bound that can hold each class
-    float U2 = INFINITY, U3 = INFINITY;
-    {
-      int s2 = -1, s3 = -1;
-      float lb2 = INFINITY, lb3 = INFINITY;
-      for (int c = (jbeg + 1) >> 5; c <= (jend - 1) >> 5; ++c) {
-        const float4 ma = meta[2 * c], mb = meta[2 * c + 1];
-        const float lb = chunk_bound(ma, mb, sel);
-        const int smin = __float_as_int(mb.z), smax = __float_as_int(mb.w);
-        bool may2, may3;
-        chunk_may(c, smin, smax, may2, may3);
-        if (may2 && lb < lb2) { lb2 = lb; s2 = c; }
-        if (may3 && lb < lb3) { lb3 = lb; s3 = c; }
-      }
-      for (int pass = 0; pass < 2; ++pass) {
-        const int c = pass ? s3 : s2;
-        if (c < 0 || (pass && s3 == s2)) continue;
-        const int ja = max(32 * c, jbeg + 1), je = min(32 * c + 32, jend);
-        for (int j = ja; j < je; ++j) {
-          if (j == best_i) continue;
-          const float4 c4 = last[j];
-          const int k = klass(j, (int)c4.w);
-          const float dd = odom_sq(c4, sel);
-          if (k == 2) U2 = fminf(U2, dd);
-          else if (k == 3) U3 = fminf(U3, dd);
-        }
-      }
-    }
-    // (3) the walks
-    float m2 = 25.0f, m3 = 25.0f;  // minPointSqDis2 / 3 (float values compared as double in the reference)
-    auto cannot_win = [&](int c) -> bool {
-      const float4 ma = meta[2 * c], mb = meta[2 * c + 1];
-      const float lb = chunk_bound(ma, mb, sel);
-      bool may2, may3;
-      chunk_may(c, __float_as_int(mb.z), __float_as_int(mb.w), may2, may3);
-      return (!may2 || lb >= m2 || lb > U2) && (!may3 || lb >= m3 || lb > U3);
-    };
-    for (int j = best_i + 1; j < jend;) {  // increasing scan line
-      if ((j & 31) == 0 || j == best_i + 1) {
-        const int c = j >> 5;
-        if (cannot_win(c)) { j = 32 * c + 32; continue; }
-      }
-      const float4 c4 = last[j];
-      const int k = klass(j, (int)c4.w);
-      const float dd = odom_sq(c4, sel);
-      if (k == 2 && dd < m2) { m2 = dd; second = j; }
-      else if (k == 3 && dd < m3) { m3 = dd; third = j; }
-      ++j;
-    }
-    for (int j = best_i - 1; j > jbeg;) {  // decreasing scan line
-      if ((j & 31) == 31 || j == best_i - 1) {
-        const int c = j >> 5;
-        if (cannot_win(c)) { j = 32 * c - 1; continue; }
-      }
-      const float4 c4 = last[j];
-      const int k = klass(j, (int)c4.w);
-      const float dd = odom_sq(c4, sel);
-      if (k == 2 && dd < m2) { m2 = dd; second = j; }
-      else if (k == 3 && dd < m3) { m3 = dd; third = j; }
-      --j;
-    }
-  }
-  // ---- the factor ----
   Sums28 S;
   S.zero();
   double ne = 0.0, np = 0.0;
-  bool used = false;
-  double rec[6] = {0, 0, 0, 0, 0, 0};
-  if (gate) {
-    const float4 a = last[best_i];
-    if (cls == 0) {
-      if (second >= 0) {
-        const float4 b = last[second];
-        const double e[3] = {(double)a.x - (double)b.x, (double)a.y - (double)b.y, (double)a.z - (double)b.z};
-        const double inv = 1.0 / sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
-        rec[0] = a.x; rec[1] = a.y; rec[2] = a.z;
-        rec[3] = e[0] * inv; rec[4] = e[1] * inv; rec[5] = e[2] * inv;
-        const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
-        accum_edge(S, pose, cp, rec, rec + 3);
-        ne = 1.0;
-        used = true;
-      }
-    } else {
-      if (second >= 0 && third >= 0) {
-        const float4 l = last[second], m = last[third];
-        const double u[3] = {(double)a.x - (double)l.x, (double)a.y - (double)l.y, (double)a.z - (double)l.z};
-        const double v[3] = {(double)a.x - (double)m.x, (double)a.y - (double)m.y, (double)a.z - (double)m.z};
-        double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
-        const double z = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
-        if (z > 0.0) { const double nn = sqrt(z); n[0] /= nn; n[1] /= nn; n[2] /= nn; }
-        rec[0] = n[0]; rec[1] = n[1]; rec[2] = n[2];
-        rec[3] = -(n[0] * (double)a.x + n[1] * (double)a.y + n[2] * (double)a.z);
-        const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
-        accum_plane(S, pose, cp, rec, rec[3]);
-        np = 1.0;
-        used = true;
-      }
-    }
-  }
   if (live) {
+    const int4 co = d.od_corr[di];
+    const float4 p = d.ds_pts[di];
+    const float4* __restrict__ last = d.od_last + d.od_last_off[cls * d.B + slot];
+    bool used = false;
+    double rec[6] = {0, 0, 0, 0, 0, 0};
+    const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
+    if (co.x >= 0 && cls == 0 && co.y >= 0) {
+      const float4 a = last[co.x], b = last[co.y];
+      const double e[3] = {(double)a.x - (double)b.x, (double)a.y - (double)b.y, (double)a.z - (double)b.z};
+      const double inv = 1.0 / sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+      rec[0] = a.x; rec[1] = a.y; rec[2] = a.z;
+      rec[3] = e[0] * inv; rec[4] = e[1] * inv; rec[5] = e[2] * inv;
+      accum_edge(S, pose, cp, rec, rec + 3);
+      ne = 1.0;
+      used = true;
+    } else if (co.x >= 0 && cls == 1 && co.y >= 0 && co.z >= 0) {
+      const float4 a = last[co.x], l = last[co.y], m = last[co.z];
+      const double u[3] = {(double)a.x - (double)l.x, (double)a.y - (double)l.y, (double)a.z - (double)l.z};
+      const double v[3] = {(double)a.x - (double)m.x, (double)a.y - (double)m.y, (double)a.z - (double)m.z};
+      double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+      const double z = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+      if (z > 0.0) { const double nn = sqrt(z); n[0] /= nn; n[1] /= nn; n[2] /= nn; }
+      rec[0] = n[0]; rec[1] = n[1]; rec[2] = n[2];
+      rec[3] = -(n[0] * (double)a.x + n[1] * (double)a.y + n[2] * (double)a.z);
+      accum_plane(S, pose, cp, rec, rec[3]);
+      np = 1.0;
+      used = true;
+    }
     if (used) {
       double2* ro = reinterpret_cast<double2*>(d.rec + 6 * (size_t)di);
       ro[0] = make_double2(rec[0], rec[1]);
@@ -1133,9 +1281,9 @@ __global__ void __launch_bounds__(kTile, S2M_OD_MINB) odom_associate_kernel(Dev 
     d.rec_valid[di] = used ? 1 : 0;
     if (kTrace) {
       const size_t o = (size_t)outer * d.cap_in + di;
-      d.tr_idx[5 * o] = gate ? best_i : -1; d.tr_idx[5 * o + 1] = second; d.tr_idx[5 * o + 2] = third;
+      d.tr_idx[5 * o] = co.x; d.tr_idx[5 * o + 1] = co.y; d.tr_idx[5 * o + 2] = co.z;
       d.tr_idx[5 * o + 3] = d.tr_idx[5 * o + 4] = -1;
-      d.tr_d2[5 * o] = best_d;
+      d.tr_d2[5 * o] = d.od_bestd[di];
       d.tr_used[o] = used;
     }
   }
@@ -1146,21 +1294,62 @@ __global__ void __launch_bounds__(kTile, S2M_OD_MINB) odom_associate_kernel(Dev 
   __shared__ LmState Ls;
   lm_tail_begin(d, slot, outer, red, &Ls);
 }
-// previous clouds ordered by x for the nearest-neighbour walk: key = [segment][ordered bits of x]
+// Previous clouds a second time, ordered by half-metre cell (x fastest) inside each cloud:
+// key = [segment][cz][cy][cx] with biased coordinates; .w of the copy = index | ring << 24.
 __global__ void odom_sort_key_kernel(Dev d, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int g = find_seg(d.od_last_off, 2 * d.B, i);
-  d.od_key[i] = ((unsigned long long)g << 32) | f2ord(d.od_last[i].x);
+  const float4 p = d.od_last[i];
+  const int cx = od_cell(p.x), cy = od_cell(p.y), cz = od_cell(p.z);
+  const int sid = (int)p.w;
+  if ((unsigned)cx > 1023u || (unsigned)cy > 1023u || (unsigned)cz > 1023u || (unsigned)sid > 255u) set_err(d, -4);  // S2M_ERR_RANGE
+  d.od_key[i] = ((unsigned long long)g << 30) | ((unsigned long long)(cz & 1023) << 20) | ((unsigned long long)(cy & 1023) << 10) |
+                (unsigned long long)(cx & 1023);
   d.od_val[i] = (uint32_t)(i - d.od_last_off[g]);
 }
 __global__ void odom_gather_sorted_kernel(Dev d, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int g = (int)(d.od_key2[i] >> 32);
+  const int g = (int)(d.od_key2[i] >> 30);
   const uint32_t l = d.od_val2[i];
   const float4 p = d.od_last[d.od_last_off[g] + l];
-  d.od_sorted[i] = make_float4(p.x, p.y, p.z, __int_as_float((int)l));
+  d.od_sorted[i] = make_float4(p.x, p.y, p.z, __uint_as_float((l & 0xFFFFFFu) | ((uint32_t)((int)p.w & 255) << 24)));
+  d.od_ckey[i] = (uint32_t)(d.od_key2[i] & 0x3FFFFFFFull);
+}
+// ring tables of every previous cloud: od_first_ge[g][r] = first index with ring >= r, od_last_le[g][r] = last
+// index with ring < r.  Built from the first / last index of every ring number.
+__global__ void odom_ring_init_kernel(Dev d) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * d.B * (kOdSid + 1)) return;
+  d.od_first_ge[t] = INT_MAX;
+  d.od_last_le[t] = -1;
+}
+__global__ void odom_ring_mark_kernel(Dev d, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = find_seg(d.od_last_off, 2 * d.B, i);
+  const int l = i - d.od_last_off[g];
+  const int sid = min(max((int)d.od_last[i].w, 0), kOdSid - 1);
+  atomicMin(d.od_first_ge + (size_t)g * (kOdSid + 1) + sid, l);      // for now: first index OF ring sid
+  atomicMax(d.od_last_le + (size_t)g * (kOdSid + 1) + sid + 1, l);   // for now: last index OF ring sid, at [sid + 1]
+}
+__global__ void odom_ring_scan_kernel(Dev d) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= 2 * d.B) return;
+  const int ln = d.od_last_off[g + 1] - d.od_last_off[g];
+  int* fg = d.od_first_ge + (size_t)g * (kOdSid + 1);
+  int* ll = d.od_last_le + (size_t)g * (kOdSid + 1);
+  int run = ln;
+  for (int r = kOdSid; r >= 0; --r) {  // suffix minimum
+    run = min(run, fg[r] == INT_MAX ? ln : fg[r]);
+    fg[r] = run;
+  }
+  int best = -1;
+  for (int r = 0; r <= kOdSid; ++r) {  // prefix maximum: entry r covers rings < r
+    best = max(best, ll[r]);
+    ll[r] = best;
+  }
 }
 // box + ring-number range of every 32-point chunk of the previous clouds (one warp per chunk):
 // meta[2c] = (min x, min y, min z, max x), meta[2c+1] = (max y, max z, bits of min ring, bits of max ring)
@@ -1635,9 +1824,12 @@ int launch_odom_sort(const Dev& d, int n, void* tmp, size_t tmp_bytes, cudaStrea
   odom_sort_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n);
   int bits = 1;
   while ((1 << bits) < 2 * d.B) ++bits;
-  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d.od_key, d.od_key2, d.od_val, d.od_val2, n, 0, 32 + bits, s);
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d.od_key, d.od_key2, d.od_val, d.od_val2, n, 0, 30 + bits, s);
   odom_gather_sorted_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n);
-  return 2;
+  odom_ring_init_kernel<<<cdiv(2 * d.B * (kOdSid + 1), 256), 256, 0, s>>>(d);
+  odom_ring_mark_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n);
+  odom_ring_scan_kernel<<<cdiv(2 * d.B, 64), 64, 0, s>>>(d);
+  return 5;
 }
 size_t odom_sort_temp_bytes(const Dev& d, int n) {
   size_t tb = 0;
@@ -1653,12 +1845,15 @@ int launch_odom_guard(const Dev& d, cudaStream_t s) {
   odom_guard_kernel<<<cdiv(d.B, 64), 64, 0, s>>>(d);
   return 1;
 }
-int launch_odom_associate(const Dev& d, int outer, int tiles, bool trace, cudaStream_t s) {
+int launch_odom_associate(const Dev& d, int outer, int tiles, int fallback_blocks, bool trace, cudaStream_t s) {
   if (tiles <= 0) return 0;
   dim3 grid(tiles, d.B);
-  if (trace) odom_associate_kernel<true><<<grid, kTile, 0, s>>>(d, outer);
-  else odom_associate_kernel<false><<<grid, kTile, 0, s>>>(d, outer);
-  return 1;
+  cudaMemsetAsync(d.od_fb_cnt, 0, sizeof(int), s);
+  odom_search_kernel<<<grid, kTile, 0, s>>>(d);
+  odom_fallback_kernel<<<fallback_blocks, kTile, 0, s>>>(d);
+  if (trace) odom_fit_kernel<true><<<grid, kTile, 0, s>>>(d, outer);
+  else odom_fit_kernel<false><<<grid, kTile, 0, s>>>(d, outer);
+  return 3;
 }
 int launch_finish_pose(const Dev& d, cudaStream_t s) {
   finish_pose_kernel<<<cdiv(d.B, 64), 64, 0, s>>>(d);
