@@ -411,7 +411,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seqs", type=int, default=64, help="independent sequences per lane (<=64)")
     ap.add_argument("--no-pipeline", action="store_true", help="synchronous batch calls instead of submit/wait with two frames in flight")
-    ap.add_argument("--ctx", "--lanes", dest="ctx", type=int, default=4, help="concurrent lanes per GPU inside the one context")
+    ap.add_argument("--ctx", "--lanes", dest="ctx", type=int, default=6, help="concurrent lanes per GPU inside the one context")
     ap.add_argument("--cap-map-corner", type=int, default=1 << 17)
     ap.add_argument("--cap-map-surf", type=int, default=1 << 17)
     ap.add_argument("--no-cpu-baseline", action="store_true")
