@@ -227,6 +227,8 @@ int s2m_shard_profile(s2m_ctx* ctx, int reset, double* allreduce_ms_total, long 
  * then q_w_curr / t_w_curr are advanced (:504-505).  `batch` independent sequences per context; the
  * four clouds of each are packed with B+1 offsets, host pointers or (device_ptrs != 0) device pointers,
  * e.g. straight from s2m_fx_device_cloud.  The first call of a slot only initialises (:267-271).
+ * Domain: int(intensity) of the less-sharp / less-flat points (the ring number, :310) in 0..255 and
+ * coordinates within +-256 m, else S2M_ERR_RANGE; cap_sharp + cap_flat < 2^20, cap_less_* < 2^24.
  * The context is an s2m_ctx: s2m_destroy, s2m_last_error, s2m_launch_count, s2m_trace_knn apply. */
 int s2m_odom_create(int device, int batch, int cap_sharp, int cap_flat, int cap_less_sharp,
                     int cap_less_flat, int trace, s2m_ctx** out);

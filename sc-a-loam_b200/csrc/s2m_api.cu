@@ -1411,7 +1411,16 @@ extern "C" int s2m_odom_step_batch(s2m_ctx* ctx, const float* sharp, const int* 
   if (lf_off[B] > 0) CK(cudaMemcpyAsync(d.od_last + ls_off[B], less_flat, sizeof(float4) * (size_t)lf_off[B], kind, s));
   ctx->launches += launch_odom_sort(d, ls_off[B] + lf_off[B], ctx->od_tmp, ctx->od_tmp_bytes, s);
   ctx->launches += launch_odom_meta(d, co[2 * B], s);
+  CK(cudaMemcpyAsync(ctx->h_err, d.err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));  // indexing may reject the clouds
   CK(cudaStreamSynchronize(s));
+  if (*ctx->h_err != 0) {
+    const int e = *ctx->h_err;
+    cudaMemsetAsync(d.err_flag, 0, sizeof(int), s);
+    cudaMemsetAsync(d.od_last_off, 0, sizeof(int) * (2 * B + 1), s);  // the rejected clouds are not kept
+    cudaMemsetAsync(d.od_chunk_off, 0, sizeof(int) * (2 * B + 1), s);
+    ctx->err = "previous-sweep clouds outside the supported domain (ring numbers 0..255, coordinates within 256 m)";
+    return e;
+  }
   return S2M_OK;
 }
 

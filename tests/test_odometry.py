@@ -120,6 +120,39 @@ def test_cuda_front_end_on_two_real_keyframes(s2m, built):
 
 
 @pytest.mark.gpu
+def test_cuda_odometry_degenerate_inputs(s2m, built):
+    """empty and tiny clouds, queries far from everything, ring numbers outside 0..255"""
+    rng = np.random.default_rng(4)
+    e = np.zeros((0, 4), np.float32)
+
+    def cloud(n, rings, spread=5.0):
+        p = np.c_[rng.uniform(-spread, spread, (n, 3)), np.sort(rng.integers(0, rings, n)) + rng.uniform(0, 0.09, n)]
+        return p.astype(np.float32)
+
+    D, O = s2m.Odometer(trace=True), oracle.Odometer()
+    seq = [(e, e, e, e),                                              # nothing at all
+           (cloud(5, 3), cloud(9, 3), cloud(20, 4), cloud(31, 4)),     # fewer previous points than one chunk
+           (e, e, cloud(40, 4), cloud(70, 4)),                         # no queries
+           (cloud(30, 4), cloud(50, 4), e, cloud(33, 4)),              # empty corner target next time
+           (cloud(30, 4), cloud(50, 4), cloud(64, 4), cloud(96, 4)),
+           (cloud(20, 4) + np.float32([300, 0, 0, 0]), cloud(20, 4) + np.float32([0, 200, 0, 0]), cloud(64, 4), cloud(96, 4)),  # > 5 m from everything
+           (cloud(30, 4), cloud(50, 4), cloud(64, 4), cloud(96, 4))]
+    for i, (a, b, c, dd) in enumerate(seq):
+        qg, tg = D.step(a, b, c, dd)
+        qo, to = O.step(a, b, c, dd)
+        assert list(D.counts[0]) == list(O.counts), i
+        if i > 0 and len(a) + len(b) > 0:
+            for outer in range(2):
+                eo, po = O.trace(outer)
+                assert np.array_equal(D.trace(outer, 0)[0][:, :2], eo) and np.array_equal(D.trace(outer, 1)[0], po), (i, outer)
+        assert np.linalg.norm(tg - to) < 1e-4 and np.abs(qg - qo).max() < 1e-5, i    # tiny random clouds: poses may be wild, but equal
+    bad = cloud(40, 4)
+    bad[:, 3] += 300.0
+    with pytest.raises(s2m.S2MError):
+        D.step(cloud(5, 3), cloud(5, 3), bad, cloud(40, 4))
+
+
+@pytest.mark.gpu
 def test_cuda_odometry_batch_slots_are_independent(s2m, built):
     """two sequences in one context (the second lags one sweep) == two single contexts, bit for bit"""
     _, feats = features_stream("VLP16", 3, 5, 0.5)
