@@ -60,9 +60,36 @@ def main():
         dt = time.perf_counter() - t0
         return args.batch * args.steps / dt, 1e3 * dt / args.steps, (F.launch_count() - l0) // args.steps
 
+    def run_two_contexts():
+        """two extractor contexts driven by two host threads on alternate batches: the H2D copy of one
+        batch overlaps the kernels of the other (each context has its own stream)"""
+        import threading
+        F2 = pkg.FeatureExtractor(sensor, mr, batch=args.batch, cap_points=max(len(x) for x in sw) + 64)
+        ctxs = [F, F2]
+        for c in ctxs:
+            for _ in range(args.warmup):
+                c.extract(host.numpy(), off)
+        torch.cuda.synchronize()
+        per = (args.steps + 1) // 2
+
+        def work(c):
+            for _ in range(per):
+                c.extract(host.numpy(), off)
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(c,)) for c in ctxs]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        F2.close()
+        return args.batch * 2 * per / dt, 1e3 * dt / (2 * per)
+
     v_dev, ms_dev, launches = run(dev, True, False)
     v_h2d, ms_h2d, _ = run(host, False, False)
     v_all, ms_all, _ = run(host, False, True)
+    v_two, ms_two = run_two_contexts()
     sizes = {k: int(F.offsets(k)[-1]) for k in ("full", "sharp", "less_sharp", "flat", "less_flat")}
     # parity spot check against the oracle on the first sweep (the checker, not the thing measured)
     want = oracle.scan_registration(sensor, sw[0], mr)
@@ -85,6 +112,8 @@ def main():
         "workload": "hdl64_feature_extraction", "metric": "sweeps_per_s", "value": v_dev, "ms_per_step": ms_dev,
         "batch": args.batch, "steps": args.steps, "raw_points_per_step": n_raw, "points_out_per_step": sizes,
         "e2e_h2d_only": {"value": v_h2d, "ms_per_step": ms_h2d, "h2d_bytes_per_step": 12 * n_raw},
+        "e2e_h2d_two_contexts": {"value": v_two, "ms_per_step": ms_two,
+                                 "note": "two contexts on two host threads: the copy of one batch overlaps the kernels of the other"},
         "e2e_with_download": {"value": v_all, "ms_per_step": ms_all,
                               "d2h_bytes_per_step": 16 * (sizes["full"] + sizes["less_sharp"] + sizes["less_flat"])},
         "gpu_launches_per_step": int(launches), "bit_identical_to_oracle": bool(ok),
