@@ -7,6 +7,9 @@
  * file-scope state, laserMapping.cpp:66-140); these entry points are what a ROS
  * shim that keeps the node's topics and its two parameters would bind
  * (INTEGRATION.md shows that shim).  Plain pointers and sizes only.
+ * Further down, the rows SURVEY.md 8f ranks next: map checkpoint (s2m_pcd_*, s2m_checkpoint_*),
+ * scan-to-scan odometry (s2m_odom_*, laserOdometry.cpp:220-591) and feature extraction
+ * (s2m_fx_*, scanRegistration.cpp:116-454).
  *
  * Conventions
  *   - point clouds are packed float[4*n]: x, y, z, intensity (pcl::PointXYZI
