@@ -106,6 +106,7 @@ __global__ void vox_bbox_init_kernel(Dev d) {
   if (i < 6 * d.G) d.bbox[i] = (i % 6) < 3 ? 0xFFFFFFFFu : 0u;
 }
 
+template <bool kNarrow>  // kNarrow: segment + voxel index fit 32 bits -> 4-byte sort keys (one radix pass and a third of the bytes less)
 __global__ void vox_key_kernel(Dev d, int n, int key_bits) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -132,12 +133,14 @@ __global__ void vox_key_kernel(Dev d, int n, int key_bits) {
     key = (uint64_t)((long long)i0 + (long long)i1 * d0 + (long long)i2 * d0 * d1) & 0x7FFFFFFFull;
   }
   if (key >> key_bits) set_err(d, -4);  // the host derived key_bits from the same boxes
-  d.vkey[i] = ((uint64_t)g << key_bits) | key;
+  if (kNarrow) reinterpret_cast<uint32_t*>(d.vkey)[i] = ((uint32_t)g << key_bits) | (uint32_t)key;
+  else d.vkey[i] = ((uint64_t)g << key_bits) | key;
   d.vval[i] = (uint32_t)i;
 }
 
 // flag[p] = 1 where a run of equal keys starts; flag[n] = 0 so scan[n] = number of runs
-__global__ void head_flag_kernel(const uint64_t* __restrict__ keys, uint32_t* __restrict__ flag, int n) {
+template <typename K>
+__global__ void head_flag_kernel(const K* __restrict__ keys, uint32_t* __restrict__ flag, int n) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p > n) return;
   flag[p] = (p < n) && (p == 0 || keys[p] != keys[p - 1]);
@@ -1739,14 +1742,23 @@ int launch_voxel_bbox(const Dev& d, int n, cudaStream_t s) {
 // the segment number sits right above it, so the sort covers key_bits + log2(segments) bits
 int launch_voxel_filter(const Dev& d, int n, int key_bits, cudaStream_t s) {
   int k = 0;
+  int gbits = 1;
+  while ((1 << gbits) < d.G) ++gbits;
+  const bool narrow = key_bits + gbits <= 32;
+  uint32_t *k32 = reinterpret_cast<uint32_t*>(d.vkey), *k32b = reinterpret_cast<uint32_t*>(d.vkey2);
   if (n > 0) {
-    vox_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n, key_bits); ++k;
     size_t tb = d.cub_tmp_bytes;
-    int gbits = 1;
-    while ((1 << gbits) < d.G) ++gbits;
-    cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n, 0, key_bits + gbits, s);
+    if (narrow) {
+      vox_key_kernel<true><<<cdiv(n, 256), 256, 0, s>>>(d, n, key_bits); ++k;
+      cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, k32, k32b, d.vval, d.vval2, n, 0, key_bits + gbits, s);
+    } else {
+      vox_key_kernel<false><<<cdiv(n, 256), 256, 0, s>>>(d, n, key_bits); ++k;
+      cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n, 0, key_bits + gbits, s);
+    }
   }
-  head_flag_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(d.vkey2, d.flag, n); ++k;
+  if (narrow) head_flag_kernel<uint32_t><<<cdiv(n + 1, 256), 256, 0, s>>>(k32b, d.flag, n);
+  else head_flag_kernel<uint64_t><<<cdiv(n + 1, 256), 256, 0, s>>>(d.vkey2, d.flag, n);
+  ++k;
   size_t tb = d.cub_tmp_bytes;
   cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.flag, d.scan, n + 1, s);
   if (n > 0) {
@@ -1881,7 +1893,7 @@ int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_s
     // the sentinel is all ones inside the sorted bit range too, so it stays at the end
     cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.vkey, d.vkey2, d.vval, d.vval2, n_delta, 0, 14 + d.delta_pbits + gbits, s);
   }
-  head_flag_kernel<<<cdiv(n_delta + 1, 256), 256, 0, s>>>(d.vkey2, d.flag, n_delta); ++k;
+  head_flag_kernel<uint64_t><<<cdiv(n_delta + 1, 256), 256, 0, s>>>(d.vkey2, d.flag, n_delta); ++k;
   size_t tb = d.cub_tmp_bytes;
   cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.flag, d.scan, n_delta + 1, s);
   cudaMemsetAsync(d.ins_key, 0xFF, sizeof(uint64_t) * (size_t)(n_delta + 1), s);
