@@ -188,7 +188,7 @@ struct s2m_ctx {
   std::vector<int> ev_phase;      // phase id that ENDS at this event (-1: frame start)
   size_t ev_used = 0;
   double phase_ms[S2M_N_PHASES] = {0};
-  double k4_bytes = 0, k4_scanned = 0, k4_cand27 = 0;
+  double k4_bytes = 0, k4_cand27 = 0;
   long long k4_launches = 0;
   int sm_count = 148;
   // sharded-map mode
@@ -252,11 +252,13 @@ static int dev_alloc(s2m_ctx* ctx, T** p, size_t n) {
   return 0;
 }
 
-static int next_pow2(int v) {
-  int p = 1;
+static long long next_pow2(long long v) {
+  long long p = 1;
   while (p < v) p <<= 1;
   return p;
 }
+// slots of a segment's cell table: a power of two >= 4 x points (<= 3 entries per point: cells + virtual x-neighbours), >= 1024
+static long long table_size(long long n_points) { return next_pow2(std::max<long long>(1024, 4 * n_points)); }
 
 extern "C" void s2m_default_params(s2m_params* p) {
   std::memset(p, 0, sizeof(*p));
@@ -337,7 +339,6 @@ static int create_impl(s2m_ctx* ctx) {
     d.vox_bits = std::min(b, 11);
     d.delta_pbits = std::max(3 * d.vox_bits, 18);
   }
-  d.use_qperm = getenv("S2M_QUERY_ORDER") ? atoi(getenv("S2M_QUERY_ORDER")) : 0;
   d.shard_world = P.shard_world;
   s2m_shard_slab(P.shard_rank, P.shard_world, &d.shard_lo, &d.shard_hi);
   d.inv_leaf[0] = 1.0f / P.line_res;   // pcl::VoxelGrid::setLeafSize: inverse_leaf_size = 1 / leaf (float)
@@ -345,8 +346,13 @@ static int create_impl(s2m_ctx* ctx) {
   const long long cap_in = (long long)B * ((long long)P.cap_corner_in + P.cap_surf_in);
   const long long cap_lp = (long long)B * ((long long)P.cap_map_corner + P.cap_map_surf);
   if (cap_in + cap_lp >= (1ll << 30)) { ctx->err = "capacities too large (packed index space is 30 bits)"; return S2M_ERR_ARG; }
+  // the per-frame arrival number of a raw point is a field of delta_pbits bits in the map-update sort key
+  if (P.cap_corner_in >= (1 << d.delta_pbits) || P.cap_surf_in >= (1 << d.delta_pbits)) {
+    ctx->err = "cap_corner_in / cap_surf_in must be below 2^" + std::to_string(d.delta_pbits) + " for these leaf sizes";
+    return S2M_ERR_ARG;
+  }
   d.cap_in = (int)cap_in; d.cap_lp = (int)cap_lp; d.cap_sort = (int)(cap_in + cap_lp);
-  d.max_tiles = (P.cap_corner_in + P.cap_surf_in + kTile - 1) / kTile;
+  d.max_tiles = (P.cap_corner_in + P.cap_surf_in + 31) / 32 + 1;  // partial rows per slot: one per 32-query unit
 
   CK(cudaMallocHost((void**)&ctx->ht, sizeof(HostTables)));
   CK(cudaMallocHost((void**)&ctx->h_out, sizeof(SlotOut) * B));
@@ -376,11 +382,10 @@ static int create_impl(s2m_ctx* ctx) {
   const size_t ccap = (size_t)std::max(d.cap_lp, d.cap_in);
   rc |= dev_alloc(ctx, &d.ckey, ccap); rc |= dev_alloc(ctx, &d.ckey2, ccap);
   rc |= dev_alloc(ctx, &d.cval, ccap); rc |= dev_alloc(ctx, &d.cval2, ccap);
-  rc |= dev_alloc(ctx, &d.cand, d.cap_lp); rc |= dev_alloc(ctx, &d.qperm, d.cap_in); rc |= dev_alloc(ctx, &d.inv, d.cap_lp);
-  rc |= dev_alloc(ctx, &d.nbr, (size_t)d.cap_in * 6); rc |= dev_alloc(ctx, &d.scanned, 2 * B); rc |= dev_alloc(ctx, &d.knn_ticket, 1);
+  rc |= dev_alloc(ctx, &d.cand, d.cap_lp); rc |= dev_alloc(ctx, &d.knn_ticket, 1);
   // cell tables: per segment a power of two >= 2 x entries, >= 1024
   long long hcap = 0;
-  for (int g = 0; g < G; ++g) hcap += next_pow2(std::max(1024, 4 * (g < B ? P.cap_map_corner : P.cap_map_surf)));
+  for (int g = 0; g < G; ++g) hcap += table_size(g < B ? P.cap_map_corner : P.cap_map_surf);
   if (hcap >= (1ll << 31)) { ctx->err = "cell tables too large (4 entries per map point)"; return S2M_ERR_ARG; }
   ctx->hash_cap_total = (int)hcap;
   rc |= dev_alloc(ctx, &d.hash_tab, (size_t)hcap); rc |= dev_alloc(ctx, &d.hash_aux, (size_t)hcap);
@@ -388,7 +393,7 @@ static int create_impl(s2m_ctx* ctx) {
   rc |= dev_alloc(ctx, &d.rec, (size_t)d.cap_in * 6); rc |= dev_alloc(ctx, &d.rec_valid, d.cap_in);
   rc |= dev_alloc(ctx, &d.partials, (size_t)B * d.max_tiles * kPartial);
   rc |= dev_alloc(ctx, &d.lm, B); rc |= dev_alloc(ctx, &d.out, B); rc |= dev_alloc(ctx, &d.err_flag, 1);
-  rc |= dev_alloc(ctx, &d.ticket, B); rc |= dev_alloc(ctx, &d.cand27, 2 * B);
+  rc |= dev_alloc(ctx, &d.ticket, B);
   rc |= dev_alloc(ctx, &d.shard_sums, (size_t)B * kPartial); rc |= dev_alloc(ctx, &d.shard_counts, G);
   rc |= dev_alloc(ctx, &ctx->lm_trace, 2 * B);
   if (P.trace) {
@@ -399,6 +404,7 @@ static int create_impl(s2m_ctx* ctx) {
   rc |= dev_alloc(ctx, &d.ins_key, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.ins_ckey, d.cap_sort + 1);
   rc |= dev_alloc(ctx, &d.ins_pt, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.ins_cpt, d.cap_sort + 1);
   rc |= dev_alloc(ctx, &d.run_off, G + 1);
+  rc |= dev_alloc(ctx, &d.upd_pos, d.cap_sort + 1);
   rc |= dev_alloc(ctx, &d.aflag, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.ascan, d.cap_sort + 1);
   d.cub_tmp_bytes = cub_temp_bytes(d.cap_sort + 1, d.cap_lp + 1);
   rc |= dev_alloc(ctx, (char**)&d.cub_tmp, d.cub_tmp_bytes);
@@ -558,7 +564,7 @@ static void fill_store_tables(s2m_ctx* ctx, int* total_lp, int* hash_total) {
   for (int g = 0; g < G; ++g) {
     const int n = ctx->slots[g < B ? g : g - B].n_store[g >= B];
     T.lp_off[g] = T.so_off[g] = acc; acc += n;
-    T.hash_off[g] = hacc; hacc += next_pow2(std::max(1024, 4 * n));  // <= 3 entries per point: cells + virtual x-neighbours
+    T.hash_off[g] = hacc; hacc += (int)table_size(n);
   }
   T.lp_off[G] = T.so_off[G] = acc; T.hash_off[G] = hacc;
   *total_lp = acc; *hash_total = hacc;
@@ -589,6 +595,15 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   const int total_in = T.in_off[G];
   bool check_pending = false;
   int tiles = 0;
+  // A frame is atomic: the device map is double buffered and only swapped at the end, the host-side slot
+  // state (window centre, valid block, pending-check flag) is restored if anything below fails.
+  struct Rollback {
+    std::vector<SlotHost>& live;
+    std::vector<SlotHost> saved;
+    bool armed = true;
+    explicit Rollback(std::vector<SlotHost>& l) : live(l), saved(l) {}
+    ~Rollback() { if (armed) live = saved; }
+  } rollback(ctx->slots);
   for (int b = 0; b < B; ++b) {
     SlotHost& sh = ctx->slots[b];
     FrameDesc& fd = T.desc[b];
@@ -630,7 +645,7 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   for (int g = 0; g < G; ++g) {
     const int n = ctx->h_lpcnt[g];
     T.lp_off[g] = total_lp; total_lp += n;
-    T.hash_off[g] = hash_total; hash_total += next_pow2(std::max(1024, 4 * n));  // <= 3 entries per point: cells + virtual x-neighbours
+    T.hash_off[g] = hash_total; hash_total += (int)table_size(n);
   }
   T.lp_off[G] = total_lp; T.hash_off[G] = hash_total;
   CK(cudaMemcpyAsync(ctx->d_ht->lp_off, T.lp_off, sizeof(int) * (G + 1), cudaMemcpyHostToDevice, s));
@@ -669,35 +684,31 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   CK(cudaEventSynchronize(ctx->ev_ds));
   const int n_ds = ctx->h_dsoff[G];
   tiles = 0;
-  int chunks = 0;  // 32-query work units of knn_kernel over all slots
+  int chunks = 0;  // 32-query work units of assoc_kernel over all slots
   for (int b = 0; b < B; ++b) {
     const int nq = (ctx->h_dsoff[b + 1] - ctx->h_dsoff[b]) + (ctx->h_dsoff[B + b + 1] - ctx->h_dsoff[B + b]);
     tiles = std::max(tiles, (nq + kTile - 1) / kTile);
     chunks += (nq + 31) / 32;
   }
-  d.count_scanned = ctx->profiling ? 1 : 0;
-  if (d.use_qperm) k += launch_query_order(d, n_ds, s);
-  // one resident wave each: S2M_K4x_MINB blocks per SM shared by the B slots
-  const int knn_blocks = std::max(1, std::min((chunks + kTile / 32 - 1) / (kTile / 32), S2M_K4A_MINB * ctx->sm_count));
-  const int fit_blocks = std::max(1, (tiles + kFitTilesPerBlock - 1) / kFitTilesPerBlock);
-  const int blocks = std::max(1, std::min(tiles, (S2M_K4A_MINB * ctx->sm_count) / B));
+  // the fused association kernel: one resident wave of persistent blocks sharing a work ticket
+  const int assoc_blocks = std::max(1, std::min((chunks + kTile / 32 - 1) / (kTile / 32), S2M_K4_MINB * ctx->sm_count));
   const int eval_blocks = std::max(1, (tiles + kEvalTilesPerBlock - 1) / kEvalTilesPerBlock);
   for (int outer = 0; outer < 2; ++outer) {  // laserMapping.cpp:563
-    if (ctx->profiling && outer == 0) {  // C-bar of the byte formula, outside the K4 event bracket
-      launch_count_candidates(d, blocks, s);
-      prof_mark(ctx, S2M_PHASE_INDEX);
-    }
-    k += launch_associate(d, outer, knn_blocks, fit_blocks, ctx->P.trace != 0, s);
-    if (sharded) {  // one 32-double block per slot across the ranks, then the LM step on every rank
+    CK(cudaMemsetAsync(d.knn_ticket, 0, sizeof(int), s));  // the association's work ticket
+    prof_mark(ctx, S2M_PHASE_READBACK);  // host wait for the down-sampled counts (outer 0); the K4 bracket starts here
+    k += launch_associate(d, outer, assoc_blocks, ctx->P.trace != 0, s);
+    prof_mark(ctx, S2M_PHASE_ASSOCIATE);
+    if (!sharded) {
+      k += launch_solve(d, outer, true, s);  // Ceres solve, max_num_iterations = 4 (:713-721)
+    } else {
+      // one 32-double block per slot across the ranks per evaluation, then the LM step on every rank
+      k += launch_reduce_units(d, s);
       int rs = shard_allreduce(ctx, d.shard_sums, (size_t)B * kPartial, nccl::kFloat64);
       if (rs != S2M_OK) return rs;
       k += launch_lm_shard(d, outer, 0, s);
-    }
-    prof_mark(ctx, S2M_PHASE_ASSOCIATE);
-    for (int it = 0; it < 4; ++it) {  // options.max_num_iterations = 4 (:716)
-      k += launch_evaluate(d, outer, eval_blocks, s);
-      if (sharded) {
-        int rs = shard_allreduce(ctx, d.shard_sums, (size_t)B * kPartial, nccl::kFloat64);
+      for (int it = 0; it < 4; ++it) {  // options.max_num_iterations = 4 (:716)
+        k += launch_evaluate(d, outer, eval_blocks, s);
+        rs = shard_allreduce(ctx, d.shard_sums, (size_t)B * kPartial, nccl::kFloat64);
         if (rs != S2M_OK) return rs;
         k += launch_lm_shard(d, outer, 1, s);
       }
@@ -713,6 +724,7 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   int rc = finish_call(ctx);
   prof_mark(ctx, S2M_PHASE_READBACK);
   if (rc != S2M_OK) return rc;
+  rollback.armed = false;
   // swap store buffers
   ctx->cur ^= 1;
   std::swap(d.st_n, d.st_n_new);
@@ -743,26 +755,20 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
     }
   }
   // algorithmic bytes of the two association launches of this frame:
-  // (Nc+Ns)(16 + 27*8) + 16 * candidates visited + 48 * accepted correspondences
+  // (Nc+Ns)(16 + 27*8) + 16 * map points in the 27 cells of the queries + 48 * accepted correspondences
   if (ctx->profiling) {
-    std::vector<unsigned long long> c27(2 * B);
-    CK(cudaMemcpy(c27.data(), d.cand27, sizeof(unsigned long long) * 2 * B, cudaMemcpyDeviceToHost));
     for (int outer = 0; outer < 2; ++outer) {
       double bytes = 0;
       for (int b = 0; b < B; ++b) {
         const SlotOut& o = ctx->h_out[b];
         if (!T.desc[b].active || !o.optimized) continue;
-        bytes += (double)(o.n_ds[0] + o.n_ds[1]) * (16.0 + 27.0 * 8.0) + 16.0 * (double)(c27[2 * b] + c27[2 * b + 1]) +
+        bytes += (double)(o.n_ds[0] + o.n_ds[1]) * (16.0 + 27.0 * 8.0) + 16.0 * (o.cand[0] + o.cand[1]) +
                  48.0 * (o.n_edge[outer] + o.n_plane[outer]);
       }
       ctx->k4_bytes += bytes;
-      ctx->k4_scanned += 0;
     }
     for (int b = 0; b < B; ++b)
-      if (T.desc[b].active && ctx->h_out[b].optimized) {
-        ctx->k4_scanned += ctx->h_out[b].cand[0] + ctx->h_out[b].cand[1];
-        ctx->k4_cand27 += (double)(c27[2 * b] + c27[2 * b + 1]);
-      }
+      if (T.desc[b].active && ctx->h_out[b].optimized) ctx->k4_cand27 += ctx->h_out[b].cand[0] + ctx->h_out[b].cand[1];
   }
   return S2M_OK;
 }
@@ -914,9 +920,8 @@ extern "C" int s2m_register_batch_dev(s2m_ctx* ctx, const float* corner, const i
 extern "C" int s2m_register(s2m_ctx* ctx, const float* corner, int nc, const float* surf, int ns,
                             const double q_wodom[4], const double t_wodom[3], double q_out[4], double t_out[3],
                             s2m_stats* stats) {
-  if (ctx && !ctx->children.empty()) return s2m_register(ctx->children[0], corner, nc, surf, ns, q_wodom, t_wodom, q_out, t_out, stats);
   if (!ctx || nc < 0 || ns < 0) return S2M_ERR_ARG;
-  const int B = ctx->d.B;
+  const int B = ctx->P.batch;  // (a multi-lane context goes through the batch call like any other: lane worker, in-flight check)
   std::vector<int> co(B + 1, nc), so(B + 1, ns), act(B, 0);
   co[0] = so[0] = 0;
   act[0] = 1;
@@ -965,7 +970,7 @@ extern "C" int s2m_transform_cloud(s2m_ctx* ctx, int slot, const float* in, int 
 extern "C" int s2m_map_upload(s2m_ctx* ctx, int slot, const float* corner, int nc, const float* surf, int ns) {
   ROUTE_SLOT(s2m_map_upload(ch, slot, corner, nc, surf, ns));
   if (!ctx || slot < 0 || slot >= ctx->d.B || nc < 0 || ns < 0) return S2M_ERR_ARG;
-  if (nc > ctx->P.cap_map_corner || ns > ctx->P.cap_map_surf || nc + ns > ctx->d.cap_in) return S2M_ERR_CAPACITY;
+  if (nc > ctx->P.cap_map_corner || ns > ctx->P.cap_map_surf) return S2M_ERR_CAPACITY;
   CK(cudaSetDevice(ctx->P.device));
   Dev& d = ctx->d;
   const int B = d.B, G = d.G;
@@ -978,38 +983,49 @@ extern "C" int s2m_map_upload(s2m_ctx* ctx, int slot, const float* corner, int n
   CK(cudaMemcpyAsync(d.st_n + B + slot, &zero, 4, cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));
   sh.n_store[0] = sh.n_store[1] = 0;
-  std::vector<int> dsoff(G + 1, 0);
-  for (int g = 0; g <= G; ++g) dsoff[g] = (g > slot ? nc : 0) + (g > B + slot ? ns : 0);
-  for (int b = 0; b < B; ++b) {
-    FrameDesc& fd = T.desc[b];
-    fd.active = (b == slot);
-    fd.allow_opt = 0;
-    if (b != slot) continue;
-    const int W[3] = {kWinI, kWinJ, kWinK};
-    for (int a = 0; a < 3; ++a) {
-      fd.win_lo[a] = -sh.cen[a]; fd.win_hi[a] = W[a] - 1 - sh.cen[a];
-      fd.val_lo[a] = 1; fd.val_hi[a] = 0;  // nothing is valid: every point stays raw
-      fd.origin[a] = 0;
+  sh.seq[0] = sh.seq[1] = 0;
+  // The map goes through the frame staging buffers (sized by cap_*_in, far smaller than the map), so it is
+  // pushed in chunks; the arrival numbers continue from chunk to chunk, which keeps the upload order.
+  const int step_c = ctx->P.cap_corner_in, step_s = ctx->P.cap_surf_in;
+  int kept = 0;
+  for (int c0 = 0, s0 = 0; c0 < nc || s0 < ns || (nc + ns == 0 && c0 == 0 && s0 == 0);) {
+    const int cn = std::min(step_c, nc - c0), sn = std::min(step_s, ns - s0);
+    std::vector<int> dsoff(G + 1, 0);
+    for (int g = 0; g <= G; ++g) dsoff[g] = (g > slot ? cn : 0) + (g > B + slot ? sn : 0);
+    for (int b = 0; b < B; ++b) {
+      FrameDesc& fd = T.desc[b];
+      fd.active = (b == slot);
+      fd.allow_opt = 0;
+      if (b != slot) continue;
+      const int W[3] = {kWinI, kWinJ, kWinK};
+      for (int a = 0; a < 3; ++a) {
+        fd.win_lo[a] = -sh.cen[a]; fd.win_hi[a] = W[a] - 1 - sh.cen[a];
+        fd.val_lo[a] = 1; fd.val_hi[a] = 0;  // nothing is valid: every point stays raw
+        fd.origin[a] = 0;
+      }
+      fd.seq_base[0] = sh.seq[0]; fd.seq_base[1] = sh.seq[1];
     }
-    fd.seq_base[0] = fd.seq_base[1] = 0;
+    int total_lp, hash_total;
+    fill_store_tables(ctx, &total_lp, &hash_total);
+    CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d.ds_off, dsoff.data(), sizeof(int) * (G + 1), cudaMemcpyHostToDevice, s));
+    if (cn) CK(cudaMemcpyAsync(d.ds_pts, corner + 4 * (size_t)c0, sizeof(float4) * (size_t)cn, cudaMemcpyHostToDevice, s));
+    if (sn) CK(cudaMemcpyAsync(d.ds_pts + cn, surf + 4 * (size_t)s0, sizeof(float4) * (size_t)sn, cudaMemcpyHostToDevice, s));
+    ctx->launches += launch_map_update(d, ctx->cur, cn + sn, total_lp, total_lp, false, true, s);
+    int rc = finish_call(ctx);
+    if (rc != S2M_OK) return rc;
+    ctx->cur ^= 1;
+    std::swap(d.st_n, d.st_n_new);
+    const SlotOut& o = ctx->h_out[slot];
+    sh.n_store[0] = o.n_store[0]; sh.n_store[1] = o.n_store[1];
+    sh.seq[0] += (unsigned long long)cn; sh.seq[1] += (unsigned long long)sn;
+    c0 += cn; s0 += sn;
+    kept = o.n_store[0] + o.n_store[1];
+    if (nc + ns == 0) break;
   }
-  int total_lp, hash_total;
-  fill_store_tables(ctx, &total_lp, &hash_total);
-  CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(d.ds_off, dsoff.data(), sizeof(int) * (G + 1), cudaMemcpyHostToDevice, s));
-  if (nc) CK(cudaMemcpyAsync(d.ds_pts, corner, sizeof(float4) * (size_t)nc, cudaMemcpyHostToDevice, s));
-  if (ns) CK(cudaMemcpyAsync(d.ds_pts + nc, surf, sizeof(float4) * (size_t)ns, cudaMemcpyHostToDevice, s));
-  ctx->launches += launch_map_update(d, ctx->cur, nc + ns, total_lp, total_lp, false, true, s);
-  int rc = finish_call(ctx);
-  if (rc != S2M_OK) return rc;
-  ctx->cur ^= 1;
-  std::swap(d.st_n, d.st_n_new);
-  const SlotOut& o = ctx->h_out[slot];
-  sh.n_store[0] = o.n_store[0]; sh.n_store[1] = o.n_store[1];
-  sh.seq[0] = (unsigned long long)nc; sh.seq[1] = (unsigned long long)ns;
   sh.force_pending_check = true;
   sh.val_lo[0] = 1; sh.val_hi[0] = 0;
-  return (nc + ns) - (o.n_store[0] + o.n_store[1]);
+  return (nc + ns) - kept;
 }
 
 static bool host_entry_dead(const SlotHost& sh, uint64_t key) {
@@ -1146,6 +1162,9 @@ extern "C" int s2m_checkpoint_load(s2m_ctx* ctx, int slot, const char* prefix) {
     pts[cls].resize(4 * (size_t)std::max(n[cls], 1));
     if (s2m_pcd_read(path.c_str(), pts[cls].data(), n[cls]) != n[cls]) { ctx->err = "cannot read the checkpoint PCD"; return S2M_ERR_IO; }
   }
+  // everything that can be checked is checked before the slot is touched
+  if (slot < 0 || slot >= ctx->P.batch) return S2M_ERR_ARG;
+  if (n[0] > ctx->P.cap_map_corner || n[1] > ctx->P.cap_map_surf) { ctx->err = "checkpoint larger than cap_map_*"; return S2M_ERR_CAPACITY; }
   int rc = restore_state(ctx, slot, cen, q, t);
   if (rc != S2M_OK) return rc;
   return s2m_map_upload(ctx, slot, pts[0].data(), n[0], pts[1].data(), n[1]);
@@ -1156,7 +1175,8 @@ static int prepare_local(s2m_ctx* ctx, int slot, const double centre_t[3], int* 
   HostTables& T = *ctx->ht;
   for (int b = 0; b < ctx->d.B; ++b) T.desc[b].active = (b == slot);
   FrameDesc& fd = T.desc[slot];
-  rows_BC(ctx->slots[slot], centre_t, fd);
+  SlotHost probe = ctx->slots[slot];  // a getter must not move the live window
+  rows_BC(probe, centre_t, fd);
   fill_store_tables(ctx, total_lp, hash_total);
   CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, ctx->stream));
   return S2M_OK;

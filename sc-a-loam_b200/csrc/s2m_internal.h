@@ -27,22 +27,15 @@
 
 namespace s2m {
 
-#ifndef S2M_K4A_PREFETCH
-#define S2M_K4A_PREFETCH 0  // 0 off, 1 prefetch.global.L2, 2 prefetch.global.L1 of each row's candidates at probe time
-#endif
 #ifndef S2M_OD_FB
 #define S2M_OD_FB 32  // blocks per SM of odom_fallback_kernel (one warp per listed query, latency-bound)
 #endif
 #ifndef S2M_OD_MINB
 #define S2M_OD_MINB 6  // resident blocks per SM of odom_associate_kernel: latency-bound walks, more warps win (3.9 -> 3.0 ms)
 #endif
-#ifndef S2M_K4A_MINB
-#define S2M_K4A_MINB 8  // resident blocks per SM the kNN kernel is compiled for
+#ifndef S2M_K4_MINB
+#define S2M_K4_MINB 4  // resident blocks per SM the fused association kernel is compiled for (128 registers)
 #endif
-#ifndef S2M_K4B_MINB
-#define S2M_K4B_MINB 4  // ... and the fit / residual kernel
-#endif
-constexpr int kFitTilesPerBlock = 2;   // tiles one fit_kernel block sums (fixed: keeps sums independent of the batch)
 constexpr int kEvalTilesPerBlock = 8;  // ... one evaluate_kernel block
 constexpr int kTile = 128;       // queries per block of the association / evaluation kernels
 constexpr int kPartial = 32;     // doubles per block partial: 28 sums, n_edge, n_plane, cand_corner, cand_surf
@@ -104,7 +97,6 @@ struct Dev {
   int B, G;                     // slots, segments
   int vox_bits;                 // bits of a voxel coordinate inside a cube (delta sort key)
   int delta_pbits;              // payload bits of the delta sort key
-  int use_qperm;                // walk the queries in map-cell order (d.qperm) instead of scan order
   int shard_world;              // >1: spatially sharded map (x-slabs per rank)
   float shard_lo, shard_hi;     // this rank's slab in world x, [lo, hi)
   double* shard_sums;           // [B][kPartial] per-rank sums awaiting the allreduce
@@ -137,11 +129,7 @@ struct Dev {
   int* lp_cnt;                  // [G] points of the local map (read back: sizes the index exactly)
   uint32_t *ckey, *ckey2, *cval, *cval2;  // [cap_lp]
   float4* cand;                 // [cap_lp] cell-sorted local points, w = local index bits
-  int* inv;                     // [cap_lp] local index -> position in cand (packed by lp_off)
-  uint32_t* qperm;              // [cap_in] query order of the association kernel (packed ds indices)
-  int* nbr;                     // [cap_in][6] K4a -> K4b: ds index (or -1 when gated out) + 5 neighbour positions
-  unsigned long long* scanned;  // [B][2] candidate points actually scanned (statistics, profiling only)
-  int* knn_ticket;              // next 32-query work unit of knn_kernel (re-armed by fit_kernel)
+  int* knn_ticket;              // next 32-query work unit of assoc_kernel
   float4* od_last;              // odometry: less-sharp / less-flat clouds of the previous sweep, class-major
   int* od_last_off;             // [2B+1]
   float4* od_sorted;            // the same clouds ordered by 1 m cell inside each segment, .w = index | ring << 24
@@ -155,17 +143,15 @@ struct Dev {
   uint32_t *od_val, *od_val2;
   float4* od_meta;              // [chunks][2] box + ring range of every 32-point chunk of od_last
   int* od_chunk_off;            // [2B+1]
-  int count_scanned;            // profiling: maintain `scanned`
   unsigned long long* hash_tab; // cell tables
   uint2* hash_aux;              // per table slot: (points of the cell itself, exact 3-cell count)
   int* cs_off;                  // [G+1] first sorted position of each segment
   // ---- association / solve
   double* rec;                  // [cap_in][6] cached correspondences
   uint8_t* rec_valid;           // [cap_in]
-  double* partials;             // [B][max_tiles][kPartial], one row per working block
-  int max_tiles;
+  double* partials;             // [B][max_tiles][kPartial]: one row per 32-query unit (association) / working block (evaluation)
+  int max_tiles;                // rows per slot
   int* ticket;                  // [B] last-block election counters
-  unsigned long long* cand27;   // [B][2] profiling: map points in the 27 cells of all queries
   LmState* lm;                  // [B]
   SlotOut* out;                 // [B]
   int* err_flag;                // device error code (0 ok)
@@ -177,6 +163,7 @@ struct Dev {
   float4* dl_pt;                // [cap_in] transformed scan points (world, float)
   uint64_t *ins_key, *ins_ckey; // [cap_sort]
   float4 *ins_pt, *ins_cpt;     // [cap_sort]
+  int* upd_pos;                 // [cap_sort] per delta run: merge-space index of the store entry it re-centroids, -1 none
   int* run_off;                 // [G+1]
   uint32_t *aflag, *ascan;      // [cap_lp + 1]
   // ---- cub temp
@@ -192,10 +179,10 @@ int launch_voxel_filter(const Dev& d, int total_in, int key_bits, cudaStream_t s
 int launch_local_ranges(const Dev& d, int cur, cudaStream_t s);
 int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, bool ranges_done, cudaStream_t s);
 int launch_guard(const Dev& d, cudaStream_t s);
-int launch_query_order(const Dev& d, int n_ds, cudaStream_t s);
-int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s);
+int launch_associate(const Dev& d, int outer, int blocks, bool trace, cudaStream_t s);
+int launch_solve(const Dev& d, int outer, bool from_units, cudaStream_t s);
+int launch_reduce_units(const Dev& d, cudaStream_t s);
 int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s);
-int launch_count_candidates(const Dev& d, int blocks_per_slot, cudaStream_t s);
 int launch_lm_shard(const Dev& d, int outer, int after, cudaStream_t s);
 int launch_odom_sort(const Dev& d, int n, void* tmp, size_t tmp_bytes, cudaStream_t s);
 size_t odom_sort_temp_bytes(const Dev& d, int n);

@@ -172,67 +172,114 @@ S2M_HD bool edge_fit(const float nb[5][3], double c[3], double u[3]) {
 // Plane fit (laserMapping.cpp:651-687): least squares A n = -1 by column-pivoted
 // Householder QR in FP64, n normalised, valid iff all five |n.p + d| <= 0.2.
 S2M_HD bool plane_fit(const float nb[5][3], double n[3], double& d) {
-  double A[5][3], b[5] = {-1, -1, -1, -1, -1};
-  for (int j = 0; j < 5; ++j) for (int k = 0; k < 3; ++k) A[j][k] = (double)nb[j][k];
+  // Columns are kept as three separate arrays and every index below is a compile-time constant
+  // (the pivot choice moves data with selects), so on the device the whole factorisation lives in
+  // registers: no local-memory array.
+  double C[3][5], b[5] = {-1, -1, -1, -1, -1};
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) C[k][j] = (double)nb[j][k];
+  }
   int perm[3] = {0, 1, 2};
   double cn[3];
-  for (int k = 0; k < 3; ++k) { double s = 0; for (int r = 0; r < 5; ++r) s += A[r][k] * A[r][k]; cn[k] = s; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double s = 0;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) s += C[k][r] * C[k][r];
+    cn[k] = s;
+  }
   const double cmax = fmax(cn[0], fmax(cn[1], cn[2]));
-  const double tiny = cmax * (DBL_EPSILON * DBL_EPSILON) ;  // rank threshold on squared norms
+  const double tiny = cmax * (DBL_EPSILON * DBL_EPSILON);  // rank threshold on squared norms
   int rank = 3;
+  double diag[3];
+#pragma unroll
   for (int k = 0; k < 3; ++k) {
     int big = k;
-    for (int j = k + 1; j < 3; ++j) if (cn[j] > cn[big]) big = j;
-    if (rank == 3 && cn[big] < tiny * (double)(5 - k) / 5.0) rank = k;
-    if (big != k) {
-      for (int r = 0; r < 5; ++r) { double t = A[r][k]; A[r][k] = A[r][big]; A[r][big] = t; }
-      double t = cn[k]; cn[k] = cn[big]; cn[big] = t;
-      int ti = perm[k]; perm[k] = perm[big]; perm[big] = ti;
+#pragma unroll
+    double cbig = cn[k];
+#pragma unroll
+    for (int j = k + 1; j < 3; ++j) if (cn[j] > cbig) { big = j; cbig = cn[j]; }
+    if (rank == 3 && cbig < tiny * (double)(5 - k) / 5.0) rank = k;
+#pragma unroll
+    for (int j = k + 1; j < 3; ++j) {
+      if (big == j) {  // swap columns k and j
+#pragma unroll
+        for (int r = 0; r < 5; ++r) { const double t = C[k][r]; C[k][r] = C[j][r]; C[j][r] = t; }
+        const double t = cn[k]; cn[k] = cn[j]; cn[j] = t;
+        const int ti = perm[k]; perm[k] = perm[j]; perm[j] = ti;
+      }
     }
     double tail2 = 0;
-    for (int r = k + 1; r < 5; ++r) tail2 += A[r][k] * A[r][k];
-    double c0 = A[k][k], tau, beta;
-    if (tail2 <= DBL_MIN) { tau = 0; beta = c0; for (int r = k + 1; r < 5; ++r) A[r][k] = 0; }
-    else {
+#pragma unroll
+    for (int r = k + 1; r < 5; ++r) tail2 += C[k][r] * C[k][r];
+    const double c0 = C[k][k];
+    double tau, beta;
+    if (tail2 <= DBL_MIN) {
+      tau = 0; beta = c0;
+#pragma unroll
+      for (int r = k + 1; r < 5; ++r) C[k][r] = 0;
+    } else {
       beta = sqrt(c0 * c0 + tail2);
       if (c0 >= 0) beta = -beta;
-      double inv = 1.0 / (c0 - beta);
-      for (int r = k + 1; r < 5; ++r) A[r][k] *= inv;
+      const double inv = 1.0 / (c0 - beta);
+#pragma unroll
+      for (int r = k + 1; r < 5; ++r) C[k][r] *= inv;
       tau = (beta - c0) / beta;
     }
-    A[k][k] = beta;
+    diag[k] = beta;
+#pragma unroll
     for (int j = k + 1; j < 3; ++j) {
-      double tmp = A[k][j];
-      for (int r = k + 1; r < 5; ++r) tmp += A[r][k] * A[r][j];
+      double tmp = C[j][k];
+#pragma unroll
+      for (int r = k + 1; r < 5; ++r) tmp += C[k][r] * C[j][r];
       tmp *= tau;
-      A[k][j] -= tmp;
-      for (int r = k + 1; r < 5; ++r) A[r][j] -= A[r][k] * tmp;
+      C[j][k] -= tmp;
+#pragma unroll
+      for (int r = k + 1; r < 5; ++r) C[j][r] -= C[k][r] * tmp;
     }
     {
       double tmp = b[k];
-      for (int r = k + 1; r < 5; ++r) tmp += A[r][k] * b[r];
+#pragma unroll
+      for (int r = k + 1; r < 5; ++r) tmp += C[k][r] * b[r];
       tmp *= tau;
       b[k] -= tmp;
-      for (int r = k + 1; r < 5; ++r) b[r] -= A[r][k] * tmp;
+#pragma unroll
+      for (int r = k + 1; r < 5; ++r) b[r] -= C[k][r] * tmp;
     }
+#pragma unroll
     for (int j = k + 1; j < 3; ++j) {  // exact recomputation of the trailing column norms
       double s = 0;
-      for (int r = k + 1; r < 5; ++r) s += A[r][j] * A[r][j];
+#pragma unroll
+      for (int r = k + 1; r < 5; ++r) s += C[j][r] * C[j][r];
       cn[j] = s;
     }
   }
+  // back substitution on R (upper triangle: R[i][j] = C[j][i], diagonal in diag), unknowns beyond the rank are 0
   double y[3] = {0, 0, 0};
-  for (int i = rank - 1; i >= 0; --i) {
-    double s = b[i];
-    for (int j = i + 1; j < rank; ++j) s -= A[i][j] * y[j];
-    y[i] = s / A[i][i];
+#pragma unroll
+  for (int i = 2; i >= 0; --i) {
+    if (i < rank) {
+      double s = b[i];
+#pragma unroll
+      for (int j = i + 1; j < 3; ++j) if (j < rank) s -= C[j][i] * y[j];
+      y[i] = s / diag[i];
+    }
   }
   double x[3] = {0, 0, 0};
-  for (int i = 0; i < rank; ++i) x[perm[i]] = y[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < rank) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) if (perm[i] == a) x[a] = y[i];
+    }
+  }
   double nn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
   d = 1.0 / nn;
   n[0] = x[0] / nn; n[1] = x[1] / nn; n[2] = x[2] / nn;
   bool ok = true;
+#pragma unroll
   for (int j = 0; j < 5; ++j)
     if (!(fabs(n[0] * (double)nb[j][0] + n[1] * (double)nb[j][1] + n[2] * (double)nb[j][2] + d) <= 0.2)) ok = false;
   return ok;

@@ -99,3 +99,22 @@ def test_plain_c_consumer_of_the_header(s2m, built, tmp_path):
     out = subprocess.run([exe, str(tmp_path / "t.pcd")], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "s2m_params 52 bytes, s2m_stats 96 bytes" in out.stdout
+
+
+def test_ros_node_source_compiles(s2m, built, tmp_path):
+    """integration/alaserMapping_s2m.cpp (the drop-in for laserMapping.cpp:908-953) is
+    type-checked against stand-ins for the ROS1 / PCL headers it includes (tests/c/ros_stubs: only the
+    signatures it uses) with -Wall -Wextra -Werror, and linked against libs2m.so: every s2m_* call in the
+    node matches include/s2m.h and resolves in the library."""
+    import subprocess
+    src = os.path.join(ROOT, "integration", "alaserMapping_s2m.cpp")
+    inc = ["-I", os.path.join(ROOT, "tests", "c", "ros_stubs"), "-I", os.path.join(ROOT, "include")]
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only"] + inc + [src])
+    libdir = os.path.dirname(s2m.LIB_PATH)
+    exe = str(tmp_path / "alaserMapping_s2m")
+    subprocess.check_call(["g++", "-std=c++17"] + inc + [src, "-o", exe, "-L", libdir, "-ls2m", "-lpthread",
+                                                        "-Wl,-rpath," + libdir])
+    nm = subprocess.run(["nm", "-u", exe], capture_output=True, text=True).stdout
+    used = sorted(set(re.findall(r"\b(s2m_[a-z0-9_]+)", nm)))
+    assert {"s2m_create", "s2m_register", "s2m_transform_cloud", "s2m_get_correction", "s2m_get_surround",
+            "s2m_map_download", "s2m_destroy"} <= set(used)

@@ -1,0 +1,122 @@
+"""Error paths and state handling of the C ABI around the hot path (round-1 advisor findings):
+frames are atomic, a checkpoint larger than the frame staging buffers loads, getters do not move
+the window, capacities are validated at create."""
+import numpy as np
+import pytest
+
+import harness
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def seq(built):
+    return harness.sequence(20261018, "HDL64", 10)
+
+
+def test_checkpoint_larger_than_the_frame_buffers_resumes_bit_exact(s2m, seq, tmp_path):
+    """cap_*_in (the per-frame staging) is far smaller than the map: s2m_map_upload / s2m_checkpoint_load push the
+    map in chunks.  Resume == uninterrupted run, map and poses bit for bit."""
+    truth, odom, frames = seq
+    max_c = max(len(c) for c, _ in frames) + 8
+    max_s = max(len(s) for _, s in frames) + 8
+    kw = dict(cap_corner_in=max_c, cap_surf_in=max_s, cap_map_corner=1 << 17, cap_map_surf=1 << 18)
+    A = s2m.Registrar(0.4, 0.8, **kw)
+    for f in range(6):
+        A.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+    n_map = len(A.map_download(0)) + len(A.map_download(1))
+    assert len(A.map_download(1)) > max_s and n_map > max_c + max_s  # the case round 1 could save but not load
+    prefix = str(tmp_path / "big")
+    A.checkpoint_save(prefix)
+    Bc = s2m.Registrar(0.4, 0.8, **kw)
+    assert Bc.checkpoint_load(prefix) == 0
+    for cls in (0, 1):
+        assert np.array_equal(bits(A.map_download(cls)), bits(Bc.map_download(cls)))
+    for f in range(6, 9):
+        ra, qa, ta = A.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+        rb, qb, tb = Bc.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+        assert ra == rb and np.array_equal(qa, qb) and np.array_equal(ta, tb), f
+    for cls in (0, 1):
+        assert np.array_equal(bits(A.map_download(cls)), bits(Bc.map_download(cls)))
+    # a checkpoint that cannot fit is refused BEFORE the slot is touched
+    small = s2m.Registrar(0.4, 0.8, cap_map_corner=64, cap_map_surf=64)
+    small.register(frames[0][0][:40], frames[0][1][:40], odom[0, :4], odom[0, 4:])
+    w0, c0 = small.window().copy(), [x.copy() for x in small.correction()]
+    with pytest.raises(s2m.S2MError):
+        small.checkpoint_load(prefix)
+    assert np.array_equal(small.window(), w0) and all(np.array_equal(a, b) for a, b in zip(small.correction(), c0))
+    assert len(small.map_download(1)) > 0
+
+
+def test_a_failed_frame_leaves_the_map_and_the_window_untouched(s2m, seq):
+    """A frame that overflows cap_map_* returns S2M_ERR_CAPACITY and changes nothing: map, window, valid block
+    and correction equal those of a context that never saw it, and so does everything registered afterwards."""
+    truth, odom, frames = seq
+    big = s2m.Registrar(0.4, 0.8, cap_map_corner=1 << 17, cap_map_surf=1 << 18)
+    for f in range(3):
+        big.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+    n_s = len(big.map_download(1))
+    tight = s2m.Registrar(0.4, 0.8, cap_map_corner=1 << 17, cap_map_surf=n_s + 200)
+    for f in range(3):
+        tight.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+    for cls in (0, 1):
+        assert np.array_equal(bits(big.map_download(cls)), bits(tight.map_download(cls)))
+    # frame 3, shifted 120 m so that it would also move the valid block, brings thousands of new surf voxels
+    far = odom[3, 4:] + np.array([120.0, 0.0, 0.0])
+    with pytest.raises(s2m.S2MError):
+        tight.register(frames[3][0], frames[3][1], odom[3, :4], far)
+    assert np.array_equal(tight.window(), big.window())
+    for cls in (0, 1):
+        assert np.array_equal(bits(big.map_download(cls)), bits(tight.map_download(cls)))
+    for a, b in zip(tight.correction(), big.correction()):
+        assert np.array_equal(a, b)
+    # both continue with a frame that fits: identical results
+    few = frames[3][1][:150]
+    ra, qa, ta = big.register(frames[3][0], few, odom[3, :4], odom[3, 4:])
+    rb, qb, tb = tight.register(frames[3][0], few, odom[3, :4], odom[3, 4:])
+    assert ra == rb and np.array_equal(qa, qb) and np.array_equal(ta, tb)
+    for cls in (0, 1):
+        assert np.array_equal(bits(big.map_download(cls)), bits(tight.map_download(cls)))
+
+
+def test_getters_do_not_move_the_window(s2m, seq):
+    """s2m_get_local_map / s2m_debug_knn around a far-away centre must not shift the live window."""
+    truth, odom, frames = seq
+    A = s2m.Registrar(0.4, 0.8)
+    Bc = s2m.Registrar(0.4, 0.8)
+    for f in range(3):
+        A.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+        Bc.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+    far = odom[2, 4:] + np.array([420.0, -380.0, 0.0])
+    A.local_map(1, far)
+    A.debug_knn(0, far, np.zeros((4, 3), np.float32))
+    assert np.array_equal(A.window(), Bc.window())
+    for f in range(3, 6):
+        ra, qa, ta = A.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+        rb, qb, tb = Bc.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+        assert ra == rb and np.array_equal(qa, qb) and np.array_equal(ta, tb)
+    for cls in (0, 1):
+        assert np.array_equal(bits(A.map_download(cls)), bits(Bc.map_download(cls)))
+
+
+def test_register_on_a_multi_lane_context_goes_through_the_lane_worker(s2m, seq):
+    truth, odom, frames = seq
+    A = s2m.Registrar(0.4, 0.8)
+    M = s2m.Registrar(0.4, 0.8, batch=2, lanes=2)
+    for f in range(4):
+        ra, qa, ta = A.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+        rm, qm, tm = M.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+        assert ra == rm and np.array_equal(qa, qm) and np.array_equal(ta, tm)
+
+
+def test_capacities_are_validated_at_create(s2m, built):
+    # leaf 4 m: 13 voxels per cube axis -> the arrival field of the update key is 18 bits
+    with pytest.raises(s2m.S2MError):
+        s2m.Registrar(4.0, 4.0, cap_corner_in=1 << 18, cap_surf_in=1024, cap_map_corner=1024, cap_map_surf=1024)
+    R = s2m.Registrar(4.0, 4.0, cap_corner_in=(1 << 18) - 1, cap_surf_in=1024, cap_map_corner=1024, cap_map_surf=1024)
+    R.close()
