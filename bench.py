@@ -358,6 +358,13 @@ def run_ours(args, rank, world, local_rank):
     phases = lane.R.phase_profile(reset=True)
     lane.close()
 
+    # arm 4: BASELINE config 5 -- the spatially sharded giant map (every rank takes part: NCCL allreduce inside)
+    sharded = None
+    if not args.no_sharded:
+        from bench_sharded import run_sharded
+        sharded = run_sharded(pkg, torch, dist, rank, world, local_rank, slots=args.sharded_slots,
+                              fill_corner=args.sharded_fill_corner, fill_surf=args.sharded_fill_surf)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -394,6 +401,8 @@ def run_ours(args, rank, world, local_rank):
                      "traffic_source": traffic.get("source") if traffic else None},
         "clocks": sampler.result(),
     }
+    if sharded is not None:
+        line["sharded"] = sharded
     if world == 1 and not args.no_cpu_baseline:
         odo = slot_odometry(worlds, N_WORLDS, 0)
         line["cpu_baseline"] = cpu_baseline(worlds, odo, n_frames)
@@ -415,6 +424,10 @@ def main():
     ap.add_argument("--cap-map-corner", type=int, default=1 << 17)
     ap.add_argument("--cap-map-surf", type=int, default=1 << 17)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded giant-map arm (BASELINE config 5)")
+    ap.add_argument("--sharded-slots", type=int, default=16)
+    ap.add_argument("--sharded-fill-corner", type=int, default=3_000_000)
+    ap.add_argument("--sharded-fill-surf", type=int, default=1_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

@@ -43,6 +43,7 @@ def lib():
         L.synth_odometry.argtypes = [u64, ci, vp, cd, cd, vp]
         L.synth_scan.argtypes = [u64, ci, vp, ci, cd, vp, ci]
         L.synth_features.argtypes = [ci, cd, vp, ci, vp, ci, vp, vp, ci, vp, vp, ci, vp]
+        L.synth_surfaces.argtypes = [u64, cd, cd, cd, cd, vp, ci, vp, vp, ci, vp]
         _lib = L
     return _lib
 
@@ -98,3 +99,27 @@ def sequence(seed, sensor, n_frames, step_m=1.0, sigma_t=0.02, sigma_r_deg=0.1, 
         xyz = scan(seed, sensor, truth[f], f, range_sigma)
         frames.append(features(sensor, xyz))
     return truth, odom, frames
+
+
+def surfaces(seed, half=525.0, surf_step=0.8, corner_step=0.4, sigma=0.02, cap=1 << 23):
+    """Every world surface inside |x|,|y| <= half sampled directly (a saturated window
+    without driving it) -> (corner xyzi, surf xyzi), world frame."""
+    corner = np.zeros((cap, 4), np.float32)
+    surf = np.zeros((cap, 4), np.float32)
+    nc, ns = ctypes.c_int(), ctypes.c_int()
+    rc = lib().synth_surfaces(seed, half, surf_step, corner_step, sigma, corner.ctypes.data, cap, ctypes.byref(nc),
+                              surf.ctypes.data, cap, ctypes.byref(ns))
+    assert rc == 0, "surface sample larger than cap"
+    return corner[:nc.value].copy(), surf[:ns.value].copy()
+
+
+def street_pose(xs, k, heading_quadrant=0):
+    """A sensor pose [qx qy qz qw tx ty tz] on the centre line y' = 80 k of the street grid at street abscissa
+    xs (never inside a building), 1.73 m above the terrain, heading along the street (+ quadrant * 90 deg)."""
+    yaw = np.deg2rad(17.0)  # synth.cpp kGridYaw
+    ys = 80.0 * k
+    c, s = np.cos(yaw), np.sin(yaw)
+    x, y = c * xs - s * ys, s * xs + c * ys
+    g = 0.3 * np.sin(2 * np.pi * xs / 40.0) * np.cos(2 * np.pi * ys / 40.0)  # synth.cpp World::ground_s
+    h = yaw + 0.5 * np.pi * heading_quadrant
+    return np.array([0.0, 0.0, np.sin(h / 2), np.cos(h / 2), x, y, g + 1.73])

@@ -678,4 +678,66 @@ int synth_features(int sensor_kind, double minimum_range, const float* xyz, int 
   return 0;
 }
 
+// Every world surface inside the square |x|, |y| <= half (world frame) sampled directly -- the "synthesise
+// directly" variant of SURVEY 8d config 3 (a saturated 21 x 21 x 11 cube window without driving it):
+//   surf   : the ground on a jittered lattice of `surf_step`, facades / car sides on a lattice of the same step
+//   corner : poles and the vertical edges of facades (building corners, recess edges) every `corner_step` in z
+// Points are xyzi (intensity 0), world frame, with `sigma` metres of Gaussian noise.  Returns -1 when a
+// buffer is too small; counts in n_corner / n_surf.
+int synth_surfaces(uint64_t seed, double half, double surf_step, double corner_step, double sigma, float* corner,
+                   int cap_corner, int* n_corner, float* surf, int cap_surf, int* n_surf) {
+  World w(seed);
+  std::vector<float> C, S;
+  uint64_t ctr = 0;
+  auto emit = [&](std::vector<float>& out, double xs, double ys, double z) {
+    double x, y;
+    w.to_world(xs, ys, x, y);
+    if (std::fabs(x) > half || std::fabs(y) > half) return;
+    const uint64_t h = hash4(seed ^ 0x5AFE, (int64_t)ctr, 7, 9);
+    ++ctr;
+    out.push_back((float)(x + sigma * gauss(h)));
+    out.push_back((float)(y + sigma * gauss(mix64(h ^ 1))));
+    out.push_back((float)(z + sigma * gauss(mix64(h ^ 2))));
+    out.push_back(0.0f);
+  };
+  const double R = half * 1.5;  // the street frame is yawed: cover the rotated square
+  // ground
+  const int ng = (int)std::ceil(2 * R / surf_step);
+  for (int i = 0; i < ng; ++i)
+    for (int j = 0; j < ng; ++j) {
+      const uint64_t h = hash4(seed ^ 0x6E0D, i, j, 3);
+      const double xs = -R + (i + u01(h)) * surf_step, ys = -R + (j + u01(mix64(h))) * surf_step;
+      emit(S, xs, ys, w.ground_s(xs, ys));
+    }
+  // vertical primitives
+  std::vector<Prim> prims;
+  collect_prims(w, 0.0, 0.0, R * 1.5, prims);
+  for (const Prim& p : prims) {
+    if (p.kind == 1) {  // pole: a vertical line of corner points
+      const double g = w.ground_s(p.ax, p.ay);
+      for (double z = g + 0.1; z < p.zhi; z += corner_step) emit(C, p.ax + p.bx, p.ay, z);
+    } else if (p.kind == 0) {  // wall segment: a lattice of surf points, its two end edges as corner lines
+      const double L = std::hypot(p.bx - p.ax, p.by - p.ay);
+      const double g0 = w.ground_s(p.ax, p.ay), g1 = w.ground_s(p.bx, p.by);
+      const int na = std::max(1, (int)std::floor(L / surf_step));
+      for (int a = 0; a <= na; ++a) {
+        const double f = (double)a / na, xs = p.ax + f * (p.bx - p.ax), ys = p.ay + f * (p.by - p.ay);
+        const double g = w.ground_s(xs, ys);
+        for (double z = g + 0.5 * surf_step; z < p.zhi; z += surf_step) emit(S, xs, ys, z);
+      }
+      for (double z = g0 + 0.1; z < p.zhi; z += corner_step) emit(C, p.ax, p.ay, z);
+      for (double z = g1 + 0.1; z < p.zhi; z += corner_step) emit(C, p.bx, p.by, z);
+    } else {  // car roof
+      for (double xs = p.ax; xs <= p.bx; xs += surf_step)
+        for (double ys = p.ay; ys <= p.by; ys += surf_step) emit(S, xs, ys, p.zhi);
+    }
+  }
+  if ((int)(C.size() / 4) > cap_corner || (int)(S.size() / 4) > cap_surf) return -1;
+  std::memcpy(corner, C.data(), C.size() * sizeof(float));
+  std::memcpy(surf, S.data(), S.size() * sizeof(float));
+  *n_corner = (int)(C.size() / 4);
+  *n_surf = (int)(S.size() / 4);
+  return 0;
+}
+
 }  // extern "C"

@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Attribute an ncu SASS-page CSV (ncu -i X.ncu-rep --page source --csv --print-source sass)
 to CUDA source lines using nvdisasm -g line markers of the same cubin.
-usage: sass_by_line.py <sass.csv> <cubin> <kernel-substring> [top_n]"""
+usage: sass_by_line.py <sass.csv> <cubin> <kernel-substring> [top_n] [samples|inst]"""
 import csv, re, subprocess, sys, collections
 
 sass_csv, cubin, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+by = sys.argv[5] if len(sys.argv) > 5 else "samples"  # or "inst"
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 # locate the function
 start = next(i for i, l in enumerate(dis) if l.strip().startswith(".text.") and kname in l)
@@ -50,5 +51,5 @@ def src(ln):
         except Exception:
             pass
     return ""
-for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][2])[:top]:
+for ln, a in sorted(agg.items(), key=lambda kv: -(kv[1][0] if by == "inst" else kv[1][2]))[:top]:
     print("%5.1f%% samp %5.1f%% inst  act %4.1f  sass %4d  %s:%d  %s" % (100 * a[2] / max(tot_samp, 1), 100 * a[0] / max(tot_inst, 1), a[1] / max(a[0], 1), a[3], ln[0], ln[1], src(ln)))

@@ -382,7 +382,7 @@ static int create_impl(s2m_ctx* ctx) {
   const size_t ccap = (size_t)std::max(d.cap_lp, d.cap_in);
   rc |= dev_alloc(ctx, &d.ckey, ccap); rc |= dev_alloc(ctx, &d.ckey2, ccap);
   rc |= dev_alloc(ctx, &d.cval, ccap); rc |= dev_alloc(ctx, &d.cval2, ccap);
-  rc |= dev_alloc(ctx, &d.cand, d.cap_lp); rc |= dev_alloc(ctx, &d.knn_ticket, 1);
+  rc |= dev_alloc(ctx, &d.cand, d.cap_lp); rc |= dev_alloc(ctx, &d.knn_ticket, 1); rc |= dev_alloc(ctx, &d.nbr, (size_t)d.cap_in * 6); rc |= dev_alloc(ctx, &d.inv, d.cap_lp);
   // cell tables: per segment a power of two >= 2 x entries, >= 1024
   long long hcap = 0;
   for (int g = 0; g < G; ++g) hcap += table_size(g < B ? P.cap_map_corner : P.cap_map_surf);
@@ -684,19 +684,20 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   CK(cudaEventSynchronize(ctx->ev_ds));
   const int n_ds = ctx->h_dsoff[G];
   tiles = 0;
-  int chunks = 0;  // 32-query work units of assoc_kernel over all slots
+  int chunks = 0;  // 32-query work units of knn_kernel over all slots
   for (int b = 0; b < B; ++b) {
     const int nq = (ctx->h_dsoff[b + 1] - ctx->h_dsoff[b]) + (ctx->h_dsoff[B + b + 1] - ctx->h_dsoff[B + b]);
     tiles = std::max(tiles, (nq + kTile - 1) / kTile);
     chunks += (nq + 31) / 32;
   }
-  // the fused association kernel: one resident wave of persistent blocks sharing a work ticket
-  const int assoc_blocks = std::max(1, std::min((chunks + kTile / 32 - 1) / (kTile / 32), S2M_K4_MINB * ctx->sm_count));
+  // K4a: one resident wave of persistent warps sharing a work ticket; K4b: one block per 128 points of a slot
+  const int knn_blocks = std::max(1, std::min((chunks + kTile / 32 - 1) / (kTile / 32), S2M_K4A_MINB * ctx->sm_count));
+  const int fit_blocks = std::max(1, tiles);
   const int eval_blocks = std::max(1, (tiles + kEvalTilesPerBlock - 1) / kEvalTilesPerBlock);
   for (int outer = 0; outer < 2; ++outer) {  // laserMapping.cpp:563
     CK(cudaMemsetAsync(d.knn_ticket, 0, sizeof(int), s));  // the association's work ticket
     prof_mark(ctx, S2M_PHASE_READBACK);  // host wait for the down-sampled counts (outer 0); the K4 bracket starts here
-    k += launch_associate(d, outer, assoc_blocks, ctx->P.trace != 0, s);
+    k += launch_associate(d, outer, knn_blocks, fit_blocks, ctx->P.trace != 0, s);
     prof_mark(ctx, S2M_PHASE_ASSOCIATE);
     if (!sharded) {
       k += launch_solve(d, outer, true, s);  // Ceres solve, max_num_iterations = 4 (:713-721)

@@ -33,8 +33,11 @@ namespace s2m {
 #ifndef S2M_OD_MINB
 #define S2M_OD_MINB 6  // resident blocks per SM of odom_associate_kernel: latency-bound walks, more warps win (3.9 -> 3.0 ms)
 #endif
-#ifndef S2M_K4_MINB
-#define S2M_K4_MINB 4  // resident blocks per SM the fused association kernel is compiled for (128 registers)
+#ifndef S2M_K4A_MINB
+#define S2M_K4A_MINB 8  // resident blocks per SM the kNN kernel is compiled for (<= 64 registers)
+#endif
+#ifndef S2M_K4B_MINB
+#define S2M_K4B_MINB 4  // ... and the fit / residual kernel (128 registers, FP64)
 #endif
 constexpr int kEvalTilesPerBlock = 8;  // ... one evaluate_kernel block
 constexpr int kTile = 128;       // queries per block of the association / evaluation kernels
@@ -129,7 +132,9 @@ struct Dev {
   int* lp_cnt;                  // [G] points of the local map (read back: sizes the index exactly)
   uint32_t *ckey, *ckey2, *cval, *cval2;  // [cap_lp]
   float4* cand;                 // [cap_lp] cell-sorted local points, w = local index bits
-  int* knn_ticket;              // next 32-query work unit of assoc_kernel
+  int* inv;                     // [cap_lp] local index -> position in cand (packed by lp_off)
+  int* nbr;                     // [cap_in][6] K4a -> K4b: (n << 1 | gate), five positions in d.cand
+  int* knn_ticket;              // next 32-query work unit of knn_kernel
   float4* od_last;              // odometry: less-sharp / less-flat clouds of the previous sweep, class-major
   int* od_last_off;             // [2B+1]
   float4* od_sorted;            // the same clouds ordered by 1 m cell inside each segment, .w = index | ring << 24
@@ -179,7 +184,7 @@ int launch_voxel_filter(const Dev& d, int total_in, int key_bits, cudaStream_t s
 int launch_local_ranges(const Dev& d, int cur, cudaStream_t s);
 int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, bool ranges_done, cudaStream_t s);
 int launch_guard(const Dev& d, cudaStream_t s);
-int launch_associate(const Dev& d, int outer, int blocks, bool trace, cudaStream_t s);
+int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s);
 int launch_solve(const Dev& d, int outer, bool from_units, cudaStream_t s);
 int launch_reduce_units(const Dev& d, cudaStream_t s);
 int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s);

@@ -276,6 +276,7 @@ __global__ void cand_build_kernel(Dev d, int cur, int total_lp) {
   const int l = (int)d.cval2[p];
   const float4 q = d.st_pt[cur][d.st_base[g] + local_to_store(d, g, l)];
   d.cand[p] = make_float4(q.x, q.y, q.z, __int_as_float(l));
+  d.inv[d.lp_off[g] + l] = p;  // local index -> position in d.cand
   if (p == 0 || d.ckey2[p - 1] != key) {
     // run of a key starting at position a (a < total_lp): its end
     auto run_end = [&](int a) {
@@ -309,35 +310,35 @@ __global__ void cand_build_kernel(Dev d, int cur, int total_lp) {
 }
 
 // ----------------------------------------------------------------------------
-// Row K: exact bounded kNN(5), warp-cooperative.
-//
-// A WARP owns a work unit of 32 queries.  Phase 1 (thread per query): the nine rows of three
-// x-adjacent cells around the query are looked up in the cell table and staged in shared memory
-// (row runs, compacted; the positions of the first 32 candidates).  Phase 2 (warp per query): the
-// lanes take one candidate each, evaluate the reference's float distance
-// ((dx*dx)+(dy*dy))+(dz*dz) (no FMA), and the five smallest (d2 bits, local index) are picked
-// with warp reductions -- float bits of a non-negative d2 order like the values, ties (equal
-// bits) by the lower index, which is the canonical order of SURVEY 8a/K.  The result is only
-// consumed when the 5th distance is < 1.0 (laserMapping.cpp:585, :653), so candidates at 1 m or
-// more are dropped at once and a query that does not collect five within 1 m fails the gate.
+// Row K: exact bounded kNN(5), thread per query
 // ----------------------------------------------------------------------------
-constexpr uint32_t kInfKey = 0xFFFFFFFFu;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kTabStride = 33;  // 32 positions per query + 1: the owner threads write columns without bank conflicts
-
-struct __align__(16) WarpStage {
-  float4 q[32];                      // transformed query; .w = bits of n, the candidates in its 27 cells
-  int cum[32][9];                    // inclusive prefix of the non-empty row counts (padded with n)
-  int base[32][9];                   // start of the row in d.cand minus the candidates before it
-  uint32_t tab[32 * kTabStride];     // position in d.cand of candidate j < 32 of every query
-  float4 nbr[32][5];                 // the five neighbours, nearest first; .w = local index bits
-  int nsel[32];                      // neighbours found within 1 m (5 = gate passed)
+// Exact bounded kNN(5) of one query over the 27 cells around it.  Distances are
+// the reference's float ((dx*dx)+(dy*dy))+(dz*dz); order is (d2, local index):
+// both live in one 64-bit key (float bits of a non-negative d2 are monotonic).
+struct Knn5 {
+  unsigned long long key[5];  // d2 bits << 32 | local index, ascending
 };
-constexpr int kSumRows = 30;         // 28 sums + n_edge + n_plane, transposed through shared memory
-constexpr int kWarpBytesA = (int)sizeof(WarpStage);
-constexpr int kWarpBytesB = kSumRows * 33 * (int)sizeof(double) + 2 * 32 * (int)sizeof(double);
-constexpr int kWarpBytes = ((kWarpBytesA > kWarpBytesB ? kWarpBytesA : kWarpBytesB) + 15) / 16 * 16;
+__device__ __forceinline__ float knn_d2(const Knn5& r, int k) { return __uint_as_float((uint32_t)(r.key[k] >> 32)); }
+__device__ __forceinline__ int knn_idx(const Knn5& r, int k) { return (int)(uint32_t)r.key[k]; }
+// "none" marker: the search starts from the reference's gate (d2 = 1.0f, index 0), see knn5_cells
+constexpr unsigned long long kKnnInit = (unsigned long long)0x3F800000u << 32;
 
+__device__ __forceinline__ void knn_offer(Knn5& r, float qx, float qy, float qz, const float4 c) {
+  const float dd = dist2(qx, qy, qz, c.x, c.y, c.z);
+  if (dd > knn_d2(r, 4)) return;  // cheap float test first; ties go through the exact 64-bit compare
+  const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | (uint32_t)__float_as_int(c.w);
+  if (key < r.key[4]) {  // replace the 5th, then bubble it up (compare-exchange chain)
+    r.key[4] = key;
+#pragma unroll
+    for (int i = 4; i > 0; --i) {
+      const unsigned long long lo = r.key[i - 1], hi = r.key[i];
+      const bool sw = hi < lo;
+      r.key[i - 1] = sw ? hi : lo;
+      r.key[i] = sw ? lo : hi;
+    }
+  }
+}
 __device__ __forceinline__ unsigned long long cell_probe(const unsigned long long* __restrict__ tab, uint32_t mask,
                                                          uint32_t k24, uint32_t& s) {
   s = cell_hash(k24) & mask;
@@ -349,196 +350,109 @@ __device__ __forceinline__ unsigned long long cell_probe(const unsigned long lon
   return e;
 }
 
-// Phase 1, one thread: the candidate runs of a world-frame query.  The cell table gives every row
-// (dy, dz) of three x-adjacent cells in ONE probe (cand_build_kernel).  Writes this query's column of
-// the staging area and returns n, the number of map points in its 27 cells.
-__device__ __forceinline__ int stage_rows(const Dev& d, int g, const int origin[3], float qx, float qy, float qz,
-                                          WarpStage& S, int t) {
-  const int cx = (int)floorf(qx) - origin[0], cy = (int)floorf(qy) - origin[1], cz = (int)floorf(qz) - origin[2];
+__device__ __forceinline__ void knn_scan_range(const float4* __restrict__ cand, int start, int count, float qx,
+                                               float qy, float qz, Knn5& r) {
+  float4 c = __ldg(cand + start);
+#pragma unroll 1
+  for (int j = 0; j < count; ++j) {  // the next point is in flight while this one is offered
+    const float4 nx = __ldg(cand + start + min(j + 1, count - 1));
+    knn_offer(r, qx, qy, qz, c);
+    c = nx;
+  }
+}
+
+// per-thread staging of the nine row probes (one column per thread)
+struct KnnStage {
+  unsigned long long run[9][kTile];  // count << 32 | start of each row's candidate run (0 = none)
+};
+
+// Rows (dy,dz) of three x-adjacent cells are visited near to far; a row is skipped when
+// a lower bound of the FLOAT distance to any point in it exceeds the current 5th
+// distance.  The bound is built with the same rounding steps as dist2() ((0 + by*by) +
+// bz*bz with by, bz the exact distances to the row's boundary planes) and rounding is
+// monotonic, so no point that could enter the result is ever skipped.
+// Returns the number of map points in the 27 cells (all nine rows, pruned or not).
+__device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[3], float qx, float qy, float qz,
+                                          Knn5& r, KnnStage& st) {
+  // The result is only used when the 5th distance is < 1.0 (laserMapping.cpp:585, :653), so the
+  // search starts from that bound: key (1.0f, index 0) is larger than every (d2 < 1, any index)
+  // and not larger than any (d2 >= 1, .) -- candidates at 1 m or more never enter.
+#pragma unroll
+  for (int k = 0; k < 5; ++k) r.key[k] = kKnnInit;
+  const float fly = floorf(qy), flz = floorf(qz);
+  const int cx = (int)floorf(qx) - origin[0], cy = (int)fly - origin[1], cz = (int)flz - origin[2];
   const int base = d.hash_off[g];
   const uint32_t mask = (uint32_t)(d.hash_off[g + 1] - base) - 1u;
   const unsigned long long* __restrict__ tab = d.hash_tab + base;
+  const int t = threadIdx.x;
+  // exact distances from the query to the cell's boundary planes (fractional parts are exact)
+  const float fy = xfsub(qy, fly), fz = xfsub(qz, flz);
+  const float gy = xfsub(1.0f, fy), gz = xfsub(1.0f, fz);
+  const int sy = fy < 0.5f ? -1 : 1, sz = fz < 0.5f ? -1 : 1;  // side of the nearer boundary
   // A query one cell outside the block in x still has one column of the block in range: probe
   // that column (its run is a superset of what is needed, which keeps the search exact).
   const int px = cx < 0 ? cx + 1 : (cx > 255 ? cx - 1 : cx);
   const bool x_ok = (unsigned)px <= 255u;
-  uint32_t k24[9], sl[9];
-  unsigned long long e[9];
+  int total = 0;
+  {  // phase 1: the nine row probes issued back to back (independent loads), near-to-far order
+    uint32_t k24[9], sl[9];
+    unsigned long long e[9];
 #pragma unroll
-  for (int o = 0; o < 9; ++o) {  // the nine probes are independent loads, issued back to back
-    const int z = cz + o / 3 - 1, y = cy + o % 3 - 1;
-    const bool ok = (unsigned)z <= 255u && (unsigned)y <= 255u && x_ok;
-    k24[o] = ((uint32_t)(z & 255) << 16) | ((uint32_t)(y & 255) << 8) | (uint32_t)(px & 255);
-    sl[o] = cell_hash(k24[o]) & mask;
-    e[o] = ok ? tab[sl[o]] : kSentinel64;
+    for (int o = 0; o < 9; ++o) {
+      // order: centre, (sy,0), (0,sz), (sy,sz), (-sy,0), (0,-sz), (-sy,sz), (sy,-sz), (-sy,-sz)
+      const int dy = (o == 1 || o == 3 || o == 7) ? sy : ((o == 4 || o == 6 || o == 8) ? -sy : 0);
+      const int dz = (o == 2 || o == 3 || o == 6) ? sz : ((o == 5 || o == 7 || o == 8) ? -sz : 0);
+      const int z = cz + dz, y = cy + dy;
+      const bool ok = (unsigned)z <= 255u && (unsigned)y <= 255u && x_ok;
+      k24[o] = ((uint32_t)(z & 255) << 16) | ((uint32_t)(y & 255) << 8) | (uint32_t)(px & 255);
+      sl[o] = cell_hash(k24[o]) & mask;
+      e[o] = ok ? tab[sl[o]] : kSentinel64;
+    }
+#pragma unroll
+    for (int o = 0; o < 9; ++o) {
+      while (e[o] != kSentinel64 && (uint32_t)(e[o] >> 40) != k24[o]) {
+        sl[o] = (sl[o] + 1) & mask;
+        e[o] = tab[sl[o]];
+      }
+      unsigned long long rn = 0ull;
+      if (e[o] != kSentinel64) {
+        uint32_t c = (uint32_t)(e[o] >> 30) & 1023u;
+        if (c == 1023u) c = d.hash_aux[base + sl[o]].y;
+        rn = ((unsigned long long)c << 32) | (e[o] & 0x3FFFFFFFull);
+      }
+      st.run[o][t] = rn;
+      total += (int)(rn >> 32);
+    }
   }
-  int n = 0, k = 0;
-  uint32_t* __restrict__ tb = S.tab + t * kTabStride;
-#pragma unroll
+  // phase 2: rows near to far (one copy of the scan code; the staging lives in shared memory)
+#pragma unroll 1
   for (int o = 0; o < 9; ++o) {
-    while (e[o] != kSentinel64 && (uint32_t)(e[o] >> 40) != k24[o]) {
-      sl[o] = (sl[o] + 1) & mask;
-      e[o] = tab[sl[o]];
-    }
-    if (e[o] == kSentinel64) continue;
-    int c = (int)((uint32_t)(e[o] >> 30) & 1023u);
-    if (c == 1023) c = (int)d.hash_aux[base + sl[o]].y;
-    if (c == 0) continue;
-    const int start = (int)(uint32_t)(e[o] & 0x3FFFFFFFull);
-    for (int i = 0, j = n; i < c && j < 32; ++i, ++j) tb[j] = (uint32_t)(start + i);
-    S.base[t][k] = start - n;
-    n += c;
-    S.cum[t][k] = n;
-    ++k;
+    const unsigned long long rn = st.run[o][t];
+    const int cnt = (int)(rn >> 32);
+    if (cnt == 0) continue;
+    const float by = (o == 0 || o == 2 || o == 5) ? 0.0f : ((o == 1 || o == 3 || o == 7) ? (sy < 0 ? fy : gy) : (sy < 0 ? gy : fy));
+    const float bz = (o == 0 || o == 1 || o == 4) ? 0.0f : ((o == 2 || o == 3 || o == 6) ? (sz < 0 ? fz : gz) : (sz < 0 ? gz : fz));
+    if (xfadd(xfmul(by, by), xfmul(bz, bz)) > knn_d2(r, 4)) continue;  // strict: a tie at the 5th distance may still win on the index
+    knn_scan_range(d.cand, (int)(uint32_t)rn, cnt, qx, qy, qz, r);
   }
-  for (; k < 9; ++k) { S.cum[t][k] = n; S.base[t][k] = 0; }
-  return n;
+  return total;
 }
 
-__device__ __forceinline__ uint32_t cand_key(const float4 qv, const float4 c, bool valid) {
-  const float dd = dist2(qv.x, qv.y, qv.z, c.x, c.y, c.z);
-  return (valid && dd < 1.0f) ? __float_as_uint(dd) : kInfKey;
-}
-// candidate `lane` (first round) of staged query qi
-__device__ __forceinline__ float4 first_round(const WarpStage& S, const float4* __restrict__ cand, int qi, int lane) {
-  const int n = __float_as_int(S.q[qi].w);
-  float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (lane < n) c = __ldg(cand + S.tab[qi * kTabStride + lane]);
-  return c;
-}
-// candidate base_j + lane of staged query qi, any base_j: the row of a candidate is the number of
-// row ends at or before it (row ends inside this window as a bit mask built by the nine lanes
-// that hold the prefix sums, plus the rows that ended before the window)
-__device__ __forceinline__ float4 later_round(const WarpStage& S, const float4* __restrict__ cand, int qi, int base_j,
-                                              int n, int lane, bool& valid) {
-  const int cr = lane < 9 ? S.cum[qi][lane] : 0x7fffffff;
-  const int e = cr - 1 - base_j;
-  const unsigned M = __reduce_or_sync(kFull, (lane < 9 && e >= 0 && e < 31) ? (1u << e) : 0u);
-  const int rowbase = __popc(__ballot_sync(kFull, lane < 9 && cr <= base_j));
-  const int row = min(rowbase + __popc(M & ((1u << lane) - 1u)), 8);
-  const int j = base_j + lane;
-  valid = j < n;
-  float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (valid) c = __ldg(cand + (S.base[qi][row] + j));
-  return c;
-}
-// The nsel smallest of the warp's keys in (d2 bits, index) order: rank = 0..nsel-1 on the lanes
-// that hold them, -1 elsewhere.  nsel <= number of finite keys.  One REDUX per pick; a pick that
-// matched two lanes (two candidates at exactly the same float distance) is redone with the index
-// as tie-break.
-__device__ __forceinline__ int select_one_slot(uint32_t key, uint32_t idx, int nsel) {
-  int rank = -1;
-  uint32_t k = key;
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
-    if (s < nsel) {
-      const uint32_t m = __reduce_min_sync(kFull, k);
-      if (k == m) { rank = s; k = kInfKey; }
-    }
-  }
-  if (__popc(__ballot_sync(kFull, rank >= 0)) != nsel) {
-    rank = -1;
-    k = key;
-    for (int s = 0; s < nsel; ++s) {
-      const uint32_t m = __reduce_min_sync(kFull, k);
-      const bool c1 = k == m;
-      const uint32_t mi = __reduce_min_sync(kFull, c1 ? idx : 0xFFFFFFFFu);
-      if (c1 && idx == mi) { rank = s; k = kInfKey; }
-    }
-  }
-  return rank;
-}
-// same over two keys per lane (A: a new candidate, B: a neighbour carried over from the rounds before)
-__device__ __forceinline__ void select_two_slots(uint32_t ka, uint32_t ia, uint32_t kb, uint32_t ib, int nsel, int& ra,
-                                                 int& rb) {
-  ra = rb = -1;
-  for (int s = 0; s < nsel; ++s) {
-    const uint32_t m = __reduce_min_sync(kFull, min(ka, kb));
-    const bool ca = ka == m, cb = kb == m;
-    const uint32_t mi = __reduce_min_sync(kFull, min(ca ? ia : 0xFFFFFFFFu, cb ? ib : 0xFFFFFFFFu));
-    if (ca && ia == mi) { ra = s; ka = kInfKey; }
-    else if (cb && ib == mi) { rb = s; kb = kInfKey; }
-  }
-}
-// Phase 2, whole warp: the five nearest candidates of staged query qi into S.nbr[qi], their
-// number into S.nsel[qi].  c0 = the query's first-round candidate of this lane (prefetched).
-__device__ __forceinline__ void warp_knn5(WarpStage& S, const float4* __restrict__ cand, int qi, int lane, float4 c0) {
-  const float4 qv = S.q[qi];
-  const int n = __float_as_int(qv.w);
-  const uint32_t key = cand_key(qv, c0, lane < n);
-  int have = min(5, __popc(__ballot_sync(kFull, key != kInfKey)));
-  if (n <= 32) {
-    if (have == 5) {
-      const int rank = select_one_slot(key, __float_as_uint(c0.w), 5);
-      if (rank >= 0) S.nbr[qi][rank] = c0;
-    }
-  } else {
-    const int rank = select_one_slot(key, __float_as_uint(c0.w), have);
-    if (rank >= 0) S.nbr[qi][rank] = c0;
-    __syncwarp();
-    for (int base_j = 32; base_j < n; base_j += 32) {
-      bool valid;
-      const float4 ca = later_round(S, cand, qi, base_j, n, lane, valid);
-      const uint32_t ka = cand_key(qv, ca, valid);
-      const int fresh = __popc(__ballot_sync(kFull, ka != kInfKey));
-      if (fresh == 0) continue;
-      float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
-      uint32_t kb = kInfKey;
-      if (lane < have) { cb = S.nbr[qi][lane]; kb = cand_key(qv, cb, true); }
-      __syncwarp();  // every carried neighbour is in a register before the list is rewritten
-      const int nsel = min(5, have + fresh);
-      int ra, rb;
-      select_two_slots(ka, __float_as_uint(ca.w), kb, __float_as_uint(cb.w), nsel, ra, rb);
-      if (ra >= 0) S.nbr[qi][ra] = ca;
-      if (rb >= 0) S.nbr[qi][rb] = cb;
-      __syncwarp();
-      have = nsel;
-    }
-  }
-  if (lane == 0) S.nsel[qi] = have;
-}
-// Phase 2 driver: every staged query of `todo` (bit per query), two candidate loads in flight
-__device__ __forceinline__ void warp_knn5_all(WarpStage& S, const float4* __restrict__ cand, unsigned todo, int lane) {
-  int q0 = -1, q1 = -1;
-  float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-  if (todo) { q0 = __ffs(todo) - 1; todo &= todo - 1; c0 = first_round(S, cand, q0, lane); }
-  if (todo) { q1 = __ffs(todo) - 1; todo &= todo - 1; c1 = first_round(S, cand, q1, lane); }
-  while (q0 >= 0) {
-    const int qa = q0;
-    const float4 ca = c0;
-    q0 = q1; c0 = c1; q1 = -1;
-    if (todo) { q1 = __ffs(todo) - 1; todo &= todo - 1; c1 = first_round(S, cand, q1, lane); }
-    warp_knn5(S, cand, qa, lane, ca);
-  }
-  __syncwarp();
-}
-
-// s2m_debug_knn: world-frame float queries against segment g, through the same two phases
-__global__ void __launch_bounds__(kTile) knn_debug_kernel(Dev d, int g, const float* __restrict__ q, int n,
-                                                          int32_t* __restrict__ idx, float* __restrict__ d2) {
-  __shared__ __align__(16) unsigned char wbuf[kTile / 32][kWarpBytes];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  WarpStage& S = *reinterpret_cast<WarpStage*>(wbuf[wid]);
-  const int i = blockIdx.x * kTile + threadIdx.x;
-  const bool live = i < n;
-  if (live) {
-    const float qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
-    const int origin[3] = {d.desc[seg_slot(d, g)].origin[0], d.desc[seg_slot(d, g)].origin[1], d.desc[seg_slot(d, g)].origin[2]};
-    const int nc = stage_rows(d, g, origin, qx, qy, qz, S, lane);
-    S.q[lane] = make_float4(qx, qy, qz, __int_as_float(nc));
-  }
-  __syncwarp();
-  warp_knn5_all(S, d.cand, __ballot_sync(kFull, live), lane);
-  if (!live) return;
-  const bool ok = S.nsel[lane] == 5;  // the reference's gate; beyond it the bounded search is not exact
-  const float4 qv = S.q[lane];
+__global__ void knn_debug_kernel(Dev d, int g, const float* __restrict__ q, int n, int32_t* __restrict__ idx,
+                                 float* __restrict__ d2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Knn5 r;
+  __shared__ KnnStage st;
+  knn5_cells(d, g, d.desc[seg_slot(d, g)].origin, q[3 * i], q[3 * i + 1], q[3 * i + 2], r, st);
+  const bool ok = knn_d2(r, 4) < 1.0f;  // the reference's gate; beyond it the bounded search is not exact
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    const float4 c = S.nbr[lane][k];
-    idx[5 * i + k] = ok ? __float_as_int(c.w) : -1;
-    d2[5 * i + k] = ok ? dist2(qv.x, qv.y, qv.z, c.x, c.y, c.z) : INFINITY;
+    idx[5 * i + k] = ok ? knn_idx(r, k) : -1;
+    d2[5 * i + k] = ok ? knn_d2(r, k) : INFINITY;
   }
 }
+
 
 // ----------------------------------------------------------------------------
 // Block-level accumulation.  Each thread adds the 28 sums of its own queries into
@@ -676,27 +590,27 @@ __global__ void lm_shard_kernel(Dev d, int outer, int after) {
 }
 
 // ----------------------------------------------------------------------------
-// K4 assoc_kernel: the fused association (laserMapping.cpp:578-706), ONE kernel per outer
-// iteration.  Work unit = 32 consecutive down-sampled scan points of one slot, taken by a warp
-// from a device-wide ticket (the results do not depend on who computes them):
-//   phase 1  thread per point : pointAssociateToMap (FP64, exact) + the nine cell-table probes,
-//                               candidate runs staged in shared memory          rows P, T
-//   phase 2  warp per point   : lanes over the staged candidates, float distances, five
-//                               nearest by warp reductions, the 1 m gate          row K
-//   phase 3  thread per point : edge PCA / plane QR (FP64), residual + tangent-space Jacobian +
-//                               Huber, 48-byte correspondence record            rows E,F,R,L,Q
-//   then the 28 sums of the unit are transposed through shared memory and added in lane order:
-//   one 32-double partial per unit.  The solver (solve_kernel) adds the partials of a slot in unit
-//   order, so every bit of the pose is independent of what else shares the launch.
-// Warps in different phases share an SM, so the integer / load work of phases 1-2 overlaps the
-// FP64 work of phase 3.
+// K4 = the association of one outer iteration (laserMapping.cpp:578-706), two back-to-back kernels:
+//   K4a knn_kernel : pointAssociateToMap (FP64, exact) + the exact bounded kNN(5) + the 1 m gate
+//                    (rows P, T, K).  Integer / float only, <= 64 registers, 8 blocks per SM.  Warps
+//                    take units of 32 consecutive scan points of a slot from a device-wide ticket.
+//   K4b fit_kernel : thread per gated point: edge PCA / plane QR (FP64), residual + tangent-space
+//                    Jacobian + Huber, 48-byte correspondence record (rows E, F, R, L, Q); the 28
+//                    sums of every 32-point unit are transposed through shared memory and added in
+//                    lane order: one 32-double partial per unit, no block barrier anywhere.
+// The hand-off is 24 bytes per point (gate + n, five positions in d.cand).  The solver
+// (solve_kernel) adds the unit partials of a slot in unit order, so every bit of the pose is
+// independent of what else shares the launch.
 // ----------------------------------------------------------------------------
 template <bool kTrace>
-__global__ void __launch_bounds__(kTile, S2M_K4_MINB) assoc_kernel(Dev d, int outer) {
-  __shared__ __align__(16) unsigned char wbuf[kTile / 32][kWarpBytes];
+__global__ void __launch_bounds__(kTile, S2M_K4A_MINB) knn_kernel(Dev d, int outer) {
+  // Work unit = 32 consecutive queries of one slot, taken by a WARP from a device-wide ticket:
+  // the trip counts of the search vary a lot between queries, so static tiles leave most of a
+  // block (and the tail of the grid) idle. The results do not depend on who computes them.
+  __shared__ KnnStage stage;
   __shared__ int chunk_off[kMaxBatch + 1];
-  const int B = d.B, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x < 32) {  // units per slot (none for a slot that is not optimised this frame), prefix-summed
+  const int B = d.B, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {  // chunks per slot (none for a slot that is not optimised this frame), prefix-summed
     int c[2], incl[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -709,131 +623,151 @@ __global__ void __launch_bounds__(kTile, S2M_K4_MINB) assoc_kernel(Dev d, int ou
       }
       incl[h] = c[h];
       for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(kFull, incl[h], o);
+        const int v = __shfl_up_sync(0xffffffffu, incl[h], o);
         if (lane >= o) incl[h] += v;
       }
     }
-    const int first = __shfl_sync(kFull, incl[0], 31);
+    const int first = __shfl_sync(0xffffffffu, incl[0], 31);
     if (lane == 0) chunk_off[0] = 0;
     chunk_off[1 + lane] = incl[0];
     if (32 + lane < kMaxBatch) chunk_off[33 + lane] = first + incl[1];
   }
   __syncthreads();
   const int total = chunk_off[B];
-  WarpStage& S = *reinterpret_cast<WarpStage*>(wbuf[wid]);
-  double* T = reinterpret_cast<double*>(wbuf[wid]);  // [kSumRows][33], reuses the staging area after phase 2
   for (;;) {
     int chunk = 0;
     if (lane == 0) chunk = atomicAdd(d.knn_ticket, 1);
-    chunk = __shfl_sync(kFull, chunk, 0);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
     if (chunk >= total) break;
     int slot = 0, hi = B;  // chunk_off[slot] <= chunk < chunk_off[hi]
     while (hi - slot > 1) {
       const int mid = (slot + hi) >> 1;
       if (chunk_off[mid] <= chunk) slot = mid; else hi = mid;
     }
-    const int unit = chunk - chunk_off[slot];
     int dc0, nc, ds0, nq;
     slot_counts(d, slot, dc0, nc, ds0, nq);
-    const int q = (unit << 5) + lane;
-    const bool live = q < nq;
-    const int cls = q >= nc;
-    const int di = cls ? ds0 + (q - nc) : dc0 + q;  // position in the packed down-sampled scan
-    double pose[7];  // accepted pose of the slot (guard_kernel / the previous solve)
-#pragma unroll
-    for (int i = 0; i < 7; ++i) pose[i] = d.lm[slot].x[i];
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool search = false;
-    int ncand = 0;
-    // ---- phase 1 ----
-    if (live) {
-      p = d.ds_pts[di];
+    const int q = ((chunk - chunk_off[slot]) << 5) + lane;
+    int visited = 0, cls = 0;
+    if (q < nq) {
+      cls = q >= nc;
+      const int pos_q = cls ? ds0 + (q - nc) : dc0 + q;  // position in the packed query list
+      const float4 p = d.ds_pts[pos_q];
       float w[3];
-      xf_point(pose, p.x, p.y, p.z, w);
-      // sharded map: a query is answered by the rank whose x-slab holds it
-      search = !(d.shard_world > 1 && !(w[0] >= d.shard_lo && w[0] < d.shard_hi));
-      if (search) {
+      xf_point(d.lm[slot].x, p.x, p.y, p.z, w);
+      if (d.shard_world > 1 && !(w[0] >= d.shard_lo && w[0] < d.shard_hi)) {
+        // sharded map: this query is answered by the rank whose x-slab holds it
+        d.nbr[6 * (size_t)pos_q] = 0;
+      } else {
         const int origin[3] = {d.desc[slot].origin[0], d.desc[slot].origin[1], d.desc[slot].origin[2]};
-        ncand = stage_rows(d, cls ? B + slot : slot, origin, w[0], w[1], w[2], S, lane);
-        S.q[lane] = make_float4(w[0], w[1], w[2], __int_as_float(ncand));
-        search = ncand >= 5;
+        Knn5 r;
+        visited = knn5_cells(d, cls ? B + slot : slot, origin, w[0], w[1], w[2], r, stage);
+        const bool gate = knn_d2(r, 4) < 1.0f;  // laserMapping.cpp:585 / :653
+        int* nb = d.nbr + 6 * (size_t)pos_q;
+        nb[0] = (visited << 1) | (gate ? 1 : 0);  // visited = map points in the query's 27 cells
+        if (gate) {  // positions in d.cand of the five neighbours (local index -> position through d.inv)
+          const int* __restrict__ inv = d.inv + d.lp_off[cls ? B + slot : slot];
+#pragma unroll
+          for (int kk = 0; kk < 5; ++kk) nb[1 + kk] = inv[knn_idx(r, kk)];
+        }
       }
     }
-    __syncwarp();
-    // ---- phase 2 ----
-    const unsigned todo = __ballot_sync(kFull, search);
-    warp_knn5_all(S, d.cand, todo, lane);
-    // ---- phase 3 ----
-    const bool gate = search && S.nsel[lane] == 5;  // laserMapping.cpp:585 / :653
-    float nb[5][3];
-    int nbi[5];
+  }
+}
+
+constexpr int kSumRows = 30;  // 28 sums + n_edge + n_plane, transposed through shared memory
+template <bool kTrace>
+__global__ void __launch_bounds__(kTile, S2M_K4B_MINB) fit_kernel(Dev d, int outer) {
+  __shared__ double Tbuf[kTile / 32][kSumRows * 33];
+  const int slot = blockIdx.y;
+  if (!d.out[slot].optimized) return;
+  int dc0, nc, ds0, nq;
+  slot_counts(d, slot, dc0, nc, ds0, nq);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int unit = blockIdx.x * (kTile / 32) + wid;
+  if (unit * 32 >= nq) return;  // whole warp; nothing below synchronises the block
+  const int q = unit * 32 + lane;
+  const bool live = q < nq;
+  const int cls = q >= nc;
+  const int di = cls ? ds0 + (q - nc) : dc0 + q;
+  double pose[7];  // accepted pose of the slot (guard_kernel / the previous solve)
+#pragma unroll
+  for (int i = 0; i < 7; ++i) pose[i] = d.lm[slot].x[i];
+  bool used = false, gate = false;
+  int ncand = 0;
+  double rec[6] = {0, 0, 0, 0, 0, 0};
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    const int* nbp = d.nbr + 6 * (size_t)di;
+    const int head = nbp[0];
+    gate = head & 1;
+    ncand = head >> 1;
+    p = d.ds_pts[di];
     if (gate) {
+      float nb[5][3];
+      int nbi[5];
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const float4 c = S.nbr[lane][k];
+        const float4 c = __ldg(d.cand + (uint32_t)nbp[1 + k]);
         nb[k][0] = c.x; nb[k][1] = c.y; nb[k][2] = c.z;
         nbi[k] = __float_as_int(c.w);
       }
-    }
-    float qw[3] = {0.f, 0.f, 0.f};
-    if (kTrace && search) { qw[0] = S.q[lane].x; qw[1] = S.q[lane].y; qw[2] = S.q[lane].z; }
-    __syncwarp();  // the staging area becomes the transposition buffer
-    Sums28 Sm;
-    Sm.zero();
-    double ne = 0.0, np = 0.0;
-    bool used = false;
-    if (gate) {
-      const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
-      double rec[6] = {0, 0, 0, 0, 0, 0};
-      if (cls == 0) {
-        used = edge_fit(nb, rec, rec + 3);
-        if (used) { accum_edge(Sm, pose, cp, rec, rec + 3); ne = 1.0; }
-      } else {
-        used = plane_fit(nb, rec, rec[3]);
-        if (used) { accum_plane(Sm, pose, cp, rec, rec[3]); np = 1.0; }
+      if (kTrace) {
+        float w[3];
+        xf_point(pose, p.x, p.y, p.z, w);
+        const size_t o = (size_t)outer * d.cap_in + di;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          d.tr_idx[5 * o + k] = nbi[k];
+          d.tr_d2[5 * o + k] = dist2(w[0], w[1], w[2], nb[k][0], nb[k][1], nb[k][2]);
+        }
       }
+      used = cls == 0 ? edge_fit(nb, rec, rec + 3) : plane_fit(nb, rec, rec[3]);
       if (used) {
         double2* ro = reinterpret_cast<double2*>(d.rec + 6 * (size_t)di);
         ro[0] = make_double2(rec[0], rec[1]);
         ro[1] = make_double2(rec[2], rec[3]);
         ro[2] = make_double2(rec[4], rec[5]);
       }
-    }
-    if (live) d.rec_valid[di] = used ? 1 : 0;
-    if (kTrace && live) {
+    } else if (kTrace) {
       const size_t o = (size_t)outer * d.cap_in + di;
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        d.tr_idx[5 * o + k] = gate ? nbi[k] : -1;
-        d.tr_d2[5 * o + k] = gate ? dist2(qw[0], qw[1], qw[2], nb[k][0], nb[k][1], nb[k][2]) : INFINITY;
-      }
-      d.tr_used[o] = used ? 1 : 0;
+      for (int k = 0; k < 5; ++k) { d.tr_idx[5 * o + k] = -1; d.tr_d2[5 * o + k] = INFINITY; }
     }
-    // ---- the unit's sums: transpose, then lane k adds row k in lane order ----
-#pragma unroll
-    for (int k = 0; k < 28; ++k) T[k * 33 + lane] = Sm.v[k];
-    T[28 * 33 + lane] = ne;
-    T[29 * 33 + lane] = np;
-    __syncwarp();
-    double v = 0.0;
-    if (lane < kSumRows) {
-      const double* row = T + lane * 33;
-#pragma unroll 8
-      for (int i = 0; i < 32; ++i) v += row[i];
-    }
-    // candidates in the 27 cells of the unit's corner / surf queries (the C-bar of SURVEY 8d's byte formula)
-    int cc = cls ? 0 : ncand, cs = cls ? ncand : 0;
-    for (int o = 16; o > 0; o >>= 1) {
-      cc += __shfl_down_sync(kFull, cc, o);
-      cs += __shfl_down_sync(kFull, cs, o);
-    }
-    cc = __shfl_sync(kFull, cc, 0);
-    cs = __shfl_sync(kFull, cs, 0);
-    if (lane == 30) v = (double)cc;
-    if (lane == 31) v = (double)cs;
-    d.partials[((size_t)slot * d.max_tiles + unit) * kPartial + lane] = v;
-    __syncwarp();  // T is rewritten by the next unit's staging
+    d.rec_valid[di] = used ? 1 : 0;
+    if (kTrace) d.tr_used[(size_t)outer * d.cap_in + di] = used ? 1 : 0;
   }
+  Sums28 Sm;
+  Sm.zero();
+  double ne = 0.0, np = 0.0;
+  if (used) {
+    const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
+    if (cls == 0) { accum_edge(Sm, pose, cp, rec, rec + 3); ne = 1.0; }
+    else { accum_plane(Sm, pose, cp, rec, rec[3]); np = 1.0; }
+  }
+  // ---- the unit's sums: transpose, then lane k adds row k in lane order ----
+  double* T = Tbuf[wid];
+#pragma unroll
+  for (int k = 0; k < 28; ++k) T[k * 33 + lane] = Sm.v[k];
+  T[28 * 33 + lane] = ne;
+  T[29 * 33 + lane] = np;
+  __syncwarp();
+  double v = 0.0;
+  if (lane < kSumRows) {
+    const double* row = T + lane * 33;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) v += row[i];
+  }
+  // candidates in the 27 cells of the unit's corner / surf queries (the C-bar of SURVEY 8d's byte formula)
+  int cc = cls ? 0 : ncand, cs = cls ? ncand : 0;
+  for (int o = 16; o > 0; o >>= 1) {
+    cc += __shfl_down_sync(kFull, cc, o);
+    cs += __shfl_down_sync(kFull, cs, o);
+  }
+  cc = __shfl_sync(kFull, cc, 0);
+  cs = __shfl_sync(kFull, cs, 0);
+  if (lane == 30) v = (double)cc;
+  if (lane == 31) v = (double)cs;
+  d.partials[((size_t)slot * d.max_tiles + unit) * kPartial + lane] = v;
 }
 
 // Sum of the unit partials of a slot in unit order (fixed: deterministic).  Whole warp; lane k returns sum k.
@@ -1945,13 +1879,19 @@ int launch_guard(const Dev& d, cudaStream_t s) {
   guard_kernel<<<cdiv(d.B, 64), 64, 0, s>>>(d);
   return 1;
 }
-// One association (rows P..Q of one outer iteration) for every optimised slot: the fused kernel,
-// `blocks` persistent blocks sharing a device-wide work ticket.
-int launch_associate(const Dev& d, int outer, int blocks, bool trace, cudaStream_t s) {
-  if (blocks <= 0) return 0;  // (the caller zeroes d.knn_ticket)
-  if (trace) assoc_kernel<true><<<blocks, kTile, 0, s>>>(d, outer);
-  else assoc_kernel<false><<<blocks, kTile, 0, s>>>(d, outer);
-  return 1;
+// One association (rows P..Q of one outer iteration) for every optimised slot: K4a with `knn_blocks`
+// persistent blocks sharing a device-wide tile ticket (the caller zeroes d.knn_ticket), then K4b.
+int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s) {
+  if (knn_blocks <= 0 || fit_blocks <= 0) return 0;
+  dim3 gb(fit_blocks, d.B);
+  if (trace) {
+    knn_kernel<true><<<knn_blocks, kTile, 0, s>>>(d, outer);
+    fit_kernel<true><<<gb, kTile, 0, s>>>(d, outer);
+  } else {
+    knn_kernel<false><<<knn_blocks, kTile, 0, s>>>(d, outer);
+    fit_kernel<false><<<gb, kTile, 0, s>>>(d, outer);
+  }
+  return 2;
 }
 // The LM solve that follows it (<= 4 iterations) in one launch: a cluster of four CTAs per slot.
 int launch_solve(const Dev& d, int outer, bool from_units, cudaStream_t s) {

@@ -21,25 +21,38 @@ def seq(built):
 
 def test_checkpoint_larger_than_the_frame_buffers_resumes_bit_exact(s2m, seq, tmp_path):
     """cap_*_in (the per-frame staging) is far smaller than the map: s2m_map_upload / s2m_checkpoint_load push the
-    map in chunks.  Resume == uninterrupted run, map and poses bit for bit."""
+    map in chunks.  Chunked upload == one-shot upload, resume == uninterrupted run, maps and poses bit for bit."""
     truth, odom, frames = seq
-    max_c = max(len(c) for c, _ in frames) + 8
-    max_s = max(len(s) for _, s in frames) + 8
-    kw = dict(cap_corner_in=max_c, cap_surf_in=max_s, cap_map_corner=1 << 17, cap_map_surf=1 << 18)
-    A = s2m.Registrar(0.4, 0.8, **kw)
+    O = oracle.Oracle(0.4, 0.8)
     for f in range(6):
-        A.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
-    n_map = len(A.map_download(0)) + len(A.map_download(1))
-    assert len(A.map_download(1)) > max_s and n_map > max_c + max_s  # the case round 1 could save but not load
+        O.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+    cm, sm = O.get_map(0), O.get_map(1)
+    small_kw = dict(cap_corner_in=2048, cap_surf_in=3000, cap_map_corner=1 << 17, cap_map_surf=1 << 17)
+    assert len(cm) > 4 * 2048 and len(sm) > 2 * 3000  # several chunks per class: the case round 1 could save but not load
+    A = s2m.Registrar(0.4, 0.8, **small_kw)
+    big = s2m.Registrar(0.4, 0.8, cap_map_corner=1 << 17, cap_map_surf=1 << 17)
+    assert A.map_upload(cm, sm) == 0 and big.map_upload(cm, sm) == 0
+    for cls in (0, 1):
+        assert np.array_equal(bits(A.map_download(cls)), bits(big.map_download(cls)))
+
+    def thin(f):  # frames that fit the small staging buffers
+        return frames[f][0][:2000], frames[f][1][::12][:2900]
+
+    for f in (6, 7):
+        c, s = thin(f)
+        ra, qa, ta = A.register(c, s, odom[f, :4], odom[f, 4:])
+        rb, qb, tb = big.register(c, s, odom[f, :4], odom[f, 4:])
+        assert ra == rb == 0 and np.array_equal(qa, qb) and np.array_equal(ta, tb), f
     prefix = str(tmp_path / "big")
     A.checkpoint_save(prefix)
-    Bc = s2m.Registrar(0.4, 0.8, **kw)
+    Bc = s2m.Registrar(0.4, 0.8, **small_kw)
     assert Bc.checkpoint_load(prefix) == 0
     for cls in (0, 1):
         assert np.array_equal(bits(A.map_download(cls)), bits(Bc.map_download(cls)))
-    for f in range(6, 9):
-        ra, qa, ta = A.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
-        rb, qb, tb = Bc.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+    for f in (8, 9):
+        c, s = thin(f)
+        ra, qa, ta = A.register(c, s, odom[f, :4], odom[f, 4:])
+        rb, qb, tb = Bc.register(c, s, odom[f, :4], odom[f, 4:])
         assert ra == rb and np.array_equal(qa, qb) and np.array_equal(ta, tb), f
     for cls in (0, 1):
         assert np.array_equal(bits(A.map_download(cls)), bits(Bc.map_download(cls)))
