@@ -31,7 +31,8 @@ sys.path.insert(0, ROOT)
 METRIC = "scan_to_map_registrations_per_s"
 UNIT = "registrations/s"
 N_WORLDS = 8          # distinct synthetic worlds/trajectories (BASELINE config 4: 8 sequences)
-PREFILL = int(os.environ.get("S2M_BENCH_PREFILL", 20))  # untimed frames that build each sequence's map before warm-up
+PREFILL = int(os.environ.get("S2M_BENCH_PREFILL", 120))  # untimed frames that build each sequence's map: 120 m driven, the
+# local map (5 x 5 x 3 cubes) is then stationary in size (~110 k points) -- the steady state of BASELINE config 1
 SENSOR = "HDL64"
 LINE_RES, PLANE_RES = 0.4, 0.8  # aloam_velodyne_HDL_64.launch:11-12
 
@@ -60,14 +61,37 @@ def make_worlds(n_frames, rank, threads):
 
 
 def slot_odometry(worlds, n_slots, rank):
-    """Slot s replays world s % N_WORLDS with its own odometry drift (so every slot is a
-    different registration problem: different guesses, poses and maps)."""
+    """Slot s replays world s % N_WORLDS (frames PREFILL..) with its own odometry drift, starting on the truth at
+    frame PREFILL (so every slot is a different registration problem: different guesses and poses).
+    Row f of the result belongs to frame PREFILL + f."""
     import harness
     odo = []
     for s in range(n_slots):
-        seed, truth, _ = worlds[s % N_WORLDS]
-        odo.append(harness.odometry(seed * 7919 + 104729 * (s // N_WORLDS) + 15485863 * rank, truth, 0.02, 0.1))
+        seed, truth = worlds[s % N_WORLDS][0], worlds[s % N_WORLDS][1]
+        odo.append(harness.odometry(seed * 7919 + 104729 * (s // N_WORLDS) + 15485863 * rank, truth[PREFILL:], 0.02, 0.1))
     return odo
+
+
+def mature_maps(pkg, worlds, device):
+    """The map every sequence has after PREFILL frames: built once per world by the engine itself (one context, one
+    slot per world, the frames registered at the true poses), downloaded, and later pushed into every slot that
+    replays that world (s2m_map_upload) -- instead of prefilling 384 slots frame by frame."""
+    if PREFILL == 0:
+        return [(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32)) for _ in worlds]
+    nw = len(worlds)
+    max_c = max(len(w[2][f][0]) for w in worlds for f in range(PREFILL)) + 64
+    max_s = max(len(w[2][f][1]) for w in worlds for f in range(PREFILL)) + 64
+    R = pkg.Registrar(LINE_RES, PLANE_RES, device=device, batch=nw, cap_corner_in=max_c, cap_surf_in=max_s,
+                      cap_map_corner=1 << 19, cap_map_surf=1 << 19)
+    for f in range(PREFILL):
+        cs, ss = [w[2][f][0] for w in worlds], [w[2][f][1] for w in worlds]
+        co = np.cumsum([0] + [len(c) for c in cs]).astype(np.int32)
+        so = np.cumsum([0] + [len(c) for c in ss]).astype(np.int32)
+        R.register_batch(np.concatenate(cs), co, np.concatenate(ss), so, np.array([w[1][f, :4] for w in worlds]),
+                         np.array([w[1][f, 4:] for w in worlds]))
+    maps = [(R.map_download(0, slot=i), R.map_download(1, slot=i)) for i in range(nw)]
+    R.close()
+    return maps
 
 
 def pack_step(worlds, n_slots, f):
@@ -131,62 +155,88 @@ def measured_peak():
 
 
 def k4_traffic():
-    """dram bytes per K4 launch from the committed ncu --set full capture, if any."""
+    """DRAM bytes per K4 launch pair from the committed ncu --set full capture -- used only if that capture was
+    taken from the kernels as they are now (sha256 of csrc/s2m_kernels.cu + s2m_math.cuh), else None."""
+    import hashlib
     p = os.path.join(ROOT, "profiles", "k4_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except Exception:
-            pass
-    return None
+    if not os.path.exists(p):
+        return None
+    try:
+        t = json.load(open(p))
+        h = hashlib.sha256()
+        for f in ("s2m_kernels.cu", "s2m_math.cuh"):
+            h.update(open(os.path.join(ROOT, "sc-a-loam_b200", "csrc", f), "rb").read())
+        return t if t.get("kernels_sha256") == h.hexdigest() else None
+    except Exception:
+        return None
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_baseline(worlds, odo, n_frames, max_seconds=25.0):
-    """Oracle (restated reference path) on ONE core over a bounded sample: each world's frames
-    after the prefill, sequence after sequence."""
+def cpu_baseline(worlds, maps, odo, n_run, max_seconds=25.0):
+    """Oracle (restated reference path) on ONE core over a bounded sample: each world's replayed frames, starting
+    from the same mature map, sequence after sequence."""
     import oracle
     regs, t_total = 0, 0.0
     per_phase = np.zeros(7)
     for w in range(N_WORLDS):
         O = oracle.Oracle(LINE_RES, PLANE_RES)
-        _, truth, frames = worlds[w]
+        frames = worlds[w][2]
+        if len(maps[w][0]) + len(maps[w][1]):
+            O.map_upload(maps[w][0], maps[w][1])
         od = odo[w]
-        for f in range(n_frames):
-            c, s = frames[f]
+        for f in range(n_run):
+            c, s = frames[PREFILL + f]
             t0 = time.perf_counter()
             O.register(c, s, od[f, :4], od[f, 4:])
             dt = time.perf_counter() - t0
-            if f >= PREFILL:
+            if f >= 1:  # (the first frame re-filters the uploaded map)
                 t_total += dt
                 regs += 1
                 per_phase += np.array(O.stats.t_ms[:7])
         if t_total > max_seconds:
             break
     return {"value": regs / t_total, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "%d registrations: frames %d..%d of %d HDL-64 worlds, sequentially on one core "
-                      "(oracle/ = CPU restatement of laserMapping.cpp:310-802; PCL/Ceres not installable here)"
-                      % (regs, PREFILL, n_frames - 1, w + 1),
+            "sample": "%d registrations: frames %d..%d of %d HDL-64 worlds against their %d-frame maps, sequentially on "
+                      "one core (oracle/ = CPU restatement of laserMapping.cpp:310-802; PCL/Ceres not installable here)"
+                      % (regs, PREFILL + 1, PREFILL + n_run - 1, w + 1, PREFILL),
             "ms_per_registration": 1e3 * t_total / regs,
             "phase_ms": {k: round(float(v) / regs, 3) for k, v in
                          zip(["shift", "tree", "data", "solver", "add", "filter", "whole"], per_phase)}}
 
 
 def run_reference(args, rank, world):
+    """The reference path's CPU restatement on all host cores, same workload: every world's map is built by the
+    restatement itself (PREFILL frames at the true poses), then one sequence per host thread is replayed."""
     if rank != 0:
         return 0
     import oracle
     cores = os.cpu_count() or 1
     n_seq = min(cores, 64)
-    n_frames = PREFILL + args.warmup + args.steps
-    worlds = make_worlds(n_frames, 0, cores)
+    n_run = args.warmup + args.steps
+    worlds = make_worlds(PREFILL + n_run, 0, cores)
     odo = slot_odometry(worlds, n_seq, 0)
+    maps = [None] * N_WORLDS
+
+    def build_map(w):
+        O = oracle.Oracle(LINE_RES, PLANE_RES)
+        truth, frames = worlds[w][1], worlds[w][2]
+        for f in range(PREFILL):
+            O.register(frames[f][0], frames[f][1], truth[f, :4], truth[f, 4:])
+        maps[w] = (O.get_map(0), O.get_map(1))
+
+    th = [threading.Thread(target=build_map, args=(w,)) for w in range(N_WORLDS)]
+    [t.start() for t in th]
+    [t.join() for t in th]
     oracles = [oracle.Oracle(LINE_RES, PLANE_RES) for _ in range(n_seq)]
+    for s_, O in enumerate(oracles):
+        cm, sm = maps[s_ % N_WORLDS]
+        if len(cm) + len(sm):
+            O.map_upload(cm, sm)
 
     def run_frames(s, f0, f1):
         frames = worlds[s % N_WORLDS][2]
         for f in range(f0, f1):
-            c, su = frames[f]
+            c, su = frames[PREFILL + f]
             oracles[s].register(c, su, odo[s][f, :4], odo[s][f, 4:])
 
     def parallel(f0, f1):
@@ -194,9 +244,9 @@ def run_reference(args, rank, world):
         [t.start() for t in th]
         [t.join() for t in th]
 
-    parallel(0, PREFILL + args.warmup)  # ctypes releases the GIL: one sequence per host thread
+    parallel(0, args.warmup)  # ctypes releases the GIL: one sequence per host thread
     t0 = time.perf_counter()
-    parallel(PREFILL + args.warmup, n_frames)
+    parallel(args.warmup, n_run)
     dt = time.perf_counter() - t0
     value = n_seq * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -204,7 +254,8 @@ def run_reference(args, rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "hdl64_batch_replay", "sensor": "HDL-64 synthetic 64x1900",
                        "line_res": LINE_RES, "plane_res": PLANE_RES, "sequences": n_seq,
-                       "distinct_worlds": N_WORLDS, "prefill_frames": PREFILL},
+                       "distinct_worlds": N_WORLDS, "prefill_frames": PREFILL,
+                       "map_points_per_sequence": float(np.mean([len(m[0]) + len(m[1]) for m in maps]))},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_seq, "kind": "port",
                              "sample": "%d sequences x %d frames, one sequence per host thread (%d cores); oracle/ "
                                        "restatement of the reference path" % (n_seq, args.steps, cores)},
@@ -214,47 +265,58 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------
-def make_worlds_distributed(n_frames, rank, world):
-    """Each rank ray-casts its share of the N_WORLDS worlds, then all ranks exchange them."""
+def prepare_worlds(pkg, n_frames, rank, world, device):
+    """Each rank ray-casts its share of the N_WORLDS worlds and builds their mature maps; then all ranks exchange
+    the replayed frames (PREFILL..) and the maps.  -> (worlds, maps); frames before PREFILL are dropped (None)."""
     if world == 1:
-        return make_worlds(n_frames, rank, os.cpu_count() or 1)
+        worlds = make_worlds(n_frames, rank, os.cpu_count() or 1)
+        maps = mature_maps(pkg, worlds, device)
+        return worlds, maps
     import harness
     import torch.distributed as dist
-    mine = {}
-    for w in range(rank, N_WORLDS, world):
+    ids = list(range(rank, N_WORLDS, world))
+    mine = []
+    for w in ids:
         seed = 20261018 + w
         truth = harness.trajectory(seed, n_frames, 1.0)
         frames = [harness.features(SENSOR, harness.scan(seed, SENSOR, truth[f], f, 0.02)) for f in range(n_frames)]
-        mine[w] = (seed, truth, frames)
+        mine.append((seed, truth, frames))
+    my_maps = mature_maps(pkg, mine, device) if mine else []
+    share = {w: ((m[0], m[1], [None] * PREFILL + m[2][PREFILL:]), mp) for w, m, mp in zip(ids, mine, my_maps)}
     parts = [None] * world
-    dist.all_gather_object(parts, mine)
+    dist.all_gather_object(parts, share)
     merged = {}
     for p in parts:
         merged.update(p)
-    return [merged[w] for w in range(N_WORLDS)]
+    return [merged[w][0] for w in range(N_WORLDS)], [merged[w][1] for w in range(N_WORLDS)]
 
 
 class Lane:
     """One context holding S sequences split over `lanes` concurrent lanes (own stream + host thread
     each, inside the library): one C-ABI call per step advances all of them."""
 
-    def __init__(self, pkg, torch, worlds, S, lanes, variant, n_frames, local_rank, args, host_buffers):
-        self.torch, self.S, self.n_frames = torch, S, n_frames
+    def __init__(self, pkg, torch, worlds, maps, S, lanes, variant, n_run, local_rank, args, host_buffers):
+        """n_run frames are replayed: step f is frame PREFILL + f of every sequence; the maps start mature."""
+        self.torch, self.S, self.n_frames = torch, S, n_run
         odo = slot_odometry(worlds, S, variant)
-        steps = [pack_step(worlds, S, f) for f in range(n_frames)]
-        self.q_all = np.array([[odo[s][f, :4] for s in range(S)] for f in range(n_frames)])
-        self.t_all = np.array([[odo[s][f, 4:] for s in range(S)] for f in range(n_frames)])
+        steps = [pack_step(worlds, S, PREFILL + f) for f in range(n_run)]
+        self.q_all = np.array([[odo[s][f, :4] for s in range(S)] for f in range(n_run)])
+        self.t_all = np.array([[odo[s][f, 4:] for s in range(S)] for f in range(n_run)])
         self.host = host_buffers
         if host_buffers:
             self.steps = [(torch.from_numpy(c).pin_memory(), co, torch.from_numpy(su).pin_memory(), so) for c, co, su, so in steps]
         else:
             self.steps = [(torch.from_numpy(c).cuda(), co, torch.from_numpy(su).cuda(), so) for c, co, su, so in steps]
-        self.h2d = float(np.mean([c.nbytes + su.nbytes for c, _, su, _ in steps[PREFILL + args.warmup:]]))
+        self.h2d = float(np.mean([c.nbytes + su.nbytes for c, _, su, _ in steps[args.warmup:]]))
         max_c = max(int(np.diff(st[1]).max()) for st in steps)
         max_s = max(int(np.diff(st[3]).max()) for st in steps)
         self.stream = torch.cuda.Stream()  # a real stream: the library fences its lanes on it, the events time it
         self.R = pkg.Registrar(LINE_RES, PLANE_RES, device=local_rank, batch=S, lanes=lanes, cap_corner_in=max_c + 64,
                                cap_surf_in=max_s + 64, cap_map_corner=args.cap_map_corner, cap_map_surf=args.cap_map_surf)
+        for sl in range(S):  # every sequence starts from the map its world has after PREFILL frames
+            cm, sm = maps[sl % N_WORLDS]
+            if len(cm) + len(sm):
+                self.R.map_upload(cm, sm, slot=sl)
         self.R.set_stream(self.stream.cuda_stream)
         self.events = None
         self.pipelined = lanes >= 1 and not args.no_pipeline
@@ -303,7 +365,7 @@ def run_ours(args, rank, world, local_rank):
     S, C = args.seqs, args.ctx
     n_frames = PREFILL + args.warmup + args.steps
     t_gen = time.perf_counter()
-    worlds = make_worlds_distributed(n_frames, rank, world)
+    worlds, maps = prepare_worlds(pkg, n_frames, rank, world, local_rank)
     t_gen = time.perf_counter() - t_gen
 
     def barrier():
@@ -311,15 +373,17 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
+    n_run = args.warmup + args.steps
+
     def timed_arm(host_buffers, sampler=None):
-        lane = Lane(pkg, torch, worlds, C * S, C, rank, n_frames, local_rank, args, host_buffers)
-        lane.run(0, PREFILL + args.warmup, False)  # untimed: map prefill + warm-up steps
+        lane = Lane(pkg, torch, worlds, maps, C * S, C, rank, n_run, local_rank, args, host_buffers)
+        lane.run(0, args.warmup, False)  # untimed warm-up steps (the first one re-filters the uploaded map)
         barrier()
         if sampler:
             sampler.start()
         l0 = lane.R.launch_count()
         wall0 = time.perf_counter()
-        lane.run(PREFILL + args.warmup, n_frames, True)
+        lane.run(args.warmup, n_run, True)
         barrier()
         wall = time.perf_counter() - wall0
         if sampler:
@@ -332,13 +396,12 @@ def run_ours(args, rank, world, local_rank):
         launches = lane.R.launch_count() - l0
         h2d = lane.h2d
         stats = [lane.R.batch_stats[s] for s in range(C * S)]
-        lanes = [lane]
         shape = {k: float(np.mean([getattr(st, k) for st in stats])) for k in
                  ("n_corner_in", "n_surf_in", "n_corner_ds", "n_surf_ds", "n_map_corner", "n_map_surf")}
         shape["n_edge"] = float(np.mean([st.n_edge[1] for st in stats]))
         shape["n_plane"] = float(np.mean([st.n_plane[1] for st in stats]))
-        for l in lanes:
-            l.close()
+        shape["lm_iterations"] = float(np.mean([st.lm_iters[0] + st.lm_iters[1] for st in stats]))
+        lane.close()
         torch.cuda.empty_cache()
         return ms, launches, wall, h2d, shape
 
@@ -348,12 +411,12 @@ def run_ours(args, rank, world, local_rank):
 
     # arm 3 (untimed for the headline): one context with profiling on -> K4 roofline and phase split
     prof_steps = min(args.steps, 6)
-    lane = Lane(pkg, torch, worlds, S, 0, rank, PREFILL + args.warmup + prof_steps, local_rank, args, False)
-    lane.run(0, PREFILL + args.warmup, False)
+    lane = Lane(pkg, torch, worlds, maps, S, 0, rank, args.warmup + prof_steps, local_rank, args, False)
+    lane.run(0, args.warmup, False)
     torch.cuda.synchronize()
     lane.R.set_profiling(True)
     lane.R.k4_profile(reset=True)
-    lane.run(PREFILL + args.warmup, PREFILL + args.warmup + prof_steps, False)
+    lane.run(args.warmup, args.warmup + prof_steps, False)
     k4_ms, k4_n, k4_bytes = lane.R.k4_profile(reset=False)
     phases = lane.R.phase_profile(reset=True)
     lane.close()
@@ -364,6 +427,12 @@ def run_ours(args, rank, world, local_rank):
         from bench_sharded import run_sharded
         sharded = run_sharded(pkg, torch, dist, rank, world, local_rank, slots=args.sharded_slots,
                               fill_corner=args.sharded_fill_corner, fill_surf=args.sharded_fill_surf)
+
+    # arm 5: BASELINE config 3 -- OS1-64 against a saturated window (a 1-GPU configuration: N = 1 only)
+    os1 = None
+    if world == 1 and not args.no_os1:
+        from bench_os1 import run_os1_saturated
+        os1 = run_os1_saturated(pkg, torch, local_rank, slots=args.os1_slots)
 
     if rank != 0:
         if world > 1:
@@ -376,6 +445,13 @@ def run_ours(args, rank, world, local_rank):
     ach = (k4_bytes / max(k4_n, 1)) / (1e-3 * k4_ms / max(k4_n, 1)) / 1e9 if k4_ms > 0 else 0.0
     traffic = k4_traffic()
     d2h = float(C * (S * 168 + 4))  # poses + per-slot counters + error flag read back every step
+    # bytes_alg per registration = 2 (B_K4 + B_K5) + B_map with B_K4 per association launch as measured
+    # above, B_K5 = 48 Nv E (E = LM evaluations executed after the first), B_map = 2*16 (Nc_in+Ns_in) + 3*16 (Nc+Ns)
+    nv = shape["n_edge"] + shape["n_plane"]
+    b_k4 = (k4_bytes / max(k4_n, 1)) / S
+    b_k5 = 48.0 * nv * (shape["lm_iterations"] / 2.0)
+    b_map = 32.0 * (shape["n_corner_in"] + shape["n_surf_in"]) + 48.0 * (shape["n_corner_ds"] + shape["n_surf_ds"])
+    bytes_reg = 2.0 * (b_k4 + b_k5) + b_map
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -384,7 +460,8 @@ def run_ours(args, rank, world, local_rank):
                    "line_res": LINE_RES, "plane_res": PLANE_RES, "sequences_per_gpu": C * S, "lanes_per_gpu": C,
                    "sequences_per_lane": S, "distinct_worlds": N_WORLDS, "prefill_frames": PREFILL,
                    "registrations_per_step": world * C * S, "parallelism": "independent sequences x%d GPUs, no collective" % world,
-                   "l2": "no flush: each step touches >300 MB per context (maps, sort buffers, clouds), larger than the 126 MB L2",
+                   "l2": "no flush: each step touches >1 GB per lane (64 maps of ~110 k points, sort buffers, clouds), far larger than the 126 MB L2",
+                   "maps": "mature: every sequence starts from the map its world has after %d frames (built by the engine, uploaded with s2m_map_upload); see per_registration_mean.n_map_*" % PREFILL,
                    "timing": "CUDA events around the K steps on the caller's stream (the library fences its lanes on it); max over ranks",
                    "per_registration_mean": shape, "datagen_s": round(t_gen, 1),
                    "phase_ms_per_step_single_lane": {k: round(v / prof_steps, 4) for k, v in phases.items()},
@@ -399,13 +476,19 @@ def run_ours(args, rank, world, local_rank):
                      "measured": "CUDA events on the launching stream, single context, profiling pass",
                      "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
                      "traffic_source": traffic.get("source") if traffic else None},
+        "registration_roofline": {"bound": "hbm", "bytes_algorithmic_per_registration": bytes_reg,
+                                  "achieved": bytes_reg * value / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": bytes_reg * value / 1e9 / peak,
+                                  "what": "whole registration (rows A..W), SURVEY 8d bytes_alg x registrations/s of the device-resident arm"},
         "clocks": sampler.result(),
     }
     if sharded is not None:
         line["sharded"] = sharded
+    if os1 is not None:
+        line["os1_saturated"] = os1
     if world == 1 and not args.no_cpu_baseline:
         odo = slot_odometry(worlds, N_WORLDS, 0)
-        line["cpu_baseline"] = cpu_baseline(worlds, odo, n_frames)
+        line["cpu_baseline"] = cpu_baseline(worlds, maps, odo, n_run)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -421,9 +504,11 @@ def main():
     ap.add_argument("--seqs", type=int, default=64, help="independent sequences per lane (<=64)")
     ap.add_argument("--no-pipeline", action="store_true", help="synchronous batch calls instead of submit/wait with two frames in flight")
     ap.add_argument("--ctx", "--lanes", dest="ctx", type=int, default=6, help="concurrent lanes per GPU inside the one context")
-    ap.add_argument("--cap-map-corner", type=int, default=1 << 17)
-    ap.add_argument("--cap-map-surf", type=int, default=1 << 17)
+    ap.add_argument("--cap-map-corner", type=int, default=1 << 18)
+    ap.add_argument("--cap-map-surf", type=int, default=1 << 18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-os1", action="store_true", help="skip the OS1-64 / saturated-window arm (BASELINE config 3)")
+    ap.add_argument("--os1-slots", type=int, default=16)
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded giant-map arm (BASELINE config 5)")
     ap.add_argument("--sharded-slots", type=int, default=16)
     ap.add_argument("--sharded-fill-corner", type=int, default=3_000_000)

@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""bench_os1.py -- BASELINE config 3: Ouster OS1-64 scans (MulRan shape, aloam_mulran.launch:9-12:
+minimum_range 0.5, 0.4 / 0.8 m) against a SATURATED 21 x 21 x 11 cube window, registrations at random poses.
+
+Every slot holds the whole saturated window of one synthetic world (every surface inside it sampled directly,
+SURVEY 8d's alternative to a lawn-mower drive; ~0.8 M corner + ~2.7 M surf points after the per-cube filter).
+One step = every slot registers one sweep taken at a random street position of the window, hundreds of metres
+from its previous one: the valid block, the pending lists and the cell index are all new every frame, and the
+local map is a full ground level of cubes (~170 k points) -- the heavy end of the single-GPU workloads.
+Used by bench.py (`os1_saturated` object of its JSON line); runnable on its own.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def run_os1_saturated(pkg, torch, local_rank, rank=0, slots=16, warmup=3, steps=10, n_worlds=2, seed=20261018):
+    import harness
+    B = slots
+    rng = np.random.default_rng(seed + 17 * rank)
+    t0 = time.perf_counter()
+    surf_maps = [harness.surfaces(seed + w) for w in range(n_worlds)]
+    n_run = warmup + steps
+    scans = []  # [step][slot] -> (corner, surf, guess pose)
+    for f in range(n_run):
+        row = []
+        for b in range(B):
+            pose = harness.street_pose(float(rng.uniform(-330.0, 330.0)), int(rng.integers(-4, 5)), int(rng.integers(0, 4)))
+            c, s = harness.features("OS1-64", harness.scan(seed + b % n_worlds, "OS1-64", pose, f))
+            guess = pose.copy()
+            guess[4:] += rng.uniform(-0.2, 0.2, 3)  # SURVEY 8d "T_init distribution"
+            row.append((c, s, guess, pose))
+        scans.append(row)
+    gen_s = time.perf_counter() - t0
+    max_c = max(len(r[0]) for row in scans for r in row) + 64
+    max_s = max(len(r[1]) for row in scans for r in row) + 64
+    R = pkg.Registrar(0.4, 0.8, device=local_rank, batch=B, cap_corner_in=max(max_c, 1 << 17), cap_surf_in=max(max_s, 1 << 18),
+                      cap_map_corner=1 << 21, cap_map_surf=1 << 22)
+    stream = torch.cuda.Stream()
+    R.set_stream(stream.cuda_stream)
+    t0 = time.perf_counter()
+    for b in range(B):
+        R.map_upload(*surf_maps[b % n_worlds], slot=b)
+    e = np.zeros((0, 4), np.float32)
+    z = np.zeros(B + 1, np.int32)
+    for cx in (-250.0, 0.0, 250.0):      # saturate: the 3 x 3 block positions that cover the window without shifting it
+        for cy in (-250.0, 0.0, 250.0):
+            R.register_batch(e, z, e, z, np.tile([0, 0, 0, 1.0], (B, 1)), np.tile([cx, cy, 0.0], (B, 1)))
+    n_map = sum(len(R.map_download(cls, slot=0)) for cls in (0, 1))
+    setup_s = time.perf_counter() - t0
+
+    def step(f):
+        cs, ss = [r[0] for r in scans[f]], [r[1] for r in scans[f]]
+        co = np.cumsum([0] + [len(c) for c in cs]).astype(np.int32)
+        so = np.cumsum([0] + [len(c) for c in ss]).astype(np.int32)
+        g = np.array([r[2] for r in scans[f]])
+        return R.register_batch(np.concatenate(cs), co, np.concatenate(ss), so, g[:, :4], g[:, 4:])
+
+    for f in range(warmup):
+        step(f)
+    R.set_profiling(True)
+    R.phase_profile(reset=True)
+    torch.cuda.synchronize()
+    err = []
+    with torch.cuda.stream(stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for f in range(warmup, n_run):
+            st, q, t = step(f)
+            err += [float(np.linalg.norm(t[b] - scans[f][b][3][4:])) for b in range(B)]
+        e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    phases = R.phase_profile()
+    stats = [R.batch_stats[b] for b in range(B)]
+    res = {
+        "workload": "os1_64_saturated_window: %d slots, each the whole 21x21x11 window of a synthetic world sampled directly, "
+                    "one OS1-64 sweep per slot per step at a random street position" % B,
+        "slots": B, "steps": steps, "warmup": warmup,
+        "registrations_per_s": B * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+        "window_map_points_per_slot": int(n_map),
+        "local_map_points_mean": float(np.mean([s.n_map_corner + s.n_map_surf for s in stats])),
+        "scan_points_mean": float(np.mean([s.n_corner_in + s.n_surf_in for s in stats])),
+        "queries_mean": float(np.mean([s.n_corner_ds + s.n_surf_ds for s in stats])),
+        "correspondences_mean": float(np.mean([s.n_edge[1] + s.n_plane[1] for s in stats])),
+        "median_error_vs_truth_m": float(np.median(err)), "max_error_vs_truth_m": float(np.max(err)),
+        "phase_ms_per_step": {k: round(v / steps, 4) for k, v in phases.items()},
+        "input": "host buffers (H2D of the sweeps inside the timed region)",
+        "datagen_s": round(gen_s, 1), "setup_s": round(setup_s, 1),
+    }
+    R.close()
+    torch.cuda.empty_cache()
+    return res
+
+
+if __name__ == "__main__":
+    import torch
+    from __graft_entry__ import load_package
+    torch.cuda.set_device(0)
+    print(json.dumps(run_os1_saturated(load_package(), torch, 0)), flush=True)

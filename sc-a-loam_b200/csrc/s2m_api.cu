@@ -258,7 +258,10 @@ static long long next_pow2(long long v) {
   return p;
 }
 // slots of a segment's cell table: a power of two >= 4 x points (<= 3 entries per point: cells + virtual x-neighbours), >= 1024
-static long long table_size(long long n_points) { return next_pow2(std::max<long long>(1024, 4 * n_points)); }
+#ifndef S2M_HASH_MULT
+#define S2M_HASH_MULT 4
+#endif
+static long long table_size(long long n_points) { return next_pow2(std::max<long long>(1024, S2M_HASH_MULT * n_points)); }
 
 extern "C" void s2m_default_params(s2m_params* p) {
   std::memset(p, 0, sizeof(*p));

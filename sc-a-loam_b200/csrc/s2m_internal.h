@@ -34,7 +34,7 @@ namespace s2m {
 #define S2M_OD_MINB 6  // resident blocks per SM of odom_associate_kernel: latency-bound walks, more warps win (3.9 -> 3.0 ms)
 #endif
 #ifndef S2M_K4A_MINB
-#define S2M_K4A_MINB 8  // resident blocks per SM the kNN kernel is compiled for (<= 64 registers)
+#define S2M_K4A_MINB 10  // resident blocks per SM the kNN kernel is compiled for (48 registers; 8 -> 10: -2 % K4 time)
 #endif
 #ifndef S2M_K4B_MINB
 #define S2M_K4B_MINB 4  // ... and the fit / residual kernel (128 registers, FP64)

@@ -350,14 +350,24 @@ __device__ __forceinline__ unsigned long long cell_probe(const unsigned long lon
   return e;
 }
 
+#ifndef S2M_KNN_PF
+#define S2M_KNN_PF 1  // candidate loads in flight per thread while the previous ones are offered
+#endif
 __device__ __forceinline__ void knn_scan_range(const float4* __restrict__ cand, int start, int count, float qx,
                                                float qy, float qz, Knn5& r) {
-  float4 c = __ldg(cand + start);
+  float4 buf[S2M_KNN_PF];
+#pragma unroll
+  for (int u = 0; u < S2M_KNN_PF; ++u) buf[u] = __ldg(cand + start + min(u, count - 1));
 #pragma unroll 1
-  for (int j = 0; j < count; ++j) {  // the next point is in flight while this one is offered
-    const float4 nx = __ldg(cand + start + min(j + 1, count - 1));
-    knn_offer(r, qx, qy, qz, c);
-    c = nx;
+  for (int j = 0; j < count; j += S2M_KNN_PF) {
+#pragma unroll
+    for (int u = 0; u < S2M_KNN_PF; ++u) {
+      if (j + u < count) {  // the next points are in flight while this one is offered
+        const float4 c = buf[u];
+        buf[u] = __ldg(cand + start + min(j + u + S2M_KNN_PF, count - 1));
+        knn_offer(r, qx, qy, qz, c);
+      }
+    }
   }
 }
 

@@ -1,7 +1,7 @@
 #!/bin/bash
-# usage: tools/ab.sh <variant>...   runs the default bench with each variants/libs2m_<v>.so, prints value / e2e / K4 us
+# usage: tools/ab.sh <variant>...   runs a short bench with each variants/libs2m_<v>.so, prints value / e2e / K4 us
 for v in "$@"; do
-  S2M_LIB=$PWD/sc-a-loam_b200/csrc/variants/libs2m_$v.so timeout 300 python bench.py --steps 10 --no-cpu-baseline > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+  S2M_LIB=$PWD/sc-a-loam_b200/csrc/variants/libs2m_$v.so timeout 300 python bench.py --steps 10 --no-cpu-baseline --no-sharded --no-os1 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python - "$v" <<'PY'
 import json, sys
 v = sys.argv[1]
