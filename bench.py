@@ -274,6 +274,7 @@ def prepare_worlds(pkg, n_frames, rank, world, device):
         return worlds, maps
     import harness
     import torch.distributed as dist
+    harness.set_threads(max(1, (os.cpu_count() or 1) // world))  # (torchrun exports OMP_NUM_THREADS=1)
     ids = list(range(rank, N_WORLDS, world))
     mine = []
     for w in ids:
@@ -382,10 +383,15 @@ def run_ours(args, rank, world, local_rank):
         if sampler:
             sampler.start()
         l0 = lane.R.launch_count()
+        ncu_range = bool(os.environ.get("S2M_NCU_RANGE")) and not host_buffers  # ncu --profile-from-start off: only the timed steps
+        if ncu_range:
+            torch.cuda.profiler.start()
         wall0 = time.perf_counter()
         lane.run(args.warmup, n_run, True)
         barrier()
         wall = time.perf_counter() - wall0
+        if ncu_range:
+            torch.cuda.profiler.stop()
         if sampler:
             sampler.stop_flag = True
         ms = lane.events[0].elapsed_time(lane.events[1])

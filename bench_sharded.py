@@ -56,6 +56,7 @@ def scatter(rng, centre, n, z_lo=-3.0, z_hi=29.0, half=120.0):
 def run_sharded(pkg, torch, dist, rank, world, local_rank, slots=16, fill_corner=3_000_000, fill_surf=1_000_000,
                 prefill=2, warmup=2, steps=5, check_slots=(0,), seed=20261018):
     import harness
+    harness.set_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
     B = slots
     n_frames = prefill + warmup + steps
     offs = slot_offsets(B)
@@ -127,7 +128,8 @@ def run_sharded(pkg, torch, dist, rank, world, local_rank, slots=16, fill_corner
     stats = [R.batch_stats[b] for b in range(B)]
     n_local = sum(st.n_map_corner + st.n_map_surf for st in stats)  # points this rank holds in the valid blocks (= searched)
     poses = np.array(poses)
-    mine = torch.tensor(np.r_[ms, phases["associate"], float(n_local)], dtype=torch.float64, device="cuda")
+    ph_names = ["input", "voxel", "index", "associate", "solve", "update", "readback"]
+    mine = torch.tensor(np.r_[ms, phases["associate"], float(n_local), [phases[k] for k in ph_names]], dtype=torch.float64, device="cuda")
     pose_t = torch.tensor(poses.view(np.int64).ravel().copy(), device="cuda")
     if world > 1:
         allv = [torch.zeros_like(mine) for _ in range(world)]
@@ -173,7 +175,8 @@ def run_sharded(pkg, torch, dist, rank, world, local_rank, slots=16, fill_corner
         "association_ms_per_step_per_rank": [round(float(v), 4) for v in assoc],
         "query_imbalance_max_over_mean": float(assoc.max() / max(assoc.mean(), 1e-12)),
         "all_ranks_bit_identical": identical, "agreement_with_one_gpu": agree,
-        "phase_ms_per_step_rank0": {k: round(v / steps, 4) for k, v in phases.items()},
+        "phase_ms_per_step_per_rank": {k: [round(float(allv[r, 3 + i]) / steps, 3) for r in range(len(allv))] for i, k in enumerate(ph_names)},
+        "phase_note": "a rank's index / solve phases contain its allreduces, i.e. the time it waits for the slowest rank",
         "upload_s": round(upload_s, 2),
         "slot_x_offsets_m": [round(float(v), 1) for v in offs[:, 0]],
     }

@@ -48,6 +48,11 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    """OpenMP threads used by scan() (torchrun exports OMP_NUM_THREADS=1 to every rank)"""
+    lib().synth_set_threads(int(n))
+
+
 def trajectory(seed, n_frames, step_m=1.0):
     poses = np.zeros((n_frames, 7), np.float64)
     lib().synth_trajectory(seed, n_frames, step_m, poses.ctypes.data)

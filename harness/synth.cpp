@@ -255,7 +255,19 @@ constexpr int kBins = 2048;
 
 }  // namespace
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 extern "C" {
+
+// OpenMP threads of the ray caster (a launcher such as torchrun exports OMP_NUM_THREADS=1 to every rank)
+void synth_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 // Closed-block trajectory at 1 m/frame (SURVEY 8d "KITTI-05 shape"): straight
 // runs along street centre lines and 90-degree left turns at 3 deg/frame.

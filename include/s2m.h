@@ -39,6 +39,7 @@ extern "C" {
 #define S2M_ERR_RANGE (-4)    /* coordinates outside the supported lattice range */
 #define S2M_ERR_NCCL (-5)
 #define S2M_ERR_IO (-6)       /* a checkpoint / PCD file could not be read or written */
+#define S2M_ERR_INTERNAL (-7) /* debug builds / S2M_GUARD_BYTES: a guard band around a device buffer was overwritten */
 
 typedef struct s2m_ctx s2m_ctx;
 
@@ -191,6 +192,12 @@ int s2m_trace_knn(s2m_ctx* ctx, int slot, int outer, int cls, int32_t* idx5, flo
  * step_norm, model_change, accepted] x 4 */
 int s2m_trace_lm(s2m_ctx* ctx, int slot, int outer, double pose7[7], double sums28[28],
                  double iters24[24], int* n_iter, int* termination);
+
+/* Debug aid (compute-sanitizer stand-in): with the environment variable S2M_GUARD_BYTES=<n> set when a context is
+ * created, every device buffer is allocated with n pattern bytes before and after it, checked after every call
+ * (an overwritten band fails the call with S2M_ERR_INTERNAL).  Returns the number of overwritten guard words so
+ * far, 0 when the mode is off. */
+int s2m_debug_guard_check(s2m_ctx* ctx);
 
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 long long s2m_launch_count(s2m_ctx* ctx);

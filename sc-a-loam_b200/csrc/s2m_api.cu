@@ -179,6 +179,9 @@ struct s2m_ctx {
   LmState* lm_trace = nullptr;   // [2][B] device
   LmState* h_lm = nullptr;       // pinned [2][B]
   std::vector<void*> allocs;
+  // debug: guard bands around every device allocation (S2M_GUARD_BYTES > 0 at create), checked after every call
+  size_t guard_bytes = 0;
+  std::vector<GuardDesc> guards;
   std::string err;
   long long launches = 0;
   int hash_cap_total = 0;
@@ -246,9 +249,15 @@ static void prof_resolve(s2m_ctx* ctx) {
 template <typename T>
 static int dev_alloc(s2m_ctx* ctx, T** p, size_t n) {
   void* q = nullptr;
-  CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+  const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 15) / 16 * 16, g = ctx->guard_bytes;
+  CK(cudaMalloc(&q, bytes + 2 * g));
   ctx->allocs.push_back(q);
-  *p = (T*)q;
+  if (g) {  // pattern before and after the payload: an out-of-bounds store of any kernel shows up in s2m_debug_guard_check
+    CK(cudaMemset(q, 0xA5, g));
+    CK(cudaMemset((char*)q + g + bytes, 0xA5, g));
+    ctx->guards.push_back(GuardDesc{(const uint32_t*)q, (const uint32_t*)((char*)q + g + bytes), (unsigned)(g / 4)});
+  }
+  *p = (T*)((char*)q + g);
   return 0;
 }
 
@@ -287,6 +296,7 @@ extern "C" const char* s2m_strerror(int code) {
     case S2M_ERR_RANGE: return "coordinates outside the supported lattice range";
     case S2M_ERR_NCCL: return "NCCL error";
     case S2M_ERR_IO: return "file could not be read or written";
+    case S2M_ERR_INTERNAL: return "internal consistency check failed";
     default: return "unknown";
   }
 }
@@ -331,6 +341,7 @@ static int create_impl(s2m_ctx* ctx) {
   CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
   ctx->stream = ctx->own_stream;
+  if (const char* gb = getenv("S2M_GUARD_BYTES")) ctx->guard_bytes = (size_t)std::max(0, atoi(gb)) / 16 * 16;
   Dev& d = ctx->d;
   std::memset(&d, 0, sizeof(d));
   const int B = P.batch, G = 2 * B;
@@ -432,6 +443,34 @@ static int create_impl(s2m_ctx* ctx) {
   CK(cudaMemset(d.ds_off, 0, sizeof(int) * (G + 1)));
   ctx->slots.assign(B, SlotHost());
   return S2M_OK;
+}
+
+// debug: number of guard words that no longer hold the pattern (0 = no out-of-bounds store so far)
+extern "C" int s2m_debug_guard_check(s2m_ctx* ctx) {
+  if (!ctx) return S2M_ERR_ARG;
+  int bad = 0;
+  for (s2m_ctx* ch : ctx->children) {
+    const int b = s2m_debug_guard_check(ch);
+    if (b < 0) return b;
+    bad += b;
+  }
+  if (ctx->guards.empty()) return bad;
+  CK(cudaSetDevice(ctx->P.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t n = ctx->guards.size();
+  GuardDesc* dg = nullptr;
+  int* dbad = nullptr;
+  CK(cudaMalloc((void**)&dg, sizeof(GuardDesc) * n));
+  CK(cudaMalloc((void**)&dbad, sizeof(int)));
+  CK(cudaMemcpy(dg, ctx->guards.data(), sizeof(GuardDesc) * n, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dbad, 0, sizeof(int)));
+  launch_guard_check(dg, (int)n, dbad, ctx->stream);
+  int h = 0;
+  CK(cudaMemcpyAsync(&h, dbad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dg);
+  cudaFree(dbad);
+  return bad + h;
 }
 
 extern "C" int s2m_create(const s2m_params* p, s2m_ctx** out) {
@@ -583,6 +622,10 @@ static int finish_call(s2m_ctx* ctx) {
     cudaMemsetAsync(ctx->d.err_flag, 0, sizeof(int), ctx->stream);
     ctx->err = std::string("device reported: ") + s2m_strerror(e);
     return e;
+  }
+  if (ctx->guard_bytes) {
+    const int bad = s2m_debug_guard_check(ctx);
+    if (bad != 0) { ctx->err = "guard band overwritten: " + std::to_string(bad) + " words (an out-of-bounds store)"; return S2M_ERR_INTERNAL; }
   }
   return S2M_OK;
 }

@@ -177,6 +177,12 @@ struct Dev {
   int cap_in, cap_sort, cap_lp;
 };
 
+struct GuardDesc {  // debug guard bands of one device allocation (S2M_GUARD_BYTES)
+  const uint32_t *front, *back;
+  unsigned words;
+};
+int launch_guard_check(const GuardDesc* g, int n, int* bad, cudaStream_t s);
+
 // launchers (s2m_kernels.cu); every one returns the number of kernels it launched
 size_t cub_temp_bytes(int cap_sort, int cap_lp);
 int launch_voxel_bbox(const Dev& d, int total_in, cudaStream_t s);

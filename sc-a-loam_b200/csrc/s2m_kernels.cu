@@ -223,14 +223,24 @@ __device__ __forceinline__ int local_to_store(const Dev& d, int g, int l) {
 
 __global__ void local_key_kernel(Dev d, int cur, int total_lp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total_lp) return;
-  const int g = find_seg(d.lp_off, d.G, i);
-  const int l = i - d.lp_off[g];
+  int g = -1;
+  bool owned = false;  // sharded map: this rank owns the point (it counts towards the guard :555)
+  if (i < total_lp) g = find_seg(d.lp_off, d.G, i);
+  const int l = i < total_lp ? i - d.lp_off[g] : 0;
   uint32_t key = kSentinel32;
-  if (l < d.loc_off[g * (kCols + 1) + kCols]) {
-    const float4 p = d.st_pt[cur][d.st_base[g] + local_to_store(d, g, l)];
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool have = i < total_lp && l < d.loc_off[g * (kCols + 1) + kCols];
+  if (have) {
+    p = d.st_pt[cur][d.st_base[g] + local_to_store(d, g, l)];
+    owned = d.shard_world > 1 && p.x >= d.shard_lo && p.x < d.shard_hi;
+  }
+  if (d.shard_world > 1) {  // one atomic per warp and segment instead of one per point (tens of millions on 2 x slots addresses)
+    const unsigned peers = __match_any_sync(0xffffffffu, owned ? g : -1);
+    if (owned && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(d.shard_counts + g, __popc(peers));
+  }
+  if (i >= total_lp) return;
+  if (have) {
     const FrameDesc& fd = d.desc[seg_slot(d, g)];
-    if (d.shard_world > 1 && p.x >= d.shard_lo && p.x < d.shard_hi) atomicAdd(d.shard_counts + g, 1);
     const int rx = (int)floorf(p.x) - fd.origin[0], ry = (int)floorf(p.y) - fd.origin[1],
               rz = (int)floorf(p.z) - fd.origin[2];
     if ((unsigned)rx > 255u || (unsigned)ry > 255u || (unsigned)rz > 255u) set_err(d, -4);
@@ -1809,6 +1819,20 @@ __global__ void surround_kernel(Dev d, int cur, int slot, float4* __restrict__ o
     for (int j = t; j < len; j += blockDim.x)
       if (off_s[r] + j < cap) out[off_s[r] + j] = d.st_pt[cur][d.st_base[g] + lo_s[r] + j];
   }
+}
+
+// debug: guard bands around every allocation must still hold their pattern
+__global__ void guard_check_kernel(const GuardDesc* __restrict__ g, int* __restrict__ bad) {
+  const GuardDesc gd = g[blockIdx.x];
+  const uint32_t* p = blockIdx.y ? gd.back : gd.front;
+  int n = 0;
+  for (unsigned i = threadIdx.x; i < gd.words; i += blockDim.x) n += p[i] != 0xA5A5A5A5u;
+  if (n) atomicAdd(bad, n);
+}
+int launch_guard_check(const GuardDesc* g, int n, int* bad, cudaStream_t s) {
+  if (n <= 0) return 0;
+  guard_check_kernel<<<dim3(n, 2), 256, 0, s>>>(g, bad);
+  return 1;
 }
 
 // ----------------------------------------------------------------------------

@@ -81,5 +81,21 @@ def main():
     print(path, os.path.getsize(path), "bytes")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--keyframes" not in sys.argv:
     main()
+
+
+def make_keyframes():
+    """tests/golden/kaist03_keyframes.npz: xyz (float32, exact) of ALL 21 real keyframe scans, packed with offsets,
+    and the poses the reference saved for them (optimized_poses.txt rows 0..20) -- the input of the -m gpu test that
+    runs the whole chain (features -> odometry -> mapping) on the device (tests/test_odometry.py)."""
+    poses = np.loadtxt(SRC + "optimized_poses.txt")[:21].reshape(21, 3, 4)
+    scans = [read_pcd(SRC + "Scans/%06d.pcd" % k)[:, :3] for k in range(21)]
+    off = np.cumsum([0] + [len(s) for s in scans]).astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "kaist03_keyframes.npz"), xyz=np.concatenate(scans).astype(np.float32),
+                        off=off, ref_poses=poses)
+    print("kaist03_keyframes.npz:", off[-1], "points")
+
+
+if __name__ == "__main__" and "--keyframes" in sys.argv:
+    make_keyframes()

@@ -18,8 +18,9 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import bench
     bench.N_WORLDS = 4  # keep the CPU test small
-    worlds = bench.make_worlds_distributed(3, rank, world)
-    assert len(worlds) == 4 and all(len(w[2]) == 3 for w in worlds)
+    bench.PREFILL = 0   # (mature maps are built on the GPU; none here)
+    worlds, maps = bench.prepare_worlds(None, 3, rank, world, 0)
+    assert len(worlds) == 4 and all(len(w[2]) == 3 for w in worlds) and len(maps) == 4
     digest = np.array([float(np.sum([c.sum() + s.sum() for c, s in w[2]])) for w in worlds])
     gathered = [None] * world
     dist.all_gather_object(gathered, digest)

@@ -200,3 +200,46 @@ def test_whole_front_end_on_the_device(s2m, built):
     # the odometry follows the true trajectory (the VLP-16 mapping on this young, street-aligned map lags
     # along the street -- an algorithm property both chains share, see test_gpu_parity)
     assert np.linalg.norm(t_od[0] - tt) < 0.05
+
+
+@pytest.mark.gpu
+def test_cuda_chain_on_all_21_real_keyframes_of_the_reference(s2m, built):
+    """SURVEY 8c item 5 on the DEVICE: the 21 real OS1-64 keyframes the reference ships (committed fixture
+    tests/golden/kaist03_keyframes.npz, generator tests/golden/make_kaist03.py --keyframes) through
+    s2m_fx_extract -> s2m_odom_step_batch -> s2m_register_batch_dev with device pointers all the way.  Anchors:
+    (a) the poses the reference itself saved for these scans (optimized_poses.txt rows 0..20): within 10 cm for
+    keyframes 1..10, 30 cm over the 23.6 m stretch -- the same bars the CPU restatements meet in the authoring
+    container; (b) the CPU chain of the three restatements on the same scans: odometry and mapping poses within
+    1e-4 m / 1e-5 rad, every feature cloud bit-identical."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kaist03_keyframes.npz"))
+    xyz_all, off, ref = g["xyz"], g["off"], g["ref_poses"]
+    assert len(off) == 22 and ref.shape == (21, 3, 4)
+    F = s2m.FeatureExtractor("OS1-64", 0.5, batch=1, cap_points=40000)   # aloam_mulran.launch:9
+    D = s2m.Odometer(cap_less_flat=1 << 16)
+    M = s2m.Registrar(0.4, 0.8)                                          # aloam_mulran.launch:11-12
+    Oo, Om = oracle.Odometer(), oracle.Oracle(0.4, 0.8)
+    names = ("sharp", "flat", "less_sharp", "less_flat")
+    worst = 0.0
+    for k in range(21):
+        xyz = np.ascontiguousarray(xyz_all[off[k]:off[k + 1]])
+        F.extract(xyz, np.array([0, len(xyz)], np.int32))
+        dev = {n: F.device_cloud(n) for n in names}
+        o = {n: F.offsets(n) for n in names}
+        q_od, t_od = D.step_batch(dev["sharp"], o["sharp"], dev["flat"], o["flat"], dev["less_sharp"], o["less_sharp"],
+                                  dev["less_flat"], o["less_flat"], device_ptrs=True)
+        st, q_w, t_w = M.register_batch_ptr(dev["less_sharp"], o["less_sharp"], dev["less_flat"], o["less_flat"],
+                                            q_od[0], t_od[0], True)
+        A = oracle.scan_registration("OS1-64", xyz, 0.5)
+        for n in names:
+            assert np.array_equal(F.cloud(n)[0].view(np.uint32), A[n].view(np.uint32)), (k, n)
+        qo, to = Oo.step(*[A[n] for n in names])
+        rc, qm, tm = Om.register(A["less_sharp"], A["less_flat"], qo, to)
+        assert st[0] == rc, k
+        assert np.linalg.norm(t_od[0] - to) < TOL_T and rot_angle(q_od[0], qo) < TOL_R, k
+        assert np.linalg.norm(t_w[0] - tm) < TOL_T and rot_angle(q_w[0], qm) < TOL_R, k
+        err = float(np.linalg.norm(t_w[0] - ref[k, :, 3]))
+        worst = max(worst, err)
+        if 1 <= k <= 10:
+            assert err < 0.10, (k, err)
+            assert err < np.linalg.norm(t_od[0] - ref[k, :, 3])      # the mapping corrects the (lagging) odometry
+    assert worst < 0.30 and np.linalg.norm(ref[20, :, 3]) > 23.0

@@ -133,3 +133,37 @@ def test_capacities_are_validated_at_create(s2m, built):
         s2m.Registrar(4.0, 4.0, cap_corner_in=1 << 18, cap_surf_in=1024, cap_map_corner=1024, cap_map_surf=1024)
     R = s2m.Registrar(4.0, 4.0, cap_corner_in=(1 << 18) - 1, cap_surf_in=1024, cap_map_corner=1024, cap_map_surf=1024)
     R.close()
+
+
+def test_guard_bands_stay_intact(s2m, seq, monkeypatch):
+    """compute-sanitizer is not available on the GPU pool: with S2M_GUARD_BYTES every device buffer gets pattern
+    bands before and after it, checked after every call.  A replay with optimisation, a window shift, a chunked
+    upload, the getters, a batch on two lanes and the odometry: no band is touched."""
+    monkeypatch.setenv("S2M_GUARD_BYTES", "4096")
+    truth, odom, frames = seq
+    R = s2m.Registrar(0.4, 0.8, trace=True, cap_map_corner=1 << 17, cap_map_surf=1 << 17)
+    for f in range(5):
+        rc, q, t = R.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+    far = odom[4, 4:] + np.array([460.0, 0.0, 0.0])     # shifts the window, evicts cubes
+    R.register(frames[5][0], frames[5][1], odom[5, :4], far)
+    R.local_map(1, far)
+    R.debug_knn(1, far, frames[5][1][:300, :3])
+    R.surround()
+    R.transform_cloud(frames[5][1])
+    cm, sm = R.map_download(0), R.map_download(1)
+    assert R.guard_check() == 0
+    S = s2m.Registrar(0.4, 0.8, cap_corner_in=1500, cap_surf_in=2000, cap_map_corner=1 << 17, cap_map_surf=1 << 17)
+    S.map_upload(cm, sm)                                  # chunked
+    S.register(frames[6][0][:1400], frames[6][1][:1900], odom[6, :4], far)
+    assert S.guard_check() == 0
+    M = s2m.Registrar(0.4, 0.8, batch=4, lanes=2)
+    for f in range(3):
+        c, s_ = frames[f]
+        M.register_batch(np.tile(c, (4, 1)), np.arange(5) * len(c), np.tile(s_, (4, 1)), np.arange(5) * len(s_),
+                         np.tile(odom[f, :4], (4, 1)), np.tile(odom[f, 4:], (4, 1)))
+    assert M.guard_check() == 0
+    D = s2m.Odometer()
+    for f in range(2):
+        A = oracle.scan_registration("HDL64", harness.scan(20261018, "HDL64", truth[f], f), 5.0)
+        D.step(A["sharp"], A["flat"], A["less_sharp"], A["less_flat"])
+    assert D.L.s2m_debug_guard_check(D.h) == 0
