@@ -40,6 +40,8 @@ struct SlotHost {
   int n_store[2] = {0, 0};                  // entries per class (after the last call)
   int val_lo[3] = {0, 0, 0}, val_hi[3] = {-1, -1, -1};
   bool force_pending_check = false;         // after an upload every entry is raw
+  bool idx_valid = false;                   // the device cell index matches the store and the valid block
+  int idx_built_n[2] = {0, 0};              // local-map points per class when the index was last built (table sizing)
   unsigned long long seq[2] = {0, 0};
   long long frames = 0;
 };
@@ -49,7 +51,9 @@ struct HostTables {  // one pinned block, copied to the device in one go
   int in_off[2 * kMaxBatch + 1];
   int lp_off[2 * kMaxBatch + 1];
   int so_off[2 * kMaxBatch + 1];
-  int hash_off[2 * kMaxBatch + 1];
+  int hash_off[2 * kMaxBatch + 1];   // static: the cell-table region of every segment (sized by cap_map_*)
+  int idx_list[4 * kMaxBatch];       // segments whose cell index is rebuilt this frame, then their new table masks (at + G)
+  int idx_poff[2 * kMaxBatch + 1];   // packed offsets of the local points of those segments
 };
 
 }  // namespace
@@ -185,6 +189,7 @@ struct s2m_ctx {
   std::string err;
   long long launches = 0;
   int hash_cap_total = 0;
+  size_t bkt_total = 0;
   // profiling: CUDA events at phase boundaries of every frame (on the launching stream)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -360,6 +365,9 @@ static int create_impl(s2m_ctx* ctx) {
   const long long cap_in = (long long)B * ((long long)P.cap_corner_in + P.cap_surf_in);
   const long long cap_lp = (long long)B * ((long long)P.cap_map_corner + P.cap_map_surf);
   if (cap_in + cap_lp >= (1ll << 30)) { ctx->err = "capacities too large (packed index space is 30 bits)"; return S2M_ERR_ARG; }
+  // cell-index tags hold a voxel coordinate inside its cube in 8 bits and a bucket number in 24
+  if ((int)(50.0f / std::min(P.line_res, P.plane_res)) + 3 > 256) { ctx->err = "mapping resolutions below 0.2 m are not supported (voxel coordinate inside a cube > 8 bits)"; return S2M_ERR_ARG; }
+  if (P.cap_map_corner >= (1 << 24) || P.cap_map_surf >= (1 << 24)) { ctx->err = "cap_map_* must be below 2^24 per slot"; return S2M_ERR_ARG; }
   // the per-frame arrival number of a raw point is a field of delta_pbits bits in the map-update sort key
   if (P.cap_corner_in >= (1 << d.delta_pbits) || P.cap_surf_in >= (1 << d.delta_pbits)) {
     ctx->err = "cap_corner_in / cap_surf_in must be below 2^" + std::to_string(d.delta_pbits) + " for these leaf sizes";
@@ -380,6 +388,7 @@ static int create_impl(s2m_ctx* ctx) {
   std::memset(ctx->ht, 0, sizeof(HostTables));
   if (dev_alloc(ctx, &ctx->d_ht, 1)) return S2M_ERR_CUDA;
   d.desc = ctx->d_ht->desc; d.in_off = ctx->d_ht->in_off; d.lp_off = ctx->d_ht->lp_off; d.so_off = ctx->d_ht->so_off; d.hash_off = ctx->d_ht->hash_off;
+  d.idx_list = ctx->d_ht->idx_list; d.idx_poff = ctx->d_ht->idx_poff;
 
   int rc = 0;
   rc |= dev_alloc(ctx, &d.st_base, G); rc |= dev_alloc(ctx, &d.st_cap, G);
@@ -393,17 +402,24 @@ static int create_impl(s2m_ctx* ctx) {
   for (int b = 0; b < 2; ++b) { rc |= dev_alloc(ctx, &d.st_key[b], d.cap_lp); rc |= dev_alloc(ctx, &d.st_pt[b], d.cap_lp); }
   rc |= dev_alloc(ctx, &d.st_n, G); rc |= dev_alloc(ctx, &d.st_n_new, G);
   rc |= dev_alloc(ctx, &d.rng_start, G * kCols); rc |= dev_alloc(ctx, &d.loc_off, G * (kCols + 1)); rc |= dev_alloc(ctx, &d.lp_cnt, G);
-  const size_t ccap = (size_t)std::max(d.cap_lp, d.cap_in);
-  rc |= dev_alloc(ctx, &d.ckey, ccap); rc |= dev_alloc(ctx, &d.ckey2, ccap);
-  rc |= dev_alloc(ctx, &d.cval, ccap); rc |= dev_alloc(ctx, &d.cval2, ccap);
-  rc |= dev_alloc(ctx, &d.cand, d.cap_lp); rc |= dev_alloc(ctx, &d.knn_ticket, 1); rc |= dev_alloc(ctx, &d.nbr, (size_t)d.cap_in * 6); rc |= dev_alloc(ctx, &d.inv, d.cap_lp);
-  // cell tables: per segment a power of two >= 2 x entries, >= 1024
+  rc |= dev_alloc(ctx, &d.knn_ticket, 1); rc |= dev_alloc(ctx, &d.nbr, (size_t)d.cap_in * 6);
+  // persistent cell index: per segment a table of a power of two >= 4 x cap_map slots (load <= 1/4) and a pool of
+  // cap_map four-entry buckets
   long long hcap = 0;
-  for (int g = 0; g < G; ++g) hcap += table_size(g < B ? P.cap_map_corner : P.cap_map_surf);
+  for (int g = 0; g < G; ++g) { ctx->ht->hash_off[g] = (int)hcap; hcap += table_size(g < B ? P.cap_map_corner : P.cap_map_surf); }
   if (hcap >= (1ll << 31)) { ctx->err = "cell tables too large (4 entries per map point)"; return S2M_ERR_ARG; }
+  ctx->ht->hash_off[G] = (int)hcap;
   ctx->hash_cap_total = (int)hcap;
-  rc |= dev_alloc(ctx, &d.hash_tab, (size_t)hcap); rc |= dev_alloc(ctx, &d.hash_aux, (size_t)hcap);
-  rc |= dev_alloc(ctx, &d.cs_off, G + 1);
+  rc |= dev_alloc(ctx, &d.hash_tab, (size_t)hcap); rc |= dev_alloc(ctx, &d.hmask, G);
+  // (a quarter more buckets than points: cells that two threads create at the same moment leak one until the next rebuild)
+  std::vector<int> boff(G + 1, 0);
+  for (int g = 0; g < G; ++g) {
+    const long long c = g < B ? P.cap_map_corner : P.cap_map_surf;
+    boff[g + 1] = boff[g] + (int)std::min<long long>(c + c / 4 + 1024, (1 << 24) - 1);
+  }
+  ctx->bkt_total = (size_t)boff[G];
+  rc |= dev_alloc(ctx, &d.bkt, ctx->bkt_total * kBktE); rc |= dev_alloc(ctx, &d.bnext, ctx->bkt_total);
+  rc |= dev_alloc(ctx, &d.bkt_off, G + 1); rc |= dev_alloc(ctx, &d.bcnt, G);
   rc |= dev_alloc(ctx, &d.rec, (size_t)d.cap_in * 6); rc |= dev_alloc(ctx, &d.rec_valid, d.cap_in);
   rc |= dev_alloc(ctx, &d.partials, (size_t)B * d.max_tiles * kPartial);
   rc |= dev_alloc(ctx, &d.lm, B); rc |= dev_alloc(ctx, &d.out, B); rc |= dev_alloc(ctx, &d.err_flag, 1);
@@ -441,6 +457,12 @@ static int create_impl(s2m_ctx* ctx) {
   CK(cudaMemset(d.out, 0, sizeof(SlotOut) * B));
   CK(cudaMemset(d.lm, 0, sizeof(LmState) * B));
   CK(cudaMemset(d.ds_off, 0, sizeof(int) * (G + 1)));
+  CK(cudaMemcpy(d.bkt_off, boff.data(), sizeof(int) * (G + 1), cudaMemcpyHostToDevice));
+  CK(cudaMemset(d.hash_tab, 0xFF, sizeof(unsigned long long) * (size_t)ctx->hash_cap_total));
+  CK(cudaMemset(d.bkt, 0xFF, sizeof(float4) * ctx->bkt_total * kBktE));
+  CK(cudaMemset(d.bnext, 0xFF, sizeof(uint32_t) * ctx->bkt_total));
+  CK(cudaMemset(d.bcnt, 0, sizeof(int) * G));
+  CK(cudaMemset(d.hmask, 0, sizeof(int) * G));
   ctx->slots.assign(B, SlotHost());
   return S2M_OK;
 }
@@ -599,17 +621,38 @@ static void rows_BC(SlotHost& s, const double t[3], FrameDesc& fd) {
 }
 
 // offsets that depend on the (host-known) store sizes
-static void fill_store_tables(s2m_ctx* ctx, int* total_lp, int* hash_total) {
+static void fill_store_tables(s2m_ctx* ctx, int* total_lp) {
   const int B = ctx->d.B, G = ctx->d.G;
   HostTables& T = *ctx->ht;
-  int acc = 0, hacc = 0;
+  int acc = 0;
   for (int g = 0; g < G; ++g) {
     const int n = ctx->slots[g < B ? g : g - B].n_store[g >= B];
     T.lp_off[g] = T.so_off[g] = acc; acc += n;
-    T.hash_off[g] = hacc; hacc += (int)table_size(n);
   }
-  T.lp_off[G] = T.so_off[G] = acc; T.hash_off[G] = hacc;
-  *total_lp = acc; *hash_total = hacc;
+  T.lp_off[G] = T.so_off[G] = acc;
+  *total_lp = acc;
+}
+// Lists the segments of the slots flagged in `rebuild` for a bulk rebuild of their cell index: their local-map
+// sizes are in ctx->h_lpcnt (read back).  Returns the number of segments; *points = their local points.
+static int plan_index_rebuild(s2m_ctx* ctx, const std::vector<char>& rebuild, int* points) {
+  const int B = ctx->d.B, G = ctx->d.G;
+  HostTables& T = *ctx->ht;
+  int n_seg = 0, acc = 0;
+  for (int g = 0; g < G; ++g) {
+    const int b = g < B ? g : g - B;
+    if (!rebuild[b]) continue;
+    const int n = ctx->h_lpcnt[g];
+    const long long region = (long long)T.hash_off[g + 1] - T.hash_off[g];
+    T.idx_list[n_seg] = g;
+    T.idx_list[G + n_seg] = (int)(std::min(table_size(n), region) - 1);
+    T.idx_poff[n_seg] = acc;
+    acc += n;
+    ++n_seg;
+    ctx->slots[b].idx_built_n[g >= B] = n;
+  }
+  T.idx_poff[n_seg] = acc;
+  *points = acc;
+  return n_seg;
 }
 
 static int finish_call(s2m_ctx* ctx) {
@@ -648,8 +691,13 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
     std::vector<SlotHost> saved;
     bool armed = true;
     explicit Rollback(std::vector<SlotHost>& l) : live(l), saved(l) {}
-    ~Rollback() { if (armed) live = saved; }
+    ~Rollback() {
+      if (!armed) return;
+      live = saved;
+      for (SlotHost& sh : live) sh.idx_valid = false;  // (the failed frame may have touched the cell index)
+    }
   } rollback(ctx->slots);
+  std::vector<char> idx_rebuild(B, 0), idx_follow(B, 0);
   for (int b = 0; b < B; ++b) {
     SlotHost& sh = ctx->slots[b];
     FrameDesc& fd = T.desc[b];
@@ -663,40 +711,47 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
     bool moved = sh.force_pending_check;
     for (int a = 0; a < 3; ++a) moved = moved || fd.val_lo[a] != sh.val_lo[a] || fd.val_hi[a] != sh.val_hi[a];
     check_pending = check_pending || moved;
+    // cell index: bulk rebuild when the valid block changed (or the index is stale); otherwise the map update keeps
+    // it in step.  A frame that merges raw points of newly valid cubes is followed by one more rebuild.
+    idx_rebuild[b] = moved || !sh.idx_valid || ctx->P.shard_world > 1;
+    idx_follow[b] = !moved && ctx->P.shard_world <= 1;
     for (int a = 0; a < 3; ++a) { sh.val_lo[a] = fd.val_lo[a]; sh.val_hi[a] = fd.val_hi[a]; }
     sh.force_pending_check = false;
     const int nq = (corner_off[b + 1] - corner_off[b]) + (surf_off[b + 1] - surf_off[b]);
     tiles = std::max(tiles, (nq + kTile - 1) / kTile);
   }
-  int total_lp, hash_total;
-  fill_store_tables(ctx, &total_lp, &hash_total);
+  int total_lp;
+  fill_store_tables(ctx, &total_lp);
   const int total_store = total_lp;
   CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, s));
 
-  // blocks per slot of the association / evaluation kernels: enough to fill the GPU
-  // (about 4 blocks of 128 threads per SM over all slots), never more than the tiles
   long long k = 0;
   prof_mark(ctx, S2M_PHASE_INPUT);
   // Two small results come back before the bulk of the frame is enqueued: the boxes of the incoming
   // clouds (exact width of PCL's voxel index = radix passes of the scan filter) and the sizes of the
-  // local maps (25 ranges of the sorted store), so the cell index costs O(local map), not O(store).
-  // The round trip is hidden by the other lanes sharing the GPU.
+  // local maps (25 ranges of the sorted store: the guard :555, the staging of raw points, the sizing of a
+  // rebuilt cell index).  The round trip is hidden by the other lanes sharing the GPU.
   k += launch_voxel_bbox(d, total_in, s);
   k += launch_local_ranges(d, ctx->cur, s);
   CK(cudaMemcpyAsync(ctx->h_bbox, d.bbox, sizeof(uint32_t) * 6 * G, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(ctx->h_lpcnt, d.lp_cnt, sizeof(int) * G, cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(ctx->ev_bbox, s));
   CK(cudaEventSynchronize(ctx->ev_bbox));
-  total_lp = hash_total = 0;
-  for (int g = 0; g < G; ++g) {
-    const int n = ctx->h_lpcnt[g];
-    T.lp_off[g] = total_lp; total_lp += n;
-    T.hash_off[g] = hash_total; hash_total += (int)table_size(n);
+  total_lp = 0;
+  for (int g = 0; g < G; ++g) { T.lp_off[g] = total_lp; total_lp += ctx->h_lpcnt[g]; }
+  T.lp_off[G] = total_lp;
+  for (int b = 0; b < B; ++b) {
+    if (!T.desc[b].active) continue;
+    const SlotHost& sh = ctx->slots[b];
+    for (int c2 = 0; c2 < 2; ++c2)  // the table was sized for the map it was built from
+      if (2 * (long long)ctx->h_lpcnt[c2 * B + b] > 3 * (long long)sh.idx_built_n[c2] + 2048) idx_rebuild[b] = 1;
+    T.desc[b].idx_flags = (idx_rebuild[b] ? 1 : 0) | (idx_follow[b] ? 2 : 0);
   }
-  T.lp_off[G] = total_lp; T.hash_off[G] = hash_total;
-  CK(cudaMemcpyAsync(ctx->d_ht->lp_off, T.lp_off, sizeof(int) * (G + 1), cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(ctx->d_ht->hash_off, T.hash_off, sizeof(int) * (G + 1), cudaMemcpyHostToDevice, s));
-  k += launch_local_index(d, ctx->cur, total_lp, hash_total, true, s);
+  for (int b = 0; b < B; ++b) if (!T.desc[b].active) { idx_rebuild[b] = 0; T.desc[b].idx_flags = 0; }
+  int idx_points = 0;
+  const int idx_segs = plan_index_rebuild(ctx, idx_rebuild, &idx_points);
+  CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, s));
+  k += launch_index_rebuild(d, ctx->cur, idx_segs, idx_points, s);
   const bool sharded = ctx->P.shard_world > 1;
   if (sharded) { int rs = shard_allreduce(ctx, d.shard_counts, (size_t)G, nccl::kInt32); if (rs != S2M_OK) return rs; }
   k += launch_guard(d, s);
@@ -743,7 +798,7 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   for (int outer = 0; outer < 2; ++outer) {  // laserMapping.cpp:563
     CK(cudaMemsetAsync(d.knn_ticket, 0, sizeof(int), s));  // the association's work ticket
     prof_mark(ctx, S2M_PHASE_READBACK);  // host wait for the down-sampled counts (outer 0); the K4 bracket starts here
-    k += launch_associate(d, outer, knn_blocks, fit_blocks, ctx->P.trace != 0, s);
+    k += launch_associate(d, outer, ctx->cur, knn_blocks, fit_blocks, ctx->P.trace != 0, s);
     prof_mark(ctx, S2M_PHASE_ASSOCIATE);
     if (!sharded) {
       k += launch_solve(d, outer, true, s);  // Ceres solve, max_num_iterations = 4 (:713-721)
@@ -785,6 +840,7 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
     sh.n_store[0] = o.n_store[0]; sh.n_store[1] = o.n_store[1];
     sh.seq[0] += (unsigned long long)o.n_ds[0]; sh.seq[1] += (unsigned long long)o.n_ds[1];
     sh.frames++;
+    sh.idx_valid = idx_follow[b] != 0;  // the map update kept the cell index in step (else: rebuilt next frame)
     for (int i = 0; i < 4; ++i) q_out[4 * b + i] = sh.pose[i];
     for (int i = 0; i < 3; ++i) t_out[3 * b + i] = sh.pose[4 + i];
     if (status) status[b] = o.optimized ? S2M_OK : S2M_MAP_TOO_SMALL;
@@ -1043,6 +1099,7 @@ extern "C" int s2m_map_upload(s2m_ctx* ctx, int slot, const float* corner, int n
       FrameDesc& fd = T.desc[b];
       fd.active = (b == slot);
       fd.allow_opt = 0;
+      fd.idx_flags = 0;
       if (b != slot) continue;
       const int W[3] = {kWinI, kWinJ, kWinK};
       for (int a = 0; a < 3; ++a) {
@@ -1052,8 +1109,8 @@ extern "C" int s2m_map_upload(s2m_ctx* ctx, int slot, const float* corner, int n
       }
       fd.seq_base[0] = sh.seq[0]; fd.seq_base[1] = sh.seq[1];
     }
-    int total_lp, hash_total;
-    fill_store_tables(ctx, &total_lp, &hash_total);
+    int total_lp;
+    fill_store_tables(ctx, &total_lp);
     CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d.ds_off, dsoff.data(), sizeof(int) * (G + 1), cudaMemcpyHostToDevice, s));
     if (cn) CK(cudaMemcpyAsync(d.ds_pts, corner + 4 * (size_t)c0, sizeof(float4) * (size_t)cn, cudaMemcpyHostToDevice, s));
@@ -1071,6 +1128,7 @@ extern "C" int s2m_map_upload(s2m_ctx* ctx, int slot, const float* corner, int n
     if (nc + ns == 0) break;
   }
   sh.force_pending_check = true;
+  sh.idx_valid = false;
   sh.val_lo[0] = 1; sh.val_hi[0] = 0;
   return (nc + ns) - kept;
 }
@@ -1217,15 +1275,32 @@ extern "C" int s2m_checkpoint_load(s2m_ctx* ctx, int slot, const char* prefix) {
   return s2m_map_upload(ctx, slot, pts[0].data(), n[0], pts[1].data(), n[1]);
 }
 
-// prepares the descriptor of `slot` for a sensor at centre_t (rows B, C) and uploads the tables
-static int prepare_local(s2m_ctx* ctx, int slot, const double centre_t[3], int* total_lp, int* hash_total) {
+// prepares the descriptor of `slot` for a sensor at centre_t (rows B, C), uploads the tables and computes the ranges of
+// the local map; with_index: also (re)builds the slot's cell index for that valid block (the live index of the slot
+// is stale afterwards and is rebuilt by the next frame)
+static int prepare_local(s2m_ctx* ctx, int slot, const double centre_t[3], bool with_index) {
   HostTables& T = *ctx->ht;
-  for (int b = 0; b < ctx->d.B; ++b) T.desc[b].active = (b == slot);
+  const int B = ctx->d.B, G = ctx->d.G;
+  for (int b = 0; b < B; ++b) { T.desc[b].active = (b == slot); T.desc[b].idx_flags = 0; }
   FrameDesc& fd = T.desc[slot];
   SlotHost probe = ctx->slots[slot];  // a getter must not move the live window
   rows_BC(probe, centre_t, fd);
-  fill_store_tables(ctx, total_lp, hash_total);
+  int total_lp;
+  fill_store_tables(ctx, &total_lp);
   CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_local_ranges(ctx->d, ctx->cur, ctx->stream);
+  if (!with_index) return S2M_OK;
+  CK(cudaMemcpyAsync(ctx->h_lpcnt, ctx->d.lp_cnt, sizeof(int) * G, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::vector<char> rebuild(B, 0);
+  rebuild[slot] = 1;
+  int points = 0;
+  const int saved_n[2] = {ctx->slots[slot].idx_built_n[0], ctx->slots[slot].idx_built_n[1]};
+  const int n_seg = plan_index_rebuild(ctx, rebuild, &points);
+  ctx->slots[slot].idx_built_n[0] = saved_n[0]; ctx->slots[slot].idx_built_n[1] = saved_n[1];
+  ctx->slots[slot].idx_valid = false;
+  CK(cudaMemcpyAsync(ctx->d_ht, ctx->ht, sizeof(HostTables), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_index_rebuild(ctx->d, ctx->cur, n_seg, points, ctx->stream);
   return S2M_OK;
 }
 
@@ -1233,10 +1308,8 @@ extern "C" int s2m_get_local_map(s2m_ctx* ctx, int slot, int cls, const double c
   ROUTE_SLOT(s2m_get_local_map(ch, slot, cls, centre_t, out, cap));
   if (!ctx || slot < 0 || slot >= ctx->d.B || cls < 0 || cls > 1 || !centre_t) return S2M_ERR_ARG;
   CK(cudaSetDevice(ctx->P.device));
-  int total_lp, hash_total;
-  int rc = prepare_local(ctx, slot, centre_t, &total_lp, &hash_total);
+  int rc = prepare_local(ctx, slot, centre_t, false);
   if (rc != S2M_OK) return rc;
-  ctx->launches += launch_local_index(ctx->d, ctx->cur, total_lp, hash_total, false, ctx->stream);
   const int g = cls * ctx->d.B + slot;
   ctx->launches += launch_gather_local(ctx->d, ctx->cur, g, ctx->d.ins_pt, ctx->stream);
   rc = finish_call(ctx);
@@ -1255,18 +1328,16 @@ extern "C" int s2m_debug_knn(s2m_ctx* ctx, int slot, int cls, const double centr
   if (!ctx || slot < 0 || slot >= ctx->d.B || cls < 0 || cls > 1 || !centre_t || n < 0) return S2M_ERR_ARG;
   if ((size_t)n * 5 > (size_t)ctx->d.cap_sort) return S2M_ERR_CAPACITY;
   CK(cudaSetDevice(ctx->P.device));
-  int total_lp, hash_total;
-  int rc = prepare_local(ctx, slot, centre_t, &total_lp, &hash_total);
+  int rc = prepare_local(ctx, slot, centre_t, true);
   if (rc != S2M_OK) return rc;
   Dev& d = ctx->d;
   cudaStream_t s = ctx->stream;
-  ctx->launches += launch_local_index(d, ctx->cur, total_lp, hash_total, false, s);
   // scratch: queries in dl_pt/ins_pt area, results in vval (int32) and flag (float bits)
   float* dq = (float*)d.ins_pt;
   int32_t* didx = (int32_t*)d.vval;
   float* dd2 = (float*)d.flag;
   if (n) CK(cudaMemcpyAsync(dq, q_xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s));
-  ctx->launches += launch_knn_debug(d, slot, cls, dq, n, didx, dd2, s);
+  ctx->launches += launch_knn_debug(d, ctx->cur, slot, cls, dq, n, didx, dd2, s);
   rc = finish_call(ctx);
   if (rc != S2M_OK) return rc;
   if (n) {

@@ -19,6 +19,12 @@
 //            position in it is the kNN index the reference would report
 //   cell     1 m lattice cell floor(p); candidates of a query are the points of
 //            its 27 neighbouring cells (exact for the reference's d2[4] < 1 gate)
+//   cell index  per segment, PERSISTENT: an open-addressing table cell -> (count, bucket) and a
+//            pool of 4-entry buckets (chained) holding (x, y, z, tag) of every local-map point.
+//            Built in bulk when the valid block changes, otherwise updated by the map update with
+//            the few thousand points a frame changes.  tag = [cube of the valid block:7]
+//            [pending:1][voxel z,y,x:3x8 | arrival rank:24] orders like the reference's gather
+//            order, so (d2, tag) ties break exactly like (d2, index)
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -34,7 +40,7 @@ namespace s2m {
 #define S2M_OD_MINB 6  // resident blocks per SM of odom_associate_kernel: latency-bound walks, more warps win (3.9 -> 3.0 ms)
 #endif
 #ifndef S2M_K4A_MINB
-#define S2M_K4A_MINB 10  // resident blocks per SM the kNN kernel is compiled for (48 registers; 8 -> 10: -2 % K4 time)
+#define S2M_K4A_MINB 8  // resident blocks per SM the kNN kernel is compiled for (<= 64 registers)
 #endif
 #ifndef S2M_K4B_MINB
 #define S2M_K4B_MINB 4  // ... and the fit / residual kernel (128 registers, FP64)
@@ -81,7 +87,7 @@ struct FrameDesc {          // per slot, written by the host every call
   int origin[3];            // first 1 m cell of the valid block: 50*val_lo - 25
   int active;               // slot takes part in this call
   int allow_opt;            // 0: skip rows K..S
-  int pad;
+  int idx_flags;            // bit 0: rebuild the cell index of this slot now; bit 1: keep it up to date in the map update
   unsigned long long seq_base[2];
 };
 
@@ -130,10 +136,7 @@ struct Dev {
   int* rng_start;               // [G][25]
   int* loc_off;                 // [G][26]
   int* lp_cnt;                  // [G] points of the local map (read back: sizes the index exactly)
-  uint32_t *ckey, *ckey2, *cval, *cval2;  // [cap_lp]
-  float4* cand;                 // [cap_lp] cell-sorted local points, w = local index bits
-  int* inv;                     // [cap_lp] local index -> position in cand (packed by lp_off)
-  int* nbr;                     // [cap_in][6] K4a -> K4b: (n << 1 | gate), five positions in d.cand
+  int* nbr;                     // [cap_in][6] K4a -> K4b: (n << 1 | gate), five entry numbers in d.bkt
   int* knn_ticket;              // next 32-query work unit of knn_kernel
   float4* od_last;              // odometry: less-sharp / less-flat clouds of the previous sweep, class-major
   int* od_last_off;             // [2B+1]
@@ -148,9 +151,15 @@ struct Dev {
   uint32_t *od_val, *od_val2;
   float4* od_meta;              // [chunks][2] box + ring range of every 32-point chunk of od_last
   int* od_chunk_off;            // [2B+1]
-  unsigned long long* hash_tab; // cell tables
-  uint2* hash_aux;              // per table slot: (points of the cell itself, exact 3-cell count)
-  int* cs_off;                  // [G+1] first sorted position of each segment
+  // ---- persistent cell index (see the vocabulary above)
+  unsigned long long* hash_tab; // [hash_off[G]] per segment: [cell:24][count:16][bucket:24], empty = all ones
+  int* hmask;                   // [G] slots of the segment's table in use - 1 (set at every rebuild)
+  float4* bkt;                  // [4 * bkt_off[G]] buckets of four (x, y, z, tag); tag -1 = unused / removed
+  uint32_t* bnext;              // [bkt_off[G]] next bucket of a cell's chain, ~0 none
+  int* bkt_off;                 // [G+1] first bucket of each segment's pool (static)
+  int* bcnt;                    // [G] buckets handed out
+  int* idx_list;                // [G] segments to rebuild this frame (compacted), count in idx_n
+  int* idx_poff;                // [G+1] packed offsets of their local points
   // ---- association / solve
   double* rec;                  // [cap_in][6] cached correspondences
   uint8_t* rec_valid;           // [cap_in]
@@ -188,9 +197,9 @@ size_t cub_temp_bytes(int cap_sort, int cap_lp);
 int launch_voxel_bbox(const Dev& d, int total_in, cudaStream_t s);
 int launch_voxel_filter(const Dev& d, int total_in, int key_bits, cudaStream_t s);
 int launch_local_ranges(const Dev& d, int cur, cudaStream_t s);
-int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, bool ranges_done, cudaStream_t s);
+int launch_index_rebuild(const Dev& d, int cur, int n_seg, int total_points, cudaStream_t s);
 int launch_guard(const Dev& d, cudaStream_t s);
-int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s);
+int launch_associate(const Dev& d, int outer, int cur, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s);
 int launch_solve(const Dev& d, int outer, bool from_units, cudaStream_t s);
 int launch_reduce_units(const Dev& d, cudaStream_t s);
 int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s);
@@ -203,7 +212,10 @@ int launch_odom_associate(const Dev& d, int outer, int tiles, int fallback_block
 int launch_finish_pose(const Dev& d, cudaStream_t s);
 int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_store, bool check_pending, bool identity_pose,
                       cudaStream_t s);
-int launch_knn_debug(const Dev& d, int slot, int cls, const float* d_q, int n, int32_t* d_idx, float* d_d2,
+constexpr int kBktE = 4;                       // entries per bucket
+constexpr uint32_t kNoBkt = 0xFFFFFFu;         // 24-bit "none" inside a table entry
+constexpr unsigned long long kCellCount1 = 1ull << 24;
+int launch_knn_debug(const Dev& d, int cur, int slot, int cls, const float* d_q, int n, int32_t* d_idx, float* d_d2,
                      cudaStream_t s);
 int launch_transform_cloud(const double* d_pose7, const float4* in, float4* out, int n, cudaStream_t s);
 int launch_gather_local(const Dev& d, int cur, int g, float4* out, cudaStream_t s);

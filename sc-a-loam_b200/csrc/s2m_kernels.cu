@@ -178,7 +178,7 @@ __global__ void ds_off_kernel(Dev d, int n) {
 }
 
 // ----------------------------------------------------------------------------
-// K3: local map (valid cubes of the store, gather order) and its 1 m cell index
+// K3a: local map = the valid cubes of the store, in gather order (25 contiguous key ranges)
 // ----------------------------------------------------------------------------
 __global__ void range_kernel(Dev d, int cur) {
   const int g = blockIdx.x, c = threadIdx.x;
@@ -221,102 +221,187 @@ __device__ __forceinline__ int local_to_store(const Dev& d, int g, int l) {
   return d.rng_start[g * kCols + a] + (l - lo[a]);
 }
 
-__global__ void local_key_kernel(Dev d, int cur, int total_lp) {
+// ----------------------------------------------------------------------------
+// K3: the persistent 1 m cell index of the local map (rows C, T: laserMapping.cpp:510-540, :559-560)
+//
+// The reference gathers the valid cubes and rebuilds two KD-trees every frame.  Here every segment keeps
+// a voxel-hash style index alive across frames: an open-addressing table cell -> [cell:24][count:16]
+// [bucket:24] and a pool of 4-entry buckets (64 B, chained) holding (x, y, z, tag) of every point of the
+// local map.  It is built in bulk only when the valid block changes (idx_build_kernel, from the sorted
+// store); between those frames the map update puts the few thousand points a frame re-centroids or adds
+// into it (idx_apply, called by delta_reduce_kernel): O(changed points) per frame, no sort.
+// tag = [cube of the valid block, gather order:7][pending:1][voxel z, y, x:3x8 | arrival rank:24]
+// orders exactly like the position in the reference's gathered cloud, so the kNN tie rule (d2, index)
+// is (d2, tag); the index itself is only materialised for the trace / debug outputs (tag_to_local).
+// ----------------------------------------------------------------------------
+constexpr unsigned long long kCellEmpty = ~0ull;
+__device__ __forceinline__ uint32_t cell_key_of(const Dev& d, const FrameDesc& fd, float x, float y, float z) {
+  const int rx = (int)floorf(x) - fd.origin[0], ry = (int)floorf(y) - fd.origin[1], rz = (int)floorf(z) - fd.origin[2];
+  if ((unsigned)rx > 255u || (unsigned)ry > 255u || (unsigned)rz > 255u) set_err(d, -4);
+  return ((uint32_t)(rz & 255) << 16) | ((uint32_t)(ry & 255) << 8) | (uint32_t)(rx & 255);
+}
+// tag of a store entry of segment g lying in the valid block of fd
+__device__ __forceinline__ uint32_t cube_rel(const FrameDesc& fd, int ci, int cj, int ck) {
+  return (uint32_t)(((ci - fd.val_lo[0]) * 5 + (cj - fd.val_lo[1])) * 3 + (ck - fd.val_lo[2]));
+}
+__device__ __forceinline__ uint32_t tag_filtered(const FrameDesc& fd, int ci, int cj, int ck, uint32_t vz, uint32_t vy, uint32_t vx) {
+  return (cube_rel(fd, ci, cj, ck) << 25) | (vz << 16) | (vy << 8) | vx;
+}
+__device__ __forceinline__ int bucket_alloc(const Dev& d, int g) {
+  const int b = atomicAdd(d.bcnt + g, 1);
+  if (b >= d.bkt_off[g + 1] - d.bkt_off[g] || b >= (int)kNoBkt) { set_err(d, -3); return -1; }
+  return b;
+}
+// entry number (index into d.bkt) of slot `slot` of the chain that starts at bucket b; grows the chain when asked
+__device__ __forceinline__ long long chain_slot(const Dev& d, int g, int b, int slot, bool grow) {
+  const int base = d.bkt_off[g];
+  for (int c = slot / kBktE; c > 0; --c) {
+    uint32_t nb = d.bnext[base + b];
+    if (nb == kSentinel32) {
+      if (!grow) return -1;
+      const int fresh = bucket_alloc(d, g);
+      if (fresh < 0) return -1;
+      const uint32_t prev = atomicCAS(d.bnext + base + b, kSentinel32, (uint32_t)fresh);
+      nb = prev == kSentinel32 ? (uint32_t)fresh : prev;  // (a lost race leaks one bucket until the next rebuild)
+    }
+    b = (int)nb;
+  }
+  return (long long)(base + b) * kBktE + slot % kBktE;
+}
+__device__ __forceinline__ void idx_insert(const Dev& d, int g, uint32_t k24, const float4 e) {
+  unsigned long long* tab = d.hash_tab + d.hash_off[g];
+  const uint32_t mask = (uint32_t)d.hmask[g];
+  uint32_t s = cell_hash(k24) & mask;
+  for (int guard = 0; guard <= (int)mask; ++guard) {
+    unsigned long long old = tab[s];
+    if (old == kCellEmpty) {
+      const int b = bucket_alloc(d, g);
+      if (b < 0) return;
+      const unsigned long long entry = ((unsigned long long)k24 << 40) | kCellCount1 | (unsigned long long)b;
+      old = atomicCAS(tab + s, kCellEmpty, entry);
+      if (old == kCellEmpty) { d.bkt[(size_t)(d.bkt_off[g] + b) * kBktE] = e; return; }
+    }
+    if ((uint32_t)(old >> 40) == k24) {
+      const unsigned long long prev = atomicAdd(tab + s, kCellCount1);
+      const int slot = (int)((prev >> 24) & 0xFFFFu);
+      if (slot >= 0xFFFF) { set_err(d, -3); return; }
+      const long long at = chain_slot(d, g, (int)(prev & kNoBkt), slot, true);
+      if (at >= 0) d.bkt[at] = e;
+      return;
+    }
+    s = (s + 1) & mask;
+  }
+  set_err(d, -3);  // table full
+}
+// entry number of the point with this tag in cell k24, -1 if it is not there
+__device__ __forceinline__ long long idx_find(const Dev& d, int g, uint32_t k24, uint32_t tag) {
+  const unsigned long long* tab = d.hash_tab + d.hash_off[g];
+  const uint32_t mask = (uint32_t)d.hmask[g];
+  uint32_t s = cell_hash(k24) & mask;
+  unsigned long long e = tab[s];
+  while (e != kCellEmpty && (uint32_t)(e >> 40) != k24) { s = (s + 1) & mask; e = tab[s]; }
+  if (e == kCellEmpty) return -1;
+  const int cnt = (int)((e >> 24) & 0xFFFFu), base = d.bkt_off[g];
+  int b = (int)(e & kNoBkt);
+  for (int i = 0; i < cnt; ++i) {
+    if (i && i % kBktE == 0) {
+      const uint32_t nb = d.bnext[base + b];
+      if (nb == kSentinel32) return -1;
+      b = (int)nb;
+    }
+    const long long at = (long long)(base + b) * kBktE + i % kBktE;
+    if (__float_as_uint(d.bkt[at].w) == tag) return at;
+  }
+  return -1;
+}
+// The map update re-centroided (had_old) or created the filtered entry `tag`: keep the index in step.
+__device__ __forceinline__ void idx_apply(const Dev& d, int g, const FrameDesc& fd, uint32_t tag, bool had_old, const float4 o,
+                                          const float4 c) {
+  const float4 e = make_float4(c.x, c.y, c.z, __uint_as_float(tag));
+  const uint32_t kn = cell_key_of(d, fd, c.x, c.y, c.z);
+  if (had_old) {
+    const uint32_t ko = cell_key_of(d, fd, o.x, o.y, o.z);
+    const long long at = idx_find(d, g, ko, tag);
+    if (at < 0) { set_err(d, -7); return; }
+    if (ko == kn) { d.bkt[at] = e; return; }
+    d.bkt[at] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kSentinel32));  // the centroid left this cell
+  }
+  idx_insert(d, g, kn, e);
+}
+
+// ---- bulk (re)build of the segments listed in d.idx_list -----------------------------------------------
+// grid (chunks, listed segments): clear the table slots that will be used and the buckets that were
+__global__ void idx_reset_kernel(Dev d, const int* __restrict__ new_mask) {
+  const int g = d.idx_list[blockIdx.y];
+  unsigned long long* tab = d.hash_tab + d.hash_off[g];
+  const int slots = new_mask[blockIdx.y] + 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += gridDim.x * blockDim.x) tab[i] = kCellEmpty;
+  const int used = min(d.bcnt[g], d.bkt_off[g + 1] - d.bkt_off[g]);
+  float4* bk = d.bkt + (size_t)d.bkt_off[g] * kBktE;
+  const float4 none = make_float4(0.f, 0.f, 0.f, __uint_as_float(kSentinel32));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < used * kBktE; i += gridDim.x * blockDim.x) bk[i] = none;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < used; i += gridDim.x * blockDim.x) d.bnext[d.bkt_off[g] + i] = kSentinel32;
+}
+__global__ void idx_arm_kernel(Dev d, const int* __restrict__ new_mask, int n_seg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_seg) return;
+  const int g = d.idx_list[i];
+  d.bcnt[g] = 0;
+  d.hmask[g] = new_mask[i];
+  if (d.shard_world > 1) d.shard_counts[g] = 0;
+}
+// one thread per local-map point of the listed segments (packed by d.idx_poff)
+__global__ void idx_build_kernel(Dev d, int cur, int n_seg, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int g = -1;
   bool owned = false;  // sharded map: this rank owns the point (it counts towards the guard :555)
-  if (i < total_lp) g = find_seg(d.lp_off, d.G, i);
-  const int l = i < total_lp ? i - d.lp_off[g] : 0;
-  uint32_t key = kSentinel32;
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool have = i < total_lp && l < d.loc_off[g * (kCols + 1) + kCols];
-  if (have) {
-    p = d.st_pt[cur][d.st_base[g] + local_to_store(d, g, l)];
-    owned = d.shard_world > 1 && p.x >= d.shard_lo && p.x < d.shard_hi;
+  if (i < total) {
+    const int si = find_seg(d.idx_poff, n_seg, i);
+    g = d.idx_list[si];
+    const int l = i - d.idx_poff[si];
+    if (l < d.loc_off[g * (kCols + 1) + kCols]) {
+      const int pos = local_to_store(d, g, l);
+      const uint64_t* keys = d.st_key[cur] + d.st_base[g];
+      const uint64_t key = keys[pos];
+      const float4 p = d.st_pt[cur][d.st_base[g] + pos];
+      const FrameDesc& fd = d.desc[seg_slot(d, g)];
+      int ci, cj, ck;
+      unpack_cube(key_cube(key), ci, cj, ck);
+      uint32_t tag;
+      if (key_pending(key)) {  // raw point of a cube that has just become valid: rank among the cube's raw points
+        const int first = lower_bound_u64(keys, d.st_n[g], store_key(key_cube(key), 1, 0));
+        tag = (cube_rel(fd, ci, cj, ck) << 25) | (1u << 24) | (uint32_t)min(pos - first, 0xFFFFFF);
+      } else {
+        const uint64_t pl = key_payload(key);
+        const uint32_t vz = (uint32_t)(pl >> 22) & 0x7FFu, vy = (uint32_t)(pl >> 11) & 0x7FFu, vx = (uint32_t)pl & 0x7FFu;
+        if ((vz | vy | vx) > 255u) set_err(d, -4);
+        tag = tag_filtered(fd, ci, cj, ck, vz, vy, vx);
+      }
+      idx_insert(d, g, cell_key_of(d, fd, p.x, p.y, p.z), make_float4(p.x, p.y, p.z, __uint_as_float(tag)));
+      owned = d.shard_world > 1 && p.x >= d.shard_lo && p.x < d.shard_hi;
+    }
   }
-  if (d.shard_world > 1) {  // one atomic per warp and segment instead of one per point (tens of millions on 2 x slots addresses)
+  if (d.shard_world > 1) {  // one atomic per warp and segment instead of one per point
     const unsigned peers = __match_any_sync(0xffffffffu, owned ? g : -1);
     if (owned && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(d.shard_counts + g, __popc(peers));
   }
-  if (i >= total_lp) return;
-  if (have) {
-    const FrameDesc& fd = d.desc[seg_slot(d, g)];
-    const int rx = (int)floorf(p.x) - fd.origin[0], ry = (int)floorf(p.y) - fd.origin[1],
-              rz = (int)floorf(p.z) - fd.origin[2];
-    if ((unsigned)rx > 255u || (unsigned)ry > 255u || (unsigned)rz > 255u) set_err(d, -4);
-    key = ((uint32_t)g << 24) | ((uint32_t)(rz & 255) << 16) | ((uint32_t)(ry & 255) << 8) | (uint32_t)(rx & 255);
-  }
-  d.ckey[i] = key;
-  d.cval[i] = (uint32_t)l;
 }
-
-__global__ void cs_off_kernel(Dev d, int total_lp) {
-  const int g = threadIdx.x + blockIdx.x * blockDim.x;
-  if (g > d.G) return;
-  d.cs_off[g] = lower_bound_u32(d.ckey2, total_lp, (uint32_t)g << 24);
-}
-
-// Cell table entry: [cell key:24][count:10][start:30].  (start, count) is the contiguous
-// run of d.cand holding the cell AND its two x-neighbours of the same (y,z) row -- cell keys
-// sort x-fastest, so one probe at the centre cell of a row yields all three cells.  An EMPTY
-// cell with an occupied x-neighbour gets a "virtual" entry whose run is its neighbour(s)
-// (contiguous too, nothing lies between them), so a row is always exactly one probe.
-// hash_aux[slot] = (points of the cell itself, exact run length); read when the 10-bit count
-// saturates (1023) and by the profiling counter.
-__device__ __forceinline__ void cell_insert(const Dev& d, int g, uint32_t k24, int start, uint32_t count, uint32_t own) {
-  const unsigned long long entry = ((unsigned long long)k24 << 40) |
-                                   ((unsigned long long)(count < 1023u ? count : 1023u) << 30) |
-                                   (unsigned long long)start;
-  const int base = d.hash_off[g];
-  const uint32_t mask = (uint32_t)(d.hash_off[g + 1] - base) - 1u;
-  uint32_t s = cell_hash(k24) & mask;
-  for (;;) {
-    unsigned long long old = atomicCAS(d.hash_tab + base + s, kSentinel64, entry);
-    if (old == kSentinel64) break;
-    s = (s + 1) & mask;
+// position in the gathered local map (the reference's kNN index) of the entry with this tag: trace / debug only
+__device__ __forceinline__ int tag_to_local(const Dev& d, int cur, int g, uint32_t tag) {
+  const FrameDesc& fd = d.desc[seg_slot(d, g)];
+  const int rel = (int)(tag >> 25);
+  const int ci = fd.val_lo[0] + rel / 15, cj = fd.val_lo[1] + (rel / 3) % 5, ck = fd.val_lo[2] + rel % 3;
+  const uint64_t* keys = d.st_key[cur] + d.st_base[g];
+  const uint32_t cube = pack_cube(ci, cj, ck);
+  int pos;
+  if ((tag >> 24) & 1u) {
+    pos = lower_bound_u64(keys, d.st_n[g], store_key(cube, 1, 0)) + (int)(tag & 0xFFFFFFu);
+  } else {
+    const uint64_t pl = ((uint64_t)((tag >> 16) & 255u) << 22) | ((uint64_t)((tag >> 8) & 255u) << 11) | (uint64_t)(tag & 255u);
+    pos = lower_bound_u64(keys, d.st_n[g], store_key(cube, 0, pl));
   }
-  d.hash_aux[base + s] = make_uint2(own, count);
-}
-__global__ void cand_build_kernel(Dev d, int cur, int total_lp) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= total_lp) return;
-  const uint32_t key = d.ckey2[p];
-  if (key == kSentinel32) return;
-  const int g = key >> 24;
-  const int l = (int)d.cval2[p];
-  const float4 q = d.st_pt[cur][d.st_base[g] + local_to_store(d, g, l)];
-  d.cand[p] = make_float4(q.x, q.y, q.z, __int_as_float(l));
-  d.inv[d.lp_off[g] + l] = p;  // local index -> position in d.cand
-  if (p == 0 || d.ckey2[p - 1] != key) {
-    // run of a key starting at position a (a < total_lp): its end
-    auto run_end = [&](int a) {
-      const uint32_t k = d.ckey2[a];
-      int e = a + 1;
-      while (e < total_lp && d.ckey2[e] == k) ++e;
-      return e;
-    };
-    const int e = run_end(p);
-    const uint32_t own = (uint32_t)(e - p);
-    const uint32_t rx = key & 255u;
-    const uint32_t k24 = key & 0xFFFFFFu;
-    const bool has_l1 = rx > 0u && p > 0 && d.ckey2[p - 1] == key - 1u;
-    const bool has_r1 = rx < 255u && e < total_lp && d.ckey2[e] == key + 1u;
-    int s3 = p, e3 = e;
-    if (has_l1) { s3 = p - 1; while (s3 > 0 && d.ckey2[s3 - 1] == key - 1u) --s3; }
-    if (has_r1) e3 = run_end(e);
-    cell_insert(d, g, k24, s3, (uint32_t)(e3 - s3), own);
-    // virtual entry for the empty right neighbour: this cell + the cell two to the right
-    if (!has_r1 && rx < 255u) {
-      int ev = e;
-      if (rx < 254u && e < total_lp && d.ckey2[e] == key + 2u) ev = run_end(e);
-      cell_insert(d, g, k24 + 1u, p, (uint32_t)(ev - p), 0u);
-    }
-    // virtual entry for the empty left neighbour, unless the cell two to the left makes it (as ITS right neighbour)
-    if (!has_l1 && rx > 0u) {
-      const bool has_l2 = rx > 1u && p > 0 && d.ckey2[p - 1] == key - 2u;
-      if (!has_l2) cell_insert(d, g, k24 - 1u, p, own, 0u);
-    }
-  }
+  const int col = (ci - fd.val_lo[0]) * 5 + (cj - fd.val_lo[1]);
+  return d.loc_off[g * (kCols + 1) + col] + (pos - d.rng_start[g * kCols + col]);
 }
 
 // ----------------------------------------------------------------------------
@@ -324,66 +409,61 @@ __global__ void cand_build_kernel(Dev d, int cur, int total_lp) {
 // ----------------------------------------------------------------------------
 constexpr unsigned kFull = 0xffffffffu;
 // Exact bounded kNN(5) of one query over the 27 cells around it.  Distances are
-// the reference's float ((dx*dx)+(dy*dy))+(dz*dz); order is (d2, local index):
+// the reference's float ((dx*dx)+(dy*dy))+(dz*dz); order is (d2, tag) == (d2, local index):
 // both live in one 64-bit key (float bits of a non-negative d2 are monotonic).
 struct Knn5 {
-  unsigned long long key[5];  // d2 bits << 32 | local index, ascending
+  unsigned long long key[5];  // d2 bits << 32 | tag, ascending
+  uint32_t at[5];             // entry number in d.bkt
 };
 __device__ __forceinline__ float knn_d2(const Knn5& r, int k) { return __uint_as_float((uint32_t)(r.key[k] >> 32)); }
-__device__ __forceinline__ int knn_idx(const Knn5& r, int k) { return (int)(uint32_t)r.key[k]; }
-// "none" marker: the search starts from the reference's gate (d2 = 1.0f, index 0), see knn5_cells
+__device__ __forceinline__ uint32_t knn_tag(const Knn5& r, int k) { return (uint32_t)r.key[k]; }
+// "none" marker: the search starts from the reference's gate (d2 = 1.0f, tag 0), see knn5_cells
 constexpr unsigned long long kKnnInit = (unsigned long long)0x3F800000u << 32;
 
-__device__ __forceinline__ void knn_offer(Knn5& r, float qx, float qy, float qz, const float4 c) {
+__device__ __forceinline__ void knn_offer(Knn5& r, float qx, float qy, float qz, const float4 c, uint32_t at) {
   const float dd = dist2(qx, qy, qz, c.x, c.y, c.z);
-  if (dd > knn_d2(r, 4)) return;  // cheap float test first; ties go through the exact 64-bit compare
-  const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | (uint32_t)__float_as_int(c.w);
+  const uint32_t tag = __float_as_uint(c.w);
+  if (tag == kSentinel32 || dd > knn_d2(r, 4)) return;  // removed entry; cheap float test first, ties go through the exact 64-bit compare
+  const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | tag;
   if (key < r.key[4]) {  // replace the 5th, then bubble it up (compare-exchange chain)
     r.key[4] = key;
+    r.at[4] = at;
 #pragma unroll
     for (int i = 4; i > 0; --i) {
       const unsigned long long lo = r.key[i - 1], hi = r.key[i];
+      const uint32_t alo = r.at[i - 1], ahi = r.at[i];
       const bool sw = hi < lo;
       r.key[i - 1] = sw ? hi : lo;
       r.key[i] = sw ? lo : hi;
+      r.at[i - 1] = sw ? ahi : alo;
+      r.at[i] = sw ? alo : ahi;
     }
   }
 }
-__device__ __forceinline__ unsigned long long cell_probe(const unsigned long long* __restrict__ tab, uint32_t mask,
-                                                         uint32_t k24, uint32_t& s) {
-  s = cell_hash(k24) & mask;
-  unsigned long long e = tab[s];
-  while (e != kSentinel64 && (uint32_t)(e >> 40) != k24) {
-    s = (s + 1) & mask;
-    e = tab[s];
-  }
-  return e;
-}
-
-#ifndef S2M_KNN_PF
-#define S2M_KNN_PF 1  // candidate loads in flight per thread while the previous ones are offered
-#endif
-__device__ __forceinline__ void knn_scan_range(const float4* __restrict__ cand, int start, int count, float qx,
-                                               float qy, float qz, Knn5& r) {
-  float4 buf[S2M_KNN_PF];
-#pragma unroll
-  for (int u = 0; u < S2M_KNN_PF; ++u) buf[u] = __ldg(cand + start + min(u, count - 1));
+// all points of one cell: `cnt` entries of the bucket chain that starts at bucket b (the entries of a bucket are
+// four independent 16-byte loads of one 64-byte line)
+__device__ __forceinline__ void knn_scan_cell(const Dev& d, int g, int b, int cnt, float qx, float qy, float qz, Knn5& r) {
+  const int base = d.bkt_off[g];
 #pragma unroll 1
-  for (int j = 0; j < count; j += S2M_KNN_PF) {
-#pragma unroll
-    for (int u = 0; u < S2M_KNN_PF; ++u) {
-      if (j + u < count) {  // the next points are in flight while this one is offered
-        const float4 c = buf[u];
-        buf[u] = __ldg(cand + start + min(j + u + S2M_KNN_PF, count - 1));
-        knn_offer(r, qx, qy, qz, c);
-      }
-    }
+  while (cnt > 0) {
+    const uint32_t at0 = (uint32_t)(base + b) * kBktE;
+    const float4* __restrict__ p = d.bkt + at0;
+    const float4 c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2), c3 = __ldg(p + 3);
+    uint32_t nb = kSentinel32;
+    if (cnt > kBktE) nb = __ldg(d.bnext + base + b);
+    knn_offer(r, qx, qy, qz, c0, at0);
+    if (cnt > 1) knn_offer(r, qx, qy, qz, c1, at0 + 1);
+    if (cnt > 2) knn_offer(r, qx, qy, qz, c2, at0 + 2);
+    if (cnt > 3) knn_offer(r, qx, qy, qz, c3, at0 + 3);
+    cnt -= kBktE;
+    if (nb == kSentinel32) break;
+    b = (int)nb;
   }
 }
 
-// per-thread staging of the nine row probes (one column per thread)
+// per-thread staging of the 27 cell probes (one column per thread): count << 24 | bucket, 0 count = empty
 struct KnnStage {
-  unsigned long long run[9][kTile];  // count << 32 | start of each row's candidate run (0 = none)
+  uint32_t cell[27][kTile];
 };
 
 // Rows (dy,dz) of three x-adjacent cells are visited near to far; a row is skipped when
@@ -395,70 +475,81 @@ struct KnnStage {
 __device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[3], float qx, float qy, float qz,
                                           Knn5& r, KnnStage& st) {
   // The result is only used when the 5th distance is < 1.0 (laserMapping.cpp:585, :653), so the
-  // search starts from that bound: key (1.0f, index 0) is larger than every (d2 < 1, any index)
+  // search starts from that bound: key (1.0f, tag 0) is larger than every (d2 < 1, any tag)
   // and not larger than any (d2 >= 1, .) -- candidates at 1 m or more never enter.
 #pragma unroll
-  for (int k = 0; k < 5; ++k) r.key[k] = kKnnInit;
+  for (int k = 0; k < 5; ++k) { r.key[k] = kKnnInit; r.at[k] = 0u; }
   const float fly = floorf(qy), flz = floorf(qz);
   const int cx = (int)floorf(qx) - origin[0], cy = (int)fly - origin[1], cz = (int)flz - origin[2];
-  const int base = d.hash_off[g];
-  const uint32_t mask = (uint32_t)(d.hash_off[g + 1] - base) - 1u;
-  const unsigned long long* __restrict__ tab = d.hash_tab + base;
+  const uint32_t mask = (uint32_t)d.hmask[g];
+  const unsigned long long* __restrict__ tab = d.hash_tab + d.hash_off[g];
   const int t = threadIdx.x;
   // exact distances from the query to the cell's boundary planes (fractional parts are exact)
   const float fy = xfsub(qy, fly), fz = xfsub(qz, flz);
   const float gy = xfsub(1.0f, fy), gz = xfsub(1.0f, fz);
   const int sy = fy < 0.5f ? -1 : 1, sz = fz < 0.5f ? -1 : 1;  // side of the nearer boundary
-  // A query one cell outside the block in x still has one column of the block in range: probe
-  // that column (its run is a superset of what is needed, which keeps the search exact).
-  const int px = cx < 0 ? cx + 1 : (cx > 255 ? cx - 1 : cx);
-  const bool x_ok = (unsigned)px <= 255u;
   int total = 0;
-  {  // phase 1: the nine row probes issued back to back (independent loads), near-to-far order
-    uint32_t k24[9], sl[9];
-    unsigned long long e[9];
+#pragma unroll 1
+  for (int o = 0; o < 9; ++o) {  // phase 1: the 27 cell probes, three rows (nine independent loads) at a time
+    // row order: centre, (sy,0), (0,sz), (sy,sz), (-sy,0), (0,-sz), (-sy,sz), (sy,-sz), (-sy,-sz)
+    const int dy = (o == 1 || o == 3 || o == 7) ? sy : ((o == 4 || o == 6 || o == 8) ? -sy : 0);
+    const int dz = (o == 2 || o == 3 || o == 6) ? sz : ((o == 5 || o == 7 || o == 8) ? -sz : 0);
+    const int z = cz + dz, y = cy + dy;
+    const bool row_ok = (unsigned)z <= 255u && (unsigned)y <= 255u;
+    uint32_t k24[3], sl[3];
+    unsigned long long e[3];
 #pragma unroll
-    for (int o = 0; o < 9; ++o) {
-      // order: centre, (sy,0), (0,sz), (sy,sz), (-sy,0), (0,-sz), (-sy,sz), (sy,-sz), (-sy,-sz)
-      const int dy = (o == 1 || o == 3 || o == 7) ? sy : ((o == 4 || o == 6 || o == 8) ? -sy : 0);
-      const int dz = (o == 2 || o == 3 || o == 6) ? sz : ((o == 5 || o == 7 || o == 8) ? -sz : 0);
-      const int z = cz + dz, y = cy + dy;
-      const bool ok = (unsigned)z <= 255u && (unsigned)y <= 255u && x_ok;
-      k24[o] = ((uint32_t)(z & 255) << 16) | ((uint32_t)(y & 255) << 8) | (uint32_t)(px & 255);
-      sl[o] = cell_hash(k24[o]) & mask;
-      e[o] = ok ? tab[sl[o]] : kSentinel64;
+    for (int a = 0; a < 3; ++a) {
+      const int x = cx + a - 1;
+      k24[a] = ((uint32_t)(z & 255) << 16) | ((uint32_t)(y & 255) << 8) | (uint32_t)(x & 255);
+      sl[a] = cell_hash(k24[a]) & mask;
+      e[a] = (row_ok && (unsigned)x <= 255u) ? tab[sl[a]] : kCellEmpty;
     }
 #pragma unroll
-    for (int o = 0; o < 9; ++o) {
-      while (e[o] != kSentinel64 && (uint32_t)(e[o] >> 40) != k24[o]) {
-        sl[o] = (sl[o] + 1) & mask;
-        e[o] = tab[sl[o]];
+    for (int a = 0; a < 3; ++a) {
+      while (e[a] != kCellEmpty && (uint32_t)(e[a] >> 40) != k24[a]) {
+        sl[a] = (sl[a] + 1) & mask;
+        e[a] = tab[sl[a]];
       }
-      unsigned long long rn = 0ull;
-      if (e[o] != kSentinel64) {
-        uint32_t c = (uint32_t)(e[o] >> 30) & 1023u;
-        if (c == 1023u) c = d.hash_aux[base + sl[o]].y;
-        rn = ((unsigned long long)c << 32) | (e[o] & 0x3FFFFFFFull);
+      uint32_t rec = 0u;
+      if (e[a] != kCellEmpty) {
+        const uint32_t c = (uint32_t)(e[a] >> 24) & 0xFFFFu;
+        total += (int)c;
+        rec = (min(c, 255u) << 24) | (uint32_t)(e[a] & kNoBkt);
       }
-      st.run[o][t] = rn;
-      total += (int)(rn >> 32);
+      st.cell[3 * o + a][t] = rec;
     }
   }
-  // phase 2: rows near to far (one copy of the scan code; the staging lives in shared memory)
+  // phase 2: rows near to far
 #pragma unroll 1
   for (int o = 0; o < 9; ++o) {
-    const unsigned long long rn = st.run[o][t];
-    const int cnt = (int)(rn >> 32);
-    if (cnt == 0) continue;
+    const uint32_t r0 = st.cell[3 * o][t], r1 = st.cell[3 * o + 1][t], r2 = st.cell[3 * o + 2][t];
+    if ((r0 | r1 | r2) >> 24 == 0u) continue;
     const float by = (o == 0 || o == 2 || o == 5) ? 0.0f : ((o == 1 || o == 3 || o == 7) ? (sy < 0 ? fy : gy) : (sy < 0 ? gy : fy));
     const float bz = (o == 0 || o == 1 || o == 4) ? 0.0f : ((o == 2 || o == 3 || o == 6) ? (sz < 0 ? fz : gz) : (sz < 0 ? gz : fz));
-    if (xfadd(xfmul(by, by), xfmul(bz, bz)) > knn_d2(r, 4)) continue;  // strict: a tie at the 5th distance may still win on the index
-    knn_scan_range(d.cand, (int)(uint32_t)rn, cnt, qx, qy, qz, r);
+    if (xfadd(xfmul(by, by), xfmul(bz, bz)) > knn_d2(r, 4)) continue;  // strict: a tie at the 5th distance may still win on the tag
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const uint32_t rec = a == 0 ? r1 : (a == 1 ? r0 : r2);  // the query's own column first
+      int cnt = (int)(rec >> 24);
+      if (cnt == 0) continue;
+      if (cnt == 255) {  // saturated staging field: the exact count is in the table
+        const int dy = (o == 1 || o == 3 || o == 7) ? sy : ((o == 4 || o == 6 || o == 8) ? -sy : 0);
+        const int dz = (o == 2 || o == 3 || o == 6) ? sz : ((o == 5 || o == 7 || o == 8) ? -sz : 0);
+        const int x = cx + (a == 0 ? 0 : (a == 1 ? -1 : 1));
+        const uint32_t kk = ((uint32_t)((cz + dz) & 255) << 16) | ((uint32_t)((cy + dy) & 255) << 8) | (uint32_t)(x & 255);
+        uint32_t s = cell_hash(kk) & mask;
+        unsigned long long ee = tab[s];
+        while (ee != kCellEmpty && (uint32_t)(ee >> 40) != kk) { s = (s + 1) & mask; ee = tab[s]; }
+        cnt = ee == kCellEmpty ? 0 : (int)((ee >> 24) & 0xFFFFu);
+      }
+      knn_scan_cell(d, g, (int)(rec & kNoBkt), cnt, qx, qy, qz, r);
+    }
   }
   return total;
 }
 
-__global__ void knn_debug_kernel(Dev d, int g, const float* __restrict__ q, int n, int32_t* __restrict__ idx,
+__global__ void knn_debug_kernel(Dev d, int cur, int g, const float* __restrict__ q, int n, int32_t* __restrict__ idx,
                                  float* __restrict__ d2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -468,11 +559,10 @@ __global__ void knn_debug_kernel(Dev d, int g, const float* __restrict__ q, int 
   const bool ok = knn_d2(r, 4) < 1.0f;  // the reference's gate; beyond it the bounded search is not exact
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    idx[5 * i + k] = ok ? knn_idx(r, k) : -1;
+    idx[5 * i + k] = ok ? tag_to_local(d, cur, g, knn_tag(r, k)) : -1;
     d2[5 * i + k] = ok ? knn_d2(r, k) : INFINITY;
   }
 }
-
 
 // ----------------------------------------------------------------------------
 // Block-level accumulation.  Each thread adds the 28 sums of its own queries into
@@ -618,7 +708,7 @@ __global__ void lm_shard_kernel(Dev d, int outer, int after) {
 //                    Jacobian + Huber, 48-byte correspondence record (rows E, F, R, L, Q); the 28
 //                    sums of every 32-point unit are transposed through shared memory and added in
 //                    lane order: one 32-double partial per unit, no block barrier anywhere.
-// The hand-off is 24 bytes per point (gate + n, five positions in d.cand).  The solver
+// The hand-off is 24 bytes per point (gate + n, five entry numbers of the cell index).  The solver
 // (solve_kernel) adds the unit partials of a slot in unit order, so every bit of the pose is
 // independent of what else shares the launch.
 // ----------------------------------------------------------------------------
@@ -684,10 +774,9 @@ __global__ void __launch_bounds__(kTile, S2M_K4A_MINB) knn_kernel(Dev d, int out
         const bool gate = knn_d2(r, 4) < 1.0f;  // laserMapping.cpp:585 / :653
         int* nb = d.nbr + 6 * (size_t)pos_q;
         nb[0] = (visited << 1) | (gate ? 1 : 0);  // visited = map points in the query's 27 cells
-        if (gate) {  // positions in d.cand of the five neighbours (local index -> position through d.inv)
-          const int* __restrict__ inv = d.inv + d.lp_off[cls ? B + slot : slot];
+        if (gate) {  // entry numbers in d.bkt of the five neighbours, nearest first
 #pragma unroll
-          for (int kk = 0; kk < 5; ++kk) nb[1 + kk] = inv[knn_idx(r, kk)];
+          for (int kk = 0; kk < 5; ++kk) nb[1 + kk] = (int)r.at[kk];
         }
       }
     }
@@ -696,7 +785,7 @@ __global__ void __launch_bounds__(kTile, S2M_K4A_MINB) knn_kernel(Dev d, int out
 
 constexpr int kSumRows = 30;  // 28 sums + n_edge + n_plane, transposed through shared memory
 template <bool kTrace>
-__global__ void __launch_bounds__(kTile, S2M_K4B_MINB) fit_kernel(Dev d, int outer) {
+__global__ void __launch_bounds__(kTile, S2M_K4B_MINB) fit_kernel(Dev d, int outer, int cur) {
   __shared__ double Tbuf[kTile / 32][kSumRows * 33];
   const int slot = blockIdx.y;
   if (!d.out[slot].optimized) return;
@@ -727,9 +816,9 @@ __global__ void __launch_bounds__(kTile, S2M_K4B_MINB) fit_kernel(Dev d, int out
       int nbi[5];
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const float4 c = __ldg(d.cand + (uint32_t)nbp[1 + k]);
+        const float4 c = __ldg(d.bkt + (uint32_t)nbp[1 + k]);
         nb[k][0] = c.x; nb[k][1] = c.y; nb[k][2] = c.z;
-        nbi[k] = __float_as_int(c.w);
+        nbi[k] = kTrace ? tag_to_local(d, cur, cls ? d.B + slot : slot, __float_as_uint(c.w)) : 0;
       }
       if (kTrace) {
         float w[3];
@@ -1667,6 +1756,12 @@ __global__ void delta_reduce_kernel(Dev d, int cur, int n_delta) {
   }
   const float c = (float)cnt;
   const float4 cen = make_float4(xfdiv(sx, c), xfdiv(sy, c), xfdiv(sz, c), xfdiv(si, c));
+  if (fd.idx_flags & 2) {  // the cell index of this slot follows the map (it is not rebuilt next frame)
+    const uint32_t vx = (uint32_t)(pl & vm), vy = (uint32_t)((pl >> vb) & vm), vz = (uint32_t)((pl >> (2 * vb)) & vm);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (exists) o = d.st_pt[cur][d.st_base[g] + pos];
+    idx_apply(d, g, fd, tag_filtered(fd, ci, cj, ck, vz, vy, vx), exists, o, cen);
+  }
   if (exists) {
     // key unchanged: the new centroid replaces the entry in the NEXT store buffer (upd_apply_kernel, after
     // the merge copy).  The current buffer is never written, so a frame that fails later -- capacity, range --
@@ -1894,36 +1989,32 @@ int launch_local_ranges(const Dev& d, int cur, cudaStream_t s) {
   range_kernel<<<d.G, 32, 0, s>>>(d, cur);
   return 1;
 }
-int launch_local_index(const Dev& d, int cur, int total_lp, int hash_total, bool ranges_done, cudaStream_t s) {
-  int k = 0;
-  if (!ranges_done) k += launch_local_ranges(d, cur, s);
-  cudaMemsetAsync(d.hash_tab, 0xFF, sizeof(unsigned long long) * (size_t)hash_total, s);
-  if (d.shard_world > 1) cudaMemsetAsync(d.shard_counts, 0, sizeof(int) * d.G, s);
-  if (total_lp > 0) {
-    local_key_kernel<<<cdiv(total_lp, 256), 256, 0, s>>>(d, cur, total_lp); ++k;
-    size_t tb = d.cub_tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, d.ckey, d.ckey2, d.cval, d.cval2, total_lp, 0, 32, s);
-  }
-  cs_off_kernel<<<cdiv(d.G + 1, 128), 128, 0, s>>>(d, total_lp); ++k;
-  if (total_lp > 0) { cand_build_kernel<<<cdiv(total_lp, 256), 256, 0, s>>>(d, cur, total_lp); ++k; }
+// Bulk (re)build of the cell index of the n_seg segments listed in d.idx_list (their new table masks follow the
+// list in the same device array); total_points = their local-map points (d.idx_poff).  Needs launch_local_ranges.
+int launch_index_rebuild(const Dev& d, int cur, int n_seg, int total_points, cudaStream_t s) {
+  if (n_seg <= 0) return 0;
+  const int* new_mask = d.idx_list + d.G;
+  idx_reset_kernel<<<dim3(64, n_seg), 256, 0, s>>>(d, new_mask);
+  idx_arm_kernel<<<cdiv(n_seg, 128), 128, 0, s>>>(d, new_mask, n_seg);
+  int k = 2;
+  if (total_points > 0) { idx_build_kernel<<<cdiv(total_points, 256), 256, 0, s>>>(d, cur, n_seg, total_points); ++k; }
   return k;
 }
-
 int launch_guard(const Dev& d, cudaStream_t s) {
   guard_kernel<<<cdiv(d.B, 64), 64, 0, s>>>(d);
   return 1;
 }
 // One association (rows P..Q of one outer iteration) for every optimised slot: K4a with `knn_blocks`
 // persistent blocks sharing a device-wide tile ticket (the caller zeroes d.knn_ticket), then K4b.
-int launch_associate(const Dev& d, int outer, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s) {
+int launch_associate(const Dev& d, int outer, int cur, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s) {
   if (knn_blocks <= 0 || fit_blocks <= 0) return 0;
   dim3 gb(fit_blocks, d.B);
   if (trace) {
     knn_kernel<true><<<knn_blocks, kTile, 0, s>>>(d, outer);
-    fit_kernel<true><<<gb, kTile, 0, s>>>(d, outer);
+    fit_kernel<true><<<gb, kTile, 0, s>>>(d, outer, cur);
   } else {
     knn_kernel<false><<<knn_blocks, kTile, 0, s>>>(d, outer);
-    fit_kernel<false><<<gb, kTile, 0, s>>>(d, outer);
+    fit_kernel<false><<<gb, kTile, 0, s>>>(d, outer, cur);
   }
   return 2;
 }
@@ -2031,10 +2122,10 @@ int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_s
   return k;
 }
 
-int launch_knn_debug(const Dev& d, int slot, int cls, const float* d_q, int n, int32_t* d_idx, float* d_d2,
+int launch_knn_debug(const Dev& d, int cur, int slot, int cls, const float* d_q, int n, int32_t* d_idx, float* d_d2,
                      cudaStream_t s) {
   if (n <= 0) return 0;
-  knn_debug_kernel<<<cdiv(n, 128), 128, 0, s>>>(d, cls * d.B + slot, d_q, n, d_idx, d_d2);
+  knn_debug_kernel<<<cdiv(n, 128), 128, 0, s>>>(d, cur, cls * d.B + slot, d_q, n, d_idx, d_d2);
   return 1;
 }
 int launch_transform_cloud(const double* d_pose7, const float4* in, float4* out, int n, cudaStream_t s) {
