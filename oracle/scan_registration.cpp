@@ -21,10 +21,17 @@
 //   less-flat points of the ring + VoxelGrid(0.2)       :396-413          -> voxel_thin() (assumption A1 of s2m_oracle.cpp)
 //
 // Assumptions (numbered on from s2m_oracle.cpp):
-//   A7 the unqualified atan / atan2 / sqrt calls (:168, :143, :218) resolve to the C double
-//      functions (only <cmath> is included by the file itself); with the float overloads the
-//      angles could differ by one float ulp, which moves a point to another ring only when it
-//      sits within that ulp of a bucket edge.
+//   A7 atan2 at :143 / :144 / :221: the file declares `using std::atan2;` (:56), so with float arguments the
+//      reference calls the FLOAT overload std::atan2(float, float) = atan2f (round-1 advisor finding; the earlier
+//      reading "resolves to the C double function" was wrong for atan2 -- it holds for the `atan` of :168 / :182 /
+//      :195 / :206, whose argument is a float expression but which is called unqualified on the C name).  atan2f is
+//      not correctly rounded in every libm: glibc 2.39 (this image) differs from the correctly rounded result in
+//      16 % of random arguments (measured, by one ulp), glibc >= 2.41 (CORE-MATH) never.  The restatement and the
+//      kernel both use the CORRECTLY ROUNDED float, (float)atan2((double)y, (double)x) -- the value every libm is
+//      within one ulp of and the newest ones return.  Effect of that ulp: the low bit of the relative-time fraction
+//      stored in the intensity channel, and the half-turn decision for a point within one ulp of the threshold;
+//      ring numbers are not affected (they come from `atan`, above).  Parity with a given reference BUILD is
+//      therefore within one ulp of `ori`, not bit-exact, unless that build's libm rounds atan2f correctly.
 //   A8 std::sort (:301) is not stable: equal curvatures inside a sector come out in an
 //      implementation-defined order.  Canonical order here: (curvature, index) ascending
 //      (tie_rule 0); tie_rule 1 runs std::sort with the reference's comparator so tests can show
@@ -58,7 +65,7 @@ void clean(const float* xyz, int n, float thres, std::vector<Pt>& out) {
 // :143-156
 void sweep_bounds(const std::vector<Pt>& c, float& start, float& end) {
   start = (float)(-::atan2((double)c.front().y, (double)c.front().x));
-  end = (float)(-::atan2((double)c.back().y, (double)c.back().x) + 2 * M_PI);
+  end = (float)((double)(float)(-::atan2((double)c.back().y, (double)c.back().x)) + 2 * M_PI);  // float atan2f, then + 2 pi in double (:144)
   if (end - start > 3 * M_PI) end = (float)(end - 2 * M_PI);
   else if (end - start < M_PI) end = (float)(end + 2 * M_PI);
 }

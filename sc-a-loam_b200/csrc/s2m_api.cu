@@ -415,7 +415,7 @@ static int create_impl(s2m_ctx* ctx) {
   std::vector<int> boff(G + 1, 0);
   for (int g = 0; g < G; ++g) {
     const long long c = g < B ? P.cap_map_corner : P.cap_map_surf;
-    boff[g + 1] = boff[g] + (int)std::min<long long>(c + c / 4 + 1024, (1 << 24) - 1);
+    boff[g + 1] = boff[g] + (int)std::min<long long>(c + c / 4 + 1024, (1 << 24) - 1);  // (a sparse map has one cell, hence one bucket, per point)
   }
   ctx->bkt_total = (size_t)boff[G];
   rc |= dev_alloc(ctx, &d.bkt, ctx->bkt_total * kBktE); rc |= dev_alloc(ctx, &d.bnext, ctx->bkt_total);

@@ -95,6 +95,8 @@ __global__ void compact_kernel(Dev d, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && d.flag[i]) d.vidx[d.fscan[i]] = i;
 }
+// scanRegistration.cpp:56 `using std::atan2;`: the reference calls the float overload; the correctly rounded float is used
+// here and in the oracle (assumption A7 of oracle/scan_registration.cpp: any libm's atan2f is within one ulp of it)
 __device__ __forceinline__ float neg_atan2f(float y, float x) { return (float)(-atan2((double)y, (double)x)); }
 constexpr double kPi = 3.14159265358979323846;
 // per-sweep start / end orientation (:143-156)
@@ -110,7 +112,7 @@ __global__ void sweep_kernel(Dev d) {
   if (v1 - v0 < 12) return;
   const int a = d.vidx[v0], z = d.vidx[v1 - 1];
   const float start = neg_atan2f(d.xyz[3 * (size_t)a + 1], d.xyz[3 * (size_t)a]);
-  float end = (float)xdadd(-atan2((double)d.xyz[3 * (size_t)z + 1], (double)d.xyz[3 * (size_t)z]), 2 * kPi);
+  float end = (float)xdadd((double)neg_atan2f(d.xyz[3 * (size_t)z + 1], d.xyz[3 * (size_t)z]), 2 * kPi);  // float atan2, then + 2 pi in double (:144)
   if ((double)xfsub(end, start) > 3 * kPi) end = (float)xdsub((double)end, 2 * kPi);
   else if ((double)xfsub(end, start) < kPi) end = (float)xdadd((double)end, 2 * kPi);
   d.ori[2 * b] = start;

@@ -20,7 +20,7 @@
 //   cell     1 m lattice cell floor(p); candidates of a query are the points of
 //            its 27 neighbouring cells (exact for the reference's d2[4] < 1 gate)
 //   cell index  per segment, PERSISTENT: an open-addressing table cell -> (count, bucket) and a
-//            pool of 4-entry buckets (chained) holding (x, y, z, tag) of every local-map point.
+//            pool of small fixed-size buckets (chained) holding (x, y, z, tag) of every local-map point.
 //            Built in bulk when the valid block changes, otherwise updated by the map update with
 //            the few thousand points a frame changes.  tag = [cube of the valid block:7]
 //            [pending:1][voxel z,y,x:3x8 | arrival rank:24] orders like the reference's gather
@@ -212,7 +212,10 @@ int launch_odom_associate(const Dev& d, int outer, int tiles, int fallback_block
 int launch_finish_pose(const Dev& d, cudaStream_t s);
 int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_store, bool check_pending, bool identity_pose,
                       cudaStream_t s);
-constexpr int kBktE = 4;                       // entries per bucket
+#ifndef S2M_BKT_E
+#define S2M_BKT_E 8
+#endif
+constexpr int kBktE = S2M_BKT_E;               // entries per bucket (a multiple of 4: 64 or 128 bytes)
 constexpr uint32_t kNoBkt = 0xFFFFFFu;         // 24-bit "none" inside a table entry
 constexpr unsigned long long kCellCount1 = 1ull << 24;
 int launch_knn_debug(const Dev& d, int cur, int slot, int cls, const float* d_q, int n, int32_t* d_idx, float* d_d2,

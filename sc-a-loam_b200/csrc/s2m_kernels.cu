@@ -440,22 +440,24 @@ __device__ __forceinline__ void knn_offer(Knn5& r, float qx, float qy, float qz,
     }
   }
 }
-// all points of one cell: `cnt` entries of the bucket chain that starts at bucket b (the entries of a bucket are
-// four independent 16-byte loads of one 64-byte line)
+// all points of one cell: `cnt` entries of the bucket chain that starts at bucket b, four at a time (four
+// independent 16-byte loads of one 64-byte line); the pointer to the next bucket is followed once per kBktE entries
 __device__ __forceinline__ void knn_scan_cell(const Dev& d, int g, int b, int cnt, float qx, float qy, float qz, Knn5& r) {
   const int base = d.bkt_off[g];
+  int sub = 0;  // entry offset inside the bucket
 #pragma unroll 1
   while (cnt > 0) {
-    const uint32_t at0 = (uint32_t)(base + b) * kBktE;
+    const uint32_t at0 = (uint32_t)(base + b) * kBktE + (uint32_t)sub;
     const float4* __restrict__ p = d.bkt + at0;
     const float4 c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2), c3 = __ldg(p + 3);
-    uint32_t nb = kSentinel32;
-    if (cnt > kBktE) nb = __ldg(d.bnext + base + b);
+    uint32_t nb = (uint32_t)b;
+    if (cnt > 4 && sub + 4 == kBktE) nb = __ldg(d.bnext + base + b);
     knn_offer(r, qx, qy, qz, c0, at0);
     if (cnt > 1) knn_offer(r, qx, qy, qz, c1, at0 + 1);
     if (cnt > 2) knn_offer(r, qx, qy, qz, c2, at0 + 2);
     if (cnt > 3) knn_offer(r, qx, qy, qz, c3, at0 + 3);
-    cnt -= kBktE;
+    cnt -= 4;
+    sub = (sub + 4) % kBktE;
     if (nb == kSentinel32) break;
     b = (int)nb;
   }
