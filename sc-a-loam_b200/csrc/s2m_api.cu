@@ -627,9 +627,9 @@ static void fill_store_tables(s2m_ctx* ctx, int* total_lp) {
   int acc = 0;
   for (int g = 0; g < G; ++g) {
     const int n = ctx->slots[g < B ? g : g - B].n_store[g >= B];
-    T.lp_off[g] = T.so_off[g] = acc; acc += n;
+    T.lp_off[g] = acc - g; T.so_off[g] = acc; acc += n + 1;  // merge index space: one extra position per segment (inserts behind the last entry)
   }
-  T.lp_off[G] = T.so_off[G] = acc;
+  T.lp_off[G] = acc - G; T.so_off[G] = acc;
   *total_lp = acc;
 }
 // Lists the segments of the slots flagged in `rebuild` for a bulk rebuild of their cell index: their local-map

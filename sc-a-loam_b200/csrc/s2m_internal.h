@@ -212,8 +212,14 @@ int launch_odom_associate(const Dev& d, int outer, int tiles, int fallback_block
 int launch_finish_pose(const Dev& d, cudaStream_t s);
 int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_store, bool check_pending, bool identity_pose,
                       cudaStream_t s);
+#ifndef S2M_KNN_PRED
+#define S2M_KNN_PRED 0   // load only the entries a bucket holds instead of always four
+#endif
+#ifndef S2M_KNN_BATCH9
+#define S2M_KNN_BATCH9 0  // issue the 27 cell probes nine at a time instead of three at a time
+#endif
 #ifndef S2M_BKT_E
-#define S2M_BKT_E 8
+#define S2M_BKT_E 4
 #endif
 constexpr int kBktE = S2M_BKT_E;               // entries per bucket (a multiple of 4: 64 or 128 bytes)
 constexpr uint32_t kNoBkt = 0xFFFFFFu;         // 24-bit "none" inside a table entry

@@ -449,7 +449,12 @@ __device__ __forceinline__ void knn_scan_cell(const Dev& d, int g, int b, int cn
   while (cnt > 0) {
     const uint32_t at0 = (uint32_t)(base + b) * kBktE + (uint32_t)sub;
     const float4* __restrict__ p = d.bkt + at0;
+#if S2M_KNN_PRED
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 c0 = __ldg(p), c1 = cnt > 1 ? __ldg(p + 1) : zero4, c2 = cnt > 2 ? __ldg(p + 2) : zero4, c3 = cnt > 3 ? __ldg(p + 3) : zero4;
+#else
     const float4 c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2), c3 = __ldg(p + 3);
+#endif
     uint32_t nb = (uint32_t)b;
     if (cnt > 4 && sub + 4 == kBktE) nb = __ldg(d.bnext + base + b);
     knn_offer(r, qx, qy, qz, c0, at0);
@@ -491,6 +496,38 @@ __device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[
   const float gy = xfsub(1.0f, fy), gz = xfsub(1.0f, fz);
   const int sy = fy < 0.5f ? -1 : 1, sz = fz < 0.5f ? -1 : 1;  // side of the nearer boundary
   int total = 0;
+#if S2M_KNN_BATCH9
+#pragma unroll 1
+  for (int ob = 0; ob < 9; ob += 3) {  // phase 1: the 27 cell probes, nine independent loads (three rows) at a time
+    uint32_t k24[9], sl[9];
+    unsigned long long e[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int o = ob + j / 3, a = j % 3;
+      const int dy = (o == 1 || o == 3 || o == 7) ? sy : ((o == 4 || o == 6 || o == 8) ? -sy : 0);
+      const int dz = (o == 2 || o == 3 || o == 6) ? sz : ((o == 5 || o == 7 || o == 8) ? -sz : 0);
+      const int z = cz + dz, y = cy + dy, x = cx + a - 1;
+      const bool ok = (unsigned)z <= 255u && (unsigned)y <= 255u && (unsigned)x <= 255u;
+      k24[j] = ((uint32_t)(z & 255) << 16) | ((uint32_t)(y & 255) << 8) | (uint32_t)(x & 255);
+      sl[j] = cell_hash(k24[j]) & mask;
+      e[j] = ok ? tab[sl[j]] : kCellEmpty;
+    }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      while (e[j] != kCellEmpty && (uint32_t)(e[j] >> 40) != k24[j]) {
+        sl[j] = (sl[j] + 1) & mask;
+        e[j] = tab[sl[j]];
+      }
+      uint32_t rec = 0u;
+      if (e[j] != kCellEmpty) {
+        const uint32_t c = (uint32_t)(e[j] >> 24) & 0xFFFFu;
+        total += (int)c;
+        rec = (min(c, 255u) << 24) | (uint32_t)(e[j] & kNoBkt);
+      }
+      st.cell[3 * ob + j][t] = rec;
+    }
+  }
+#else
 #pragma unroll 1
   for (int o = 0; o < 9; ++o) {  // phase 1: the 27 cell probes, three rows (nine independent loads) at a time
     // row order: centre, (sy,0), (0,sz), (sy,sz), (-sy,0), (0,-sz), (-sy,sz), (sy,-sz), (-sy,-sz)
@@ -522,6 +559,7 @@ __device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[
       st.cell[3 * o + a][t] = rec;
     }
   }
+#endif
   // phase 2: rows near to far
 #pragma unroll 1
   for (int o = 0; o < 9; ++o) {
@@ -1782,10 +1820,7 @@ __global__ void upd_apply_kernel(Dev d, int cur, int n_runs_max) {
   const int i = d.upd_pos[r];
   if (i < 0 || !d.aflag[i]) return;
   const int g = find_seg(d.so_off, d.G, i);
-  const int l = i - d.so_off[g];
-  const uint64_t key = d.st_key[cur][d.st_base[g] + l];
-  const int io = d.run_off[g], nins = d.run_off[g + 1] - io;
-  const int pos = (int)(d.ascan[i] - d.ascan[d.so_off[g]]) + lower_bound_u64(d.ins_ckey + io, nins, key);
+  const int pos = (int)(d.ascan[i] - d.ascan[d.so_off[g]]) + (int)d.flag[i] - 1;
   if (pos >= d.st_cap[g]) return;  // merge_old_kernel raised the error
   d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.ins_pt[r];
 }
@@ -1817,7 +1852,20 @@ __device__ __forceinline__ bool entry_dead(const FrameDesc& fd, uint64_t key) {
   if (!in_box(ci, cj, ck, fd.win_lo, fd.win_hi)) return true;           // cube left the window (:346-347 ...)
   return key_pending(key) && in_box(ci, cj, ck, fd.val_lo, fd.val_hi);  // raw point merged by this re-filter
 }
-__global__ void alive_flag_kernel(Dev d, int cur, int total_store) {
+// The merge of the old store with the frame's sorted inserts, without a search per old entry: every insert marks
+// the old position it goes in front of (ins_mark_kernel: one binary search per INSERT), one prefix sum over
+// "alive + inserts in front" then gives every survivor and every insert its place.  The index space (d.so_off) has
+// one extra position per segment for the inserts that go behind its last entry.
+__global__ void ins_mark_kernel(Dev d, int cur, int n_max) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_max || j >= d.run_off[d.G]) return;
+  const int g = find_seg(d.run_off, d.G, j);
+  const int lb = lower_bound_u64(d.st_key[cur] + d.st_base[g], d.st_n[g], d.ins_ckey[j]);
+  d.vval2[j] = (uint32_t)lb;
+  atomicAdd(d.flag + d.so_off[g] + lb, 1u);
+}
+// d.aflag = the entry survives; d.flag += that (d.flag holds the inserts in front of the position)
+__global__ void alive_flag_kernel(Dev d, int cur, int total_store, bool any_dead) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > total_store) return;
   uint32_t f = 0;
@@ -1826,8 +1874,9 @@ __global__ void alive_flag_kernel(Dev d, int cur, int total_store) {
     const int l = i - d.so_off[g];
     if (l < d.st_n[g]) {
       const FrameDesc& fd = d.desc[seg_slot(d, g)];
-      f = fd.active ? !entry_dead(fd, d.st_key[cur][d.st_base[g] + l]) : 1u;
+      f = (any_dead && fd.active) ? !entry_dead(fd, d.st_key[cur][d.st_base[g] + l]) : 1u;  // (nothing dies unless the valid block moved)
     }
+    d.flag[i] += f;
   }
   d.aflag[i] = f;
 }
@@ -1835,30 +1884,28 @@ __global__ void merge_old_kernel(Dev d, int cur, int total_store) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total_store || !d.aflag[i]) return;
   const int g = find_seg(d.so_off, d.G, i);
-  const int l = i - d.so_off[g];
-  const int src = d.st_base[g] + l;
-  const uint64_t key = d.st_key[cur][src];
-  const int io = d.run_off[g], nins = d.run_off[g + 1] - io;
-  const int pos = (int)(d.ascan[i] - d.ascan[d.so_off[g]]) + lower_bound_u64(d.ins_ckey + io, nins, key);
+  const int src = d.st_base[g] + (i - d.so_off[g]);
+  const int pos = (int)(d.ascan[i] - d.ascan[d.so_off[g]]) + (int)d.flag[i] - 1;  // survivors + inserts before it, inserts in front of it
   if (pos >= d.st_cap[g]) { set_err(d, -3); return; }
-  d.st_key[cur ^ 1][d.st_base[g] + pos] = key;
+  d.st_key[cur ^ 1][d.st_base[g] + pos] = d.st_key[cur][src];
   d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.st_pt[cur][src];
 }
 __global__ void merge_new_kernel(Dev d, int cur, int n_max) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_max || j >= d.run_off[d.G]) return;
   const int g = find_seg(d.run_off, d.G, j);
-  const uint64_t key = d.ins_ckey[j];
-  const int lb = lower_bound_u64(d.st_key[cur] + d.st_base[g], d.st_n[g], key);
-  const int pos = (j - d.run_off[g]) + (int)(d.ascan[d.so_off[g] + lb] - d.ascan[d.so_off[g]]);
+  const uint32_t lb = d.vval2[j];
+  int first = j;  // inserts that go in front of the same old entry are consecutive (sorted by key)
+  while (first > d.run_off[g] && d.vval2[first - 1] == lb) --first;
+  const int pos = (int)(d.ascan[d.so_off[g] + (int)lb] - d.ascan[d.so_off[g]]) + (j - first);
   if (pos >= d.st_cap[g]) { set_err(d, -3); return; }
-  d.st_key[cur ^ 1][d.st_base[g] + pos] = key;
+  d.st_key[cur ^ 1][d.st_base[g] + pos] = d.ins_ckey[j];
   d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.ins_cpt[j];
 }
 __global__ void store_count_kernel(Dev d) {
   const int g = threadIdx.x + blockIdx.x * blockDim.x;
   if (g >= d.G) return;
-  const int n = (int)(d.ascan[d.so_off[g + 1]] - d.ascan[d.so_off[g]]) + (d.run_off[g + 1] - d.run_off[g]);
+  const int n = (int)(d.ascan[d.so_off[g + 1]] - d.ascan[d.so_off[g]]);  // survivors + inserts
   if (n > d.st_cap[g]) set_err(d, -3);
   d.st_n_new[g] = min(n, d.st_cap[g]);
   d.out[seg_slot(d, g)].n_store[seg_cls(d, g)] = n;
@@ -2113,10 +2160,12 @@ int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_s
   cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.aflag, d.ascan, n_delta + 1, s);
   if (n_delta > 0) { ins_compact_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, n_delta); ++k; }
   ins_off_kernel<<<cdiv(d.G + 1, 128), 128, 0, s>>>(d, n_delta); ++k;
-  // survivors of the old store
-  alive_flag_kernel<<<cdiv(total_store + 1, 256), 256, 0, s>>>(d, cur, total_store); ++k;
+  // survivors of the old store and the places of the inserts between them
+  cudaMemsetAsync(d.flag, 0, sizeof(uint32_t) * (size_t)(total_store + 1), s);
+  if (n_delta > 0) { ins_mark_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, cur, n_delta); ++k; }
+  alive_flag_kernel<<<cdiv(total_store + 1, 256), 256, 0, s>>>(d, cur, total_store, check_pending); ++k;
   tb = d.cub_tmp_bytes;
-  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.aflag, d.ascan, total_store + 1, s);
+  cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.flag, d.ascan, total_store + 1, s);
   if (total_store > 0) { merge_old_kernel<<<cdiv(total_store, 256), 256, 0, s>>>(d, cur, total_store); ++k; }
   if (n_delta > 0) { merge_new_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, cur, n_delta); ++k; }
   if (n_delta > 0 && total_store > 0) { upd_apply_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, cur, n_delta); ++k; }
