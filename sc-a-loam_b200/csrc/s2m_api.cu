@@ -419,7 +419,7 @@ static int create_impl(s2m_ctx* ctx) {
   }
   ctx->bkt_total = (size_t)boff[G];
   rc |= dev_alloc(ctx, &d.bkt, ctx->bkt_total * kBktE); rc |= dev_alloc(ctx, &d.bnext, ctx->bkt_total);
-  rc |= dev_alloc(ctx, &d.bkt_off, G + 1); rc |= dev_alloc(ctx, &d.bcnt, G);
+  rc |= dev_alloc(ctx, &d.bkt_off, G + 1); rc |= dev_alloc(ctx, &d.bcnt, G); rc |= dev_alloc(ctx, &d.idx_soff, G + 1);
   rc |= dev_alloc(ctx, &d.rec, (size_t)d.cap_in * 6); rc |= dev_alloc(ctx, &d.rec_valid, d.cap_in);
   rc |= dev_alloc(ctx, &d.partials, (size_t)B * d.max_tiles * kPartial);
   rc |= dev_alloc(ctx, &d.lm, B); rc |= dev_alloc(ctx, &d.out, B); rc |= dev_alloc(ctx, &d.err_flag, 1);

@@ -160,6 +160,7 @@ struct Dev {
   int* bcnt;                    // [G] buckets handed out
   int* idx_list;                // [G] segments to rebuild this frame (compacted), count in idx_n
   int* idx_poff;                // [G+1] packed offsets of their local points
+  int* idx_soff;                // [G+1] first position of each listed segment in the cell-sorted order (bulk build)
   // ---- association / solve
   double* rec;                  // [cap_in][6] cached correspondences
   uint8_t* rec_valid;           // [cap_in]

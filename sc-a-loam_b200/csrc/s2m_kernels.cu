@@ -227,8 +227,8 @@ __device__ __forceinline__ int local_to_store(const Dev& d, int g, int l) {
 // The reference gathers the valid cubes and rebuilds two KD-trees every frame.  Here every segment keeps
 // a voxel-hash style index alive across frames: an open-addressing table cell -> [cell:24][count:16]
 // [bucket:24] and a pool of 4-entry buckets (64 B, chained) holding (x, y, z, tag) of every point of the
-// local map.  It is built in bulk only when the valid block changes (idx_build_kernel, from the sorted
-// store); between those frames the map update puts the few thousand points a frame re-centroids or adds
+// local map.  It is built in bulk only when the valid block changes (launch_index_rebuild: the points are
+// sorted by cell once, so a cell's buckets start out consecutive); between those frames the map update puts the few thousand points a frame re-centroids or adds
 // into it (idx_apply, called by delta_reduce_kernel): O(changed points) per frame, no sort.
 // tag = [cube of the valid block, gather order:7][pending:1][voxel z, y, x:3x8 | arrival rank:24]
 // orders exactly like the position in the reference's gathered cloud, so the kNN tie rule (d2, index)
@@ -350,8 +350,9 @@ __global__ void idx_arm_kernel(Dev d, const int* __restrict__ new_mask, int n_se
   d.hmask[g] = new_mask[i];
   if (d.shard_world > 1) d.shard_counts[g] = 0;
 }
-// one thread per local-map point of the listed segments (packed by d.idx_poff)
-__global__ void idx_build_kernel(Dev d, int cur, int n_seg, int total) {
+// The build sorts the points by cell once, so a cell's buckets are consecutive and need no atomics:
+// 1. one thread per local-map point of the listed segments (packed by d.idx_poff): sort key [list position:7][cell:24]
+__global__ void idx_key_kernel(Dev d, int cur, int n_seg, int total, uint32_t* __restrict__ keys) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int g = -1;
   bool owned = false;  // sharded map: this rank owns the point (it counts towards the guard :555)
@@ -359,32 +360,74 @@ __global__ void idx_build_kernel(Dev d, int cur, int n_seg, int total) {
     const int si = find_seg(d.idx_poff, n_seg, i);
     g = d.idx_list[si];
     const int l = i - d.idx_poff[si];
+    uint32_t key = (uint32_t)n_seg << 24;  // (not a local point: behind every segment)
     if (l < d.loc_off[g * (kCols + 1) + kCols]) {
-      const int pos = local_to_store(d, g, l);
-      const uint64_t* keys = d.st_key[cur] + d.st_base[g];
-      const uint64_t key = keys[pos];
-      const float4 p = d.st_pt[cur][d.st_base[g] + pos];
-      const FrameDesc& fd = d.desc[seg_slot(d, g)];
-      int ci, cj, ck;
-      unpack_cube(key_cube(key), ci, cj, ck);
-      uint32_t tag;
-      if (key_pending(key)) {  // raw point of a cube that has just become valid: rank among the cube's raw points
-        const int first = lower_bound_u64(keys, d.st_n[g], store_key(key_cube(key), 1, 0));
-        tag = (cube_rel(fd, ci, cj, ck) << 25) | (1u << 24) | (uint32_t)min(pos - first, 0xFFFFFF);
-      } else {
-        const uint64_t pl = key_payload(key);
-        const uint32_t vz = (uint32_t)(pl >> 22) & 0x7FFu, vy = (uint32_t)(pl >> 11) & 0x7FFu, vx = (uint32_t)pl & 0x7FFu;
-        if ((vz | vy | vx) > 255u) set_err(d, -4);
-        tag = tag_filtered(fd, ci, cj, ck, vz, vy, vx);
-      }
-      idx_insert(d, g, cell_key_of(d, fd, p.x, p.y, p.z), make_float4(p.x, p.y, p.z, __uint_as_float(tag)));
+      const float4 p = d.st_pt[cur][d.st_base[g] + local_to_store(d, g, l)];
+      key = ((uint32_t)si << 24) | cell_key_of(d, d.desc[seg_slot(d, g)], p.x, p.y, p.z);
       owned = d.shard_world > 1 && p.x >= d.shard_lo && p.x < d.shard_hi;
     }
+    keys[i] = key;
+    d.vval[i] = (uint32_t)l;
   }
   if (d.shard_world > 1) {  // one atomic per warp and segment instead of one per point
     const unsigned peers = __match_any_sync(0xffffffffu, owned ? g : -1);
     if (owned && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(d.shard_counts + g, __popc(peers));
   }
+}
+// 2. (after the sort) first sorted position of every listed segment
+__global__ void idx_segs_kernel(Dev d, int n_seg, int total, const uint32_t* __restrict__ keys) {
+  const int si = threadIdx.x + blockIdx.x * blockDim.x;
+  if (si > n_seg) return;
+  d.idx_soff[si] = lower_bound_u32(keys, total, (uint32_t)si << 24);
+}
+// 3. one thread per sorted point.  Cell number c of a segment (d.scan = cells that start before a position), whose
+// first point is the segment's sorted point number s, owns the buckets from c + s / 4 on: consecutive cells never
+// overlap ((s + n) / 4 >= s / 4 + n / 4) and at most one bucket per cell stays unused.  The last point of a cell
+// publishes the cell in the table.
+__global__ void idx_fill_kernel(Dev d, int cur, int n_seg, int total, const uint32_t* __restrict__ keys) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const uint32_t key = keys[p];
+  const int si = (int)(key >> 24);
+  if (si >= n_seg) return;
+  const int g = d.idx_list[si], first = d.idx_soff[si];
+  int p0 = p;
+  while (p0 > first && keys[p0 - 1] == key) --p0;
+  const int j = p - p0, pool = d.bkt_off[g + 1] - d.bkt_off[g];
+  const int b0 = (int)(d.scan[p0] - d.scan[first]) + (p0 - first) / kBktE, b = b0 + j / kBktE;
+  if (b >= pool || b >= (int)kNoBkt || j >= 0xFFFF) { set_err(d, -3); return; }
+  const int pos = local_to_store(d, g, (int)d.vval2[p]);
+  const uint64_t* skeys = d.st_key[cur] + d.st_base[g];
+  const uint64_t skey = skeys[pos];
+  const float4 pt = d.st_pt[cur][d.st_base[g] + pos];
+  const FrameDesc& fd = d.desc[seg_slot(d, g)];
+  int ci, cj, ck;
+  unpack_cube(key_cube(skey), ci, cj, ck);
+  uint32_t tag;
+  if (key_pending(skey)) {  // raw point of a cube that has just become valid: rank among the cube's raw points
+    const int pfirst = lower_bound_u64(skeys, d.st_n[g], store_key(key_cube(skey), 1, 0));
+    tag = (cube_rel(fd, ci, cj, ck) << 25) | (1u << 24) | (uint32_t)min(pos - pfirst, 0xFFFFFF);
+  } else {
+    const uint64_t pl = key_payload(skey);
+    const uint32_t vz = (uint32_t)(pl >> 22) & 0x7FFu, vy = (uint32_t)(pl >> 11) & 0x7FFu, vx = (uint32_t)pl & 0x7FFu;
+    if ((vz | vy | vx) > 255u) set_err(d, -4);
+    tag = tag_filtered(fd, ci, cj, ck, vz, vy, vx);
+  }
+  const int base = d.bkt_off[g];
+  d.bkt[(size_t)(base + b) * kBktE + j % kBktE] = make_float4(pt.x, pt.y, pt.z, __uint_as_float(tag));
+  if (j > 0 && j % kBktE == 0) d.bnext[base + b - 1] = (uint32_t)b;
+  if (p + 1 < total && keys[p + 1] == key) return;
+  // ---- last point of its cell ----
+  if (p + 1 >= total || (int)(keys[p + 1] >> 24) != si) d.bcnt[g] = b + 1;  // ... and of its segment: buckets handed out
+  unsigned long long* tab = d.hash_tab + d.hash_off[g];
+  const uint32_t mask = (uint32_t)d.hmask[g];
+  const unsigned long long entry = ((unsigned long long)(key & 0xFFFFFFu) << 40) | ((unsigned long long)(j + 1) << 24) | (unsigned long long)b0;
+  uint32_t s = cell_hash(key & 0xFFFFFFu) & mask;
+  for (uint32_t guard = 0; guard <= mask; ++guard) {
+    if (atomicCAS(tab + s, kCellEmpty, entry) == kCellEmpty) return;
+    s = (s + 1) & mask;
+  }
+  set_err(d, -3);  // table full
 }
 // position in the gathered local map (the reference's kNN index) of the entry with this tag: trace / debug only
 __device__ __forceinline__ int tag_to_local(const Dev& d, int cur, int g, uint32_t tag) {
@@ -1856,13 +1899,13 @@ __device__ __forceinline__ bool entry_dead(const FrameDesc& fd, uint64_t key) {
 // the old position it goes in front of (ins_mark_kernel: one binary search per INSERT), one prefix sum over
 // "alive + inserts in front" then gives every survivor and every insert its place.  The index space (d.so_off) has
 // one extra position per segment for the inserts that go behind its last entry.
-__global__ void ins_mark_kernel(Dev d, int cur, int n_max) {
+__global__ void ins_mark_kernel(Dev d, int cur, int n_max, bool count) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_max || j >= d.run_off[d.G]) return;
   const int g = find_seg(d.run_off, d.G, j);
   const int lb = lower_bound_u64(d.st_key[cur] + d.st_base[g], d.st_n[g], d.ins_ckey[j]);
   d.vval2[j] = (uint32_t)lb;
-  atomicAdd(d.flag + d.so_off[g] + lb, 1u);
+  if (count) atomicAdd(d.flag + d.so_off[g] + lb, 1u);
 }
 // d.aflag = the entry survives; d.flag += that (d.flag holds the inserts in front of the position)
 __global__ void alive_flag_kernel(Dev d, int cur, int total_store, bool any_dead) {
@@ -1901,6 +1944,63 @@ __global__ void merge_new_kernel(Dev d, int cur, int n_max) {
   if (pos >= d.st_cap[g]) { set_err(d, -3); return; }
   d.st_key[cur ^ 1][d.st_base[g] + pos] = d.ins_ckey[j];
   d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.ins_cpt[j];
+}
+// ---- the same merge when nothing dies (the valid block did not move: no eviction, no raw points to absorb): every old
+// entry only shifts by the number of inserts that go in front of it or of an earlier entry, which a short binary search
+// in the frame's sorted insert positions (d.vval2, ins_mark_kernel) gives -- no flags, no prefix sum over the store.
+__device__ __forceinline__ int inserts_up_to(const uint32_t* __restrict__ lb, int a, int b, uint32_t l) {  // first j in [a, b) with lb[j] > l
+  while (a < b) {
+    const int m = (a + b) >> 1;
+    if (lb[m] <= l) a = m + 1; else b = m;
+  }
+  return a;
+}
+__global__ void shift_old_kernel(Dev d, int cur, int total_store) {
+  __shared__ int win[2];  // the inserts that can fall among this block's entries (when it lies inside one segment)
+  const int i0 = blockIdx.x * blockDim.x, i = i0 + threadIdx.x, i1 = min(i0 + (int)blockDim.x, total_store) - 1;
+  const int g0 = find_seg(d.so_off, d.G, i0), g1 = find_seg(d.so_off, d.G, i1);
+  if (threadIdx.x < 2 && g0 == g1) {
+    const int l = (threadIdx.x == 0 ? i0 - 1 : i1) - d.so_off[g0];  // inserts in front of entries before the block / up to its last entry
+    win[threadIdx.x] = l < 0 ? d.run_off[g0] : inserts_up_to(d.vval2, d.run_off[g0], d.run_off[g0 + 1], (uint32_t)l);
+  }
+  __syncthreads();
+  if (i >= total_store) return;
+  const int g = g0 == g1 ? g0 : find_seg(d.so_off, d.G, i);
+  const int l = i - d.so_off[g];
+  if (l >= d.st_n[g]) return;  // (the extra position behind the segment's last entry)
+  const int a = g0 == g1 ? win[0] : d.run_off[g], b = g0 == g1 ? win[1] : d.run_off[g + 1];
+  const int pos = l + inserts_up_to(d.vval2, a, b, (uint32_t)l) - d.run_off[g];
+  if (pos >= d.st_cap[g]) { set_err(d, -3); return; }
+  const int src = d.st_base[g] + l;
+  d.st_key[cur ^ 1][d.st_base[g] + pos] = d.st_key[cur][src];
+  d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.st_pt[cur][src];
+}
+// inserts and re-centroided entries of the same case; also the new sizes
+__global__ void shift_new_kernel(Dev d, int cur, int n_max) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < d.G) {
+    const int g = j, n = d.st_n[g] + d.run_off[g + 1] - d.run_off[g];
+    if (n > d.st_cap[g]) set_err(d, -3);
+    d.st_n_new[g] = min(n, d.st_cap[g]);
+    d.out[seg_slot(d, g)].n_store[seg_cls(d, g)] = n;
+  }
+  if (j < n_max && j < d.run_off[d.G]) {
+    const int g = find_seg(d.run_off, d.G, j);
+    const int pos = (int)d.vval2[j] + (j - d.run_off[g]);
+    if (pos < d.st_cap[g]) {
+      d.st_key[cur ^ 1][d.st_base[g] + pos] = d.ins_ckey[j];
+      d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.ins_cpt[j];
+    }
+  }
+  if (j < n_max) {
+    const int i = d.upd_pos[j];
+    if (i >= 0) {
+      const int g = find_seg(d.so_off, d.G, i);
+      const int l = i - d.so_off[g];
+      const int pos = l + inserts_up_to(d.vval2, d.run_off[g], d.run_off[g + 1], (uint32_t)l) - d.run_off[g];
+      if (pos < d.st_cap[g]) d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.ins_pt[j];
+    }
+  }
 }
 __global__ void store_count_kernel(Dev d) {
   const int g = threadIdx.x + blockIdx.x * blockDim.x;
@@ -2046,7 +2146,20 @@ int launch_index_rebuild(const Dev& d, int cur, int n_seg, int total_points, cud
   idx_reset_kernel<<<dim3(64, n_seg), 256, 0, s>>>(d, new_mask);
   idx_arm_kernel<<<cdiv(n_seg, 128), 128, 0, s>>>(d, new_mask, n_seg);
   int k = 2;
-  if (total_points > 0) { idx_build_kernel<<<cdiv(total_points, 256), 256, 0, s>>>(d, cur, n_seg, total_points); ++k; }
+  if (total_points > 0) {
+    // (the sort buffers of the scan voxel filter and of the map update are idle at this point of a frame)
+    uint32_t *ka = reinterpret_cast<uint32_t*>(d.vkey), *kb = reinterpret_cast<uint32_t*>(d.vkey2);
+    idx_key_kernel<<<cdiv(total_points, 256), 256, 0, s>>>(d, cur, n_seg, total_points, ka); ++k;
+    int sbits = 1;
+    while ((1 << sbits) <= n_seg) ++sbits;
+    size_t tb = d.cub_tmp_bytes;
+    cub::DeviceRadixSort::SortPairs(d.cub_tmp, tb, ka, kb, d.vval, d.vval2, total_points, 0, 24 + sbits, s);
+    head_flag_kernel<uint32_t><<<cdiv(total_points + 1, 256), 256, 0, s>>>(kb, d.flag, total_points); ++k;
+    tb = d.cub_tmp_bytes;
+    cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.flag, d.scan, total_points + 1, s);
+    idx_segs_kernel<<<cdiv(n_seg + 1, 128), 128, 0, s>>>(d, n_seg, total_points, kb); ++k;
+    idx_fill_kernel<<<cdiv(total_points, 256), 256, 0, s>>>(d, cur, n_seg, total_points, kb); ++k;
+  }
   return k;
 }
 int launch_guard(const Dev& d, cudaStream_t s) {
@@ -2160,9 +2273,15 @@ int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_s
   cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.aflag, d.ascan, n_delta + 1, s);
   if (n_delta > 0) { ins_compact_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, n_delta); ++k; }
   ins_off_kernel<<<cdiv(d.G + 1, 128), 128, 0, s>>>(d, n_delta); ++k;
+  if (!check_pending) {  // nothing dies: old entries only shift
+    if (n_delta > 0) { ins_mark_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, cur, n_delta, false); ++k; }
+    if (total_store > 0) { shift_old_kernel<<<cdiv(total_store, 256), 256, 0, s>>>(d, cur, total_store); ++k; }
+    shift_new_kernel<<<cdiv(max(n_delta, d.G), 256), 256, 0, s>>>(d, cur, n_delta); ++k;
+    return k;
+  }
   // survivors of the old store and the places of the inserts between them
   cudaMemsetAsync(d.flag, 0, sizeof(uint32_t) * (size_t)(total_store + 1), s);
-  if (n_delta > 0) { ins_mark_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, cur, n_delta); ++k; }
+  if (n_delta > 0) { ins_mark_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, cur, n_delta, true); ++k; }
   alive_flag_kernel<<<cdiv(total_store + 1, 256), 256, 0, s>>>(d, cur, total_store, check_pending); ++k;
   tb = d.cub_tmp_bytes;
   cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.flag, d.ascan, total_store + 1, s);

@@ -219,7 +219,6 @@ S2M_HD bool plane_fit(const float nb[5][3], double n[3], double& d) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     int big = k;
-#pragma unroll
     double cbig = cn[k];
 #pragma unroll
     for (int j = k + 1; j < 3; ++j) if (cn[j] > cbig) { big = j; cbig = cn[j]; }

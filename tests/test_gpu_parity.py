@@ -131,19 +131,23 @@ def test_knn_bit_exact_on_uploaded_map(s2m, seq_hdl):
     assert ties <= 2
 
 
-def test_registration_matches_oracle_on_uploaded_map(s2m, seq_hdl):
+@pytest.mark.parametrize("sensor", ["hdl", "vlp", "os1"])
+def test_registration_matches_oracle_on_uploaded_map(s2m, seq_hdl, seq_vlp, seq_os1, sensor):
     """One full registration (rows A..W) from identical maps: kNN of the first outer iteration
-    bit-exact inside the real flow, reduced normal equations and poses within tolerance."""
-    O1, _ = run_oracle(seq_hdl, 8, 0.4, 0.8)
-    truth, odom, frames = seq_hdl
+    bit-exact inside the real flow, reduced normal equations and poses within tolerance -- for the
+    three sensors / launch-file resolutions of BASELINE configs 1-3."""
+    seq, line, plane = pick(sensor, seq_hdl, seq_vlp, seq_os1)
+    truth, odom, frames = seq
+    k = len(frames) - 1  # map from all frames but the last, which is then registered
+    O1, _ = run_oracle(seq, k, line, plane)
     cm, sm = O1.get_map(0), O1.get_map(1)
-    R = s2m.Registrar(0.4, 0.8, trace=True)
-    O = oracle.Oracle(0.4, 0.8, trace=True, use_kdtree=False)
+    R = s2m.Registrar(line, plane, trace=True)
+    O = oracle.Oracle(line, plane, trace=True, use_kdtree=False)
     R.map_upload(cm, sm)
     O.map_upload(cm, sm)
-    c, s = frames[8]
-    rg, qg, tg = R.register(c, s, odom[8, :4], odom[8, 4:])
-    ro, qo, to = O.register(c, s, odom[8, :4], odom[8, 4:])
+    c, s = frames[k]
+    rg, qg, tg = R.register(c, s, odom[k, :4], odom[k, 4:])
+    ro, qo, to = O.register(c, s, odom[k, :4], odom[k, 4:])
     assert rg == ro == 0
     assert (R.stats.n_map_corner, R.stats.n_map_surf) == (O.stats.n_map_corner, O.stats.n_map_surf)
     for cls in (0, 1):
