@@ -434,6 +434,7 @@ static int create_impl(s2m_ctx* ctx) {
   rc |= dev_alloc(ctx, &d.ins_key, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.ins_ckey, d.cap_sort + 1);
   rc |= dev_alloc(ctx, &d.ins_pt, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.ins_cpt, d.cap_sort + 1);
   rc |= dev_alloc(ctx, &d.run_off, G + 1);
+  rc |= dev_alloc(ctx, &d.dead_n, G); rc |= dev_alloc(ctx, &d.dead_lo, (size_t)G * kValidCubes); rc |= dev_alloc(ctx, &d.dead_cum, (size_t)G * (kValidCubes + 1));
   rc |= dev_alloc(ctx, &d.upd_pos, d.cap_sort + 1);
   rc |= dev_alloc(ctx, &d.aflag, d.cap_sort + 1); rc |= dev_alloc(ctx, &d.ascan, d.cap_sort + 1);
   d.cub_tmp_bytes = cub_temp_bytes(d.cap_sort + 1, d.cap_lp + 1);
@@ -682,7 +683,7 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   HostTables& T = *ctx->ht;
   cudaStream_t s = ctx->stream;
   const int total_in = T.in_off[G];
-  bool check_pending = false;
+  bool check_pending = false, window_shift = false;
   int tiles = 0;
   // A frame is atomic: the device map is double buffered and only swapped at the end, the host-side slot
   // state (window centre, valid block, pending-check flag) is restored if anything below fails.
@@ -706,9 +707,14 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
     if (!fd.active) continue;
     row_A(sh, q_wodom + 4 * b, t_wodom + 3 * b);
     std::memcpy(fd.pose, sh.pose, sizeof(fd.pose));
+    const int cen_before[3] = {sh.cen[0], sh.cen[1], sh.cen[2]};
     rows_BC(sh, sh.pose + 4, fd);
     fd.seq_base[0] = sh.seq[0]; fd.seq_base[1] = sh.seq[1];
     bool moved = sh.force_pending_check;
+    // entries can only leave the store (cubes that left the window) when the window moved; an uploaded or restored
+    // store is treated the same way
+    window_shift = window_shift || sh.force_pending_check || sh.cen[0] != cen_before[0] || sh.cen[1] != cen_before[1] ||
+                   sh.cen[2] != cen_before[2];
     for (int a = 0; a < 3; ++a) moved = moved || fd.val_lo[a] != sh.val_lo[a] || fd.val_hi[a] != sh.val_hi[a];
     check_pending = check_pending || moved;
     // cell index: bulk rebuild when the valid block changed (or the index is stale); otherwise the map update keeps
@@ -820,7 +826,7 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
       CK(cudaMemcpyAsync(ctx->lm_trace + (size_t)outer * B, d.lm, sizeof(LmState) * B, cudaMemcpyDeviceToDevice, s));
   }
   k += launch_finish_pose(d, s);
-  k += launch_map_update(d, ctx->cur, n_ds, total_lp, total_store, check_pending, false, s);
+  k += launch_map_update(d, ctx->cur, n_ds, total_lp, total_store, check_pending, window_shift, false, s);
   prof_mark(ctx, S2M_PHASE_UPDATE);
   ctx->launches += k;
   int rc = finish_call(ctx);
@@ -1115,7 +1121,7 @@ extern "C" int s2m_map_upload(s2m_ctx* ctx, int slot, const float* corner, int n
     CK(cudaMemcpyAsync(d.ds_off, dsoff.data(), sizeof(int) * (G + 1), cudaMemcpyHostToDevice, s));
     if (cn) CK(cudaMemcpyAsync(d.ds_pts, corner + 4 * (size_t)c0, sizeof(float4) * (size_t)cn, cudaMemcpyHostToDevice, s));
     if (sn) CK(cudaMemcpyAsync(d.ds_pts + cn, surf + 4 * (size_t)s0, sizeof(float4) * (size_t)sn, cudaMemcpyHostToDevice, s));
-    ctx->launches += launch_map_update(d, ctx->cur, cn + sn, total_lp, total_lp, false, true, s);
+    ctx->launches += launch_map_update(d, ctx->cur, cn + sn, total_lp, total_lp, false, false, true, s);
     int rc = finish_call(ctx);
     if (rc != S2M_OK) return rc;
     ctx->cur ^= 1;

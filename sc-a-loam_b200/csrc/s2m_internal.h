@@ -180,6 +180,7 @@ struct Dev {
   float4 *ins_pt, *ins_cpt;     // [cap_sort]
   int* upd_pos;                 // [cap_sort] per delta run: merge-space index of the store entry it re-centroids, -1 none
   int* run_off;                 // [G+1]
+  int *dead_n, *dead_lo, *dead_cum; // [G], [G][75], [G][76]: store ranges of the raw points a frame absorbs (pending_gather_kernel)
   uint32_t *aflag, *ascan;      // [cap_lp + 1]
   // ---- cub temp
   void* cub_tmp;
@@ -211,8 +212,8 @@ int launch_odom_meta(const Dev& d, int nchunks, cudaStream_t s);
 int launch_odom_guard(const Dev& d, cudaStream_t s);
 int launch_odom_associate(const Dev& d, int outer, int tiles, int fallback_blocks, bool trace, cudaStream_t s);
 int launch_finish_pose(const Dev& d, cudaStream_t s);
-int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_store, bool check_pending, bool identity_pose,
-                      cudaStream_t s);
+int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_store, bool check_pending, bool window_shift,
+                      bool identity_pose, cudaStream_t s);
 #ifndef S2M_KNN_PRED
 #define S2M_KNN_PRED 0   // load only the entries a bucket holds instead of always four
 #endif

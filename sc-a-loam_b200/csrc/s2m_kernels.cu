@@ -1753,14 +1753,19 @@ __global__ void delta_key_kernel(Dev d, int front, int n_delta, bool identity_po
 }
 
 // raw points already sitting in cubes that are valid now: they join this frame's re-filter
+// grid (segments, cubes of the valid block): block (g, c) stages the raw points of cube c; block (g, 0) also
+// publishes where they lie in the store -- they die in this frame's merge (d.dead_*: non-empty ranges in key order)
 __global__ void pending_gather_kernel(Dev d, int cur) {
-  const int g = blockIdx.x;
+  const int g = blockIdx.x, c = blockIdx.y;
   const FrameDesc& fd = d.desc[seg_slot(d, g)];
-  if (!fd.active) return;
+  const int t = threadIdx.x;
+  if (!fd.active) {
+    if (c == 0 && t == 0) { d.dead_n[g] = 0; d.dead_cum[g * (kValidCubes + 1)] = 0; }
+    return;
+  }
   __shared__ int lo_s[kValidCubes], off_s[kValidCubes + 1];
   const uint64_t* keys = d.st_key[cur] + d.st_base[g];
   const int n = d.st_n[g];
-  const int t = threadIdx.x;
   if (t < kValidCubes) {
     const int ci = fd.val_lo[0] + t / 15, cj = fd.val_lo[1] + (t / 3) % 5, ck = fd.val_lo[2] + t % 3;
     int lo = 0, len = 0;
@@ -1776,18 +1781,25 @@ __global__ void pending_gather_kernel(Dev d, int cur) {
   if (t == 0) {
     off_s[0] = 0;
     for (int k = 0; k < kValidCubes; ++k) off_s[k + 1] += off_s[k];
+    if (c == 0) {
+      int m = 0;
+      int* dl = d.dead_lo + g * kValidCubes;
+      int* dc = d.dead_cum + g * (kValidCubes + 1);
+      for (int k = 0; k < kValidCubes; ++k)
+        if (off_s[k + 1] > off_s[k]) { dl[m] = lo_s[k]; dc[m] = off_s[k]; ++m; }
+      dc[m] = off_s[kValidCubes];
+      d.dead_n[g] = m;
+    }
   }
   __syncthreads();
-  for (int c = 0; c < kValidCubes; ++c) {
-    const int len = off_s[c + 1] - off_s[c];
-    const int ci = fd.val_lo[0] + c / 15, cj = fd.val_lo[1] + (c / 3) % 5, ck = fd.val_lo[2] + c % 3;
-    for (int j = t; j < len; j += blockDim.x) {
-      const int src = d.st_base[g] + lo_s[c] + j;
-      const float4 p = d.st_pt[cur][src];
-      const int pos = d.lp_off[g] + off_s[c] + j;
-      d.vkey[pos] = delta_key(d, g, fd, ci, cj, ck, 0, voxel_payload(d, seg_cls(d, g), p.x, p.y, p.z, ci, cj, ck));
-      d.vval[pos] = 0x80000000u | (uint32_t)src;
-    }
+  const int len = off_s[c + 1] - off_s[c];
+  const int ci = fd.val_lo[0] + c / 15, cj = fd.val_lo[1] + (c / 3) % 5, ck = fd.val_lo[2] + c % 3;
+  for (int j = t; j < len; j += blockDim.x) {
+    const int src = d.st_base[g] + lo_s[c] + j;
+    const float4 p = d.st_pt[cur][src];
+    const int pos = d.lp_off[g] + off_s[c] + j;
+    d.vkey[pos] = delta_key(d, g, fd, ci, cj, ck, 0, voxel_payload(d, seg_cls(d, g), p.x, p.y, p.z, ci, cj, ck));
+    d.vval[pos] = 0x80000000u | (uint32_t)src;
   }
 }
 
@@ -1889,6 +1901,14 @@ __global__ void ins_off_kernel(Dev d, int n_delta) {
   d.run_off[g] = (int)d.ascan[run];  // ascan here = exclusive scan of insert flags over runs
 }
 
+// d.vval2 holds, per insert of a segment (sorted), the old position it goes in front of
+__device__ __forceinline__ int inserts_up_to(const uint32_t* __restrict__ lb, int a, int b, uint32_t l) {  // first j in [a, b) with lb[j] > l
+  while (a < b) {
+    const int m = (a + b) >> 1;
+    if (lb[m] <= l) a = m + 1; else b = m;
+  }
+  return a;
+}
 __device__ __forceinline__ bool entry_dead(const FrameDesc& fd, uint64_t key) {
   int ci, cj, ck;
   unpack_cube(key_cube(key), ci, cj, ck);
@@ -1938,24 +1958,34 @@ __global__ void merge_new_kernel(Dev d, int cur, int n_max) {
   if (j >= n_max || j >= d.run_off[d.G]) return;
   const int g = find_seg(d.run_off, d.G, j);
   const uint32_t lb = d.vval2[j];
-  int first = j;  // inserts that go in front of the same old entry are consecutive (sorted by key)
-  while (first > d.run_off[g] && d.vval2[first - 1] == lb) --first;
+  // inserts that go in front of the same old entry are consecutive (sorted by key); a cube whose raw points have just
+  // been filtered puts thousands in front of one entry
+  const int first = lb == 0u ? d.run_off[g] : inserts_up_to(d.vval2, d.run_off[g], j, lb - 1u);
   const int pos = (int)(d.ascan[d.so_off[g] + (int)lb] - d.ascan[d.so_off[g]]) + (j - first);
   if (pos >= d.st_cap[g]) { set_err(d, -3); return; }
   d.st_key[cur ^ 1][d.st_base[g] + pos] = d.ins_ckey[j];
   d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.ins_cpt[j];
 }
-// ---- the same merge when nothing dies (the valid block did not move: no eviction, no raw points to absorb): every old
-// entry only shifts by the number of inserts that go in front of it or of an earlier entry, which a short binary search
-// in the frame's sorted insert positions (d.vval2, ins_mark_kernel) gives -- no flags, no prefix sum over the store.
-__device__ __forceinline__ int inserts_up_to(const uint32_t* __restrict__ lb, int a, int b, uint32_t l) {  // first j in [a, b) with lb[j] > l
+// ---- the same merge when the window did not shift: the only entries that can die are the raw points of the valid
+// cubes (<= 75 contiguous key ranges per segment, published by pending_gather_kernel; none when the valid block did not
+// move).  Every survivor then moves by (inserts that go in front of it or of an earlier entry) - (dead entries before
+// it): two short binary searches, no flags and no prefix sum over the store.
+// dead entries of segment g in front of store position l; *dead = position l itself dies
+__device__ __forceinline__ int dead_before(const Dev& d, int g, int l, bool* dead) {
+  const int* lo = d.dead_lo + g * kValidCubes;
+  const int* cum = d.dead_cum + g * (kValidCubes + 1);
+  int a = 0, b = d.dead_n[g];  // number of ranges that start at or before l
   while (a < b) {
     const int m = (a + b) >> 1;
-    if (lb[m] <= l) a = m + 1; else b = m;
+    if (lo[m] <= l) a = m + 1; else b = m;
   }
-  return a;
+  *dead = false;
+  if (a == 0) return 0;
+  const int len = cum[a] - cum[a - 1], in = l - lo[a - 1];
+  *dead = in < len;
+  return cum[a - 1] + min(in, len);
 }
-__global__ void shift_old_kernel(Dev d, int cur, int total_store) {
+__global__ void shift_old_kernel(Dev d, int cur, int total_store, bool deaths) {
   __shared__ int win[2];  // the inserts that can fall among this block's entries (when it lies inside one segment)
   const int i0 = blockIdx.x * blockDim.x, i = i0 + threadIdx.x, i1 = min(i0 + (int)blockDim.x, total_store) - 1;
   const int g0 = find_seg(d.so_off, d.G, i0), g1 = find_seg(d.so_off, d.G, i1);
@@ -1969,24 +1999,32 @@ __global__ void shift_old_kernel(Dev d, int cur, int total_store) {
   const int l = i - d.so_off[g];
   if (l >= d.st_n[g]) return;  // (the extra position behind the segment's last entry)
   const int a = g0 == g1 ? win[0] : d.run_off[g], b = g0 == g1 ? win[1] : d.run_off[g + 1];
-  const int pos = l + inserts_up_to(d.vval2, a, b, (uint32_t)l) - d.run_off[g];
+  int pos = l + inserts_up_to(d.vval2, a, b, (uint32_t)l) - d.run_off[g];
+  if (deaths) {
+    bool dead;
+    pos -= dead_before(d, g, l, &dead);
+    if (dead) return;
+  }
   if (pos >= d.st_cap[g]) { set_err(d, -3); return; }
   const int src = d.st_base[g] + l;
   d.st_key[cur ^ 1][d.st_base[g] + pos] = d.st_key[cur][src];
   d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.st_pt[cur][src];
 }
 // inserts and re-centroided entries of the same case; also the new sizes
-__global__ void shift_new_kernel(Dev d, int cur, int n_max) {
+__global__ void shift_new_kernel(Dev d, int cur, int n_max, bool deaths) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  bool dead;
   if (j < d.G) {
-    const int g = j, n = d.st_n[g] + d.run_off[g + 1] - d.run_off[g];
+    const int g = j;
+    const int n = d.st_n[g] + d.run_off[g + 1] - d.run_off[g] - (deaths ? d.dead_cum[g * (kValidCubes + 1) + d.dead_n[g]] : 0);
     if (n > d.st_cap[g]) set_err(d, -3);
     d.st_n_new[g] = min(n, d.st_cap[g]);
     d.out[seg_slot(d, g)].n_store[seg_cls(d, g)] = n;
   }
   if (j < n_max && j < d.run_off[d.G]) {
     const int g = find_seg(d.run_off, d.G, j);
-    const int pos = (int)d.vval2[j] + (j - d.run_off[g]);
+    const int lb = (int)d.vval2[j];
+    const int pos = lb + (j - d.run_off[g]) - (deaths ? dead_before(d, g, lb, &dead) : 0);
     if (pos < d.st_cap[g]) {
       d.st_key[cur ^ 1][d.st_base[g] + pos] = d.ins_ckey[j];
       d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.ins_cpt[j];
@@ -1997,7 +2035,8 @@ __global__ void shift_new_kernel(Dev d, int cur, int n_max) {
     if (i >= 0) {
       const int g = find_seg(d.so_off, d.G, i);
       const int l = i - d.so_off[g];
-      const int pos = l + inserts_up_to(d.vval2, d.run_off[g], d.run_off[g + 1], (uint32_t)l) - d.run_off[g];
+      const int pos = l + inserts_up_to(d.vval2, d.run_off[g], d.run_off[g + 1], (uint32_t)l) - d.run_off[g] -
+                      (deaths ? dead_before(d, g, l, &dead) : 0);
       if (pos < d.st_cap[g]) d.st_pt[cur ^ 1][d.st_base[g] + pos] = d.ins_pt[j];
     }
   }
@@ -2242,8 +2281,10 @@ int launch_finish_pose(const Dev& d, cudaStream_t s) {
 
 // total_lp: points of the local maps (d.lp_off spacing, the pending-point staging area);
 // total_store: entries of the whole stores (d.so_off spacing, the merge)
+// check_pending: some valid block moved (raw points of its cubes are absorbed); window_shift: some window moved or a
+// store was replaced (entries anywhere may have to go) -- implies check_pending
 int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_store, bool check_pending,
-                      bool identity_pose, cudaStream_t s) {
+                      bool window_shift, bool identity_pose, cudaStream_t s) {
   const int total_in = n_ds;  // exact number of down-sampled points (host read it back)
   int k = 0;
   const int front = check_pending ? total_lp : 0;
@@ -2251,7 +2292,7 @@ int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_s
   if (front > 0) {
     cudaMemsetAsync(d.vkey, 0xFF, sizeof(uint64_t) * (size_t)front, s);
     cudaMemsetAsync(d.vval, 0, sizeof(uint32_t) * (size_t)front, s);
-    pending_gather_kernel<<<d.G, 128, 0, s>>>(d, cur); ++k;
+    pending_gather_kernel<<<dim3(d.G, kValidCubes), 128, 0, s>>>(d, cur); ++k;
   }
   if (n_delta > 0) {
     delta_key_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, front, n_delta, identity_pose); ++k;
@@ -2273,10 +2314,11 @@ int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_s
   cub::DeviceScan::ExclusiveSum(d.cub_tmp, tb, d.aflag, d.ascan, n_delta + 1, s);
   if (n_delta > 0) { ins_compact_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, n_delta); ++k; }
   ins_off_kernel<<<cdiv(d.G + 1, 128), 128, 0, s>>>(d, n_delta); ++k;
-  if (!check_pending) {  // nothing dies: old entries only shift
+  if (!window_shift) {  // only the raw points of the valid cubes can die: old entries shift by two counts
     if (n_delta > 0) { ins_mark_kernel<<<cdiv(n_delta, 256), 256, 0, s>>>(d, cur, n_delta, false); ++k; }
-    if (total_store > 0) { shift_old_kernel<<<cdiv(total_store, 256), 256, 0, s>>>(d, cur, total_store); ++k; }
-    shift_new_kernel<<<cdiv(max(n_delta, d.G), 256), 256, 0, s>>>(d, cur, n_delta); ++k;
+    const bool deaths = front > 0;  // (pending_gather_kernel ran and published the ranges)
+    if (total_store > 0) { shift_old_kernel<<<cdiv(total_store, 256), 256, 0, s>>>(d, cur, total_store, deaths); ++k; }
+    shift_new_kernel<<<cdiv(max(n_delta, d.G), 256), 256, 0, s>>>(d, cur, n_delta, deaths); ++k;
     return k;
   }
   // survivors of the old store and the places of the inserts between them
