@@ -991,11 +991,14 @@ __global__ void reduce_units_kernel(Dev d) {
 // ----------------------------------------------------------------------------
 constexpr int kSolveThreads = 256;  // 128 registers each: a CTA takes half an SM, so solves of one lane interleave with other lanes' kernels
 constexpr int kSolveCtas = 4;       // CTAs per cluster = per slot
+constexpr int kSolveWin = 8 * kSolveThreads;  // queries whose accepted correspondences are compacted at a time
 struct SolveShared {
   double red[kSolveCtas][kPartial];  // [0] this CTA's sums, [r] those of CTA r (used in CTA 0 only)
   double pose[7];            // candidate under evaluation
   int go;                    // another evaluation is wanted
   double col[kSumRows][kSolveThreads / 4 + 1];
+  int list[kSolveWin];       // queries of the current window that carry a correspondence, in query order
+  int woff[8 * (kSolveThreads / 32) + 1];  // per (pass, warp) of the compaction: count, then offset; [last] = total
 };
 __device__ __forceinline__ void solve_block_reduce(SolveShared& sh, const Sums28& Sm, double ne, double np) {
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -1040,6 +1043,7 @@ __global__ void __cluster_dims__(kSolveCtas, 1, 1) __launch_bounds__(kSolveThrea
   };
   int dc0, nc, ds0, nq;
   slot_counts(d, slot, dc0, nc, ds0, nq);
+  const int per_cta = (nq + kSolveCtas - 1) / kSolveCtas, q_lo = half * per_cta, q_hi = min(nq, q_lo + per_cta);
   // ---- start of the solve: sums of the first evaluation, lm_begin ----
   if (half == 0) {
     lm_load(&Ls, d.lm + slot);
@@ -1065,9 +1069,41 @@ __global__ void __cluster_dims__(kSolveCtas, 1, 1) __launch_bounds__(kSolveThrea
     Sums28 Sm;
     Sm.zero();
     double ne = 0.0, np = 0.0;
-    for (int q = half * kSolveThreads + t; q < nq; q += kSolveCtas * kSolveThreads) {
-      const int di = q < nc ? dc0 + q : ds0 + (q - nc);
-      if (d.rec_valid[di]) {
+    // This CTA's quarter of the slot's queries, a window at a time: about a third carry a correspondence, so they
+    // are compacted first (ballot + prefix, query order) and the evaluation runs on dense lanes.
+    for (int w0 = q_lo; w0 < q_hi; w0 += kSolveWin) {
+      const int lane = t & 31, wid = t >> 5;
+      unsigned have[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int q = w0 + k * kSolveThreads + t;
+        const bool v = q < q_hi && d.rec_valid[q < nc ? dc0 + q : ds0 + (q - nc)];
+        have[k] = __ballot_sync(kFull, v);
+        if (lane == 0) sh.woff[k * (kSolveThreads / 32) + wid] = __popc(have[k]);
+      }
+      __syncthreads();
+      if (wid == 0) {  // exclusive prefix over the 64 counts, two per lane
+        const int a = sh.woff[2 * lane], b = sh.woff[2 * lane + 1];
+        int incl = a + b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += v;
+        }
+        sh.woff[2 * lane] = incl - a - b;
+        sh.woff[2 * lane + 1] = incl - b;
+        if (lane == 31) sh.woff[8 * (kSolveThreads / 32)] = incl;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if ((have[k] >> lane) & 1u)
+          sh.list[sh.woff[k * (kSolveThreads / 32) + wid] + __popc(have[k] & ((1u << lane) - 1u))] = w0 + k * kSolveThreads + t;
+      __syncthreads();
+      const int n_list = sh.woff[8 * (kSolveThreads / 32)];
+      for (int e = t; e < n_list; e += kSolveThreads) {
+        const int q = sh.list[e];
+        const int di = q < nc ? dc0 + q : ds0 + (q - nc);
         const float4 p = d.ds_pts[di];
         const double cp[3] = {(double)p.x, (double)p.y, (double)p.z};
         const double2* ri = reinterpret_cast<const double2*>(d.rec + 6 * (size_t)di);
@@ -1076,6 +1112,7 @@ __global__ void __cluster_dims__(kSolveCtas, 1, 1) __launch_bounds__(kSolveThrea
         if (q < nc) { accum_edge(Sm, sh.pose, cp, rec, rec + 3); ne += 1.0; }
         else { accum_plane(Sm, sh.pose, cp, rec, rec[3]); np += 1.0; }
       }
+      __syncthreads();  // (the list is rebuilt by the next window)
     }
     solve_block_reduce(sh, Sm, ne, np);
     if (half != 0 && t < kPartial) peer0->red[half][t] = sh.red[0][t];
@@ -1986,15 +2023,18 @@ __device__ __forceinline__ int dead_before(const Dev& d, int g, int l, bool* dea
   return cum[a - 1] + min(in, len);
 }
 __global__ void shift_old_kernel(Dev d, int cur, int total_store, bool deaths) {
-  __shared__ int win[2];  // the inserts that can fall among this block's entries (when it lies inside one segment)
+  // per block: its segment(s) and the inserts that can fall among its entries (when it lies inside one segment)
+  __shared__ int seg[2], win[2];
   const int i0 = blockIdx.x * blockDim.x, i = i0 + threadIdx.x, i1 = min(i0 + (int)blockDim.x, total_store) - 1;
-  const int g0 = find_seg(d.so_off, d.G, i0), g1 = find_seg(d.so_off, d.G, i1);
-  if (threadIdx.x < 2 && g0 == g1) {
-    const int l = (threadIdx.x == 0 ? i0 - 1 : i1) - d.so_off[g0];  // inserts in front of entries before the block / up to its last entry
-    win[threadIdx.x] = l < 0 ? d.run_off[g0] : inserts_up_to(d.vval2, d.run_off[g0], d.run_off[g0 + 1], (uint32_t)l);
+  if (threadIdx.x < 2) {
+    const int g = find_seg(d.so_off, d.G, threadIdx.x == 0 ? i0 : i1);
+    seg[threadIdx.x] = g;
+    const int l = (threadIdx.x == 0 ? i0 - 1 : i1) - d.so_off[g];  // inserts in front of entries before the block / up to its last entry
+    win[threadIdx.x] = l < 0 ? d.run_off[g] : inserts_up_to(d.vval2, d.run_off[g], d.run_off[g + 1], (uint32_t)l);
   }
   __syncthreads();
   if (i >= total_store) return;
+  const int g0 = seg[0], g1 = seg[1];
   const int g = g0 == g1 ? g0 : find_seg(d.so_off, d.G, i);
   const int l = i - d.so_off[g];
   if (l >= d.st_n[g]) return;  // (the extra position behind the segment's last entry)
