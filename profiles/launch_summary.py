@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv) by kernel: total, share, count, mean.
-usage: launch_summary.py <launches.csv> [top_n]"""
+usage: launch_summary.py <launches.csv> [top_n] [last_k]   (last_k: only the last k launches, e.g. the timed steps)"""
 import collections
 import csv
 import re
@@ -9,6 +9,8 @@ import sys
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 hdr, rows = rows[0], rows[1:]
+if len(sys.argv) > 3:
+    rows = rows[-int(sys.argv[3]):]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
 tot, cnt = collections.Counter(), collections.Counter()
 for r in rows:

@@ -178,7 +178,7 @@ struct s2m_ctx {
   int* h_dsoff = nullptr;        // pinned [G+1]: down-sampled counts read back mid-frame
   cudaEvent_t ev_ds = nullptr;
   uint32_t* h_bbox = nullptr;    // pinned [G][6]: boxes of the incoming clouds (ordered-uint encoding)
-  int* h_lpcnt = nullptr;        // pinned [G]: local-map sizes of this frame
+  int* h_lpcnt = nullptr;        // pinned [2G]: local-map sizes of this frame, then how many of those points are still raw
   cudaEvent_t ev_bbox = nullptr;
   LmState* lm_trace = nullptr;   // [2][B] device
   LmState* h_lm = nullptr;       // pinned [2][B]
@@ -382,7 +382,7 @@ static int create_impl(s2m_ctx* ctx) {
   CK(cudaMallocHost((void**)&ctx->h_dsoff, sizeof(int) * (2 * kMaxBatch + 1)));
   CK(cudaEventCreateWithFlags(&ctx->ev_ds, cudaEventDisableTiming));
   CK(cudaMallocHost((void**)&ctx->h_bbox, sizeof(uint32_t) * 6 * 2 * kMaxBatch));
-  CK(cudaMallocHost((void**)&ctx->h_lpcnt, sizeof(int) * 2 * kMaxBatch));
+  CK(cudaMallocHost((void**)&ctx->h_lpcnt, sizeof(int) * 4 * kMaxBatch));
   CK(cudaEventCreateWithFlags(&ctx->ev_bbox, cudaEventDisableTiming));
   CK(cudaMallocHost((void**)&ctx->h_lm, sizeof(LmState) * 2 * B));
   std::memset(ctx->ht, 0, sizeof(HostTables));
@@ -401,7 +401,7 @@ static int create_impl(s2m_ctx* ctx) {
   rc |= dev_alloc(ctx, &d.ds_pts, d.cap_in); rc |= dev_alloc(ctx, &d.ds_off, G + 1);
   for (int b = 0; b < 2; ++b) { rc |= dev_alloc(ctx, &d.st_key[b], d.cap_lp); rc |= dev_alloc(ctx, &d.st_pt[b], d.cap_lp); }
   rc |= dev_alloc(ctx, &d.st_n, G); rc |= dev_alloc(ctx, &d.st_n_new, G);
-  rc |= dev_alloc(ctx, &d.rng_start, G * kCols); rc |= dev_alloc(ctx, &d.loc_off, G * (kCols + 1)); rc |= dev_alloc(ctx, &d.lp_cnt, G);
+  rc |= dev_alloc(ctx, &d.rng_start, G * kCols); rc |= dev_alloc(ctx, &d.loc_off, G * (kCols + 1)); rc |= dev_alloc(ctx, &d.lp_cnt, 2 * G);
   rc |= dev_alloc(ctx, &d.knn_ticket, 1); rc |= dev_alloc(ctx, &d.nbr, (size_t)d.cap_in * 6);
   // persistent cell index: per segment a table of a power of two >= 4 x cap_map slots (load <= 1/4) and a pool of
   // cap_map four-entry buckets
@@ -740,11 +740,11 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   k += launch_voxel_bbox(d, total_in, s);
   k += launch_local_ranges(d, ctx->cur, s);
   CK(cudaMemcpyAsync(ctx->h_bbox, d.bbox, sizeof(uint32_t) * 6 * G, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(ctx->h_lpcnt, d.lp_cnt, sizeof(int) * G, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->h_lpcnt, d.lp_cnt, sizeof(int) * 2 * G, cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(ctx->ev_bbox, s));
   CK(cudaEventSynchronize(ctx->ev_bbox));
-  total_lp = 0;
-  for (int g = 0; g < G; ++g) { T.lp_off[g] = total_lp; total_lp += ctx->h_lpcnt[g]; }
+  total_lp = 0;  // the staging area of the raw points the merge absorbs: sized by their exact number
+  for (int g = 0; g < G; ++g) { T.lp_off[g] = total_lp; total_lp += ctx->h_lpcnt[G + g]; }
   T.lp_off[G] = total_lp;
   for (int b = 0; b < B; ++b) {
     if (!T.desc[b].active) continue;

@@ -114,7 +114,7 @@ struct Dev {
   // ---- per call small tables (device copies of host arrays)
   FrameDesc* desc;              // [B]
   int* in_off;                  // [G+1] packed offsets of the incoming clouds
-  int* lp_off;                  // [G+1] packed offsets of the local maps (exact in a frame: sizes are read back)
+  int* lp_off;                  // [G+1] packed offsets of the raw local-map points a merge absorbs (exact: counts are read back)
   int* so_off;                  // [G+1] packed offsets of the whole stores (merge index space)
   int* st_base;                 // [G]   base of each segment in the store arrays
   int* st_cap;                  // [G]
@@ -135,7 +135,7 @@ struct Dev {
   // ---- local map + cell index
   int* rng_start;               // [G][25]
   int* loc_off;                 // [G][26]
-  int* lp_cnt;                  // [G] points of the local map (read back: sizes the index exactly)
+  int* lp_cnt;                  // [2G] points of the local map (read back: sizes the index exactly), then how many of them are raw
   int* nbr;                     // [cap_in][6] K4a -> K4b: (n << 1 | gate), five entry numbers in d.bkt
   int* knn_ticket;              // next 32-query work unit of knn_kernel
   float4* od_last;              // odometry: less-sharp / less-flat clouds of the previous sweep, class-major

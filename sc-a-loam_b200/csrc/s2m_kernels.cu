@@ -185,13 +185,17 @@ __global__ void range_kernel(Dev d, int cur) {
   const FrameDesc& fd = d.desc[seg_slot(d, g)];
   const uint64_t* keys = d.st_key[cur] + d.st_base[g];
   const int n = d.st_n[g];
-  int lo = 0, len = 0;
+  int lo = 0, len = 0, raw = 0;  // raw: points of the column's cubes that are still unfiltered (absorbed by this frame's merge)
   if (c < kCols && fd.active) {
     const int wi = fd.val_lo[0] + c / 5, wj = fd.val_lo[1] + c % 5;
     if (wi <= fd.val_hi[0] && wj <= fd.val_hi[1] && fd.val_lo[2] <= fd.val_hi[2]) {
       lo = lower_bound_u64(keys, n, store_key(pack_cube(wi, wj, fd.val_lo[2]), 0, 0));
       const int hi = lower_bound_u64(keys, n, store_key(pack_cube(wi, wj, fd.val_hi[2]) + 1, 0, 0));
       len = hi - lo;
+      for (int wk = fd.val_lo[2]; wk <= fd.val_hi[2] && len > 0; ++wk) {
+        const uint32_t cube = pack_cube(wi, wj, wk);
+        raw += lower_bound_u64(keys + lo, len, store_key(cube + 1, 0, 0)) - lower_bound_u64(keys + lo, len, store_key(cube, 1, 0));
+      }
     }
   }
   int incl = len;
@@ -199,6 +203,8 @@ __global__ void range_kernel(Dev d, int cur) {
     int v = __shfl_up_sync(0xffffffffu, incl, o);
     if (c >= o) incl += v;
   }
+  for (int o = 16; o > 0; o >>= 1) raw += __shfl_xor_sync(0xffffffffu, raw, o);
+  if (c == 0) d.lp_cnt[d.G + g] = raw;
   if (c < kCols) {
     d.rng_start[g * kCols + c] = lo;
     d.loc_off[g * (kCols + 1) + c] = incl - len;
