@@ -68,6 +68,9 @@ def run_os1_saturated(pkg, torch, local_rank, rank=0, slots=16, warmup=3, steps=
     R.phase_profile(reset=True)
     torch.cuda.synchronize()
     err = []
+    ncu_range = bool(os.environ.get("S2M_NCU_RANGE"))  # ncu --profile-from-start off: only the timed steps
+    if ncu_range:
+        torch.cuda.profiler.start()
     with torch.cuda.stream(stream):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -76,6 +79,8 @@ def run_os1_saturated(pkg, torch, local_rank, rank=0, slots=16, warmup=3, steps=
             err += [float(np.linalg.norm(t[b] - scans[f][b][3][4:])) for b in range(B)]
         e1.record(stream)
     torch.cuda.synchronize()
+    if ncu_range:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     phases = R.phase_profile()
     stats = [R.batch_stats[b] for b in range(B)]

@@ -27,7 +27,12 @@ rows = list(csv.reader(open(sass_csv)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 col = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+data = []
+for r in rows[hi + 1:]:
+    if r and r[0] in ("Kernel Name", "Address"):  # (some ncu versions print the page once per view)
+        break
+    if len(r) == len(hdr):
+        data.append(r)
 print("sass rows", len(data), "nvdisasm instr", len(lines))
 agg = collections.defaultdict(lambda: [0, 0, 0, 0])
 n = min(len(data), len(lines))
