@@ -31,7 +31,8 @@ def run_os1_saturated(pkg, torch, local_rank, rank=0, slots=16, warmup=3, steps=
     for f in range(n_run):
         row = []
         for b in range(B):
-            pose = harness.street_pose(float(rng.uniform(-330.0, 330.0)), int(rng.integers(-4, 5)), int(rng.integers(0, 4)))
+            # (|x|, |y| stay below 375 m after the 17 degree rotation of the street grid: the window never shifts)
+            pose = harness.street_pose(float(rng.uniform(-270.0, 270.0)), int(rng.integers(-3, 4)), int(rng.integers(0, 4)))
             c, s = harness.features("OS1-64", harness.scan(seed + b % n_worlds, "OS1-64", pose, f))
             guess = pose.copy()
             guess[4:] += rng.uniform(-0.2, 0.2, 3)  # SURVEY 8d "T_init distribution"
@@ -96,6 +97,7 @@ def run_os1_saturated(pkg, torch, local_rank, rank=0, slots=16, warmup=3, steps=
         "correspondences_mean": float(np.mean([s.n_edge[1] + s.n_plane[1] for s in stats])),
         "median_error_vs_truth_m": float(np.median(err)), "max_error_vs_truth_m": float(np.max(err)),
         "phase_ms_per_step": {k: round(v / steps, 4) for k, v in phases.items()},
+        "window_centre_after": [[int(v) for v in R.window(b)] for b in (0, B - 1)],  # [10, 10, 5] = never shifted: still saturated
         "input": "host buffers (H2D of the sweeps inside the timed region)",
         "datagen_s": round(gen_s, 1), "setup_s": round(setup_s, 1),
     }
