@@ -199,6 +199,10 @@ int s2m_trace_lm(s2m_ctx* ctx, int slot, int outer, double pose7[7], double sums
  * far, 0 when the mode is off. */
 int s2m_debug_guard_check(s2m_ctx* ctx);
 
+/* Queries the grouped kNN kernel handed to the thread-per-query search so far (candidate box larger than the
+ * shared-memory pool, or too many ties at the fifth distance); both searches are exact, this is a tuning counter. */
+long long s2m_debug_knn_fallbacks(s2m_ctx* ctx);
+
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 long long s2m_launch_count(s2m_ctx* ctx);
 /* CUDA-event time (ms) of the fused association kernel (K4) launches since the

@@ -29,7 +29,7 @@ EXPORTS = [
     "s2m_register_batch_wait", "s2m_get_correction",
     "s2m_transform_cloud", "s2m_map_upload", "s2m_map_download", "s2m_pcd_write", "s2m_pcd_read", "s2m_checkpoint_save",
     "s2m_checkpoint_load", "s2m_get_local_map", "s2m_get_surround",
-    "s2m_get_window", "s2m_debug_knn", "s2m_debug_guard_check", "s2m_trace_cloud", "s2m_trace_knn", "s2m_trace_lm",
+    "s2m_get_window", "s2m_debug_knn", "s2m_debug_knn_fallbacks", "s2m_debug_guard_check", "s2m_trace_cloud", "s2m_trace_knn", "s2m_trace_lm",
     "s2m_launch_count", "s2m_set_profiling", "s2m_k4_profile", "s2m_phase_profile", "s2m_shard_unique_id", "s2m_shard_slab", "s2m_shard_init",
     "s2m_shard_profile",
     "s2m_odom_create", "s2m_odom_step_batch",
@@ -120,6 +120,8 @@ def load_library(path=LIB_PATH):
     L.s2m_launch_count.restype = cll
     L.s2m_set_profiling.argtypes = [vp, ci]
     L.s2m_k4_profile.argtypes = [vp, ci, vp, vp, vp]
+    L.s2m_debug_knn_fallbacks.argtypes = [vp]
+    L.s2m_debug_knn_fallbacks.restype = ctypes.c_longlong
     L.s2m_phase_profile.argtypes = [vp, ci, vp]
     L.s2m_shard_unique_id.argtypes = [vp]
     L.s2m_shard_slab.argtypes = [ci, ci, vp, vp]
@@ -527,6 +529,10 @@ class Registrar:
         ms, n = ctypes.c_double(), ctypes.c_longlong()
         self._check(self.L.s2m_shard_profile(self.h, int(reset), ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def knn_fallbacks(self):
+        """queries the grouped kNN kernel handed to the thread-per-query search so far (tuning counter)"""
+        return int(self.L.s2m_debug_knn_fallbacks(self.h))
 
     def guard_check(self):
         """debug (S2M_GUARD_BYTES set at create): guard words overwritten so far, 0 = no out-of-bounds store"""

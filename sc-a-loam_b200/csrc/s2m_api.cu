@@ -403,6 +403,9 @@ static int create_impl(s2m_ctx* ctx) {
   rc |= dev_alloc(ctx, &d.st_n, G); rc |= dev_alloc(ctx, &d.st_n_new, G);
   rc |= dev_alloc(ctx, &d.rng_start, G * kCols); rc |= dev_alloc(ctx, &d.loc_off, G * (kCols + 1)); rc |= dev_alloc(ctx, &d.lp_cnt, 2 * G);
   rc |= dev_alloc(ctx, &d.knn_ticket, 1); rc |= dev_alloc(ctx, &d.nbr, (size_t)d.cap_in * 6);
+  rc |= dev_alloc(ctx, &d.qs_key, d.cap_in); rc |= dev_alloc(ctx, &d.qs_key2, d.cap_in);
+  rc |= dev_alloc(ctx, &d.qs_val2, d.cap_in);
+  rc |= dev_alloc(ctx, &d.cand27, d.cap_in); rc |= dev_alloc(ctx, &d.knn_stats, 4);
   // persistent cell index: per segment a table of a power of two >= 4 x cap_map slots (load <= 1/4) and a pool of
   // cap_map four-entry buckets
   long long hcap = 0;
@@ -455,6 +458,9 @@ static int create_impl(s2m_ctx* ctx) {
   CK(cudaMemset(d.err_flag, 0, sizeof(int)));
   CK(cudaMemset(d.ticket, 0, sizeof(int) * B));
   CK(cudaMemset(d.knn_ticket, 0, sizeof(int)));
+  CK(cudaMemset(d.knn_stats, 0, 4 * sizeof(unsigned long long)));
+  CK(cudaMemset(d.cand27, 0, sizeof(int) * (size_t)d.cap_in));
+  d.count_cand = 0;
   CK(cudaMemset(d.out, 0, sizeof(SlotOut) * B));
   CK(cudaMemset(d.lm, 0, sizeof(LmState) * B));
   CK(cudaMemset(d.ds_off, 0, sizeof(int) * (G + 1)));
@@ -469,6 +475,20 @@ static int create_impl(s2m_ctx* ctx) {
 }
 
 // debug: number of guard words that no longer hold the pattern (0 = no out-of-bounds store so far)
+extern "C" long long s2m_debug_knn_fallbacks(s2m_ctx* ctx) {
+  if (!ctx) return S2M_ERR_ARG;
+  long long n = 0;
+  for (s2m_ctx* ch : ctx->children) {
+    const long long c = s2m_debug_knn_fallbacks(ch);
+    if (c < 0) return c;
+    n += c;
+  }
+  if (!ctx->d.knn_stats) return n;
+  if (cudaSetDevice(ctx->P.device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) return S2M_ERR_CUDA;
+  unsigned long long v = 0;
+  if (cudaMemcpy(&v, ctx->d.knn_stats, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return S2M_ERR_CUDA;
+  return n + (long long)v;
+}
 extern "C" int s2m_debug_guard_check(s2m_ctx* ctx) {
   if (!ctx) return S2M_ERR_ARG;
   int bad = 0;
@@ -798,13 +818,22 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
     chunks += (nq + 31) / 32;
   }
   // K4a: one resident wave of persistent warps sharing a work ticket; K4b: one block per 128 points of a slot
-  const int knn_blocks = std::max(1, std::min((chunks + kTile / 32 - 1) / (kTile / 32), S2M_K4A_MINB * ctx->sm_count));
+#if S2M_KNN_GROUP
+  chunks = (n_ds + 31) / 32;  // ... of the grouped search: 32 consecutive points of the block-sorted order
+  const int knn_resident = S2M_K4G_MINB;
+#else
+  const int knn_resident = S2M_K4A_MINB;
+#endif
+  const int knn_blocks = std::max(1, std::min((chunks + kTile / 32 - 1) / (kTile / 32), knn_resident * ctx->sm_count));
   const int fit_blocks = std::max(1, tiles);
   const int eval_blocks = std::max(1, (tiles + kEvalTilesPerBlock - 1) / kEvalTilesPerBlock);
+  d.count_cand = ctx->profiling ? 1 : 0;
+  if (ctx->profiling) k += launch_count27(d, n_ds, s);  // the byte count of the roofline: outside the K4 bracket
   for (int outer = 0; outer < 2; ++outer) {  // laserMapping.cpp:563
     CK(cudaMemsetAsync(d.knn_ticket, 0, sizeof(int), s));  // the association's work ticket
     prof_mark(ctx, S2M_PHASE_READBACK);  // host wait for the down-sampled counts (outer 0); the K4 bracket starts here
-    k += launch_associate(d, outer, ctx->cur, knn_blocks, fit_blocks, ctx->P.trace != 0, s);
+    if (outer == 0) k += launch_query_sort(d, n_ds, s);  // (the grouped search's query order: part of K4's time)
+    k += launch_associate(d, outer, ctx->cur, knn_blocks, fit_blocks, n_ds, ctx->P.trace != 0, s);
     prof_mark(ctx, S2M_PHASE_ASSOCIATE);
     if (!sharded) {
       k += launch_solve(d, outer, true, s);  // Ceres solve, max_num_iterations = 4 (:713-721)

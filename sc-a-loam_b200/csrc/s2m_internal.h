@@ -42,6 +42,12 @@ namespace s2m {
 #ifndef S2M_K4A_MINB
 #define S2M_K4A_MINB 8  // resident blocks per SM the kNN kernel is compiled for (<= 64 registers)
 #endif
+#ifndef S2M_KNN_GROUP
+#define S2M_KNN_GROUP 1  // K4a: 1 = grouped search over shared-memory candidate pools, 0 = thread per query
+#endif
+#ifndef S2M_K4G_MINB
+#define S2M_K4G_MINB 4  // resident blocks per SM of the grouped kNN kernel (shared-memory bound)
+#endif
 #ifndef S2M_K4B_MINB
 #define S2M_K4B_MINB 4  // ... and the fit / residual kernel (128 registers, FP64)
 #endif
@@ -138,6 +144,11 @@ struct Dev {
   int* lp_cnt;                  // [2G] points of the local map (read back: sizes the index exactly), then how many of them are raw
   int* nbr;                     // [cap_in][6] K4a -> K4b: (n << 1 | gate), five entry numbers in d.bkt
   int* knn_ticket;              // next 32-query work unit of knn_kernel
+  uint32_t *qs_key, *qs_key2;   // [cap_in] (segment, 2 m block) key of every scan point: in scan order / bucketed by block
+  uint32_t* qs_val2;            // [cap_in] position in ds_pts of the bucketed points
+  int* cand27;                  // [cap_in] map points in the 27 cells of a query (profiling only)
+  int count_cand;               // fit_kernel adds cand27 into the slot's candidate counters
+  unsigned long long* knn_stats;  // [4] queries the grouped search handed to the per-thread search
   float4* od_last;              // odometry: less-sharp / less-flat clouds of the previous sweep, class-major
   int* od_last_off;             // [2B+1]
   float4* od_sorted;            // the same clouds ordered by 1 m cell inside each segment, .w = index | ring << 24
@@ -201,7 +212,9 @@ int launch_voxel_filter(const Dev& d, int total_in, int key_bits, cudaStream_t s
 int launch_local_ranges(const Dev& d, int cur, cudaStream_t s);
 int launch_index_rebuild(const Dev& d, int cur, int n_seg, int total_points, cudaStream_t s);
 int launch_guard(const Dev& d, cudaStream_t s);
-int launch_associate(const Dev& d, int outer, int cur, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s);
+int launch_associate(const Dev& d, int outer, int cur, int knn_blocks, int fit_blocks, int n_ds, bool trace, cudaStream_t s);
+int launch_query_sort(const Dev& d, int n_ds, cudaStream_t s);
+int launch_count27(const Dev& d, int n_ds, cudaStream_t s);
 int launch_solve(const Dev& d, int outer, bool from_units, cudaStream_t s);
 int launch_reduce_units(const Dev& d, cudaStream_t s);
 int launch_evaluate(const Dev& d, int outer, int blocks_per_slot, cudaStream_t s);

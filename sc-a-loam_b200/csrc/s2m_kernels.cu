@@ -52,6 +52,8 @@ __device__ __forceinline__ uint32_t cell_hash(uint32_t k) {
   k *= 0x9E3779B1u;
   return k ^ (k >> 15);
 }
+// First slot probed for a cell: always an even one, so a 16-byte load fetches the first two slots of the probe sequence.
+__device__ __forceinline__ uint32_t cell_home(uint32_t k, uint32_t mask) { return cell_hash(k) & mask & ~1u; }
 
 // ----------------------------------------------------------------------------
 // K1: scan voxel-grid filter (pcl::VoxelGrid semantics)
@@ -277,7 +279,7 @@ __device__ __forceinline__ long long chain_slot(const Dev& d, int g, int b, int 
 __device__ __forceinline__ void idx_insert(const Dev& d, int g, uint32_t k24, const float4 e) {
   unsigned long long* tab = d.hash_tab + d.hash_off[g];
   const uint32_t mask = (uint32_t)d.hmask[g];
-  uint32_t s = cell_hash(k24) & mask;
+  uint32_t s = cell_home(k24, mask);
   for (int guard = 0; guard <= (int)mask; ++guard) {
     unsigned long long old = tab[s];
     if (old == kCellEmpty) {
@@ -303,7 +305,7 @@ __device__ __forceinline__ void idx_insert(const Dev& d, int g, uint32_t k24, co
 __device__ __forceinline__ long long idx_find(const Dev& d, int g, uint32_t k24, uint32_t tag) {
   const unsigned long long* tab = d.hash_tab + d.hash_off[g];
   const uint32_t mask = (uint32_t)d.hmask[g];
-  uint32_t s = cell_hash(k24) & mask;
+  uint32_t s = cell_home(k24, mask);
   unsigned long long e = tab[s];
   while (e != kCellEmpty && (uint32_t)(e >> 40) != k24) { s = (s + 1) & mask; e = tab[s]; }
   if (e == kCellEmpty) return -1;
@@ -428,7 +430,7 @@ __global__ void idx_fill_kernel(Dev d, int cur, int n_seg, int total, const uint
   unsigned long long* tab = d.hash_tab + d.hash_off[g];
   const uint32_t mask = (uint32_t)d.hmask[g];
   const unsigned long long entry = ((unsigned long long)(key & 0xFFFFFFu) << 40) | ((unsigned long long)(j + 1) << 24) | (unsigned long long)b0;
-  uint32_t s = cell_hash(key & 0xFFFFFFu) & mask;
+  uint32_t s = cell_home(key & 0xFFFFFFu, mask);
   for (uint32_t guard = 0; guard <= mask; ++guard) {
     if (atomicCAS(tab + s, kCellEmpty, entry) == kCellEmpty) return;
     s = (s + 1) & mask;
@@ -517,9 +519,9 @@ __device__ __forceinline__ void knn_scan_cell(const Dev& d, int g, int b, int cn
   }
 }
 
-// per-thread staging of the 27 cell probes (one column per thread): count << 24 | bucket, 0 count = empty
+// per-thread staging of the 27 cell probes (one column per lane of a warp): count << 24 | bucket, 0 count = empty
 struct KnnStage {
-  uint32_t cell[27][kTile];
+  uint32_t cell[27][32];
 };
 
 // Rows (dy,dz) of three x-adjacent cells are visited near to far; a row is skipped when
@@ -539,7 +541,7 @@ __device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[
   const int cx = (int)floorf(qx) - origin[0], cy = (int)fly - origin[1], cz = (int)flz - origin[2];
   const uint32_t mask = (uint32_t)d.hmask[g];
   const unsigned long long* __restrict__ tab = d.hash_tab + d.hash_off[g];
-  const int t = threadIdx.x;
+  const int t = threadIdx.x & 31;
   // exact distances from the query to the cell's boundary planes (fractional parts are exact)
   const float fy = xfsub(qy, fly), fz = xfsub(qz, flz);
   const float gy = xfsub(1.0f, fy), gz = xfsub(1.0f, fz);
@@ -558,7 +560,7 @@ __device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[
       const int z = cz + dz, y = cy + dy, x = cx + a - 1;
       const bool ok = (unsigned)z <= 255u && (unsigned)y <= 255u && (unsigned)x <= 255u;
       k24[j] = ((uint32_t)(z & 255) << 16) | ((uint32_t)(y & 255) << 8) | (uint32_t)(x & 255);
-      sl[j] = cell_hash(k24[j]) & mask;
+      sl[j] = cell_home(k24[j], mask);
       e[j] = ok ? tab[sl[j]] : kCellEmpty;
     }
 #pragma unroll
@@ -590,7 +592,7 @@ __device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[
     for (int a = 0; a < 3; ++a) {
       const int x = cx + a - 1;
       k24[a] = ((uint32_t)(z & 255) << 16) | ((uint32_t)(y & 255) << 8) | (uint32_t)(x & 255);
-      sl[a] = cell_hash(k24[a]) & mask;
+      sl[a] = cell_home(k24[a], mask);
       e[a] = (row_ok && (unsigned)x <= 255u) ? tab[sl[a]] : kCellEmpty;
     }
 #pragma unroll
@@ -627,7 +629,7 @@ __device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[
         const int dz = (o == 2 || o == 3 || o == 6) ? sz : ((o == 5 || o == 7 || o == 8) ? -sz : 0);
         const int x = cx + (a == 0 ? 0 : (a == 1 ? -1 : 1));
         const uint32_t kk = ((uint32_t)((cz + dz) & 255) << 16) | ((uint32_t)((cy + dy) & 255) << 8) | (uint32_t)(x & 255);
-        uint32_t s = cell_hash(kk) & mask;
+        uint32_t s = cell_home(kk, mask);
         unsigned long long ee = tab[s];
         while (ee != kCellEmpty && (uint32_t)(ee >> 40) != kk) { s = (s + 1) & mask; ee = tab[s]; }
         cnt = ee == kCellEmpty ? 0 : (int)((ee >> 24) & 0xFFFFu);
@@ -643,8 +645,8 @@ __global__ void knn_debug_kernel(Dev d, int cur, int g, const float* __restrict_
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Knn5 r;
-  __shared__ KnnStage st;
-  knn5_cells(d, g, d.desc[seg_slot(d, g)].origin, q[3 * i], q[3 * i + 1], q[3 * i + 2], r, st);
+  __shared__ KnnStage st[4];  // (launched with 128 threads)
+  knn5_cells(d, g, d.desc[seg_slot(d, g)].origin, q[3 * i], q[3 * i + 1], q[3 * i + 2], r, st[threadIdx.x >> 5]);
   const bool ok = knn_d2(r, 4) < 1.0f;  // the reference's gate; beyond it the bounded search is not exact
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
@@ -806,7 +808,8 @@ __global__ void __launch_bounds__(kTile, S2M_K4A_MINB) knn_kernel(Dev d, int out
   // Work unit = 32 consecutive queries of one slot, taken by a WARP from a device-wide ticket:
   // the trip counts of the search vary a lot between queries, so static tiles leave most of a
   // block (and the tail of the grid) idle. The results do not depend on who computes them.
-  __shared__ KnnStage stage;
+  __shared__ KnnStage stage_w[kTile / 32];
+  KnnStage& stage = stage_w[threadIdx.x >> 5];
   __shared__ int chunk_off[kMaxBatch + 1];
   const int B = d.B, lane = threadIdx.x & 31;
   if (threadIdx.x < 32) {  // chunks per slot (none for a slot that is not optimised this frame), prefix-summed
@@ -872,6 +875,534 @@ __global__ void __launch_bounds__(kTile, S2M_K4A_MINB) knn_kernel(Dev d, int out
   }
 }
 
+// ----------------------------------------------------------------------------
+// K4a, grouped form (the default): queries that share a 2 m block of cells search together.
+//
+// The scan points are sorted once per frame by (segment, 2 m block of the cell under the initial guess)
+// (qsort_key_kernel + one radix sort), so the 32 queries a warp takes are spatial neighbours.  Lanes whose
+// ACTUAL cells (this outer iteration's pose) lie in the same block form a group (match.any); the group's
+// candidate set is every map point in the box of cells [min cell - 1, max cell + 1] (3..4 cells per axis), a
+// superset of each member's 27 cells -- points outside a query's 27 cells are at least 1 m away in the
+// reference's float arithmetic and can never pass the d2[4] < 1 gate, so the result is unchanged.
+//   1. the warp probes the cells of all its groups' boxes, one (group, cell) item per lane and step;
+//      occupied cells go to a hit list, their point counts to per-group totals (shared-memory atomics);
+//   2. the groups' candidate ranges are laid out in the warp's shared-memory pool (prefix sum; groups that
+//      do not fit wait for the next round) and the lanes copy the hit cells' bucket chains into it;
+//   3. pass 1: every lane runs over ITS GROUP's candidates -- one broadcast 16-byte shared load per
+//      candidate, the reference's float distance, and a branch-free five-deep min/max network that keeps the
+//      five smallest distances (seeded with the gate, 1.0f);
+//   4. pass 2: the candidates with d2 <= the fifth distance are appended to a short per-lane list (exactly
+//      five unless distances tie at the fifth place), their tags fetched, and the list ordered by the
+//      reference's (d2, index) rule as 64-bit keys (d2 bits, tag).
+// No loop depends on a lane's own data except through its group, so the lanes of a warp stay together.
+// Lanes whose group is too large for the pool, or that see more than kGList ties, fall back to the
+// thread-per-query search (knn5_cells); d.knn_stats counts them.
+// ----------------------------------------------------------------------------
+#ifndef S2M_KNN_POOL
+#define S2M_KNN_POOL 512
+#endif
+constexpr int kGPool = S2M_KNN_POOL;  // candidates a warp stages per round (16 bytes each)
+constexpr int kGHits = 256;           // occupied cells a warp may stage per chunk
+constexpr int kGIdxBits = 10;         // a candidate's position in its group's range rides in the low bits of its distance
+static_assert(kGPool <= (1 << kGIdxBits) && kGPool * sizeof(float4) >= sizeof(KnnStage), "positions are 10 bits; the fallback stages in the pool");
+struct KnnGroupSmem {
+  float4 pool[kGPool];        // (x, y, z, entry number in d.bkt) of the staged candidates
+  uint2 hits[kGHits];         // .x = first bucket | group << 24, .y = count << 16 | offset in the group's range
+  int gtot[32];               // per group: map points in its box
+  int gstart[32];             // first pool entry of the group this round, -1: not in this round
+  int gibase[33];             // first probe item of the group
+  int4 gbox[32];              // lowest cell of the box (x, y, z), dims dx | dy << 8 | dz << 16
+  int gtab[32], gmask[32], gbkt[32];  // hash_off, hmask, bkt_off of the group's segment
+};
+
+// Block key of a cell (relative to the valid block's origin): cells -1..256 -> blocks 0..129
+__device__ __forceinline__ bool cell_near_block(int cx, int cy, int cz) {
+  return (unsigned)(cx + 1) <= 257u && (unsigned)(cy + 1) <= 257u && (unsigned)(cz + 1) <= 257u;
+}
+__device__ __forceinline__ uint32_t block_key(int g, int cx, int cy, int cz) {
+  return ((uint32_t)g << 24) | ((uint32_t)((cz + 2) >> 1) << 16) | ((uint32_t)((cy + 2) >> 1) << 8) | (uint32_t)((cx + 2) >> 1);
+}
+// Once per frame: the scan points of every segment bucketed by the 2 m block they fall into under the pose the frame
+// starts from (a counting sort over a hash of the block, one thread block per segment, histogram and cursors in
+// shared memory).  All the grouped search needs is that the points of a block end up next to each other -- the
+// order inside a bucket is whatever the atomics make it, and no result depends on it.
+constexpr int kQBins = 2048;
+__global__ void __launch_bounds__(1024) qgroup_kernel(Dev d) {
+  __shared__ int hist[kQBins];
+  __shared__ int wsum[32];
+  const int g = blockIdx.x, slot = seg_slot(d, g), t = threadIdx.x;
+  const int base = d.ds_off[g], n = d.ds_off[g + 1] - base;
+  if (n <= 0) return;
+  if (!d.out[slot].optimized) {  // not searched this frame
+    for (int i = t; i < n; i += 1024) d.qs_key2[base + i] = kSentinel32;
+    return;
+  }
+  for (int i = t; i < kQBins; i += 1024) hist[i] = 0;
+  __syncthreads();
+  double pose[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) pose[i] = d.lm[slot].x[i];
+  const int o0 = d.desc[slot].origin[0], o1 = d.desc[slot].origin[1], o2 = d.desc[slot].origin[2];
+  for (int i = t; i < n; i += 1024) {
+    const float4 p = d.ds_pts[base + i];
+    float w[3];
+    xf_point(pose, p.x, p.y, p.z, w);
+    const float fx = floorf(w[0]) - (float)o0, fy = floorf(w[1]) - (float)o1, fz = floorf(w[2]) - (float)o2;
+    uint32_t key = ((uint32_t)g << 24) | 0xFFFFFFu;
+    if (fabsf(fx) < 1e6f && fabsf(fy) < 1e6f && fabsf(fz) < 1e6f && cell_near_block((int)fx, (int)fy, (int)fz))
+      key = block_key(g, (int)fx, (int)fy, (int)fz);
+    d.qs_key[base + i] = key;
+    atomicAdd(&hist[cell_hash(key) & (kQBins - 1)], 1);
+  }
+  __syncthreads();
+  {  // exclusive prefix sum of the histogram: two bins per thread
+    const int a = hist[2 * t], b = hist[2 * t + 1];
+    int v = a + b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, o);
+      if ((t & 31) >= o) v += u;
+    }
+    if ((t & 31) == 31) wsum[t >> 5] = v;
+    __syncthreads();
+    if (t < 32) {
+      int s = wsum[t];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, s, o);
+        if (t >= o) s += u;
+      }
+      wsum[t] = s;
+    }
+    __syncthreads();
+    const int excl = v - (a + b) + (t >= 32 ? wsum[(t >> 5) - 1] : 0);
+    hist[2 * t] = excl;
+    hist[2 * t + 1] = excl + a;
+  }
+  __syncthreads();
+  for (int i = t; i < n; i += 1024) {
+    const uint32_t key = d.qs_key[base + i];
+    const int pos = atomicAdd(&hist[cell_hash(key) & (kQBins - 1)], 1);
+    d.qs_key2[base + pos] = key;
+    d.qs_val2[base + pos] = (uint32_t)(base + i);
+  }
+}
+// profiling only: map points in the 27 cells of every query (the C-bar of SURVEY 8d's byte formula)
+__global__ void count27_kernel(Dev d, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = find_seg(d.ds_off, d.G, i), slot = seg_slot(d, g);
+  int total = 0;
+  if (d.out[slot].optimized) {
+    const float4 p = d.ds_pts[i];
+    float w[3];
+    xf_point(d.lm[slot].x, p.x, p.y, p.z, w);
+    const int* o = d.desc[slot].origin;
+    const float fx = floorf(w[0]) - (float)o[0], fy = floorf(w[1]) - (float)o[1], fz = floorf(w[2]) - (float)o[2];
+    if (fabsf(fx) < 1e6f && fabsf(fy) < 1e6f && fabsf(fz) < 1e6f && cell_near_block((int)fx, (int)fy, (int)fz) &&
+        !(d.shard_world > 1 && !(w[0] >= d.shard_lo && w[0] < d.shard_hi))) {
+      const unsigned long long* __restrict__ tab = d.hash_tab + d.hash_off[g];
+      const uint32_t mask = (uint32_t)d.hmask[g];
+      for (int j = 0; j < 27; ++j) {
+        const int x = (int)fx + j % 3 - 1, y = (int)fy + (j / 3) % 3 - 1, z = (int)fz + j / 9 - 1;
+        if ((unsigned)x > 255u || (unsigned)y > 255u || (unsigned)z > 255u) continue;
+        const uint32_t k24 = ((uint32_t)z << 16) | ((uint32_t)y << 8) | (uint32_t)x;
+        uint32_t sl = cell_home(k24, mask);
+        unsigned long long e = tab[sl];
+        while (e != kCellEmpty && (uint32_t)(e >> 40) != k24) { sl = (sl + 1) & mask; e = tab[sl]; }
+        if (e != kCellEmpty) total += (int)((e >> 24) & 0xFFFFu);
+      }
+    }
+  }
+  d.cand27[i] = total;
+}
+
+// The grouped search of one warp: lane = one query (valid or not) at world point (qx, qy, qz) of segment g whose
+// cell relative to the valid block's origin is (cx, cy, cz).  Returns the gate (laserMapping.cpp:585 / :653) and,
+// if it holds, the five neighbours in r.  Every lane of the warp must call it.
+__device__ __forceinline__ bool knn5_group(const Dev& d, KnnGroupSmem& S, bool valid, int g, const int origin[3], int cx, int cy,
+                                           int cz, float qx, float qy, float qz, Knn5& r) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  // ---- groups
+  const uint32_t bkey = valid ? block_key(g, cx, cy, cz) : (0x80000000u | (uint32_t)lane);
+  const unsigned gm = __match_any_sync(kFull, bkey);
+  const int leader = __ffs(gm) - 1;
+  const bool is_leader = lane == leader;
+  const unsigned leaders = __ballot_sync(kFull, is_leader);
+  const int gnum = __popc(leaders & ((1u << leader) - 1u)), ng = __popc(leaders);
+  // The members' cells are the block's low (2k-2) or high (2k-1) cell per axis: the box is one cell wider on
+  // each side of the cells that occur (3 or 4 cells per axis).
+  const int px = (cx + 2) & 1, py = (cy + 2) & 1, pz = (cz + 2) & 1;
+  const unsigned ox = __ballot_sync(kFull, px != 0) & gm, oy = __ballot_sync(kFull, py != 0) & gm, oz = __ballot_sync(kFull, pz != 0) & gm;
+  const int lox = cx - px - (ox != gm ? 1 : 0), loy = cy - py - (oy != gm ? 1 : 0), loz = cz - pz - (oz != gm ? 1 : 0);
+  const int dx = 3 + ((ox != gm && ox != 0u) ? 1 : 0), dy = 3 + ((oy != gm && oy != 0u) ? 1 : 0), dz = 3 + ((oz != gm && oz != 0u) ? 1 : 0);
+  const int ncell = valid ? dx * dy * dz : 0;
+  int incl = is_leader ? ncell : 0;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int items = __shfl_sync(kFull, incl, 31);
+  if (is_leader) {
+    S.gibase[gnum] = incl - ncell;
+    S.gbox[gnum] = make_int4(lox, loy, loz, dx | (dy << 8) | (dz << 16));
+    S.gtot[gnum] = 0;
+    S.gtab[gnum] = valid ? d.hash_off[g] : 0;
+    S.gmask[gnum] = valid ? d.hmask[g] : 0;
+    S.gbkt[gnum] = valid ? d.bkt_off[g] : 0;
+  }
+  if (lane == 0) S.gibase[ng] = items;
+  __syncwarp();
+  // ---- 1. probes: item = (group, cell of its box); every lane takes four items per step, their table loads (the
+  // first two slots of each probe sequence in one 16-byte load) in flight together
+  int nh = 0, gp = 0;
+#pragma unroll 1
+  for (int it0 = 0; it0 < items; it0 += 128) {
+    ulonglong2 e2[4];
+    uint32_t k24[4], sl[4];
+    int gq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int it = it0 + 32 * j + lane;
+      e2[j] = make_ulonglong2(kCellEmpty, kCellEmpty); k24[j] = 0u; sl[j] = 0u;
+      gq[j] = gp;
+      if (it0 + 32 * j >= items) continue;  // (whole warp)
+      if (it < items) {
+        while (S.gibase[gp + 1] <= it) ++gp;
+        const int ci = it - S.gibase[gp];
+        const int4 box = S.gbox[gp];
+        const int bx = box.w & 255, by = (box.w >> 8) & 255;
+        // ci = (iz * by + iy) * bx + ix with bx, by in {3, 4}
+        const int row = bx == 4 ? ci >> 2 : (ci * 43) >> 7;
+        const int ix = ci - row * bx;
+        const int iz = by == 4 ? row >> 2 : (row * 43) >> 7;
+        const int iy = row - iz * by;
+        const int x = box.x + ix, y = box.y + iy, z = box.z + iz;
+        if ((unsigned)x <= 255u && (unsigned)y <= 255u && (unsigned)z <= 255u) {
+          k24[j] = ((uint32_t)z << 16) | ((uint32_t)y << 8) | (uint32_t)x;
+          sl[j] = cell_home(k24[j], (uint32_t)S.gmask[gp]);
+          e2[j] = *reinterpret_cast<const ulonglong2*>(d.hash_tab + S.gtab[gp] + sl[j]);
+        }
+      }
+      gq[j] = gp;
+    }
+    unsigned long long e[4];
+    bool open[4];  // neither of the two slots settled the probe
+    bool any_open = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool m0 = e2[j].x == kCellEmpty || (uint32_t)(e2[j].x >> 40) == k24[j];
+      const bool m1 = e2[j].y == kCellEmpty || (uint32_t)(e2[j].y >> 40) == k24[j];
+      e[j] = m0 ? e2[j].x : e2[j].y;
+      open[j] = !m0 && !m1;
+      any_open = any_open || open[j];
+    }
+    if (__any_sync(kFull, any_open)) {  // (both slots taken by other cells: linear probing, the four sequences together)
+      for (;;) {
+        bool again = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (open[j]) {
+            const uint32_t mask = (uint32_t)S.gmask[gq[j]];
+            sl[j] = (sl[j] + 2) & mask;
+            e2[j] = *reinterpret_cast<const ulonglong2*>(d.hash_tab + S.gtab[gq[j]] + sl[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (open[j]) {
+            const bool m0 = e2[j].x == kCellEmpty || (uint32_t)(e2[j].x >> 40) == k24[j];
+            const bool m1 = e2[j].y == kCellEmpty || (uint32_t)(e2[j].y >> 40) == k24[j];
+            e[j] = m0 ? e2[j].x : e2[j].y;
+            open[j] = !m0 && !m1;
+            again = again || open[j];
+          }
+        }
+        if (!__any_sync(kFull, again)) break;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (it0 + 32 * j >= items) continue;  // (whole warp)
+      const uint32_t cnt = e[j] != kCellEmpty ? (uint32_t)(e[j] >> 24) & 0xFFFFu : 0u;
+      const bool hit = cnt > 0u;
+      uint32_t off = 0;
+      if (hit) off = (uint32_t)atomicAdd(&S.gtot[gq[j]], (int)cnt);
+      const unsigned hm = __ballot_sync(kFull, hit);
+      if (hit) {
+        const int h = nh + __popc(hm & lt);
+        if (h < kGHits) S.hits[h] = make_uint2((uint32_t)(e[j] & kNoBkt) | ((uint32_t)gq[j] << 24), (cnt << 16) | min(off, 0xFFFFu));
+      }
+      nh += __popc(hm);
+    }
+  }
+  bool fb = false, done = !valid, gate = false;
+  unsigned done_groups = 0u;
+  if (nh > kGHits) {  // (more occupied cells than the hit list holds: the whole warp searches per thread)
+    fb = valid;
+    done = true;
+    done_groups = kFull;
+  }
+  __syncwarp();
+  // ---- rounds: as many groups as fit the pool at a time
+  const float4 far4 = make_float4(3e18f, 3e18f, 3e18f, 0.f);
+#pragma unroll 1
+  for (;;) {
+    const bool pending = lane < ng && !((done_groups >> lane) & 1u);
+    const int v = pending ? S.gtot[lane] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += u;
+    }
+    const unsigned pend_mask = __ballot_sync(kFull, pending);
+    if (pend_mask == 0u) break;
+    const bool fits = pending && inc <= kGPool;
+    const unsigned fit_mask = __ballot_sync(kFull, fits);
+    if (fit_mask == 0u) {  // the first pending group alone exceeds the pool
+      const int first = __ffs(pend_mask) - 1;
+      if (!done && gnum == first) { fb = true; done = true; }
+      done_groups |= 1u << first;
+      continue;
+    }
+    if (lane < ng) S.gstart[lane] = fits ? inc - v : -1;
+    __syncwarp();
+    // ---- 2. copy the hit cells of this round's groups into the pool: two cells per lane and step, the loads of their
+    // first buckets in flight together
+#pragma unroll 1
+    for (int h0 = lane; h0 < nh; h0 += 64) {
+      uint2 hr[2];
+      int st[2], cnt[2], base[2];
+      float4 c[2][kBktE];
+      uint32_t nb[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int h = h0 + 32 * u;
+        st[u] = -1; cnt[u] = 0; base[u] = 0; nb[u] = kSentinel32;
+        hr[u] = make_uint2(0u, 0u);
+        if (h < nh) {
+          hr[u] = S.hits[h];
+          const int gq = (int)(hr[u].x >> 24);
+          st[u] = S.gstart[gq];
+          base[u] = S.gbkt[gq];
+          cnt[u] = st[u] >= 0 ? (int)(hr[u].y >> 16) : 0;
+        }
+        const uint32_t b0 = hr[u].x & kNoBkt;
+        const float4* __restrict__ p = d.bkt + (size_t)(base[u] + (int)b0) * kBktE;
+#pragma unroll
+        for (int e = 0; e < kBktE; ++e)
+          if (e < cnt[u]) c[u][e] = __ldg(p + e);
+        if (cnt[u] > kBktE) nb[u] = __ldg(d.bnext + base[u] + b0);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (cnt[u] == 0) continue;
+        float4* __restrict__ dst = S.pool + st[u] + (int)(hr[u].y & 0xFFFFu);
+        uint32_t b = hr[u].x & kNoBkt;
+        const uint32_t at0 = (uint32_t)(base[u] + (int)b) * kBktE;
+#pragma unroll
+        for (int e = 0; e < kBktE; ++e) {
+          if (e < cnt[u]) {
+            float4 v = c[u][e];
+            if (__float_as_uint(v.w) == kSentinel32) v = far4;  // removed entry
+            v.w = __uint_as_float(at0 + (uint32_t)e);
+            dst[e] = v;
+          }
+        }
+        int j = min(cnt[u], kBktE);
+        b = nb[u];
+#pragma unroll 1
+        while (j < cnt[u] && b != kSentinel32) {  // the rest of a longer chain
+          const uint32_t at1 = (uint32_t)(base[u] + (int)b) * kBktE;
+          const float4* __restrict__ p = d.bkt + at1;
+          const int m = min(cnt[u] - j, kBktE);
+          uint32_t nx = kSentinel32;
+          if (cnt[u] - j > kBktE) nx = __ldg(d.bnext + base[u] + b);
+#pragma unroll
+          for (int e = 0; e < kBktE; ++e) {
+            if (e < m) {
+              float4 v = __ldg(p + e);
+              if (__float_as_uint(v.w) == kSentinel32) v = far4;
+              v.w = __uint_as_float(at1 + (uint32_t)e);
+              dst[j + e] = v;
+            }
+          }
+          j += m;
+          b = nx;
+        }
+        for (; j < cnt[u]; ++j) dst[j] = far4;  // (a chain shorter than its count: never seen; keeps the pool defined)
+      }
+    }
+    __syncwarp();
+    // ---- 3. one pass over the group's candidates: the six smallest (truncated distance | position) keys
+    const int gs = done ? -1 : S.gstart[gnum];
+    if (gs >= 0) {
+      const float4* __restrict__ P = S.pool + gs;
+      const int U = S.gtot[gnum];
+      // position bits riding in a key: 8 for the usual group, kGIdxBits for the large ones (fewer near-ties)
+      const uint32_t kIdxMask = U <= 256 ? 0xFFu : (1u << kGIdxBits) - 1u;
+      float a0 = 1.0f, a1 = 1.0f, a2 = 1.0f, a3 = 1.0f, a4 = 1.0f, a5 = 1.0f;  // the search starts from the gate
+#pragma unroll 4
+      for (int i = 0; i < U; ++i) {
+        const float4 c = P[i];
+        const float dd = dist2(qx, qy, qz, c.x, c.y, c.z);
+        float t = __uint_as_float((__float_as_uint(dd) & ~kIdxMask) | (uint32_t)i), m;
+        m = fminf(a0, t); t = fmaxf(a0, t); a0 = m;
+        m = fminf(a1, t); t = fmaxf(a1, t); a1 = m;
+        m = fminf(a2, t); t = fmaxf(a2, t); a2 = m;
+        m = fminf(a3, t); t = fmaxf(a3, t); a3 = m;
+        m = fminf(a4, t); t = fmaxf(a4, t); a4 = m;
+        a5 = fminf(a5, t);
+      }
+      // Keys order like (d2 with its low bits cleared, position).  If the fifth and sixth key differ above the
+      // position bits, every candidate that was not kept is strictly farther than the five kept ones, so they ARE
+      // the five nearest; their exact order (d2, tag) is settled below.  Otherwise (a near-tie at the fifth place)
+      // the lane runs over the candidates once more and orders everything up to the fifth key's truncated distance
+      // exactly.
+      const uint32_t k4 = __float_as_uint(a4), k5 = __float_as_uint(a5);
+      if (k4 < 0x3F800000u) {  // five candidates below 1.0f: laserMapping.cpp:585 / :653
+        gate = true;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { r.key[k] = kKnnInit; r.at[k] = 0u; }
+        if ((k4 & ~kIdxMask) == (k5 & ~kIdxMask)) {
+          const uint32_t t4 = k4 & ~kIdxMask;
+#pragma unroll 1
+          for (int i = 0; i < U; ++i) {
+            const float4 c = P[i];
+            const float dd = dist2(qx, qy, qz, c.x, c.y, c.z);
+            if ((__float_as_uint(dd) & ~kIdxMask) > t4) continue;
+            const uint32_t at = __float_as_uint(c.w);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | __float_as_uint(__ldg(&d.bkt[at].w));
+            if (key < r.key[4]) {
+              r.key[4] = key;
+              r.at[4] = at;
+#pragma unroll
+              for (int q = 4; q > 0; --q) {
+                const unsigned long long lo = r.key[q - 1], hi = r.key[q];
+                const uint32_t alo = r.at[q - 1], ahi = r.at[q];
+                const bool sw = hi < lo;
+                r.key[q - 1] = sw ? hi : lo;
+                r.key[q] = sw ? lo : hi;
+                r.at[q - 1] = sw ? ahi : alo;
+                r.at[q] = sw ? alo : ahi;
+              }
+            }
+          }
+          atomicAdd(d.knn_stats + 1, 1ull);
+        } else {
+          const float ak[5] = {a0, a1, a2, a3, a4};
+          uint32_t db[5], atk[5];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const float4 c = P[__float_as_uint(ak[j]) & kIdxMask];
+            atk[j] = __float_as_uint(c.w);
+            db[j] = __float_as_uint(dist2(qx, qy, qz, c.x, c.y, c.z));
+          }
+          bool tie = false;  // the tags only matter between equal distances
+#pragma unroll
+          for (int j = 1; j < 5; ++j)
+#pragma unroll
+            for (int i = 0; i < j; ++i) tie = tie || db[i] == db[j];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const uint32_t at = atk[j];
+            const uint32_t tag = tie ? __float_as_uint(__ldg(&d.bkt[at].w)) : 0u;
+            const unsigned long long key = ((unsigned long long)db[j] << 32) | tag;
+            r.key[4] = key;  // (always below the seed in slot 4: fewer than five real keys so far)
+            r.at[4] = at;
+#pragma unroll
+            for (int i = 4; i > 0; --i) {
+              const unsigned long long lo = r.key[i - 1], hi = r.key[i];
+              const uint32_t alo = r.at[i - 1], ahi = r.at[i];
+              const bool sw = hi < lo;
+              r.key[i - 1] = sw ? hi : lo;
+              r.key[i] = sw ? lo : hi;
+              r.at[i - 1] = sw ? ahi : alo;
+              r.at[i] = sw ? alo : ahi;
+            }
+          }
+        }
+      }
+      done = true;
+    }
+    done_groups |= fit_mask;
+    __syncwarp();  // the pool is reused by the next round
+  }
+  // ---- lanes the grouped search could not serve
+  if (__any_sync(kFull, fb)) {
+    if (fb) {
+      KnnStage& st = *reinterpret_cast<KnnStage*>(S.pool);
+      knn5_cells(d, g, origin, qx, qy, qz, r, st);
+      gate = knn_d2(r, 4) < 1.0f;
+      atomicAdd(d.knn_stats, 1ull);
+    }
+    __syncwarp();
+  }
+  return gate;
+}
+
+__global__ void __launch_bounds__(kTile, S2M_K4G_MINB) knn_group_kernel(Dev d, int outer, int n_sorted) {
+  extern __shared__ __align__(16) unsigned char knn_group_smem[];
+  KnnGroupSmem& S = reinterpret_cast<KnnGroupSmem*>(knn_group_smem)[threadIdx.x >> 5];
+  const int B = d.B, lane = threadIdx.x & 31;
+  const int total = (n_sorted + 31) >> 5;
+  // The next work unit (32 consecutive points of the block-sorted order, taken from a device-wide ticket) is
+  // fetched while the current one is searched.
+  int chunk = 0;
+  if (lane == 0) chunk = atomicAdd(d.knn_ticket, 1);
+  chunk = __shfl_sync(kFull, chunk, 0);
+  uint32_t skey = kSentinel32, spos = 0u;
+  if (chunk < total && (chunk << 5) + lane < n_sorted) { skey = d.qs_key2[(chunk << 5) + lane]; spos = d.qs_val2[(chunk << 5) + lane]; }
+  float4 sp = d.ds_pts[spos];
+  while (chunk < total) {
+    int nchunk = 0;
+    if (lane == 0) nchunk = atomicAdd(d.knn_ticket, 1);
+    nchunk = __shfl_sync(kFull, nchunk, 0);
+    uint32_t nkey = kSentinel32, npos = 0u;
+    if (nchunk < total && (nchunk << 5) + lane < n_sorted) { nkey = d.qs_key2[(nchunk << 5) + lane]; npos = d.qs_val2[(nchunk << 5) + lane]; }
+    const float4 np = d.ds_pts[npos];
+    bool valid = skey != kSentinel32;
+    int g = 0, slot = 0, cx = 0, cy = 0, cz = 0;
+    const int pos_q = (int)spos;
+    float w[3] = {0.f, 0.f, 0.f};
+    int origin[3] = {0, 0, 0};
+    if (valid) {
+      g = (int)(skey >> 24);
+      slot = g >= B ? g - B : g;
+      const float4 p = sp;
+      xf_point(d.lm[slot].x, p.x, p.y, p.z, w);
+      origin[0] = d.desc[slot].origin[0]; origin[1] = d.desc[slot].origin[1]; origin[2] = d.desc[slot].origin[2];
+      if (d.shard_world > 1 && !(w[0] >= d.shard_lo && w[0] < d.shard_hi)) {
+        d.nbr[6 * (size_t)pos_q] = 0;  // sharded map: this query is answered by the rank whose x-slab holds it
+        valid = false;
+      } else {
+        const float fx = floorf(w[0]) - (float)origin[0], fy = floorf(w[1]) - (float)origin[1], fz = floorf(w[2]) - (float)origin[2];
+        const bool near = fabsf(fx) < 1e6f && fabsf(fy) < 1e6f && fabsf(fz) < 1e6f && cell_near_block((int)fx, (int)fy, (int)fz);
+        if (!near) {
+          d.nbr[6 * (size_t)pos_q] = 0;  // no map cell within reach: the gate fails
+          valid = false;
+        } else {
+          cx = (int)fx; cy = (int)fy; cz = (int)fz;
+        }
+      }
+    }
+    Knn5 r;
+    const bool gate = knn5_group(d, S, valid, g, origin, cx, cy, cz, w[0], w[1], w[2], r);
+    if (valid) {
+      int* nb = d.nbr + 6 * (size_t)pos_q;
+      nb[0] = gate ? 1 : 0;
+      if (gate) {  // entry numbers in d.bkt of the five neighbours, nearest first
+#pragma unroll
+        for (int kk = 0; kk < 5; ++kk) nb[1 + kk] = (int)r.at[kk];
+      }
+    }
+    chunk = nchunk; skey = nkey; spos = npos; sp = np;
+  }
+}
+
 constexpr int kSumRows = 30;  // 28 sums + n_edge + n_plane, transposed through shared memory
 template <bool kTrace>
 __global__ void __launch_bounds__(kTile, S2M_K4B_MINB) fit_kernel(Dev d, int outer, int cur) {
@@ -898,7 +1429,7 @@ __global__ void __launch_bounds__(kTile, S2M_K4B_MINB) fit_kernel(Dev d, int out
     const int* nbp = d.nbr + 6 * (size_t)di;
     const int head = nbp[0];
     gate = head & 1;
-    ncand = head >> 1;
+    ncand = d.count_cand ? d.cand27[di] : 0;
     p = d.ds_pts[di];
     if (gate) {
       float nb[5][3];
@@ -2253,17 +2784,39 @@ int launch_guard(const Dev& d, cudaStream_t s) {
 }
 // One association (rows P..Q of one outer iteration) for every optimised slot: K4a with `knn_blocks`
 // persistent blocks sharing a device-wide tile ticket (the caller zeroes d.knn_ticket), then K4b.
-int launch_associate(const Dev& d, int outer, int cur, int knn_blocks, int fit_blocks, bool trace, cudaStream_t s) {
+int launch_associate(const Dev& d, int outer, int cur, int knn_blocks, int fit_blocks, int n_ds, bool trace, cudaStream_t s) {
   if (knn_blocks <= 0 || fit_blocks <= 0) return 0;
   dim3 gb(fit_blocks, d.B);
-  if (trace) {
-    knn_kernel<true><<<knn_blocks, kTile, 0, s>>>(d, outer);
-    fit_kernel<true><<<gb, kTile, 0, s>>>(d, outer, cur);
-  } else {
-    knn_kernel<false><<<knn_blocks, kTile, 0, s>>>(d, outer);
-    fit_kernel<false><<<gb, kTile, 0, s>>>(d, outer, cur);
+#if S2M_KNN_GROUP
+  constexpr size_t smem = sizeof(KnnGroupSmem) * (kTile / 32);
+  static bool armed = false;  // (one device per process)
+  if (!armed) {
+    if (cudaFuncSetAttribute(knn_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    armed = true;
   }
+  knn_group_kernel<<<knn_blocks, kTile, smem, s>>>(d, outer, n_ds);
+#else
+  knn_kernel<false><<<knn_blocks, kTile, 0, s>>>(d, outer);
+#endif
+  if (trace) fit_kernel<true><<<gb, kTile, 0, s>>>(d, outer, cur);
+  else fit_kernel<false><<<gb, kTile, 0, s>>>(d, outer, cur);
   return 2;
+}
+// profiling: the map points in every query's 27 cells (the roofline's byte count)
+int launch_count27(const Dev& d, int n_ds, cudaStream_t s) {
+  if (n_ds <= 0) return 0;
+  count27_kernel<<<cdiv(n_ds, 256), 256, 0, s>>>(d, n_ds);
+  return 1;
+}
+// Once per frame, before the first association: the scan points bucketed by (segment, 2 m block) for the grouped search.
+int launch_query_sort(const Dev& d, int n_ds, cudaStream_t s) {
+  if (n_ds <= 0) return 0;
+  int k = 0;
+#if S2M_KNN_GROUP
+  qgroup_kernel<<<d.G, 1024, 0, s>>>(d);
+  k += 1;
+#endif
+  return k;
 }
 // The LM solve that follows it (<= 4 iterations) in one launch: a cluster of four CTAs per slot.
 int launch_solve(const Dev& d, int outer, bool from_units, cudaStream_t s) {
