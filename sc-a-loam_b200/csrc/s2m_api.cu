@@ -19,6 +19,7 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <sched.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -152,6 +153,7 @@ struct s2m_ctx {
   std::vector<LaneWorker*> workers;
   std::vector<cudaEvent_t> lane_done;   // [2 frames in flight][lanes]
   cudaEvent_t lane_start[2] = {nullptr, nullptr};
+  cudaEvent_t ev_done = nullptr;        // blocking-sync stand-in for cudaStreamSynchronize (host_waits_block)
   std::deque<std::unique_ptr<PendingFrame>> in_flight;
   int frame_seq = 0;
   int lane_batch = 0;
@@ -206,6 +208,22 @@ struct s2m_ctx {
   double ar_ms = 0;
   long long ar_count = 0;
 };
+
+// How the host threads wait for the device (three short waits per frame and lane): S2M_SYNC = spin (default: the
+// driver's own policy, lowest latency; measured fine down to 4 cores for 6 lanes, gpurun_out/g10_sync.log) | block
+// (the waits sleep on blocking-sync events: for hosts with fewer cores than ranks).
+static thread_local int tl_parent_lanes = 0;  // lanes of the multi-lane context whose sub-contexts are being created
+static bool host_waits_block(int lanes) {
+  (void)lanes;
+  const char* e = getenv("S2M_SYNC");
+  return e && !strcmp(e, "block");
+}
+// wait for everything enqueued on the context's stream so far
+static cudaError_t wait_stream(s2m_ctx* ctx) {
+  if (!ctx->ev_done) return cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaEventRecord(ctx->ev_done, ctx->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->ev_done);
+}
 
 static int prof_mark(s2m_ctx* ctx, int phase) {
   if (!ctx->profiling) return 0;
@@ -327,6 +345,7 @@ extern "C" void s2m_destroy(s2m_ctx* ctx) {
   if (ctx->h_err) cudaFreeHost(ctx->h_err);
   if (ctx->h_dsoff) cudaFreeHost(ctx->h_dsoff);
   if (ctx->ev_ds) cudaEventDestroy(ctx->ev_ds);
+  if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
   if (ctx->h_bbox) cudaFreeHost(ctx->h_bbox);
   if (ctx->h_lpcnt) cudaFreeHost(ctx->h_lpcnt);
   if (ctx->ev_bbox) cudaEventDestroy(ctx->ev_bbox);
@@ -380,10 +399,12 @@ static int create_impl(s2m_ctx* ctx) {
   CK(cudaMallocHost((void**)&ctx->h_out, sizeof(SlotOut) * B));
   CK(cudaMallocHost((void**)&ctx->h_err, sizeof(int)));
   CK(cudaMallocHost((void**)&ctx->h_dsoff, sizeof(int) * (2 * kMaxBatch + 1)));
-  CK(cudaEventCreateWithFlags(&ctx->ev_ds, cudaEventDisableTiming));
+  const unsigned wait_flags = cudaEventDisableTiming | (host_waits_block(std::max(1, tl_parent_lanes)) ? cudaEventBlockingSync : 0);
+  CK(cudaEventCreateWithFlags(&ctx->ev_ds, wait_flags));
+  if (wait_flags & cudaEventBlockingSync) CK(cudaEventCreateWithFlags(&ctx->ev_done, wait_flags));
   CK(cudaMallocHost((void**)&ctx->h_bbox, sizeof(uint32_t) * 6 * 2 * kMaxBatch));
   CK(cudaMallocHost((void**)&ctx->h_lpcnt, sizeof(int) * 4 * kMaxBatch));
-  CK(cudaEventCreateWithFlags(&ctx->ev_bbox, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->ev_bbox, wait_flags));
   CK(cudaMallocHost((void**)&ctx->h_lm, sizeof(LmState) * 2 * B));
   std::memset(ctx->ht, 0, sizeof(HostTables));
   if (dev_alloc(ctx, &ctx->d_ht, 1)) return S2M_ERR_CUDA;
@@ -536,12 +557,14 @@ extern "C" int s2m_create(const s2m_params* p, s2m_ctx** out) {
       int rc = S2M_OK;
       for (int i = 0; i * ctx->lane_batch < p->batch && rc == S2M_OK; ++i) {
         s2m_params cp = *p;
+        tl_parent_lanes = p->lanes;
         cp.lanes = 0;
         cp.batch = std::min(ctx->lane_batch, p->batch - i * ctx->lane_batch);
         s2m_ctx* ch = nullptr;
         rc = s2m_create(&cp, &ch);
         if (rc == S2M_OK) ctx->children.push_back(ch);
       }
+      tl_parent_lanes = 0;
       if (rc == S2M_OK && (cudaSetDevice(p->device) != cudaSuccess ||
                            cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
                            cudaEventCreateWithFlags(&ctx->lane_start[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -679,7 +702,7 @@ static int plan_index_rebuild(s2m_ctx* ctx, const std::vector<char>& rebuild, in
 static int finish_call(s2m_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->h_out, ctx->d.out, sizeof(SlotOut) * ctx->d.B, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_err, ctx->d.err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(wait_stream(ctx));
   CK(cudaGetLastError());
   if (*ctx->h_err != 0) {
     int e = *ctx->h_err;
