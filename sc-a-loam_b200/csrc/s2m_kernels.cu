@@ -640,21 +640,6 @@ __device__ __forceinline__ int knn5_cells(const Dev& d, int g, const int origin[
   return total;
 }
 
-__global__ void knn_debug_kernel(Dev d, int cur, int g, const float* __restrict__ q, int n, int32_t* __restrict__ idx,
-                                 float* __restrict__ d2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Knn5 r;
-  __shared__ KnnStage st[4];  // (launched with 128 threads)
-  knn5_cells(d, g, d.desc[seg_slot(d, g)].origin, q[3 * i], q[3 * i + 1], q[3 * i + 2], r, st[threadIdx.x >> 5]);
-  const bool ok = knn_d2(r, 4) < 1.0f;  // the reference's gate; beyond it the bounded search is not exact
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    idx[5 * i + k] = ok ? tag_to_local(d, cur, g, knn_tag(r, k)) : -1;
-    d2[5 * i + k] = ok ? knn_d2(r, k) : INFINITY;
-  }
-}
-
 // ----------------------------------------------------------------------------
 // Block-level accumulation.  Each thread adds the 28 sums of its own queries into
 // its column of a shared array; the block reduces the columns once, in a fixed
@@ -878,25 +863,26 @@ __global__ void __launch_bounds__(kTile, S2M_K4A_MINB) knn_kernel(Dev d, int out
 // ----------------------------------------------------------------------------
 // K4a, grouped form (the default): queries that share a 2 m block of cells search together.
 //
-// The scan points are sorted once per frame by (segment, 2 m block of the cell under the initial guess)
-// (qsort_key_kernel + one radix sort), so the 32 queries a warp takes are spatial neighbours.  Lanes whose
-// ACTUAL cells (this outer iteration's pose) lie in the same block form a group (match.any); the group's
-// candidate set is every map point in the box of cells [min cell - 1, max cell + 1] (3..4 cells per axis), a
-// superset of each member's 27 cells -- points outside a query's 27 cells are at least 1 m away in the
-// reference's float arithmetic and can never pass the d2[4] < 1 gate, so the result is unchanged.
-//   1. the warp probes the cells of all its groups' boxes, one (group, cell) item per lane and step;
-//      occupied cells go to a hit list, their point counts to per-group totals (shared-memory atomics);
+// The scan points are bucketed once per frame by (segment, 2 m block of the cell under the initial guess)
+// (qgroup_kernel), so the 32 queries a warp takes contain whole blocks.  Lanes whose ACTUAL cells (this outer
+// iteration's pose) lie in the same block form a group (match.any); the group's candidate set is every map
+// point in the box of cells [lowest cell - 1, highest cell + 1] (3..4 cells per axis), a superset of each
+// member's 27 cells -- points outside a query's 27 cells are at least 1 m away in the reference's float
+// arithmetic and can never pass the d2[4] < 1 gate, so the result is unchanged.
+//   1. the warp probes the cells of all its groups' boxes, four (group, cell) items per lane and step, each
+//      probe one 16-byte load of the first two slots of the cell's probe sequence; occupied cells go to a hit
+//      list, their point counts to per-group totals (shared-memory atomics);
 //   2. the groups' candidate ranges are laid out in the warp's shared-memory pool (prefix sum; groups that
 //      do not fit wait for the next round) and the lanes copy the hit cells' bucket chains into it;
-//   3. pass 1: every lane runs over ITS GROUP's candidates -- one broadcast 16-byte shared load per
-//      candidate, the reference's float distance, and a branch-free five-deep min/max network that keeps the
-//      five smallest distances (seeded with the gate, 1.0f);
-//   4. pass 2: the candidates with d2 <= the fifth distance are appended to a short per-lane list (exactly
-//      five unless distances tie at the fifth place), their tags fetched, and the list ordered by the
-//      reference's (d2, index) rule as 64-bit keys (d2 bits, tag).
+//   3. every lane runs over ITS GROUP's candidates -- one broadcast 16-byte shared load per candidate, the
+//      reference's float distance, its low bits replaced by the candidate's position in the range, and a
+//      branch-free six-deep min/max network on those keys (seeded with the gate, 1.0f);
+//   4. if the fifth and sixth key differ above the position bits the five kept candidates are the five nearest
+//      and are put into the reference's (d2, index) order as 64-bit keys (exact d2 bits, tag); otherwise the
+//      lane runs over the range once more and orders everything up to the fifth key exactly.
 // No loop depends on a lane's own data except through its group, so the lanes of a warp stay together.
-// Lanes whose group is too large for the pool, or that see more than kGList ties, fall back to the
-// thread-per-query search (knn5_cells); d.knn_stats counts them.
+// Lanes whose group is too large for the pool (or a warp with more occupied cells than the hit list holds)
+// fall back to the thread-per-query search (knn5_cells); d.knn_stats counts them.
 // ----------------------------------------------------------------------------
 #ifndef S2M_KNN_POOL
 #define S2M_KNN_POOL 512
@@ -1342,6 +1328,44 @@ __device__ __forceinline__ bool knn5_group(const Dev& d, KnnGroupSmem& S, bool v
     __syncwarp();
   }
   return gate;
+}
+
+// s2m_debug_knn: world-frame queries against segment g.  Runs the grouped search (the production path; groups form
+// among whatever queries share a warp) AND the thread-per-query search; the two exact searches must agree bit for
+// bit, else the call fails with S2M_ERR_INTERNAL.
+__global__ void __launch_bounds__(kTile) knn_debug_kernel(Dev d, int cur, int g, const float* __restrict__ q, int n,
+                                                          int32_t* __restrict__ idx, float* __restrict__ d2) {
+  extern __shared__ __align__(16) unsigned char knn_group_smem[];
+  KnnGroupSmem& S = reinterpret_cast<KnnGroupSmem*>(knn_group_smem)[threadIdx.x >> 5];
+  __shared__ KnnStage st[kTile / 32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int* o = d.desc[seg_slot(d, g)].origin;
+  const int origin[3] = {o[0], o[1], o[2]};
+  bool valid = i < n;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  int cx = 0, cy = 0, cz = 0;
+  if (valid) {
+    qx = q[3 * i]; qy = q[3 * i + 1]; qz = q[3 * i + 2];
+    const float fx = floorf(qx) - (float)origin[0], fy = floorf(qy) - (float)origin[1], fz = floorf(qz) - (float)origin[2];
+    valid = fabsf(fx) < 1e6f && fabsf(fy) < 1e6f && fabsf(fz) < 1e6f && cell_near_block((int)fx, (int)fy, (int)fz);
+    if (valid) { cx = (int)fx; cy = (int)fy; cz = (int)fz; }
+  }
+  Knn5 r, r2;
+  const bool ok = knn5_group(d, S, valid, g, origin, cx, cy, cz, qx, qy, qz, r);
+  if (i >= n) return;
+  knn5_cells(d, g, origin, qx, qy, qz, r2, st[threadIdx.x >> 5]);
+  const bool ok2 = knn_d2(r2, 4) < 1.0f;  // the reference's gate; beyond it the bounded search is not exact
+  bool same = ok == ok2;
+  if (ok && ok2) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) same = same && knn_d2(r, k) == knn_d2(r2, k) && r.at[k] == r2.at[k];
+  }
+  if (!same) set_err(d, -7);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    idx[5 * i + k] = ok ? tag_to_local(d, cur, g, __float_as_uint(d.bkt[r.at[k]].w)) : -1;
+    d2[5 * i + k] = ok ? knn_d2(r, k) : INFINITY;
+  }
 }
 
 __global__ void __launch_bounds__(kTile, S2M_K4G_MINB) knn_group_kernel(Dev d, int outer, int n_sorted) {
@@ -2936,7 +2960,9 @@ int launch_map_update(const Dev& d, int cur, int n_ds, int total_lp, int total_s
 int launch_knn_debug(const Dev& d, int cur, int slot, int cls, const float* d_q, int n, int32_t* d_idx, float* d_d2,
                      cudaStream_t s) {
   if (n <= 0) return 0;
-  knn_debug_kernel<<<cdiv(n, 128), 128, 0, s>>>(d, cur, cls * d.B + slot, d_q, n, d_idx, d_d2);
+  constexpr size_t smem = sizeof(KnnGroupSmem) * (kTile / 32);
+  if (cudaFuncSetAttribute(knn_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  knn_debug_kernel<<<cdiv(n, kTile), kTile, smem, s>>>(d, cur, cls * d.B + slot, d_q, n, d_idx, d_d2);
   return 1;
 }
 int launch_transform_cloud(const double* d_pose7, const float4* in, float4* out, int n, cudaStream_t s) {

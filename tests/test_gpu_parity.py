@@ -131,6 +131,42 @@ def test_knn_bit_exact_on_uploaded_map(s2m, seq_hdl):
     assert ties <= 2
 
 
+def test_knn_ties_on_a_lattice_map(s2m, built):
+    """Row K on a map whose points sit on a regular lattice: every query has many candidates at exactly equal float
+    distances, including at the fifth place, so the (d2, index) tie rule decides both WHICH five neighbours are
+    returned and their order.  Queries come clustered (whole groups of the grouped search share a 2 m block) and
+    spread out; s2m_debug_knn also cross-checks the grouped search against the thread-per-query one on the device."""
+    g = np.arange(-6.0, 6.01, 0.5, dtype=np.float32)
+    X, Y, Z = np.meshgrid(g + 3.0, g - 2.0, g[:9] + 1.0, indexing="ij")
+    lat = np.c_[X.ravel(), Y.ravel(), Z.ravel(), np.zeros(X.size)].astype(np.float32)
+    rng = np.random.default_rng(11)
+    cm = lat[rng.permutation(len(lat))]          # arrival order decides the index inside a cube's cloud
+    sm = lat[::3].copy()
+    R = s2m.Registrar(0.4, 0.8)
+    O = oracle.Oracle(0.4, 0.8)
+    assert R.map_upload(cm, sm) == 0 and O.map_upload(cm, sm) == 0
+    centre = np.array([3.0, -2.0, 1.0])
+    # lattice nodes, cell centres and face centres (maximal ties), jittered points, far points
+    nodes = lat[rng.integers(0, len(lat), 1500), :3]
+    q = np.r_[nodes, nodes + np.float32(0.25), nodes + np.array([0.25, 0.0, 0.0], np.float32),
+              nodes + rng.normal(size=nodes.shape).astype(np.float32) * 0.1,
+              rng.uniform(-40, 40, (300, 3))].astype(np.float32)
+    for cls in (0, 1):
+        lg, lo = R.local_map(cls, centre), O.local_map(cls, centre)
+        assert np.array_equal(bits(lg), bits(lo)) and len(lg) > 1000
+        for order in (np.arange(len(q)), np.lexsort((q[:, 0], q[:, 1], q[:, 2]))):
+            ig, dg = R.debug_knn(cls, centre, q[order])
+            ib, db = O.debug_knn(cls, centre, q[order], method=0)
+            gate = db[:, 4] < 1.0
+            assert gate.sum() > 1000
+            assert np.array_equal(gate, dg[:, 4] < 1.0)
+            assert np.array_equal(ig[gate], ib[gate])
+            assert np.array_equal(bits(dg[gate]), bits(db[gate]))
+            if cls == 0:
+                tied_fifth = db[gate][:, 3] == db[gate][:, 4]
+                assert tied_fifth.sum() > 500      # the tie rule really is exercised
+
+
 @pytest.mark.parametrize("sensor", ["hdl", "vlp", "os1"])
 def test_registration_matches_oracle_on_uploaded_map(s2m, seq_hdl, seq_vlp, seq_os1, sensor):
     """One full registration (rows A..W) from identical maps: kNN of the first outer iteration
