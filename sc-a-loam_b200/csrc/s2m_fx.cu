@@ -34,7 +34,6 @@ constexpr int kRings = 64;        // ring slots per sweep (N_SCANS <= 64, scanRe
 constexpr int kSectors = 6;       // :295
 constexpr int kSecPerScan = kRings * kSectors;
 constexpr int kLess = 20, kSharp = 2, kFlat = 4;  // :317-327, :366
-constexpr int kWarps = 4;
 
 struct Dev {
   int B, sensor;
@@ -324,83 +323,224 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
   }
   return v;
 }
-__global__ void __launch_bounds__(32 * kWarps) select_kernel(Dev d) {
+// The picks of one sector (:305-394) on a private state array `ps` (ps[0] = the sector's first point, five points of
+// margin on either side; bit0 picked, bit1 gap-to-previous, bits 2-3 label).  One warp.
+__device__ __forceinline__ void select_sector(const Dev& d, unsigned char* ps, const float* __restrict__ cv, int n, int sec, int base,
+                                              int lane) {
+  int n_less = 0, n_sharp = 0, n_flat = 0;
+  for (int pick = 0; pick < kLess; ++pick) {  // :305-356
+    unsigned long long best = 0ull;
+    for (int t = lane; t < n; t += 32) {
+      const float c = cv[t];
+      if ((double)c > 0.1 && !(ps[t] & 1)) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | (uint32_t)t;
+        best = key > best ? key : best;
+      }
+    }
+    best = warp_max_u64(best);
+    if (best == 0ull) break;
+    if (lane == 0) {
+      const int li = (int)(uint32_t)best;
+      if (pick < kSharp) {
+        ps[li] |= 2 << 2;
+        d.i_sharp[sec * kSharp + n_sharp++] = base + li;
+      } else {
+        ps[li] |= 1 << 2;
+      }
+      d.i_less[sec * kLess + n_less++] = base + li;
+      ps[li] |= 1;
+      suppress(ps, li);
+    }
+    __syncwarp();
+  }
+  for (int pick = 0; pick < kFlat; ++pick) {  // :358-394
+    unsigned long long best = ~0ull;
+    for (int t = lane; t < n; t += 32) {
+      const float c = cv[t];
+      if ((double)c < 0.1 && !(ps[t] & 1)) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | (uint32_t)t;
+        best = key < best ? key : best;
+      }
+    }
+    best = warp_min_u64(best);
+    if (best == ~0ull) break;
+    if (lane == 0) {
+      const int li = (int)(uint32_t)best;
+      ps[li] |= 3 << 2;
+      d.i_flat[sec * kFlat + n_flat++] = base + li;
+      if (pick < kFlat - 1) {  // the fourth flat point ends the walk before it is marked (:367-370)
+        ps[li] |= 1;
+        suppress(ps, li);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) { d.n_sharp[sec] = n_sharp; d.n_less[sec] = n_less; d.n_flat[sec] = n_flat; }
+}
+// The same picks with the sector's curvatures held in registers (lane l owns points l, l + 32, ...; KMAX per lane)
+// and the "already picked / suppressed" state as two bit masks per lane: a pick is two warp-wide redux operations
+// (largest curvature, then the position among equals), and the neighbour suppression is computed by every lane from
+// the gap flags (`gap`, shared memory, gap[t] <-> point t of the sector, t in [-5, n + 5)) instead of by one lane.
+// in_marks: marks an earlier sector left on points 0..4.  Returns through om / pk the marks left on the next
+// sector's first five points and which of the own first five points were picked.
+template <int KMAX>
+__device__ __forceinline__ void select_sector_reg(const Dev& d, const unsigned char* gap, const float* __restrict__ cv, int n, int sec,
+                                                  int base, int lane, unsigned in_marks, unsigned& om, unsigned& pk, int& n_sharp_out,
+                                                  int& n_less_out, int& n_flat_out) {
+  uint32_t cb[KMAX];
+  uint32_t av_sharp = 0u, av_flat = 0u;  // bit k: point lane + 32 k is a corner / flat candidate and still free
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int t = lane + 32 * k;
+    cb[k] = 0u;
+    if (t < n) {
+      const float c = cv[t];
+      cb[k] = __float_as_uint(c);  // curvatures are sums of squares: non-negative, the bit pattern orders like the value
+      const bool free_pt = !(t < 5 && ((in_marks >> t) & 1u));
+      if (free_pt && (double)c > 0.1) av_sharp |= 1u << k;
+      if (free_pt && (double)c < 0.1) av_flat |= 1u << k;
+    }
+  }
+  om = 0u; pk = 0u;
+  int n_less = 0, n_sharp = 0, n_flat = 0;
+  // the neighbours a pick at li suppresses (:332-352): the run [lo, hi] around li that no gap interrupts
+  auto exclude = [&](int li) {
+    uint32_t win = 0u;  // bit i: a gap in front of point li - 5 + i (eleven independent shared-memory loads)
+#pragma unroll
+    for (int i = 0; i < 11; ++i) win |= (uint32_t)((gap[li - 5 + i] >> 1) & 1) << i;
+    const uint32_t fw = (win >> 6) & 31u;  // gaps in front of li+1 .. li+5: the forward walk stops at the first
+    const uint32_t bw = (win >> 1) & 31u;  // gaps in front of li-4 .. li: the backward walk stops at the first from li down
+    const int hi = li + (fw ? __ffs((int)fw) - 1 : 5);
+    const int lo = li - (bw ? __clz((int)bw) - 27 : 5);
+    const int x = lo + ((lane - lo) & 31);  // the one point of [lo, hi] this lane owns, if any
+    if (x <= hi && x >= 0 && x < n) { av_sharp &= ~(1u << (x >> 5)); av_flat &= ~(1u << (x >> 5)); }
+    for (int p2 = n; p2 <= hi; ++p2) om |= 1u << (p2 - n);
+  };
+  for (int pick = 0; pick < kLess; ++pick) {  // :305-356: largest (curvature, index) first
+    uint32_t bv = 0u;
+    int bk = 0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (((av_sharp >> k) & 1u) && cb[k] >= bv) { bv = cb[k]; bk = k; }
+    const uint32_t gmax = __reduce_max_sync(0xffffffffu, bv);
+    if (gmax == 0u) break;
+    const int li = __reduce_max_sync(0xffffffffu, (bv == gmax && ((av_sharp >> bk) & 1u)) ? lane + 32 * bk : -1);
+    if (lane == 0) {
+      if (pick < kSharp) d.i_sharp[sec * kSharp + n_sharp] = base + li;
+      d.i_less[sec * kLess + n_less] = base + li;
+    }
+    if (pick < kSharp) ++n_sharp;
+    ++n_less;
+    if (li < 5) pk |= 1u << li;
+    exclude(li);
+  }
+  for (int pick = 0; pick < kFlat; ++pick) {  // :358-394: smallest (curvature, index) first
+    uint32_t bv = 0xFFFFFFFFu;
+    int bk = 0;
+#pragma unroll
+    for (int k = KMAX - 1; k >= 0; --k)
+      if (((av_flat >> k) & 1u) && cb[k] <= bv) { bv = cb[k]; bk = k; }
+    const bool have = av_flat != 0u;
+    const uint32_t gmin = __reduce_min_sync(0xffffffffu, have ? bv : 0xFFFFFFFFu);
+    if (__ballot_sync(0xffffffffu, have) == 0u) break;
+    const int li = __reduce_min_sync(0xffffffffu, (have && bv == gmin) ? lane + 32 * bk : 0x7FFFFFFF);
+    if (lane == 0) d.i_flat[sec * kFlat + n_flat] = base + li;
+    ++n_flat;
+    if (li < 5) pk |= 1u << li;
+    if (pick < kFlat - 1) exclude(li);  // the fourth flat point ends the walk before it is marked (:367-370)
+  }
+  if (lane == 0) { d.n_sharp[sec] = n_sharp; d.n_less[sec] = n_less; d.n_flat[sec] = n_flat; }
+  n_sharp_out = n_sharp; n_less_out = n_less; n_flat_out = n_flat;
+}
+// One block per (sweep, ring), one warp per sector.  The reference walks the six sectors of a ring in order, and
+// the only thing a sector hands to the next one is the neighbour-suppression marks its picks leave on the next
+// sector's first five points (:332-339).  The six warps therefore run their sectors AT THE SAME TIME, assuming no
+// incoming marks; afterwards the sectors are validated in order: if the marks sector j really leaves do not touch
+// a point sector j+1 picked, excluding those points from j+1's arg-max/arg-min walks would not have changed any
+// pick, so its result stands -- otherwise sector j+1 is redone with the marks set (and the check moves on with its
+// new outgoing marks).  Rings whose sectors exceed the staging (more than kSecCap points) or are shorter than the
+// reach of a mark take the serial walk on the global state array.
+constexpr int kSecCap = 1000, kSecPad = 5;
+__global__ void __launch_bounds__(32 * kSectors) select_kernel(Dev d) {
+  __shared__ unsigned char priv[kSectors][kSecCap + 2 * kSecPad + 6];
+  __shared__ unsigned out_marks[kSectors], picked5[kSectors];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rid = blockIdx.x * kWarps + w;
-  if (rid >= d.B * kRings) return;
+  const int rid = blockIdx.x;
   const int rs = d.ring_off[rid], re = d.ring_off[rid + 1], len = re - rs;
   const int first = rs + 5, last = re - 6;
   if (last - first < 6) {  // :294
-    if (lane < kSectors) d.n_sharp[rid * kSectors + lane] = d.n_less[rid * kSectors + lane] = d.n_flat[rid * kSectors + lane] = 0;
-    if (lane == 0) d.lf_cnt[rid] = 0;
+    if (w == 0) {
+      if (lane < kSectors) d.n_sharp[rid * kSectors + lane] = d.n_less[rid * kSectors + lane] = d.n_flat[rid * kSectors + lane] = 0;
+      if (lane == 0) d.lf_cnt[rid] = 0;
+    }
     return;
   }
   unsigned char* st = d.state + rs;
-  for (int t = lane; t < len; t += 32) st[t] = d.gapf[rs + t] ? 2 : 0;
-  __syncwarp();
-  for (int j = 0; j < kSectors; ++j) {
-    const int sp = first + (last - first) * j / 6, ep = first + (last - first) * (j + 1) / 6 - 1;
-    const int n = ep - sp + 1;
-    const int sec = rid * kSectors + j;
-    const float* __restrict__ cv = d.curv + sp;
-    unsigned char* ss = st + (sp - rs);
-    int n_less = 0, n_sharp = 0, n_flat = 0;
-    for (int pick = 0; pick < kLess; ++pick) {  // :305-356
-      unsigned long long best = 0ull;
-      for (int t = lane; t < n; t += 32) {
-        const float c = cv[t];
-        if ((double)c > 0.1 && !(ss[t] & 1)) {
-          const unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | (uint32_t)t;
-          best = key > best ? key : best;
-        }
+  const int sp = first + (last - first) * w / 6, ep = first + (last - first) * (w + 1) / 6 - 1;
+  const int n = ep - sp + 1;
+  // every sector of the ring fits the staging and has at least five points (marks reach one sector ahead at most)
+  const bool staged = (last - first + 5) / 6 + 1 <= kSecCap && last - first >= 36;
+  if (staged) {
+    unsigned char* gap = priv[w] + kSecPad;  // gap[t] <-> cloud point sp + t, t in [-5, n + 5)
+    const int sec = rid * kSectors + w;
+    for (int t = lane - kSecPad; t < n + kSecPad; t += 32) gap[t] = d.gapf[sp + t] ? 2 : 0;
+    __syncwarp();
+    int n_sharp = 0, n_less = 0, n_flat = 0;
+    for (unsigned in_marks = 0u, pass = 0u;; ++pass) {
+      // pass 0: every sector, speculatively without incoming marks; pass j = 1..5: sector j again if it has to
+      bool run = pass == 0u;
+      if (pass > 0u) {
+        __syncthreads();
+        if (pass >= (unsigned)kSectors) break;
+        in_marks = out_marks[pass - 1];
+        run = (unsigned)w == pass && (in_marks & picked5[w]) != 0u;
       }
-      best = warp_max_u64(best);
-      if (best == 0ull) break;
-      if (lane == 0) {
-        const int li = sp - rs + (int)(uint32_t)best;
-        if (pick < kSharp) {
-          st[li] |= 2 << 2;
-          d.i_sharp[sec * kSharp + n_sharp++] = rs + li;
-        } else {
-          st[li] |= 1 << 2;
-        }
-        d.i_less[sec * kLess + n_less++] = rs + li;
-        st[li] |= 1;
-        suppress(st, li);
+      if (run) {
+        unsigned om, pk;
+        if (n <= 256) select_sector_reg<8>(d, gap, d.curv + sp, n, sec, sp, lane, in_marks, om, pk, n_sharp, n_less, n_flat);
+        else if (n <= 512) select_sector_reg<16>(d, gap, d.curv + sp, n, sec, sp, lane, in_marks, om, pk, n_sharp, n_less, n_flat);
+        else select_sector_reg<32>(d, gap, d.curv + sp, n, sec, sp, lane, in_marks, om, pk, n_sharp, n_less, n_flat);
+        if (lane == 0) { out_marks[w] = om; picked5[w] = pk; }
       }
+    }
+    // labels of the sector's points for the less-flat pass below (1 less sharp, 2 sharp, 3 flat), from the final lists
+    for (int t = lane; t < n; t += 32) st[sp - rs + t] = 0;
+    __syncwarp();
+    if (lane < n_less) st[d.i_less[sec * kLess + lane] - rs] = (lane < n_sharp ? 2 : 1) << 2;
+    if (lane < n_flat) st[d.i_flat[sec * kFlat + lane] - rs] = 3 << 2;
+  } else if (w == 0) {
+    for (int t = lane; t < len; t += 32) st[t] = d.gapf[rs + t] ? 2 : 0;
+    __syncwarp();
+    for (int j = 0; j < kSectors; ++j) {
+      const int sp2 = first + (last - first) * j / 6, ep2 = first + (last - first) * (j + 1) / 6 - 1;
+      select_sector(d, st + (sp2 - rs), d.curv + sp2, ep2 - sp2 + 1, rid * kSectors + j, sp2, lane);
       __syncwarp();
     }
-    for (int pick = 0; pick < kFlat; ++pick) {  // :358-394
-      unsigned long long best = ~0ull;
-      for (int t = lane; t < n; t += 32) {
-        const float c = cv[t];
-        if ((double)c < 0.1 && !(ss[t] & 1)) {
-          const unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | (uint32_t)t;
-          best = key < best ? key : best;
-        }
-      }
-      best = warp_min_u64(best);
-      if (best == ~0ull) break;
-      if (lane == 0) {
-        const int li = sp - rs + (int)(uint32_t)best;
-        st[li] |= 3 << 2;
-        d.i_flat[sec * kFlat + n_flat++] = rs + li;
-        if (pick < kFlat - 1) {  // the fourth flat point ends the walk before it is marked (:367-370)
-          st[li] |= 1;
-          suppress(st, li);
-        }
-      }
-      __syncwarp();
-    }
-    if (lane == 0) { d.n_sharp[sec] = n_sharp; d.n_less[sec] = n_less; d.n_flat[sec] = n_flat; }
   }
-  // less-flat points of the ring (:396-402): label <= 0 over first .. last-1, in position order
-  int running = 0;
-  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int base = first; base < last; base += 32) {
+  __syncthreads();
+  // less-flat points of the ring (:396-402): label <= 0 over first .. last-1, in position order; every warp packs
+  // its own sector behind the sectors before it
+  __shared__ int lf_n[kSectors];
+  __shared__ float lf_box[kSectors][6];
+  int mine = 0;
+  for (int base = sp; base <= ep; base += 32) {
     const int k = base + lane;
     bool keep = false;
-    if (k < last) {
+    if (k <= ep) {
+      const int lab = (st[k - rs] >> 2) & 3;
+      keep = lab == 0 || lab == 3;
+    }
+    mine += __popc(__ballot_sync(0xffffffffu, keep));
+  }
+  if (lane == 0) lf_n[w] = mine;
+  __syncthreads();
+  int running = 0;
+  for (int j = 0; j < w; ++j) running += lf_n[j];
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int base = sp; base <= ep; base += 32) {
+    const int k = base + lane;
+    bool keep = false;
+    if (k <= ep) {
       const int lab = (st[k - rs] >> 2) & 3;
       keep = lab == 0 || lab == 3;
     }
@@ -419,9 +559,17 @@ __global__ void __launch_bounds__(32 * kWarps) select_kernel(Dev d) {
       mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
       mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
     }
-  if (lane == 0) {
-    d.lf_cnt[rid] = running;
-    for (int a = 0; a < 3; ++a) { d.rbox[6 * rid + a] = mn[a]; d.rbox[6 * rid + 3 + a] = mx[a]; }
+  if (lane == 0) for (int a = 0; a < 3; ++a) { lf_box[w][a] = mn[a]; lf_box[w][3 + a] = mx[a]; }
+  __syncthreads();
+  if (w == 0 && lane == 0) {
+    int total = 0;
+    for (int j = 0; j < kSectors; ++j) total += lf_n[j];
+    d.lf_cnt[rid] = total;
+    for (int a = 0; a < 3; ++a) {
+      float lo = lf_box[0][a], hi = lf_box[0][3 + a];
+      for (int j = 1; j < kSectors; ++j) { lo = fminf(lo, lf_box[j][a]); hi = fmaxf(hi, lf_box[j][3 + a]); }
+      d.rbox[6 * rid + a] = lo; d.rbox[6 * rid + 3 + a] = hi;
+    }
   }
 }
 
@@ -655,7 +803,7 @@ extern "C" int s2m_fx_extract(s2m_fx* fx, const float* xyz, const int* off, int 
     gather_kernel<<<cdivi(n, T), T, 0, s>>>(d, n); ++k;
     curv_kernel<<<cdivi(n, T), T, 0, s>>>(d, n); ++k;
   }
-  select_kernel<<<cdivi(B * kRings, kWarps), 32 * kWarps, 0, s>>>(d); ++k;
+  select_kernel<<<B * kRings, 32 * kSectors, 0, s>>>(d); ++k;
   const int ns = B * kSecPerScan;
   tb = fx->cub_bytes; cub::DeviceScan::ExclusiveSum(fx->cub_tmp, tb, d.n_sharp, d.o_sharp, ns + 1, s);
   tb = fx->cub_bytes; cub::DeviceScan::ExclusiveSum(fx->cub_tmp, tb, d.n_less, d.o_less, ns + 1, s);
