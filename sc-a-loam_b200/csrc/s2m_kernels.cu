@@ -72,18 +72,21 @@ __global__ void vox_bbox_kernel(Dev d, int n) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int g = -1;
   uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+  // segment of the first and of the last point of the block: equal (almost always) => no search per point and one
+  // reduction per block
+  __shared__ int gs[2];
+  __shared__ uint32_t sm[6][8];
+  const int last = min(n - 1 - (int)(blockIdx.x * blockDim.x), (int)blockDim.x - 1);
+  if (threadIdx.x == 0) gs[0] = find_seg(d.in_off, d.G, i);
+  if ((int)threadIdx.x == last && last > 0) gs[1] = find_seg(d.in_off, d.G, i);
+  __syncthreads();
+  if (last == 0 && threadIdx.x == 0) gs[1] = gs[0];
+  __syncthreads();
   if (i < n) {
-    g = find_seg(d.in_off, d.G, i);
+    g = gs[0] == gs[1] ? gs[0] : find_seg(d.in_off, d.G, i);
     const float4 p = d.in_pts[i];
     mn[0] = mx[0] = f2ord(p.x); mn[1] = mx[1] = f2ord(p.y); mn[2] = mx[2] = f2ord(p.z);
   }
-  // segment of the first and of the last point of the block: equal => one reduction per block
-  __shared__ int gs[2];
-  __shared__ uint32_t sm[6][8];
-  if (threadIdx.x == 0) gs[0] = g;
-  const int last = min(n - 1 - (int)(blockIdx.x * blockDim.x), (int)blockDim.x - 1);
-  if ((int)threadIdx.x == last) gs[1] = g;
-  __syncthreads();
   if (gs[0] == gs[1]) {
 #pragma unroll
     for (int k = 0; k < 3; ++k)
@@ -112,8 +115,15 @@ __global__ void vox_bbox_init_kernel(Dev d) {
 template <bool kNarrow>  // kNarrow: segment + voxel index fit 32 bits -> 4-byte sort keys (one radix pass and a third of the bytes less)
 __global__ void vox_key_kernel(Dev d, int n, int key_bits) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // the block's points almost always belong to one segment: two searches per block instead of one per point
+  __shared__ int gs[2];
+  if (threadIdx.x == 0) {
+    gs[0] = find_seg(d.in_off, d.G, min(i, n - 1));
+    gs[1] = find_seg(d.in_off, d.G, min(i + (int)blockDim.x - 1, n - 1));
+  }
+  __syncthreads();
   if (i >= n) return;
-  const int g = find_seg(d.in_off, d.G, i);
+  const int g = gs[0] == gs[1] ? gs[0] : find_seg(d.in_off, d.G, i);
   const float inv = d.inv_leaf[seg_cls(d, g)];
   float bb[6];
 #pragma unroll
@@ -1868,12 +1878,28 @@ __global__ void __launch_bounds__(kTile, S2M_OD_MINB) odom_search_kernel(Dev d) 
         if (C.ckey[mid] < klo) a = mid + 1; else b = mid;
       }
       rlo[r] = a;
-      for (int e = a; e < C.ln && C.ckey[e] <= klo + 2u; ++e) {
-        const float4 c4 = C.sorted[e];
-        const float dd = dist2(sel[0], sel[1], sel[2], c4.x, c4.y, c4.z);
-        const uint32_t w = __float_as_uint(c4.w);
-        const int idx = (int)(w & 0xFFFFFFu);
-        if (dd < best_d || (dd == best_d && idx < best_i)) { best_d = dd; best_i = idx; best_w = w; }
+      // the row's run of entries, four at a time (their loads in flight together; the run ends at the first key beyond the row)
+      for (int e = a; e < C.ln; e += 4) {
+        uint32_t ck[4];
+        float4 c4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int eu = min(e + u, C.ln - 1);
+          ck[u] = C.ckey[eu];
+          c4[u] = C.sorted[eu];
+        }
+        bool more = true;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          more = more && e + u < C.ln && ck[u] <= klo + 2u;
+          if (more) {
+            const float dd = dist2(sel[0], sel[1], sel[2], c4[u].x, c4[u].y, c4[u].z);
+            const uint32_t w = __float_as_uint(c4[u].w);
+            const int idx = (int)(w & 0xFFFFFFu);
+            if (dd < best_d || (dd == best_d && idx < best_i)) { best_d = dd; best_i = idx; best_w = w; }
+          }
+        }
+        if (!more) break;
       }
     }
     if (!(best_i >= 0 && best_d < kOdSettled)) flags = kOdNeedNN;  // not settled: something outside the cells may be nearer
@@ -1888,18 +1914,33 @@ __global__ void __launch_bounds__(kTile, S2M_OD_MINB) odom_search_kernel(Dev d) 
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       const uint32_t khi = (((uint32_t)(cz + r / 3 - 1) << 20) | ((uint32_t)(cy + r % 3 - 1) << 10) | (uint32_t)(cx - 1)) + 2u;
-      for (int e = rlo[r]; e < C.ln && C.ckey[e] <= khi; ++e) {
-        const float4 c4 = C.sorted[e];
-        const uint32_t w = __float_as_uint(c4.w);
-        const int j = (int)(w & 0xFFFFFFu);
-        if (j <= jbeg || j >= jend || j == best_i) continue;
-        const bool fwd = j > best_i;
-        const int k = od_class(cls, fwd, (int)(w >> 24), id);
-        if (k == 0) continue;
-        const float dd = odom_sq(c4, sel);
-        const int rank = fwd ? j - best_i : C.ln + best_i - j;
-        if (k == 2) { if (dd < m2 || (dd == m2 && rank < k2)) { m2 = dd; k2 = rank; second = j; } }
-        else if (dd < m3 || (dd == m3 && rank < k3)) { m3 = dd; k3 = rank; third = j; }
+      for (int e0 = rlo[r]; e0 < C.ln; e0 += 4) {
+        uint32_t ck[4];
+        float4 c44[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int eu = min(e0 + u, C.ln - 1);
+          ck[u] = C.ckey[eu];
+          c44[u] = C.sorted[eu];
+        }
+        bool more = true;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          more = more && e0 + u < C.ln && ck[u] <= khi;
+          if (!more) continue;
+          const float4 c4 = c44[u];
+          const uint32_t w = __float_as_uint(c4.w);
+          const int j = (int)(w & 0xFFFFFFu);
+          if (j <= jbeg || j >= jend || j == best_i) continue;
+          const bool fwd = j > best_i;
+          const int k = od_class(cls, fwd, (int)(w >> 24), id);
+          if (k == 0) continue;
+          const float dd = odom_sq(c4, sel);
+          const int rank = fwd ? j - best_i : C.ln + best_i - j;
+          if (k == 2) { if (dd < m2 || (dd == m2 && rank < k2)) { m2 = dd; k2 = rank; second = j; } }
+          else if (dd < m3 || (dd == m3 && rank < k3)) { m3 = dd; k3 = rank; third = j; }
+        }
+        if (!more) break;
       }
     }
     if (!(m2 < kOdSettled) || (cls == 1 && !(m3 < kOdSettled))) { flags = kOdNeedWalk; second = third = -1; }
