@@ -420,7 +420,7 @@ def run_ours(args, rank, world, local_rank):
     lane = Lane(pkg, torch, worlds, maps, S, 0, rank, args.warmup + prof_steps, local_rank, args, False)
     lane.run(0, args.warmup, False)
     torch.cuda.synchronize()
-    lane.R.set_profiling(True)
+    lane.R.set_profiling(True, count_candidates=True)
     lane.R.k4_profile(reset=True)
     lane.run(args.warmup, args.warmup + prof_steps, False)
     k4_ms, k4_n, k4_bytes = lane.R.k4_profile(reset=False)
@@ -476,7 +476,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d + C * 64 * 128, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "association = knn_kernel + fit_kernel (transform + exact kNN5 + edge PCA / plane QR + residual/J + Huber + reduce)",
+        "roofline": {"bound": "hbm", "kernel": "association = knn_group_kernel + fit_kernel, plus qgroup_kernel once per frame (transform + exact kNN5 + edge PCA / plane QR + residual/J + Huber + reduce)",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                      "bytes_per_launch_algorithmic": k4_bytes / max(k4_n, 1), "launches": int(k4_n),
                      "avg_launch_us": 1e3 * k4_ms / max(k4_n, 1), "slots_per_launch": S,

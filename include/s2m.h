@@ -205,9 +205,10 @@ long long s2m_debug_knn_fallbacks(s2m_ctx* ctx);
 
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 long long s2m_launch_count(s2m_ctx* ctx);
-/* CUDA-event time (ms) of the fused association kernel (K4) launches since the
- * last call with reset!=0, their count, and the algorithmic bytes they processed
- * (SURVEY.md 8d's B_K4). Requires s2m_set_profiling(ctx,1). */
+/* CUDA-event time (ms) of the association (K4) launches since the last call with reset!=0, their count, and the
+ * algorithmic bytes they processed (SURVEY.md 8d's B_K4). s2m_set_profiling: 0 off, 1 events at the phase boundaries
+ * of every frame, 2 additionally one small kernel per frame (outside the K4 bracket) that counts the map points in
+ * every query's 27 cells -- the candidate term of B_K4; s2m_k4_profile's alg_bytes needs level 2. */
 int s2m_set_profiling(s2m_ctx* ctx, int on);
 int s2m_k4_profile(s2m_ctx* ctx, int reset, double* ms_total, long long* launches,
                    double* alg_bytes);

@@ -542,8 +542,9 @@ class Registrar:
     def launch_count(self):
         return int(self.L.s2m_launch_count(self.h))
 
-    def set_profiling(self, on=True):
-        self._check(self.L.s2m_set_profiling(self.h, int(on)))
+    def set_profiling(self, on=True, count_candidates=False):
+        """events at the phase boundaries of every frame; count_candidates: also the candidate term of K4's bytes"""
+        self._check(self.L.s2m_set_profiling(self.h, (2 if count_candidates else 1) if on else 0))
 
     PHASES = ["input", "voxel", "index", "associate", "solve", "update", "readback"]
 

@@ -194,6 +194,7 @@ struct s2m_ctx {
   size_t bkt_total = 0;
   // profiling: CUDA events at phase boundaries of every frame (on the launching stream)
   bool profiling = false;
+  bool count_candidates = false;  // profiling level 2: also count the map points in every query's 27 cells (K4's algorithmic bytes)
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> ev_phase;      // phase id that ENDS at this event (-1: frame start)
   size_t ev_used = 0;
@@ -850,8 +851,8 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   const int knn_blocks = std::max(1, std::min((chunks + kTile / 32 - 1) / (kTile / 32), knn_resident * ctx->sm_count));
   const int fit_blocks = std::max(1, tiles);
   const int eval_blocks = std::max(1, (tiles + kEvalTilesPerBlock - 1) / kEvalTilesPerBlock);
-  d.count_cand = ctx->profiling ? 1 : 0;
-  if (ctx->profiling) k += launch_count27(d, n_ds, s);  // the byte count of the roofline: outside the K4 bracket
+  d.count_cand = ctx->count_candidates ? 1 : 0;
+  if (ctx->count_candidates) k += launch_count27(d, n_ds, s);  // the byte count of the roofline: outside the K4 bracket
   for (int outer = 0; outer < 2; ++outer) {  // laserMapping.cpp:563
     CK(cudaMemsetAsync(d.knn_ticket, 0, sizeof(int), s));  // the association's work ticket
     prof_mark(ctx, S2M_PHASE_READBACK);  // host wait for the down-sampled counts (outer 0); the K4 bracket starts here
@@ -1625,6 +1626,7 @@ extern "C" int s2m_set_profiling(s2m_ctx* ctx, int on) {
   if (!ctx) return S2M_ERR_ARG;
   for (s2m_ctx* ch : ctx->children) s2m_set_profiling(ch, on);
   ctx->profiling = on != 0;
+  ctx->count_candidates = on >= 2;
   return S2M_OK;
 }
 extern "C" int s2m_k4_profile(s2m_ctx* ctx, int reset, double* ms_total, long long* launches, double* alg_bytes) {
