@@ -353,7 +353,30 @@ class Lane:
         self.steps = None
 
 
+def bind_near_gpu(device, world):
+    """N > 1: run this rank (its lane threads inherit it) on the cores NVML reports as closest to its GPU, so that the
+    pinned staging buffers are first touched -- allocated -- on that NUMA node and the copies do not cross sockets.
+    Skipped for one rank (nothing to contend with) and when the environment disables it (S2M_NO_BIND=1)."""
+    if world <= 1 or os.environ.get("S2M_NO_BIND"):
+        return "none"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return "none (empty NVML affinity)"
+        os.sched_setaffinity(0, cpus)
+        return "%d cores near GPU %d (NVML affinity)" % (len(cpus), device)
+    except Exception as e:  # no NVML / not permitted: run unbound
+        return "none (%s)" % type(e).__name__
+
+
 def run_ours(args, rank, world, local_rank):
+    binding = bind_near_gpu(local_rank, world)
     import torch
     import torch.distributed as dist
     from __graft_entry__ import load_package
@@ -470,6 +493,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "no flush: each step touches >1 GB per lane (64 maps of ~110 k points, sort buffers, clouds), far larger than the 126 MB L2",
                    "maps": "mature: every sequence starts from the map its world has after %d frames (built by the engine, uploaded with s2m_map_upload); see per_registration_mean.n_map_*" % PREFILL,
                    "timing": "CUDA events around the K steps on the caller's stream (the library fences its lanes on it); max over ranks",
+                   "cpu_binding": binding,
                    "per_registration_mean": shape, "datagen_s": round(t_gen, 1),
                    "phase_ms_per_step_single_lane": {k: round(v / prof_steps, 4) for k, v in phases.items()},
                    "host_wall_ms_per_step": round(1e3 * wall_dev / args.steps, 3)},
