@@ -292,6 +292,29 @@ def prepare_worlds(pkg, n_frames, rank, world, device):
     return [merged[w][0] for w in range(N_WORLDS)], [merged[w][1] for w in range(N_WORLDS)]
 
 
+class WcBuffer:
+    """A host copy of `a` in write-combined pinned memory (cudaHostAlloc, cuda-python): what an application would use
+    for buffers the CPU only fills and the GPU only reads; the DMA reads do not snoop the CPU caches."""
+
+    def __init__(self, a):
+        import ctypes
+        from cuda.bindings import runtime as rt
+        a = np.ascontiguousarray(a)
+        err, ptr = rt.cudaHostAlloc(max(a.nbytes, 16), rt.cudaHostAllocWriteCombined | rt.cudaHostAllocPortable)
+        if int(err) != 0:
+            raise RuntimeError("cudaHostAlloc(write-combined) failed: %s" % err)
+        self.ptr, self.nbytes, self._rt = int(ptr), a.nbytes, rt
+        ctypes.memmove(self.ptr, a.ctypes.data, a.nbytes)
+
+    def data_ptr(self):
+        return self.ptr
+
+    def __del__(self):
+        if getattr(self, "ptr", 0):
+            self._rt.cudaFreeHost(self.ptr)
+            self.ptr = 0
+
+
 class Lane:
     """One context holding S sequences split over `lanes` concurrent lanes (own stream + host thread
     each, inside the library): one C-ABI call per step advances all of them."""
@@ -304,7 +327,9 @@ class Lane:
         self.q_all = np.array([[odo[s][f, :4] for s in range(S)] for f in range(n_run)])
         self.t_all = np.array([[odo[s][f, 4:] for s in range(S)] for f in range(n_run)])
         self.host = host_buffers
-        if host_buffers:
+        if host_buffers and args.staging == "wc":
+            self.steps = [(WcBuffer(c), co, WcBuffer(su), so) for c, co, su, so in steps]
+        elif host_buffers:
             self.steps = [(torch.from_numpy(c).pin_memory(), co, torch.from_numpy(su).pin_memory(), so) for c, co, su, so in steps]
         else:
             self.steps = [(torch.from_numpy(c).cuda(), co, torch.from_numpy(su).cuda(), so) for c, co, su, so in steps]
@@ -493,7 +518,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "no flush: each step touches >1 GB per lane (64 maps of ~110 k points, sort buffers, clouds), far larger than the 126 MB L2",
                    "maps": "mature: every sequence starts from the map its world has after %d frames (built by the engine, uploaded with s2m_map_upload); see per_registration_mean.n_map_*" % PREFILL,
                    "timing": "CUDA events around the K steps on the caller's stream (the library fences its lanes on it); max over ranks",
-                   "cpu_binding": binding,
+                   "cpu_binding": binding, "e2e_host_buffers": args.staging,
                    "per_registration_mean": shape, "datagen_s": round(t_gen, 1),
                    "phase_ms_per_step_single_lane": {k: round(v / prof_steps, 4) for k, v in phases.items()},
                    "host_wall_ms_per_step": round(1e3 * wall_dev / args.steps, 3)},
@@ -536,6 +561,7 @@ def main():
     ap.add_argument("--seqs", type=int, default=64, help="independent sequences per lane (<=64)")
     ap.add_argument("--no-pipeline", action="store_true", help="synchronous batch calls instead of submit/wait with two frames in flight")
     ap.add_argument("--ctx", "--lanes", dest="ctx", type=int, default=6, help="concurrent lanes per GPU inside the one context")
+    ap.add_argument("--staging", choices=["pinned", "wc"], default="pinned", help="host buffers of the end-to-end arm: torch pinned memory, or write-combined pinned memory")
     ap.add_argument("--cap-map-corner", type=int, default=1 << 18)
     ap.add_argument("--cap-map-surf", type=int, default=1 << 18)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -218,6 +218,69 @@ def test_lm_converges_like_scipy_on_plane_only_problem(built):
     assert min(np.abs(x[:4] - qs).max(), np.abs(x[:4] + qs).max()) < 1e-6
 
 
+def test_lm_matches_an_independent_minimiser_on_a_mixed_robust_problem(built):
+    """Rows R1 + R2 + L + Q + S together: edge blocks (3 residuals, lidarFactor.hpp:12-55) and plane blocks
+    (lidarFactor.hpp:106-138) under HuberLoss(0.1) applied per BLOCK (laserMapping.cpp:566), with outliers so the
+    robust branch is active.  The restated Ceres trust-region solver run to convergence must reach the minimiser an
+    independent solver (scipy BFGS on the explicitly written robust cost, axis-angle parametrisation, numerical
+    gradients) finds."""
+    from scipy.optimize import minimize
+    rng = np.random.default_rng(23)
+    L = oracle.lib()
+    qt = np.array([-0.015, 0.02, 0.06, 0.0])
+    qt[3] = np.sqrt(1 - qt[:3] @ qt[:3])
+    tt = np.array([0.6, 1.4, -0.3])
+    n_edge, n_plane = 120, 260
+    nb = n_edge + n_plane
+    kinds = np.r_[np.zeros(n_edge, np.int32), np.ones(n_plane, np.int32)]
+    data = np.zeros((nb, 10))
+    for i in range(nb):
+        cp = rng.normal(size=3) * 12
+        w = _rot(qt, cp) + tt
+        noise = 0.02 if rng.uniform() > 0.15 else 0.6       # 15 % outliers, far beyond the Huber scale
+        if kinds[i] == 0:
+            u = rng.normal(size=3)
+            u /= np.linalg.norm(u)
+            c = w + rng.normal(size=3) * noise
+            data[i, :3], data[i, 3:6], data[i, 6:9] = cp, c + 0.1 * u, c - 0.1 * u
+        else:
+            n = rng.normal(size=3)
+            n /= np.linalg.norm(n)
+            data[i, :3], data[i, 3:6], data[i, 6] = cp, n, -(n @ w) + rng.normal() * noise
+    x = np.array([0, 0, 0, 1, 0.55, 1.45, -0.25])
+    ni, te = ctypes.c_int(), ctypes.c_int()
+    L.orc_solve(kinds.ctypes.data, data.ctypes.data, nb, x.ctypes.data, 100, None, ctypes.byref(ni), ctypes.byref(te))
+
+    def quat(p):
+        a = np.linalg.norm(p[:3])
+        return np.r_[np.sin(a / 2) * p[:3] / a, np.cos(a / 2)] if a > 0 else np.array([0, 0, 0, 1.0])
+
+    def cost(p):
+        q, t = quat(p), p[3:]
+        total = 0.0
+        for i in range(nb):
+            lp = _rot(q, data[i, :3]) + t
+            if kinds[i] == 0:
+                a, b = data[i, 3:6], data[i, 6:9]
+                r = np.cross(lp - a, lp - b) / np.linalg.norm(a - b)
+                s2 = r @ r
+            else:
+                s2 = (data[i, 3:6] @ lp + data[i, 6]) ** 2
+            total += 0.5 * (s2 if s2 <= 0.01 else 2 * 0.1 * np.sqrt(s2) - 0.01)     # ceres::HuberLoss(0.1)
+        return total
+
+    sol = minimize(cost, np.r_[1e-3, 1e-3, 1e-3, 0.55, 1.45, -0.25], method="BFGS", options={"gtol": 1e-10, "maxiter": 500})
+    qs = quat(sol.x)
+    assert cost(np.r_[0, 0, 0, x[4:]]) > 0        # (sanity: the cost function runs on the oracle's translation too)
+    assert np.allclose(x[4:], sol.x[3:], atol=2e-5), (x[4:], sol.x[3:])
+    assert min(np.abs(x[:4] - qs).max(), np.abs(x[:4] + qs).max()) < 2e-6
+    # and under the same cost the solver's end point is as good as the independent one, up to Ceres' own stopping
+    # rule (function_tolerance 1e-6, relative)
+    ang = 2 * np.arccos(min(1.0, abs(x[3])))
+    ax = x[:3] / max(np.linalg.norm(x[:3]), 1e-300) * (1 if x[3] >= 0 else -1)
+    assert cost(np.r_[ax * ang, x[4:]]) <= sol.fun * (1 + 1e-6)
+
+
 def test_mapper_first_frame_and_guard(built):
     import harness
     truth, odom, frames = harness.sequence(5, "VLP16", 3)
