@@ -127,6 +127,21 @@ def test_register_on_a_multi_lane_context_goes_through_the_lane_worker(s2m, seq)
         assert ra == rm and np.array_equal(qa, qm) and np.array_equal(ta, tm)
 
 
+def test_blocking_host_waits_change_nothing_but_the_waiting(s2m, seq, monkeypatch):
+    """S2M_SYNC=block: the three host waits of a frame sleep on blocking-sync events instead of spinning (hosts with
+    fewer cores than ranks x lanes).  Same poses, bit for bit, for a plain and a two-lane context."""
+    truth, odom, frames = seq
+    A = s2m.Registrar(0.4, 0.8)
+    ref = [A.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:]) for f in range(4)]
+    monkeypatch.setenv("S2M_SYNC", "block")
+    B = s2m.Registrar(0.4, 0.8)
+    M = s2m.Registrar(0.4, 0.8, batch=2, lanes=2)
+    for f in range(4):
+        for R in (B, M):
+            rc, q, t = R.register(frames[f][0], frames[f][1], odom[f, :4], odom[f, 4:])
+            assert rc == ref[f][0] and np.array_equal(q, ref[f][1]) and np.array_equal(t, ref[f][2])
+
+
 def test_capacities_are_validated_at_create(s2m, built):
     # leaf 4 m: 13 voxels per cube axis -> the arrival field of the update key is 18 bits
     with pytest.raises(s2m.S2MError):
