@@ -898,10 +898,7 @@ __global__ void __launch_bounds__(kTile, S2M_K4A_MINB) knn_kernel(Dev d, int out
 #define S2M_KNN_POOL 512
 #endif
 constexpr int kGPool = S2M_KNN_POOL;  // candidates a warp stages per round (16 bytes each)
-#ifndef S2M_KNN_HITS
-#define S2M_KNN_HITS 256
-#endif
-constexpr int kGHits = S2M_KNN_HITS;  // occupied cells a warp may stage per chunk
+constexpr int kGHits = 256;           // occupied cells a warp may stage per chunk
 constexpr int kGIdxBits = 10;         // a candidate's position in its group's range rides in the low bits of its distance
 static_assert(kGPool <= (1 << kGIdxBits) && kGPool * sizeof(float4) >= sizeof(KnnStage), "positions are 10 bits; the fallback stages in the pool");
 struct KnnGroupSmem {
