@@ -781,7 +781,9 @@ static int run_frame(s2m_ctx* ctx, const int* corner_off, const int* surf_off, c
   // clouds (exact width of PCL's voxel index = radix passes of the scan filter) and the sizes of the
   // local maps (25 ranges of the sorted store: the guard :555, the staging of raw points, the sizing of a
   // rebuilt cell index).  The round trip is hidden by the other lanes sharing the GPU.
-  k += launch_voxel_bbox(d, total_in, s);
+  int longest_in = 0;
+  for (int g = 0; g < G; ++g) longest_in = std::max(longest_in, T.in_off[g + 1] - T.in_off[g]);
+  k += launch_voxel_bbox(d, total_in, longest_in, s);
   k += launch_local_ranges(d, ctx->cur, s);
   CK(cudaMemcpyAsync(ctx->h_bbox, d.bbox, sizeof(uint32_t) * 6 * G, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(ctx->h_lpcnt, d.lp_cnt, sizeof(int) * 2 * G, cudaMemcpyDeviceToHost, s));

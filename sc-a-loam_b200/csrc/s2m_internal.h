@@ -207,7 +207,7 @@ int launch_guard_check(const GuardDesc* g, int n, int* bad, cudaStream_t s);
 
 // launchers (s2m_kernels.cu); every one returns the number of kernels it launched
 size_t cub_temp_bytes(int cap_sort, int cap_lp);
-int launch_voxel_bbox(const Dev& d, int total_in, cudaStream_t s);
+int launch_voxel_bbox(const Dev& d, int total_in, int longest_segment, cudaStream_t s);
 int launch_voxel_filter(const Dev& d, int total_in, int key_bits, cudaStream_t s);
 int launch_local_ranges(const Dev& d, int cur, cudaStream_t s);
 int launch_index_rebuild(const Dev& d, int cur, int n_seg, int total_points, cudaStream_t s);

@@ -66,45 +66,35 @@ __device__ __forceinline__ uint32_t f2ord(float f) {
 __device__ __forceinline__ float ord2f(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
-// bbox[g][0..2] = min (init 0xFFFFFFFF), bbox[g][3..5] = max (init 0), ordered-uint encoded
-__global__ void vox_bbox_kernel(Dev d, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int g = -1;
-  uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
-  // segment of the first and of the last point of the block: equal (almost always) => no search per point and one
-  // reduction per block
-  __shared__ int gs[2];
+// bbox[g][0..2] = min (init 0xFFFFFFFF), bbox[g][3..5] = max (init 0), ordered-uint encoded.
+// grid (chunks of the longest segment, segments): a block covers kBoxPts consecutive points of ONE segment
+// (kBoxPts / 256 per thread, strided so the loads coalesce) and adds its box with six atomics.
+constexpr int kBoxPts = 2048;
+__global__ void __launch_bounds__(256) vox_bbox_kernel(Dev d) {
+  const int g = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int p0 = d.in_off[g] + blockIdx.x * kBoxPts, p1 = min(p0 + kBoxPts, d.in_off[g + 1]);
+  if (p0 >= p1) return;
   __shared__ uint32_t sm[6][8];
-  const int last = min(n - 1 - (int)(blockIdx.x * blockDim.x), (int)blockDim.x - 1);
-  if (threadIdx.x == 0) gs[0] = find_seg(d.in_off, d.G, i);
-  if ((int)threadIdx.x == last && last > 0) gs[1] = find_seg(d.in_off, d.G, i);
-  __syncthreads();
-  if (last == 0 && threadIdx.x == 0) gs[1] = gs[0];
-  __syncthreads();
-  if (i < n) {
-    g = gs[0] == gs[1] ? gs[0] : find_seg(d.in_off, d.G, i);
+  uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+  for (int i = p0 + (int)threadIdx.x; i < p1; i += 256) {
     const float4 p = d.in_pts[i];
-    mn[0] = mx[0] = f2ord(p.x); mn[1] = mx[1] = f2ord(p.y); mn[2] = mx[2] = f2ord(p.z);
+    const uint32_t ox = f2ord(p.x), oy = f2ord(p.y), oz = f2ord(p.z);
+    mn[0] = min(mn[0], ox); mn[1] = min(mn[1], oy); mn[2] = min(mn[2], oz);
+    mx[0] = max(mx[0], ox); mx[1] = max(mx[1], oy); mx[2] = max(mx[2], oz);
   }
-  if (gs[0] == gs[1]) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
-      for (int o = 16; o > 0; o >>= 1) {
-        mn[k] = min(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-        mx[k] = max(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-      }
-    if (lane == 0) for (int k = 0; k < 3; ++k) { sm[k][wid] = mn[k]; sm[3 + k][wid] = mx[k]; }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-      uint32_t v = sm[threadIdx.x][0];
-      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = threadIdx.x < 3 ? min(v, sm[threadIdx.x][w]) : max(v, sm[threadIdx.x][w]);
-      if (threadIdx.x < 3) atomicMin(d.bbox + 6 * gs[0] + threadIdx.x, v);
-      else atomicMax(d.bbox + 6 * gs[0] + threadIdx.x, v);
+  for (int k = 0; k < 3; ++k)
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[k] = min(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+      mx[k] = max(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
     }
-  } else if (g >= 0) {  // block straddles a segment boundary (at most G of them)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { atomicMin(d.bbox + 6 * g + k, mn[k]); atomicMax(d.bbox + 6 * g + 3 + k, mx[k]); }
+  if (lane == 0) for (int k = 0; k < 3; ++k) { sm[k][wid] = mn[k]; sm[3 + k][wid] = mx[k]; }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    uint32_t v = sm[threadIdx.x][0];
+    for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? min(v, sm[threadIdx.x][w]) : max(v, sm[threadIdx.x][w]);
+    if (threadIdx.x < 3) atomicMin(d.bbox + 6 * g + threadIdx.x, v);
+    else atomicMax(d.bbox + 6 * g + threadIdx.x, v);
   }
 }
 __global__ void vox_bbox_init_kernel(Dev d) {
@@ -2776,11 +2766,11 @@ size_t cub_temp_bytes(int cap_sort, int cap_lp) {
   return std::max(std::max(a, b), std::max(c, e)) + 256;
 }
 
-int launch_voxel_bbox(const Dev& d, int n, cudaStream_t s) {
+int launch_voxel_bbox(const Dev& d, int n, int longest_segment, cudaStream_t s) {
   int k = 0;
   if (n > 0) {
     vox_bbox_init_kernel<<<cdiv(6 * d.G, 256), 256, 0, s>>>(d); ++k;
-    vox_bbox_kernel<<<cdiv(n, 256), 256, 0, s>>>(d, n); ++k;
+    vox_bbox_kernel<<<dim3(cdiv(std::max(longest_segment, 1), kBoxPts), d.G), 256, 0, s>>>(d); ++k;
   }
   return k;
 }
