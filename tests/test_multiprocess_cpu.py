@@ -52,3 +52,20 @@ def test_slabs_partition_the_window(s2m, built):
         for a, b in zip(slabs[:-1], slabs[1:]):
             assert a[1] == b[0] and a[0] < a[1]
             assert (a[1] + 25.0) % 50.0 == 0.0  # slab faces are cube faces (laserMapping.cpp:313-315)
+
+
+def test_rank_binding_is_harmless_without_a_gpu(built, monkeypatch):
+    """bench.bind_near_gpu: one rank is never bound; several ranks bind to the cores NVML reports as nearest to their
+    GPU and fall back to "none (...)" -- leaving the affinity untouched -- when NVML or the device is not there."""
+    sys.path.insert(0, ROOT)
+    import bench
+    before = os.sched_getaffinity(0)
+    assert bench.bind_near_gpu(0, 1) == "none"
+    monkeypatch.setenv("S2M_NO_BIND", "1")
+    assert bench.bind_near_gpu(0, 8) == "none"
+    monkeypatch.delenv("S2M_NO_BIND")
+    msg = bench.bind_near_gpu(0, 8)
+    assert isinstance(msg, str) and (msg.startswith("none") or "cores near GPU" in msg)
+    if msg.startswith("none"):
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
